@@ -1,0 +1,101 @@
+"""ctypes binding of libgi2d.so (the C ABI declared in include/gi2d.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or a call fails, the product
+path raises.  (The CPU oracle under oracle/ is test infrastructure and is never imported here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libgi2d.so")
+
+GI2D_OK = 0
+ERR_NAMES = {-1: "GI2D_ERR_INVALID", -2: "GI2D_ERR_CUDA", -3: "GI2D_ERR_WORKSPACE"}
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+_SZ = C.c_size_t
+
+
+class FitParams(C.Structure):
+    """struct gi2d_fit_params (include/gi2d.h)"""
+    _fields_ = [
+        ("num_points", C.c_int32), ("img_width", C.c_int32), ("img_height", C.c_int32),
+        ("tiles_x", C.c_int32), ("tiles_y", C.c_int32),
+        ("tile_row_begin", C.c_int32), ("tile_row_end", C.c_int32),
+        ("isect_capacity", C.c_int32),
+        ("clip_coe", C.c_float), ("radius_clip", C.c_float),
+        ("lr0", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("lr_step_size", C.c_int32), ("lr_gamma", C.c_float),
+        ("color_sigmoid", C.c_int32), ("loss_scale", C.c_float),
+    ]
+
+
+class FitBuffers(C.Structure):
+    """struct gi2d_fit_buffers (include/gi2d.h)"""
+    _fields_ = [
+        ("xyz", _P), ("cov", _P), ("cov_bound", _P), ("rgb", _P),
+        ("m_xyz", _P), ("v_xyz", _P), ("m_cov", _P), ("v_cov", _P), ("m_rgb", _P), ("v_rgb", _P),
+        ("gt_hwc", _P), ("out_img", _P),
+        ("grads", _P), ("proj", _P), ("sorted_keys", _P), ("tile_bins", _P), ("stats", _P),
+        ("workspace", _P), ("workspace_bytes", _SZ),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/gi2d.h declares
+SIGNATURES = {
+    "gi2d_abi_version": (_I, []),
+    "gi2d_last_error": (C.c_char_p, []),
+    "gi2d_project_cov_fwd": (_I, [_I, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "gi2d_project_chol_fwd": (_I, [_I, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "gi2d_project_rs_fwd": (_I, [_I, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "gi2d_compute_cov2d_bounds": (_I, [_I, _F, _P, _P, _P, _P]),
+    "gi2d_project_cov_bwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gi2d_project_chol_bwd": (_I, [_I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gi2d_project_rs_bwd": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gi2d_scan_workspace_size": (_SZ, [_I]),
+    "gi2d_cumsum_i32": (_I, [_I, _P, _P, _P, _P, _SZ, _P]),
+    "gi2d_map_gaussian_to_intersects": (_I, [_I, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P]),
+    "gi2d_sort_workspace_size": (_SZ, [_I]),
+    "gi2d_sort_pairs_i64": (_I, [_I, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
+    "gi2d_get_tile_bin_edges": (_I, [_I, _P, _P, _I, _P]),
+    "gi2d_rasterize_sum_fwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gi2d_rasterize_sum_bwd": (_I, [_I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gi2d_fit_workspace_size": (_SZ, [C.POINTER(FitParams)]),
+    "gi2d_fit_forward_backward": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _P]),
+    "gi2d_fit_adam": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _P]),
+    "gi2d_fit_reset": (_I, [C.POINTER(FitBuffers), _I, _P]),
+}
+
+_lib = None
+
+
+class Gi2dError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libgi2d.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Gi2dError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C gaussianimage_plus_b200/csrc`.  There is no CPU fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != GI2D_OK:
+        msg = load().gi2d_last_error().decode(errors="replace")
+        raise Gi2dError(f"{what or 'gi2d'} failed: {ERR_NAMES.get(rc, rc)}: {msg}")

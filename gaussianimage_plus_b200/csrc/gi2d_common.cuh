@@ -1,0 +1,103 @@
+// gi2d_common.cuh -- shared device helpers for libgi2d (sm_100a).
+//
+// Floating-point discipline: every operation that decides an INTEGER (radius, tile bbox,
+// cull tests) is spelled with explicit round-to-nearest intrinsics in the exact order the
+// reference's -O3 build executes them (SASS of csrc/foward2d.cu:192-288 and
+// csrc/helpers.cuh:16-50,179-206 for sm_100a), so the compiler can neither contract nor
+// re-associate them.  That is what makes radii / num_tiles_hit / tile ranges bit-exact.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/gi2d.h"
+
+namespace gi2d {
+
+constexpr int kTile = GI2D_TILE;
+constexpr int kTilePixels = kTile * kTile;
+constexpr int kMaxPerTile = GI2D_MAX_PER_TILE;
+
+void set_error(const char *fmt, ...);
+int check_launch(const char *what);
+
+#define GI2D_REQUIRE(cond, msg)                         \
+    do {                                                \
+        if (!(cond)) {                                  \
+            gi2d::set_error("%s: %s", __func__, msg);   \
+            return GI2D_ERR_INVALID;                    \
+        }                                               \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- (int) cast of the reference: cvt.rzi.s32.f32 (truncate, saturate, NaN -> 0). SURVEY Q9.
+__device__ __forceinline__ int f2i_rz(float v) { return __float2int_rz(v); }
+
+// ---- helpers.cuh:179-206 compute_cov2d_bounds, op-for-op as the -O3 SASS:
+//   det = fma(x, z, -(y*y));  inv = 1/det (IEEE);  conic = (z*inv, y*(-inv), x*inv)
+//   b = (x+z)*0.5;  t = max(fma(b,b,-det), 0.1);  s = sqrt(t);  v1 = b+s, v2 = b-s
+//   radius = ceil(clip * sqrt(max|min(v1,v2)))
+struct Cov2dBounds {
+    float a, b, c;   // conic
+    float rx, ry;    // radius.x (major), radius.y (minor); may be NaN / inf
+    bool ok;         // false when det == 0
+};
+
+__device__ __forceinline__ Cov2dBounds cov2d_bounds(float sx, float sxy, float sy, float clip_coe) {
+    Cov2dBounds o;
+    const float det = __fmaf_rn(sx, sy, -__fmul_rn(sxy, sxy));
+    o.ok = !(det == 0.f);
+    if (!o.ok) {
+        o.a = o.b = o.c = 0.f;
+        o.rx = o.ry = 0.f;
+        return o;
+    }
+    const float inv = __frcp_rn(det);
+    o.a = __fmul_rn(sy, inv);
+    o.b = __fmul_rn(sxy, -inv);
+    o.c = __fmul_rn(sx, inv);
+    const float hb = __fmul_rn(__fadd_rn(sx, sy), 0.5f);
+    const float t = fmaxf(__fmaf_rn(hb, hb, -det), 0.1f);
+    const float s = __fsqrt_rn(t);
+    const float v1 = __fadd_rn(hb, s);
+    const float v2 = __fsub_rn(hb, s);
+    o.rx = ceilf(__fmul_rn(__fsqrt_rn(fmaxf(v1, v2)), clip_coe));
+    o.ry = ceilf(__fmul_rn(__fsqrt_rn(fminf(v1, v2)), clip_coe));
+    return o;
+}
+
+// ---- helpers.cuh:16-50 get_bbox/get_tile_bbox: /16 is an exact scaling, so
+//   min = clamp((int)(c/16 - r/16), 0, tb),  max = clamp((int)((c/16 + r/16) + 1), 0, tb)
+struct TileBox {
+    int x0, y0, x1, y1;  // inclusive min, exclusive max, in tiles
+};
+
+__device__ __forceinline__ TileBox tile_bbox(float cx, float cy, float radius, int tiles_x, int tiles_y) {
+    const float r16 = __fmul_rn(radius, 0.0625f);
+    const float tx = __fmul_rn(cx, 0.0625f), ty = __fmul_rn(cy, 0.0625f);
+    TileBox t;
+    t.x0 = min(max(0, f2i_rz(__fsub_rn(tx, r16))), tiles_x);
+    t.x1 = min(max(0, f2i_rz(__fadd_rn(__fadd_rn(tx, r16), 1.f))), tiles_x);
+    t.y0 = min(max(0, f2i_rz(__fsub_rn(ty, r16))), tiles_y);
+    t.y1 = min(max(0, f2i_rz(__fadd_rn(__fadd_rn(ty, r16), 1.f))), tiles_y);
+    return t;
+}
+
+// ---- the pair evaluation of csrc/forward.cu:652-661, op-for-op as the -O3 SASS:
+//   sigma = fma(dy, b*dx, 0.5*fma(dx, a*dx, dy*(c*dy)));  vis = ex2(-sigma*log2e)
+// ex2.approx.ftz differs from the reference's guarded ex2.approx only for results below
+// 2^-126, which both fail alpha >= 1/255.
+__device__ __forceinline__ float pair_sigma(float a, float b, float c, float dx, float dy) {
+    const float q = __fmaf_rn(dx, __fmul_rn(a, dx), __fmul_rn(dy, __fmul_rn(c, dy)));
+    return __fmaf_rn(dy, __fmul_rn(b, dx), __fmul_rn(q, 0.5f));
+}
+
+__device__ __forceinline__ float fast_exp_neg(float sigma) {
+    float r;
+    const float t = __fmul_rn(sigma, -1.4426950216293334961f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
+}
+
+constexpr float kAlphaMin = 1.f / 255.f;
+
+}  // namespace gi2d

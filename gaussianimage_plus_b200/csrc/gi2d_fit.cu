@@ -1,0 +1,579 @@
+// gi2d_fit.cu -- the fused, synchronisation-free fit step: everything one
+// `train_iter` of models/gaussianimage_covariance.py:249-259 does on the device, in 5 launches
+// for images of up to 2048 tiles (768x512) and 8 beyond, with no host round trip, no allocation
+// and a device-side step counter, so the whole iteration replays from one CUDA graph.
+//
+//   K1 fit_project_kernel   projection (R1) + colour activation + packed 32-B record per
+//                           Gaussian + zeroing of the gradient rows + per-CTA digit histogram of
+//                           the tile ids the Gaussian touches                       [HBM/latency]
+//   K2 fit_scan_kernel      prefix sum over the per-tile (digit) overlap counts -> scatter
+//                           offsets, tile ranges, num_intersects                    [latency]
+//   K3 fit_scatter_kernel   stable counting-sort scatter of 64-bit (tile<<32|gaussian) keys:
+//                           one LSD radix pass of up to 11 bits, ranks by warp match_any over a
+//                           load-balanced expansion of the tile boxes               [HBM/latency]
+//      (+ gi2d radix pass + tile edges for images with more than 2048 tiles)
+//   K4 fit_raster_kernel    per 16x16 tile: rasterize-sum forward (R5), L2 loss gradient and
+//                           squared error, rasterize-sum backward (R6) with register
+//                           accumulation + transposed warp reduction + one red.global per
+//                           (tile, Gaussian, component)                             [FP32 issue]
+//   K5 fit_adam_kernel      projection backward (R7) + Adam + StepLR on xyz/cov/rgb [HBM]
+//
+// Ordering inside a tile is ascending Gaussian id (what the reference's stable sort of
+// (tile<<32|depth=0) keys emitted Gaussian-major yields), so tile ranges, sorted ids and the
+// rendered image are bit-identical to the reference-shaped path in gi2d_binning.cu/gi2d_raster.cu.
+#include "gi2d_project_core.cuh"
+#include "gi2d_raster_core.cuh"
+#include "gi2d_scan.cuh"
+
+namespace gi2d {
+
+// implemented in gi2d_binning.cu: one 8-bit-digit LSD pass over u64 keys (no payload)
+int radix_pass_keys_u64(int n_capacity, const int32_t *n_dev, const uint64_t *keys_in, uint64_t *keys_out,
+                        int shift, int bits, void *workspace, size_t workspace_bytes, cudaStream_t st);
+size_t radix_pass_workspace_size(int n_capacity);
+int tile_edges_from_keys_u64(int n_capacity, const int32_t *n_dev, const uint64_t *keys, int32_t *tile_bins,
+                             int rows, cudaStream_t st);
+
+namespace {
+
+constexpr int kMaxDigitBits = 11;                 // 2048 bins: a 768x512 image sorts in ONE pass
+constexpr int kProjThreads = 256;
+constexpr int kScatterWarps = 4;
+constexpr int kScatterThreads = kScatterWarps * 32;
+constexpr int kRasterThreads = 256;
+
+struct Plan {
+    int tile_bits;     // bits needed for a tile id
+    int bits0;         // digit width of the in-kernel pass
+    int gpb;           // Gaussians per CTA of K1/K3 (multiple of kScatterThreads)
+    int nblocks;       // CTAs of K1/K3
+    int extra_passes;  // additional 8-bit passes over the high tile bits
+};
+
+Plan make_plan(const gi2d_fit_params &p) {
+    Plan pl;
+    const int tiles = p.tiles_x * p.tiles_y;
+    int tb = 1;
+    while ((1 << tb) < tiles) ++tb;
+    pl.tile_bits = tb;
+    pl.bits0 = tb < kMaxDigitBits ? tb : kMaxDigitBits;
+    pl.extra_passes = (tb - pl.bits0 + 7) / 8;
+    // keep the count matrix (nblocks x 2^bits0) scannable by one CTA: <= ~1184 CTAs
+    int gpb = kScatterThreads;
+    while ((long long)gpb * 1184 < p.num_points) gpb *= 2;
+    pl.gpb = gpb;
+    pl.nblocks = p.num_points > 0 ? cdiv(p.num_points, gpb) : 1;
+    return pl;
+}
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct Workspace {
+    int32_t *counts;      // [nblocks][D] per-CTA digit counts -> per-CTA exclusive offsets
+    int32_t *digit_base;  // [D]
+    ushort4 *boxes;       // [N] clipped tile box per Gaussian
+    int32_t *n_isect;     // [1] device copy of num_intersects (clamped to capacity)
+    uint64_t *keys_tmp;   // [capacity] ping-pong buffer for multi-pass sorts
+    void *radix_ws;
+    size_t radix_ws_bytes;
+    size_t total;
+};
+
+Workspace carve(const gi2d_fit_params &p, const Plan &pl, void *base) {
+    Workspace w;
+    char *c = (char *)base;
+    size_t off = 0;
+    const size_t D = (size_t)1 << pl.bits0;
+    w.counts = (int32_t *)(c + off);      off += align_up((size_t)pl.nblocks * D * 4);
+    w.digit_base = (int32_t *)(c + off);  off += align_up(D * 4);
+    w.boxes = (ushort4 *)(c + off);       off += align_up((size_t)(p.num_points > 0 ? p.num_points : 1) * 8);
+    w.n_isect = (int32_t *)(c + off);     off += 256;
+    w.keys_tmp = nullptr;
+    w.radix_ws = nullptr;
+    w.radix_ws_bytes = 0;
+    if (pl.extra_passes > 0) {
+        w.keys_tmp = (uint64_t *)(c + off);  off += align_up((size_t)p.isect_capacity * 8);
+        w.radix_ws = (void *)(c + off);
+        w.radix_ws_bytes = radix_pass_workspace_size(p.isect_capacity);
+        off += align_up(w.radix_ws_bytes);
+    }
+    w.total = off;
+    return w;
+}
+
+__device__ __forceinline__ float sigmoidf(float v) { return 1.f / (1.f + expf(-v)); }
+
+// ------------------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(kProjThreads)
+fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, const float *__restrict__ xyz,
+                   const float *__restrict__ cov, const float *__restrict__ cov_bound,
+                   const float *__restrict__ rgb, float4 *__restrict__ proj,
+                   float4 *__restrict__ grads, ushort4 *__restrict__ boxes,
+                   int32_t *__restrict__ counts, double *__restrict__ stats, int with_backward) {
+    extern __shared__ int s_hist[];
+    const int D = 1 << bits0;
+    const int mask = D - 1;
+    for (int d = threadIdx.x; d < D; d += kProjThreads) s_hist[d] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < GI2D_STAT_SSE_SLOTS) stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        stats[GI2D_STAT_OVERFLOW] = 0.0;
+        if (with_backward) stats[GI2D_STAT_STEP] += 1.0;
+    }
+    __syncthreads();
+    const int g0 = blockIdx.x * gpb;
+    const int g1 = min(p.num_points, g0 + gpb);
+    for (int g = g0 + threadIdx.x; g < g1; g += kProjThreads) {
+        const float2 m = __ldg(reinterpret_cast<const float2 *>(xyz) + g);
+        // get_cov2d_elements = _cov2d + cholesky_bound (gaussianimage_covariance.py:169)
+        const float sx = __fadd_rn(__ldg(cov + 3 * g), __ldg(cov_bound + 3 * g));
+        const float sxy = __fadd_rn(__ldg(cov + 3 * g + 1), __ldg(cov_bound + 3 * g + 1));
+        const float sy = __fadd_rn(__ldg(cov + 3 * g + 2), __ldg(cov_bound + 3 * g + 2));
+        float cr = __ldg(rgb + 3 * g), cg = __ldg(rgb + 3 * g + 1), cb = __ldg(rgb + 3 * g + 2);
+        if (p.color_sigmoid) { cr = sigmoidf(cr); cg = sigmoidf(cg); cb = sigmoidf(cb); }
+        const Projected pr = project_cov(m.x, m.y, sx, sxy, sy, p.clip_coe, p.radius_clip, p.tiles_x, p.tiles_y);
+        proj[2 * g] = make_float4(pr.x, pr.y, pr.a, pr.b);
+        proj[2 * g + 1] = make_float4(pr.c, cr, cg, cb);
+        if (with_backward) {
+            grads[2 * g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            grads[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // the map kernel's own cull (forward.cu:161) and the band owned by this rank
+        int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+        if (pr.ntiles > 0 && !((float)pr.radius < p.radius_clip)) {
+            x0 = pr.box.x0; x1 = pr.box.x1;
+            y0 = max(pr.box.y0, p.tile_row_begin);
+            y1 = min(pr.box.y1, p.tile_row_end);
+            if (y1 <= y0) { x0 = x1 = y0 = y1 = 0; }
+        }
+        boxes[g] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+        for (int ty = y0; ty < y1; ++ty)
+            for (int tx = x0; tx < x1; ++tx) atomicAdd(&s_hist[(ty * p.tiles_x + tx) & mask], 1);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += kProjThreads) counts[(size_t)blockIdx.x * D + d] = s_hist[d];
+}
+
+// ------------------------------------------------------------------------------------ K2
+// One CTA.  counts[b][d] -> exclusive prefix over b (in place); digit_base[d] = exclusive prefix
+// over d of the column totals.  With a single pass (D covers every tile id) the tile ranges
+// fall out directly.
+__global__ void __launch_bounds__(1024)
+fit_scan_kernel(int nblocks, int bits0, int num_tiles, int single_pass, int capacity,
+                int32_t *__restrict__ counts, int32_t *__restrict__ digit_base,
+                int32_t *__restrict__ tile_bins, int32_t *__restrict__ n_isect,
+                double *__restrict__ stats) {
+    __shared__ int s_tot[1 << kMaxDigitBits];
+    __shared__ int s_warp[32];
+    const int D = 1 << bits0;
+    for (int d = threadIdx.x; d < D; d += 1024) {
+        int run = 0;
+        int32_t *col = counts + d;
+#pragma unroll 8
+        for (int b = 0; b < nblocks; ++b) {
+            const int c = col[(size_t)b * D];
+            col[(size_t)b * D] = run;
+            run += c;
+        }
+        s_tot[d] = run;
+    }
+    __syncthreads();
+    // exclusive scan of s_tot[0..D): each thread owns a contiguous pair (D <= 2048)
+    const int per = (D + 1023) / 1024;  // 1 or 2
+    int v0 = 0, v1 = 0;
+    const int i0 = threadIdx.x * per;
+    if (i0 < D) v0 = s_tot[i0];
+    if (per == 2 && i0 + 1 < D) v1 = s_tot[i0 + 1];
+    int total;
+    const int incl = block_scan_inclusive<1024>(v0 + v1, s_warp, &total);
+    const int excl = incl - (v0 + v1);
+    if (i0 < D) {
+        digit_base[i0] = excl;
+        if (single_pass && i0 < num_tiles) {
+            tile_bins[2 * i0] = excl;
+            tile_bins[2 * i0 + 1] = excl + v0;
+        }
+    }
+    if (per == 2 && i0 + 1 < D) {
+        digit_base[i0 + 1] = excl + v0;
+        if (single_pass && i0 + 1 < num_tiles) {
+            tile_bins[2 * (i0 + 1)] = excl + v0;
+            tile_bins[2 * (i0 + 1) + 1] = excl + v0 + v1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        stats[GI2D_STAT_ISECTS] = (double)total;
+        if (total > capacity) stats[GI2D_STAT_OVERFLOW] = 1.0;
+        *n_isect = total > capacity ? capacity : total;
+    }
+}
+
+// ------------------------------------------------------------------------------------ K3
+// Walk the intersections of a warp's Gaussians in emission order (Gaussian-major, tiles
+// row-major: forward.cu:187-196), 32 at a time, load balanced: lane i of a chunk owns Gaussian
+// i, an inclusive scan of the box areas gives every intersection its slot, a 5-step shuffle
+// search gives every slot its owner.  `visit(valid, tile, gaussian)` is called warp-converged.
+template <class Visit>
+__device__ __forceinline__ void walk_intersections(int g_begin, int g_end, int tiles_x,
+                                                   const ushort4 *__restrict__ boxes, Visit visit) {
+    const int lane = threadIdx.x & 31;
+    for (int base = g_begin; base < g_end; base += 32) {
+        const int g = base + lane;
+        ushort4 bx = make_ushort4(0, 0, 0, 0);
+        if (g < g_end) bx = boxes[g];
+        const int w = (int)bx.z - (int)bx.x;
+        const int n = w * ((int)bx.w - (int)bx.y);
+        const int incl = warp_scan_inclusive(n);
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int s = 0; s < total; s += 32) {
+            const int it = s + lane;
+            // owner = smallest j with incl_j > it
+            int lo = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+                if (probe <= it) lo += step;
+            }
+            const int owner = min(lo, 31);
+            const int o_incl = __shfl_sync(0xffffffffu, incl, owner);
+            const int o_n = __shfl_sync(0xffffffffu, n, owner);
+            const int o_w = __shfl_sync(0xffffffffu, w, owner);
+            const int o_x0 = __shfl_sync(0xffffffffu, (int)bx.x, owner);
+            const int o_y0 = __shfl_sync(0xffffffffu, (int)bx.y, owner);
+            const bool valid = it < total;
+            int tile = 0;
+            if (valid) {
+                const int k = it - (o_incl - o_n);
+                const int ry = k / o_w;
+                tile = (o_y0 + ry) * tiles_x + o_x0 + (k - ry * o_w);
+            }
+            visit(valid, tile, base + owner);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kScatterThreads)
+fit_scatter_kernel(int num_points, int gpb, int bits0, int tiles_x, int capacity,
+                   const ushort4 *__restrict__ boxes, const int32_t *__restrict__ counts,
+                   const int32_t *__restrict__ digit_base, uint64_t *__restrict__ keys_out) {
+    extern __shared__ int s_cnt[];  // [kScatterWarps][D]
+    const int D = 1 << bits0;
+    const int mask = D - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kScatterWarps * D; i += kScatterThreads) s_cnt[i] = 0;
+    __syncthreads();
+    const int gpw = gpb / kScatterWarps;
+    const int g_begin = min(num_points, blockIdx.x * gpb + warp * gpw);
+    const int g_end = min(num_points, g_begin + gpw);
+    int *my_cnt = s_cnt + warp * D;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // phase A: per-warp digit counts
+    walk_intersections(g_begin, g_end, tiles_x, boxes, [&](bool valid, int tile, int) {
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const int d = tile & mask;
+            const unsigned peers = __match_any_sync(act, d);
+            if (lane == __ffs(peers) - 1) my_cnt[d] += __popc(peers);
+        }
+        __syncwarp();
+    });
+    __syncthreads();
+    // phase B: per digit, exclusive scan over the warps on top of the global offset of (CTA, digit)
+    for (int d = threadIdx.x; d < D; d += kScatterThreads) {
+        int run = counts[(size_t)blockIdx.x * D + d] + digit_base[d];
+#pragma unroll
+        for (int w = 0; w < kScatterWarps; ++w) {
+            const int c = s_cnt[w * D + d];
+            s_cnt[w * D + d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // phase C: same walk, now ranking and writing
+    walk_intersections(g_begin, g_end, tiles_x, boxes, [&](bool valid, int tile, int g) {
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const int d = tile & mask;
+            const unsigned peers = __match_any_sync(act, d);
+            const int leader = __ffs(peers) - 1;
+            int old = 0;
+            if (lane == leader) {
+                old = my_cnt[d];
+                my_cnt[d] = old + __popc(peers);
+            }
+            old = __shfl_sync(peers, old, leader);
+            const int pos = old + __popc(peers & lt_mask);
+            if (pos < capacity) keys_out[pos] = ((uint64_t)(uint32_t)tile << 32) | (uint32_t)g;
+        }
+        __syncwarp();
+    });
+}
+
+// ------------------------------------------------------------------------------------ K4
+enum class RasterMode { Render, Fit };
+
+template <RasterMode kMode>
+__global__ void __launch_bounds__(kRasterThreads)
+fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
+                  const int32_t *__restrict__ tile_bins, const float4 *__restrict__ proj,
+                  const float *__restrict__ gt, float *__restrict__ out_img,
+                  float *__restrict__ grads, double *__restrict__ stats) {
+    __shared__ TileRecords sg;
+    __shared__ int s_ids[kMaxPerTile];
+    __shared__ float s_v[3][kTilePixels];
+    __shared__ float s_red[kRasterThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_y = p.tile_row_begin + blockIdx.y;
+    const int tile_id = tile_y * p.tiles_x + blockIdx.x;
+    const int2 range = __ldg(reinterpret_cast<const int2 *>(tile_bins) + tile_id);
+    const int cnt = max(0, min(kMaxPerTile, min(range.y, p.isect_capacity) - range.x));
+    if (tid < cnt) {
+        const int g = (int)(uint32_t)__ldg(sorted_keys + range.x + tid);
+        s_ids[tid] = g;
+        sg.xyab[tid] = __ldg(proj + 2 * g);
+        sg.crgb[tid] = __ldg(proj + 2 * g + 1);
+    }
+    __syncthreads();
+    // ---- forward: thread = pixel
+    const int j = blockIdx.x * kTile + (tid & 15);
+    const int i = tile_y * kTile + (tid >> 4);
+    const bool inside = i < p.img_height && j < p.img_width;
+    float r = 0.f, g = 0.f, b = 0.f;
+    int last = -1;
+    if (inside) forward_sweep(sg, cnt, (float)j, (float)i, r, g, b, last);
+    const size_t pix = (size_t)i * p.img_width + j;
+    if (kMode == RasterMode::Render) {
+        // the model's `render`: clamp to [0,1], CHW planar (gaussianimage_covariance.py:210-211)
+        if (inside && out_img) {
+            const size_t plane = (size_t)p.img_width * p.img_height;
+            out_img[pix] = fminf(fmaxf(r, 0.f), 1.f);
+            out_img[plane + pix] = fminf(fmaxf(g, 0.f), 1.f);
+            out_img[2 * plane + pix] = fminf(fmaxf(b, 0.f), 1.f);
+        }
+        return;
+    }
+    // ---- L2 loss: d/d out = loss_scale * (clamp(out) - gt) where 0 <= out <= 1 (torch.clamp
+    //      backward mask), squared error of the clamped render for PSNR
+    float se = 0.f, vr = 0.f, vg = 0.f, vb = 0.f;
+    if (inside) {
+        const float tr = __ldg(gt + 3 * pix), tg = __ldg(gt + 3 * pix + 1), tb = __ldg(gt + 3 * pix + 2);
+        const float dr = fminf(fmaxf(r, 0.f), 1.f) - tr;
+        const float dg = fminf(fmaxf(g, 0.f), 1.f) - tg;
+        const float db = fminf(fmaxf(b, 0.f), 1.f) - tb;
+        se = dr * dr + dg * dg + db * db;
+        vr = (r >= 0.f && r <= 1.f) ? p.loss_scale * dr : 0.f;
+        vg = (g >= 0.f && g <= 1.f) ? p.loss_scale * dg : 0.f;
+        vb = (b >= 0.f && b <= 1.f) ? p.loss_scale * db : 0.f;
+        if (out_img) {
+            out_img[3 * pix] = r;
+            out_img[3 * pix + 1] = g;
+            out_img[3 * pix + 2] = b;
+        }
+    }
+    s_v[0][tid] = vr;
+    s_v[1][tid] = vg;
+    s_v[2][tid] = vb;
+    se = warp_sum(se);
+    if (lane == 0) s_red[warp] = se;
+    __syncthreads();
+    if (tid == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < kRasterThreads / 32; ++w) tot += s_red[w];
+        atomicAdd(stats + GI2D_STAT_SSE + (tile_id & (GI2D_STAT_SSE_SLOTS - 1)), (double)tot);
+    }
+    if (cnt == 0) return;
+    // ---- backward: warp = Gaussian (4 at a time), lane = 8 pixels (column lane&15, rows
+    //      (lane>>4)+2s)
+    LanePixels lp;
+    {
+        const int px = blockIdx.x * kTile + (lane & 15);
+        const int py0 = tile_y * kTile + (lane >> 4);
+        lp.px = (float)px;
+        lp.py0 = (float)py0;
+        lp.inside = 0;
+#pragma unroll
+        for (int st = 0; st < 8; ++st) {
+            const int lp_idx = ((lane >> 4) + 2 * st) * kTile + (lane & 15);
+            lp.vr[st] = s_v[0][lp_idx];
+            lp.vg[st] = s_v[1][lp_idx];
+            lp.vb[st] = s_v[2][lp_idx];
+            if (px < p.img_width && py0 + 2 * st < p.img_height) lp.inside |= 1u << st;
+        }
+    }
+    for (int q = warp; 4 * q < cnt; q += kRasterThreads / 32) {
+        float v[32];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int t = 4 * q + jj;
+            if (t < cnt) {
+                backward_accumulate<false>(sg, t, lp, &v[8 * jj], nullptr);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[8 * jj + k] = 0.f;
+            }
+        }
+        const float total = warp_reduce_scatter32(v);
+        const int t = 4 * q + (lane >> 3);
+        if (t < cnt && total != 0.f) atomicAdd(grads + 8 * (size_t)s_ids[t] + (lane & 7), total);
+    }
+}
+
+// ------------------------------------------------------------------------------------ K5
+__global__ void __launch_bounds__(256)
+fit_adam_kernel(gi2d_fit_params p, float *__restrict__ xyz, float *__restrict__ cov,
+                float *__restrict__ rgb, float *__restrict__ m_xyz, float *__restrict__ v_xyz,
+                float *__restrict__ m_cov, float *__restrict__ v_cov, float *__restrict__ m_rgb,
+                float *__restrict__ v_rgb, const float4 *__restrict__ proj,
+                const float4 *__restrict__ grads, double *__restrict__ stats) {
+    __shared__ float s_h[4];  // step_size, 1/sqrt(bias2), 1-b1, 1-b2
+    if (threadIdx.x == 0) {
+        // torch/optim/adam.py (_single_tensor_adam) evaluates these in double precision;
+        // StepLR.step() runs after optimizer.step(), so step k uses gamma^floor((k-1)/size)
+        const double step = stats[GI2D_STAT_STEP];
+        const double lr = (double)p.lr0 * pow((double)p.lr_gamma, floor((step - 1.0) / (double)p.lr_step_size));
+        const double bc1 = 1.0 - pow((double)p.beta1, step);
+        const double bc2 = 1.0 - pow((double)p.beta2, step);
+        s_h[0] = (float)(lr / bc1);
+        s_h[1] = (float)sqrt(bc2);
+        s_h[2] = (float)(1.0 - (double)p.beta1);
+        s_h[3] = (float)(1.0 - (double)p.beta2);
+        if (blockIdx.x == 0) stats[GI2D_STAT_LR] = lr;
+    }
+    __syncthreads();
+    if (stats[GI2D_STAT_OVERFLOW] != 0.0) return;  // capacity exceeded: the host re-runs the step
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= p.num_points) return;
+    const float step_size = s_h[0], bc2_sqrt = s_h[1], w1 = s_h[2], w2 = s_h[3];
+    const float4 p0 = proj[2 * g], p1 = proj[2 * g + 1];
+    const float4 g0 = grads[2 * g], g1 = grads[2 * g + 1];
+    // R7, backward2d.cu:157-214: v_cov = -X G X (off-diagonal summed), v_mean = v_xy.
+    // For culled Gaussians (radii<=0) conic == 0 and the incoming gradients are 0: same zeros.
+    float gc0, gc1, gc2;
+    conic_vjp(p0.z, p0.w, p1.x, g0.z, g0.w, g1.x, gc0, gc1, gc2);
+    float gr = g1.y, gg = g1.z, gb = g1.w;
+    if (p.color_sigmoid) {
+        gr *= p1.y * (1.f - p1.y);
+        gg *= p1.z * (1.f - p1.z);
+        gb *= p1.w * (1.f - p1.w);
+    }
+    auto adam = [&](float *param, float *m, float *v, float grad) {
+        const float mm = *m + (grad - *m) * w1;                 // exp_avg.lerp_(grad, 1-beta1)
+        const float vv = *v * p.beta2 + w2 * grad * grad;       // mul_(beta2).addcmul_(grad, grad, 1-beta2)
+        const float denom = sqrtf(vv) / bc2_sqrt + p.eps;
+        *m = mm;
+        *v = vv;
+        *param = *param - step_size * (mm / denom);             // addcdiv_(exp_avg, denom, -step_size)
+    };
+    adam(xyz + 2 * g, m_xyz + 2 * g, v_xyz + 2 * g, g0.x);
+    adam(xyz + 2 * g + 1, m_xyz + 2 * g + 1, v_xyz + 2 * g + 1, g0.y);
+    adam(cov + 3 * g, m_cov + 3 * g, v_cov + 3 * g, gc0);
+    adam(cov + 3 * g + 1, m_cov + 3 * g + 1, v_cov + 3 * g + 1, gc1);
+    adam(cov + 3 * g + 2, m_cov + 3 * g + 2, v_cov + 3 * g + 2, gc2);
+    adam(rgb + 3 * g, m_rgb + 3 * g, v_rgb + 3 * g, gr);
+    adam(rgb + 3 * g + 1, m_rgb + 3 * g + 1, v_rgb + 3 * g + 1, gg);
+    adam(rgb + 3 * g + 2, m_rgb + 3 * g + 2, v_rgb + 3 * g + 2, gb);
+}
+
+__global__ void fit_reset_kernel(double *stats, int step) {
+    const int i = threadIdx.x;
+    if (i < GI2D_STAT_COUNT) stats[i] = i == GI2D_STAT_STEP ? (double)step : 0.0;
+}
+
+int validate(const gi2d_fit_params *p, const gi2d_fit_buffers *b) {
+    GI2D_REQUIRE(p && b, "null params");
+    GI2D_REQUIRE(p->num_points >= 0 && p->img_width > 0 && p->img_height > 0, "bad sizes");
+    GI2D_REQUIRE(p->tiles_x == cdiv(p->img_width, kTile) && p->tiles_y == cdiv(p->img_height, kTile),
+                 "tile grid must be ceil(size/16)");
+    GI2D_REQUIRE(p->tiles_x <= 65535 && p->tiles_y <= 65535, "image too large");
+    GI2D_REQUIRE(0 <= p->tile_row_begin && p->tile_row_begin <= p->tile_row_end && p->tile_row_end <= p->tiles_y,
+                 "bad tile row band");
+    GI2D_REQUIRE(p->isect_capacity > 0, "isect_capacity must be positive");
+    GI2D_REQUIRE(b->stats && b->workspace && b->proj && b->sorted_keys && b->tile_bins, "null buffer");
+    return GI2D_OK;
+}
+
+}  // namespace
+}  // namespace gi2d
+
+using namespace gi2d;
+
+extern "C" size_t gi2d_fit_workspace_size(const gi2d_fit_params *p) {
+    if (!p) return 0;
+    const Plan pl = make_plan(*p);
+    return carve(*p, pl, nullptr).total;
+}
+
+extern "C" int gi2d_fit_reset(const gi2d_fit_buffers *b, int step, gi2d_stream_t stream) {
+    GI2D_REQUIRE(b && b->stats, "null stats");
+    fit_reset_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(b->stats, step);
+    return check_launch(__func__);
+}
+
+extern "C" int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fit_buffers *b,
+                                         int with_backward, gi2d_stream_t stream) {
+    const int rc = validate(p, b);
+    if (rc != GI2D_OK) return rc;
+    GI2D_REQUIRE(p->num_points == 0 || (b->xyz && b->cov && b->cov_bound && b->rgb), "null parameter buffer");
+    GI2D_REQUIRE(!with_backward || (b->grads && b->gt_hwc), "fit needs grads and gt_hwc");
+    const Plan pl = make_plan(*p);
+    const Workspace w = carve(*p, pl, b->workspace);
+    if (b->workspace_bytes < w.total) {
+        set_error("%s: workspace too small (%zu < %zu)", __func__, b->workspace_bytes, w.total);
+        return GI2D_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = 1 << pl.bits0;
+    const int num_tiles = p->tiles_x * p->tiles_y;
+    const bool single = pl.extra_passes == 0;
+    fit_project_kernel<<<pl.nblocks, kProjThreads, D * sizeof(int), st>>>(
+        *p, pl.gpb, pl.bits0, b->xyz, b->cov, b->cov_bound, b->rgb, (float4 *)b->proj, (float4 *)b->grads,
+        w.boxes, w.counts, b->stats, with_backward);
+    fit_scan_kernel<<<1, 1024, 0, st>>>(pl.nblocks, pl.bits0, num_tiles, single ? 1 : 0, p->isect_capacity,
+                                        w.counts, w.digit_base, b->tile_bins, w.n_isect, b->stats);
+    // pass 0 lands in sorted_keys when the number of remaining passes is even
+    uint64_t *dst0 = (pl.extra_passes % 2 == 0) ? b->sorted_keys : w.keys_tmp;
+    const size_t scatter_smem = (size_t)kScatterWarps * D * sizeof(int);  // <= 32 KiB
+    fit_scatter_kernel<<<pl.nblocks, kScatterThreads, scatter_smem, st>>>(
+        p->num_points, pl.gpb, pl.bits0, p->tiles_x, p->isect_capacity, w.boxes, w.counts, w.digit_base, dst0);
+    if (!single) {
+        uint64_t *src = dst0;
+        for (int e = 0; e < pl.extra_passes; ++e) {
+            uint64_t *dst = (src == b->sorted_keys) ? w.keys_tmp : b->sorted_keys;
+            const int shift = 32 + pl.bits0 + 8 * e;
+            const int bits = min(8, pl.tile_bits - pl.bits0 - 8 * e);
+            const int r2 = radix_pass_keys_u64(p->isect_capacity, w.n_isect, src, dst, shift, bits, w.radix_ws,
+                                               w.radix_ws_bytes, st);
+            if (r2 != GI2D_OK) return r2;
+            src = dst;
+        }
+        const int r3 = tile_edges_from_keys_u64(p->isect_capacity, w.n_isect, b->sorted_keys, b->tile_bins,
+                                                num_tiles, st);
+        if (r3 != GI2D_OK) return r3;
+    }
+    const int band = p->tile_row_end - p->tile_row_begin;
+    if (band > 0) {
+        dim3 grid(p->tiles_x, band);
+        if (with_backward)
+            fit_raster_kernel<RasterMode::Fit><<<grid, kRasterThreads, 0, st>>>(
+                *p, b->sorted_keys, b->tile_bins, (const float4 *)b->proj, b->gt_hwc, b->out_img, b->grads,
+                b->stats);
+        else
+            fit_raster_kernel<RasterMode::Render><<<grid, kRasterThreads, 0, st>>>(
+                *p, b->sorted_keys, b->tile_bins, (const float4 *)b->proj, nullptr, b->out_img, nullptr,
+                b->stats);
+    }
+    return check_launch(__func__);
+}
+
+extern "C" int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, gi2d_stream_t stream) {
+    const int rc = validate(p, b);
+    if (rc != GI2D_OK) return rc;
+    if (p->num_points == 0) return GI2D_OK;
+    GI2D_REQUIRE(b->xyz && b->cov && b->rgb && b->m_xyz && b->v_xyz && b->m_cov && b->v_cov && b->m_rgb &&
+                     b->v_rgb && b->grads,
+                 "null buffer");
+    fit_adam_kernel<<<cdiv(p->num_points, 256), 256, 0, (cudaStream_t)stream>>>(
+        *p, b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb,
+        (const float4 *)b->proj, (const float4 *)b->grads, b->stats);
+    return check_launch(__func__);
+}

@@ -1,0 +1,235 @@
+/*
+ * gi2d.h -- C ABI of libgi2d.so: a B200 (sm_100a) native 2-D Gaussian image rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of Sweethyh/GaussianImage_plus:
+ *   project -> bin/sort -> rasterize-sum forward -> rasterize-sum backward -> project backward (+Adam)
+ *
+ * Every entry point replaces one function of the reference's pybind11 module
+ * (`gsplat/gsplat/cuda/csrc/ext.cpp:4-69`, implemented in `csrc/bindings.cu`) or one
+ * third-party PyTorch call on the path (`gsplat/gsplat/utils.py:248,301,302`).  The
+ * reference binding each one replaces is cited next to its declaration.
+ *
+ * Conventions
+ *   - plain pointers and sizes only: all pointers are DEVICE pointers unless the name ends
+ *     in `_host`; no torch types; outputs and workspaces are caller-owned.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises, never allocates; safe to capture in a CUDA graph.
+ *   - return value: 0 on success, a negative GI2D_ERR_* otherwise; gi2d_last_error()
+ *     returns a thread-local message.  Launch errors are checked (the reference never does).
+ *   - array layouts are the reference's: xys f32[N,2], conics f32[N,3] = (a,b,c),
+ *     colors f32[N,3], images f32[H,W,3] interleaved, tile_bins i32[rows,2],
+ *     tiles are 16x16 pixels (`csrc/config.h:1-4`).
+ */
+#ifndef GI2D_H_
+#define GI2D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GI2D_ABI_VERSION 1
+#define GI2D_TILE 16 /* BLOCK_X == BLOCK_Y, csrc/config.h:1-2 */
+#define GI2D_MAX_PER_TILE 256 /* the live rasterizer stops after one 256-batch, csrc/forward.cu:673 */
+
+#define GI2D_OK 0
+#define GI2D_ERR_INVALID (-1)   /* bad argument (null pointer, negative size, unsupported value) */
+#define GI2D_ERR_CUDA (-2)      /* a CUDA launch or runtime call failed */
+#define GI2D_ERR_WORKSPACE (-3) /* workspace too small; see the *_workspace_size query */
+
+typedef void *gi2d_stream_t; /* cudaStream_t */
+
+int gi2d_abi_version(void);
+const char *gi2d_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * R1-R3  projection forward (one thread per Gaussian)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces `project_gaussians_2d_covariance_forward` (ext.cpp:38, bindings.cu:1455-1513,
+ * kernel foward2d.cu:192-288).  means2d f32[N,2] in pixels, cov2d f32[N,3]=(sxx,sxy,syy).
+ * Outputs are fully written (culled Gaussians get radii=0, num_tiles_hit=0, depths=0 and
+ * zeroed xys/conics exactly like the reference's torch::zeros + early return). */
+int gi2d_project_cov_fwd(int num_points, const float *means2d, const float *cov2d,
+                         int img_width, int img_height, int tiles_x, int tiles_y,
+                         float clip_coe, float radius_clip,
+                         float *xys, float *depths, int32_t *radii, float *conics,
+                         int32_t *num_tiles_hit, gi2d_stream_t stream);
+
+/* Replaces `project_gaussians_2d_forward` (ext.cpp:31, bindings.cu:1317-1381, kernel
+ * foward2d.cu:12-69).  means2d in [-1,1], L f32[N,3]=(l11,l21,l22). */
+int gi2d_project_chol_fwd(int num_points, const float *means2d, const float *L_elements,
+                          int img_width, int img_height, int tiles_x, int tiles_y,
+                          float clip_coe, float radius_clip,
+                          float *xys, float *depths, int32_t *radii, float *conics,
+                          int32_t *num_tiles_hit, gi2d_stream_t stream);
+
+/* Replaces `project_gaussians_2d_scale_rot_forward` (ext.cpp:33, bindings.cu:1384-1448,
+ * kernel foward2d.cu:130-187).  scales f32[N,2], rotation f32[N]. */
+int gi2d_project_rs_fwd(int num_points, const float *means2d, const float *scales2d,
+                        const float *rotation, int img_width, int img_height, int tiles_x,
+                        int tiles_y, float clip_coe, float radius_clip,
+                        float *xys, float *depths, int32_t *radii, float *conics,
+                        int32_t *num_tiles_hit, gi2d_stream_t stream);
+
+/* Replaces `compute_cov2d_bounds` (ext.cpp:58, bindings.cu:21-39,41-67).
+ * radii_f32 f32[N] = radius.x (the reference returns the float major radius). */
+int gi2d_compute_cov2d_bounds(int num_points, float clip_coe, const float *cov2d,
+                              float *conics, float *radii_f32, gi2d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * R7  projection backward.  All outputs fully written (zeros where radii<=0).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces `project_gaussians_2d_covariance_backward` (ext.cpp:39, bindings.cu:1565-1612,
+ * kernel backward2d.cu:157-214). */
+int gi2d_project_cov_bwd(int num_points, const int32_t *radii, const float *conics,
+                         const float *v_xy, const float *v_conic,
+                         float *v_cov2d, float *v_mean2d, float *v_L, gi2d_stream_t stream);
+
+/* Replaces `project_gaussians_2d_backward` (ext.cpp:32, bindings.cu:1516-1562,
+ * kernel backward2d.cu:8-51) -- including the doubled off-diagonal term. */
+int gi2d_project_chol_bwd(int num_points, const float *L_elements, int img_width,
+                          int img_height, const int32_t *radii, const float *conics,
+                          const float *v_xy, const float *v_conic,
+                          float *v_cov2d, float *v_mean2d, float *v_L, gi2d_stream_t stream);
+
+/* Replaces `project_gaussians_2d_scale_rot_backward` (ext.cpp:34, bindings.cu:1615-1668,
+ * kernel backward2d.cu:53-101). */
+int gi2d_project_rs_bwd(int num_points, const float *scales2d, const float *rotation,
+                        const int32_t *radii, const float *conics, const float *v_xy,
+                        const float *v_conic, float *v_cov2d, float *v_mean2d,
+                        float *v_scale, float *v_rot, gi2d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * R4  binning -- integer exact
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces `torch.cumsum(num_tiles_hit, dtype=int32)` (gsplat/utils.py:248): inclusive scan.
+ * `total` (nullable) receives cum[N-1] on the device.  Workspace: gi2d_scan_workspace_size. */
+size_t gi2d_scan_workspace_size(int num_points);
+int gi2d_cumsum_i32(int num_points, const int32_t *num_tiles_hit, int32_t *cum_tiles_hit,
+                    int32_t *total, void *workspace, size_t workspace_bytes,
+                    gi2d_stream_t stream);
+
+/* Replaces `map_gaussian_to_intersects` (ext.cpp:60, bindings.cu:283-365, kernel
+ * forward.cu:141-206): isect_ids[k] = (tile_id<<32) | sign-extended bits(depth). */
+int gi2d_map_gaussian_to_intersects(int num_points, const float *xys, const float *depths,
+                                    const int32_t *radii, const int32_t *cum_tiles_hit,
+                                    int tiles_x, int tiles_y, float radius_clip,
+                                    int64_t *isect_ids, int32_t *gaussian_ids,
+                                    gi2d_stream_t stream);
+
+/* Replaces `torch.sort(isect_ids)` + `torch.gather(gaussian_ids, perm)` (gsplat/utils.py:
+ * 301-302): stable LSD radix sort of signed 64-bit keys carrying 32-bit values.  Only bits
+ * [begin_bit,end_bit) are inspected (0,64 = full signed order). */
+size_t gi2d_sort_workspace_size(int num_items);
+int gi2d_sort_pairs_i64(int num_items, const int64_t *keys_in, const int32_t *vals_in,
+                        int64_t *keys_out, int32_t *vals_out, int begin_bit, int end_bit,
+                        void *workspace, size_t workspace_bytes, gi2d_stream_t stream);
+
+/* Replaces `get_tile_bin_edges` (ext.cpp:66, bindings.cu:368-383, kernel forward.cu:211-233).
+ * tile_bins i32[num_bins_rows,2] is zero-filled first (the reference's torch::zeros), rows
+ * whose tile id is >= num_bins_rows are skipped instead of written out of bounds. */
+int gi2d_get_tile_bin_edges(int num_intersects, const int64_t *isect_ids_sorted,
+                            int32_t *tile_bins, int num_bins_rows, gi2d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * R5/R6  rasterize-sum forward / backward (3 channels, 16x16 tiles, first 256 per tile)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces `rasterize_sum_plus_forward` / `rasterize_sum_forward` (ext.cpp:23,16,
+ * bindings.cu:529-610, kernel forward.cu:570-691).  out_img f32[H,W,3], final_Ts f32[H,W]
+ * (== 1), final_idx i32[H,W]; all fully written.  tile_bins must have >= tiles_x*tiles_y rows
+ * OR num_bins_rows gives the number of valid rows (tiles beyond it are treated as empty). */
+int gi2d_rasterize_sum_fwd(int tiles_x, int tiles_y, int img_width, int img_height,
+                           const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                           int num_bins_rows, const float *xys, const float *conics,
+                           const float *colors, const float *opacities,
+                           float *out_img, float *final_Ts, int32_t *final_idx,
+                           gi2d_stream_t stream);
+
+/* Replaces `rasterize_sum_plus_backward` / `rasterize_sum_backward` (ext.cpp:24,17,
+ * bindings.cu:1241-1314, kernel backward.cu:1168-1350).  v_xy f32[N,2], v_conic f32[N,3],
+ * v_colors f32[N,3], v_opacity f32[N] are zero-filled by the call, then accumulated. */
+int gi2d_rasterize_sum_bwd(int num_points, int tiles_x, int tiles_y, int img_width,
+                           int img_height, const int32_t *gaussian_ids_sorted,
+                           const int32_t *tile_bins, int num_bins_rows, const float *xys,
+                           const float *conics, const float *colors, const float *opacities,
+                           const int32_t *final_idx, const float *v_output,
+                           float *v_xy, float *v_conic, float *v_colors, float *v_opacity,
+                           gi2d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused fit step: the whole `train_iter` of
+ * models/gaussianimage_covariance.py:249-259 for the covariance model with L2 loss, with no
+ * host synchronisation: project+count -> tile scan -> stable scatter (64-bit tile|gaussian
+ * keys) -> rasterize fwd + L2 loss gradient + backward -> project backward + Adam.
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct gi2d_fit_params {
+    int32_t num_points;
+    int32_t img_width, img_height;
+    int32_t tiles_x, tiles_y;   /* full image tile grid */
+    int32_t tile_row_begin;     /* this rank renders tile rows [begin,end) (multi-GPU split) */
+    int32_t tile_row_end;
+    int32_t isect_capacity;     /* rows of sorted_keys (and of the workspace copy) */
+    float clip_coe, radius_clip;
+    float lr0, beta1, beta2, eps; /* Adam (torch.optim.Adam, eps=1e-15 in the reference) */
+    int32_t lr_step_size;       /* StepLR(step_size, gamma): lr = lr0 * gamma^floor((step-1)/size) */
+    float lr_gamma;
+    int32_t color_sigmoid;      /* 1: colours = sigmoid(features) (the reference's color_norm) */
+    float loss_scale;           /* dL/d(out) = loss_scale * (clamp(out) - gt); 2/(3*H*W) for mse */
+} gi2d_fit_params;
+
+/* stats layout (f64): the device-side step counter makes the step graph-replayable with no
+ * per-iteration host input. */
+#define GI2D_STAT_STEP 0        /* number of Adam steps taken so far */
+#define GI2D_STAT_ISECTS 1      /* num_intersects of the last forward */
+#define GI2D_STAT_OVERFLOW 2    /* != 0: num_intersects exceeded isect_capacity (step skipped) */
+#define GI2D_STAT_LR 3          /* lr used by the last Adam step */
+#define GI2D_STAT_SSE 8         /* 64 partial sums of squared error of the clamped render */
+#define GI2D_STAT_SSE_SLOTS 64
+#define GI2D_STAT_COUNT (GI2D_STAT_SSE + GI2D_STAT_SSE_SLOTS)
+
+typedef struct gi2d_fit_buffers {
+    /* parameters + optimiser state (updated in place) */
+    float *xyz;        /* f32[N,2] pixel coords          (_xyz) */
+    float *cov;        /* f32[N,3] raw covariance params (_cov2d) */
+    float *cov_bound;  /* f32[N,3] added to cov          (cholesky_bound) */
+    float *rgb;        /* f32[N,3]                       (_features_dc) */
+    float *m_xyz, *v_xyz, *m_cov, *v_cov, *m_rgb, *v_rgb; /* Adam exp_avg / exp_avg_sq */
+    /* target and outputs */
+    const float *gt_hwc; /* f32[H,W,3] target image, interleaved (nullable for render-only) */
+    float *out_img;      /* nullable.  fit: f32[H,W,3] unclamped render (== rasterize output);
+                            render-only (with_backward=0): f32[3,H,W] clamped to [0,1], i.e. the
+                            model's `render` tensor (gaussianimage_covariance.py:210-211) */
+    /* per-step scratch, caller-owned */
+    float *grads;          /* f32[N,8] = v_xy(2) v_conic(3) v_rgb(3); atomically accumulated */
+    float *proj;           /* f32[N,8] = x, y, conic a,b,c, colour r,g,b */
+    uint64_t *sorted_keys; /* u64[capacity] (tile<<32 | gaussian), ascending */
+    int32_t *tile_bins;    /* i32[tiles_x*tiles_y, 2] */
+    double *stats;         /* f64[GI2D_STAT_COUNT] */
+    void *workspace;
+    size_t workspace_bytes;
+} gi2d_fit_buffers;
+
+size_t gi2d_fit_workspace_size(const gi2d_fit_params *p);
+
+/* Zero the stats block (and set the step counter): call once before the first step. */
+int gi2d_fit_reset(const gi2d_fit_buffers *b, int step, gi2d_stream_t stream);
+
+/* project + bin + rasterize; with_backward != 0 also computes the L2 loss gradient and the
+ * rasterize backward into b->grads and advances the step counter. */
+int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fit_buffers *b,
+                              int with_backward, gi2d_stream_t stream);
+/* projection backward + Adam on xyz/cov/rgb from b->grads.  Separate from the call above so a
+ * multi-GPU caller can all-reduce b->grads (and the SSE) in between. */
+int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, gi2d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GI2D_H_ */
