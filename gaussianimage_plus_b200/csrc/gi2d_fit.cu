@@ -340,6 +340,9 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
     float r = 0.f, g = 0.f, b = 0.f;
     int last = -1;
     if (inside) forward_sweep(sg, cnt, (float)j, (float)i, r, g, b, last);
+    // no intersection at all: the reference returns ones * background (== 1) and no gradient
+    // (rasterize_sum_plus.py:110-118)
+    if (stats[GI2D_STAT_ISECTS] == 0.0) r = g = b = 1.f;
     const size_t pix = (size_t)i * p.img_width + j;
     if (kMode == RasterMode::Render) {
         // the model's `render`: clamp to [0,1], CHW planar (gaussianimage_covariance.py:210-211)
@@ -503,14 +506,44 @@ extern "C" size_t gi2d_fit_workspace_size(const gi2d_fit_params *p) {
     return carve(*p, pl, nullptr).total;
 }
 
+extern "C" int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward) {
+    if (!p) return 0;
+    const Plan pl = make_plan(*p);
+    int n = 4;  // project, scan, scatter, raster
+    if (pl.extra_passes > 0) {
+        const int nb = cdiv(p->isect_capacity, 2048);
+        const int cumsum_nb = cdiv(nb * 256, 2048);
+        n += pl.extra_passes * (2 + (cumsum_nb > 1 ? 3 : 1));  // hist + cumsum + scatter per pass
+        n += 1;                                                 // tile edges (the memset is not a kernel)
+    }
+    return n + (with_backward ? 1 : 0);  // + adam
+}
+
 extern "C" int gi2d_fit_reset(const gi2d_fit_buffers *b, int step, gi2d_stream_t stream) {
     GI2D_REQUIRE(b && b->stats, "null stats");
     fit_reset_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(b->stats, step);
     return check_launch(__func__);
 }
 
+namespace gi2d { namespace {
+struct Marks {            // optional per-kernel timing marks (gi2d_fit_profile)
+    cudaEvent_t ev[8];
+    int n = 0;
+    bool on = false;
+    void mark(cudaStream_t st) { if (on && n < 8) cudaEventRecord(ev[n++], st); }
+};
+int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int with_backward,
+                              cudaStream_t st, Marks *mk);
+} }  // namespace gi2d::<anon>
+
 extern "C" int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fit_buffers *b,
                                          int with_backward, gi2d_stream_t stream) {
+    return fit_forward_backward_impl(p, b, with_backward, (cudaStream_t)stream, nullptr);
+}
+
+namespace gi2d { namespace {
+int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int with_backward,
+                              cudaStream_t st, Marks *mk) {
     const int rc = validate(p, b);
     if (rc != GI2D_OK) return rc;
     GI2D_REQUIRE(p->num_points == 0 || (b->xyz && b->cov && b->cov_bound && b->rgb), "null parameter buffer");
@@ -521,15 +554,17 @@ extern "C" int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fi
         set_error("%s: workspace too small (%zu < %zu)", __func__, b->workspace_bytes, w.total);
         return GI2D_ERR_WORKSPACE;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     const int D = 1 << pl.bits0;
     const int num_tiles = p->tiles_x * p->tiles_y;
     const bool single = pl.extra_passes == 0;
+    if (mk) mk->mark(st);
     fit_project_kernel<<<pl.nblocks, kProjThreads, D * sizeof(int), st>>>(
         *p, pl.gpb, pl.bits0, b->xyz, b->cov, b->cov_bound, b->rgb, (float4 *)b->proj, (float4 *)b->grads,
         w.boxes, w.counts, b->stats, with_backward);
+    if (mk) mk->mark(st);
     fit_scan_kernel<<<1, 1024, 0, st>>>(pl.nblocks, pl.bits0, num_tiles, single ? 1 : 0, p->isect_capacity,
                                         w.counts, w.digit_base, b->tile_bins, w.n_isect, b->stats);
+    if (mk) mk->mark(st);
     // pass 0 lands in sorted_keys when the number of remaining passes is even
     uint64_t *dst0 = (pl.extra_passes % 2 == 0) ? b->sorted_keys : w.keys_tmp;
     const size_t scatter_smem = (size_t)kScatterWarps * D * sizeof(int);  // <= 32 KiB
@@ -550,6 +585,7 @@ extern "C" int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fi
                                                 num_tiles, st);
         if (r3 != GI2D_OK) return r3;
     }
+    if (mk) mk->mark(st);
     const int band = p->tile_row_end - p->tile_row_begin;
     if (band > 0) {
         dim3 grid(p->tiles_x, band);
@@ -562,6 +598,73 @@ extern "C" int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fi
                 *p, b->sorted_keys, b->tile_bins, (const float4 *)b->proj, nullptr, b->out_img, nullptr,
                 b->stats);
     }
+    if (mk) mk->mark(st);
+    return check_launch("gi2d_fit_forward_backward");
+}
+} }  // namespace gi2d::<anon>
+
+// Measurement utility (bench.py): one full fit step with a CUDA event between the kernels, on
+// `stream`; SYNCHRONISES.  ms[0..4] = project, scan, scatter(+extra passes+edges), raster, adam.
+extern "C" int gi2d_fit_profile(const gi2d_fit_params *p, const gi2d_fit_buffers *b, float *ms_host,
+                                gi2d_stream_t stream) {
+    GI2D_REQUIRE(ms_host, "null ms_host");
+    cudaStream_t st = (cudaStream_t)stream;
+    Marks mk;
+    mk.on = true;
+    for (int i = 0; i < 8; ++i) cudaEventCreate(&mk.ev[i]);
+    int rc = fit_forward_backward_impl(p, b, 1, st, &mk);
+    if (rc == GI2D_OK) rc = gi2d_fit_adam(p, b, stream);
+    mk.mark(st);
+    cudaStreamSynchronize(st);
+    for (int i = 0; i < 5; ++i) {
+        ms_host[i] = 0.f;
+        if (rc == GI2D_OK && i + 1 < mk.n) cudaEventElapsedTime(&ms_host[i], mk.ev[i], mk.ev[i + 1]);
+    }
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(mk.ev[i]);
+    return rc;
+}
+
+// Measurement utility: FP32 FMA issue peak of this GPU (the roofline denominator of the raster
+// kernels; MEASURED_PEAKS.json only carries HBM and bf16 tensor figures).  Returns TFLOP/s.
+namespace gi2d { namespace {
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters) {
+    float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;
+}
+} }  // namespace gi2d::<anon>
+
+extern "C" int gi2d_measure_fp32_peak(float *tflops_host, gi2d_stream_t stream) {
+    GI2D_REQUIRE(tflops_host, "null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *d = nullptr;
+    cudaMalloc(&d, 4);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int iters = 1 << 14, grid = sms * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 0.f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, st);
+        fma_peak_kernel<<<grid, 256, 0, st>>>(d, iters);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const float tf = (float)((double)grid * 256.0 * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12);
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops_host = best;
     return check_launch(__func__);
 }
 

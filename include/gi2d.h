@@ -218,6 +218,9 @@ typedef struct gi2d_fit_buffers {
 
 size_t gi2d_fit_workspace_size(const gi2d_fit_params *p);
 
+/* Number of kernels one gi2d_fit_forward_backward (+ gi2d_fit_adam when with_backward) launches. */
+int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward);
+
 /* Zero the stats block (and set the step counter): call once before the first step. */
 int gi2d_fit_reset(const gi2d_fit_buffers *b, int step, gi2d_stream_t stream);
 
@@ -228,6 +231,19 @@ int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fit_buffers *
 /* projection backward + Adam on xyz/cov/rgb from b->grads.  Separate from the call above so a
  * multi-GPU caller can all-reduce b->grads (and the SSE) in between. */
 int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, gi2d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement utilities for bench.py (these two SYNCHRONISE; never call them while capturing).
+ * ------------------------------------------------------------------------------------------ */
+
+/* One full fit step with a CUDA event between kernels.  ms_host[0..4] (HOST pointer) =
+ * project, scan, scatter (+ extra radix passes + tile edges), raster fwd+bwd, adam. */
+int gi2d_fit_profile(const gi2d_fit_params *p, const gi2d_fit_buffers *b, float *ms_host,
+                     gi2d_stream_t stream);
+
+/* FP32 FMA throughput of the current device in TFLOP/s (HOST pointer): the roofline denominator
+ * of the rasterize kernels. */
+int gi2d_measure_fp32_peak(float *tflops_host, gi2d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -186,12 +186,13 @@ def rasterize_sum_bwd(H, W, gids_sorted, tile_bins, xys, conics, colors, opaciti
     v_colors = np.zeros((n, 3), np.float32)
     v_opacity = np.zeros((n,), np.float32)
     slack = np.zeros((n, 9), np.float32) if with_slack else None
+    mag = np.zeros((n, 9), np.float32) if with_slack else None
     lib().orc_rasterize_sum_bwd(C.c_int(n), C.c_int(tb[0]), C.c_int(tb[1]), C.c_int(W), C.c_int(H),
                                 _p(gids_sorted), _p(tile_bins), C.c_int(tile_bins.shape[0]), _p(xys),
                                 _p(conics), _p(colors), _p(opac), _p(v_output), _p(v_xy), _p(v_conic),
-                                _p(v_colors), _p(v_opacity), _p(slack))
+                                _p(v_colors), _p(v_opacity), _p(slack), _p(mag))
     res = (v_xy, v_conic, v_colors, v_opacity)
-    return res + (slack,) if with_slack else res
+    return res + (slack, mag) if with_slack else res
 
 
 class FitCfg(C.Structure):

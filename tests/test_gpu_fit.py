@@ -1,0 +1,192 @@
+"""GPU: the fused fit step (gi2d_fit_forward_backward / gi2d_fit_adam through GaussianImageFitter)
+against the oracle's restatement of the reference train_iter, and size-independent properties at
+BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from gaussianimage_plus_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def N_(t):
+    return t.detach().cpu().numpy()
+
+
+def make_fitter(N, H, W, seed, colors="rand", cov_scale=1.0, use_graph=False, keep_render=True, **kw):
+    from gaussianimage_plus_b200.fit import GaussianImageFitter
+
+    xyz, cov, bound, rgb = synth.init_covariance_model(N, H, W, seed=seed, colors=colors, cov_scale=cov_scale)
+    gt = synth.target_image(H, W, seed=seed)
+    fit = GaussianImageFitter(N, H, W, device=DEV, use_graph=use_graph, **kw)
+    fit.keep_render = keep_render
+    for dst, src in ((fit._xyz, xyz), (fit._cov2d, cov), (fit.cholesky_bound, bound), (fit._features_dc, rgb)):
+        dst.copy_(torch.from_numpy(src))
+    fit.set_target(torch.from_numpy(gt))
+    fit._bind()
+    return fit, (xyz, cov, bound, rgb, gt)
+
+
+@pytest.mark.parametrize("N,H,W,scale", [(400, 96, 128, 1.0), (5000, 512, 768, 1.0), (5000, 512, 768, 4.0),
+                                          (20000, 1356, 2040, 1.0), (3000, 64, 64, 3.0)])
+def test_fit_binning_bit_exact(oracle, N, H, W, scale):
+    """sorted (tile|gaussian) keys, tile ranges and num_intersects of the fused path == oracle
+    (== the reference's cumsum + map + sort + gather + edges), including the multi-pass case
+    (2040x1356: 10880 tiles > 2048 bins)."""
+    fit, (xyz, cov, bound, rgb, gt) = make_fitter(N, H, W, seed=5, cov_scale=scale)
+    fit.forward()
+    st = fit.stats()
+    tb = oracle.tile_bounds(H, W)
+    xys, depths, radii, conics, nth = oracle.project_cov_fwd(xyz, cov + bound, H, W, tb)
+    total, cum, ids, gids, ids_s, gids_s, bins = oracle.bin_and_sort(xys, depths, radii, nth, tb)
+    assert st["num_intersects"] == total and not st["overflow"]
+    keys = N_(fit.sorted_keys[:total])
+    np.testing.assert_array_equal(keys >> 32, ids_s >> 32)
+    np.testing.assert_array_equal((keys & 0xFFFFFFFF).astype(np.int32), gids_s)
+    np.testing.assert_array_equal(N_(fit.tile_bins), bins)
+    assert (np.diff(keys) > 0).all()  # a strictly ascending 64-bit sequence
+    proj = N_(fit.proj)
+    np.testing.assert_array_equal(proj[:, 0:2], xys)
+    np.testing.assert_array_equal(proj[:, 2:5], conics)
+
+
+def test_render_matches_operator_path_bitwise(oracle):
+    """fused render == clamp/permute of the stand-alone operator path (same kernels' math, same order)."""
+    from gaussianimage_plus_b200.gsplat import project_gaussians_2d_covariance, rasterize_gaussians_plus
+
+    N, H, W = 5000, 512, 768
+    fit, (xyz, cov, bound, rgb, gt) = make_fitter(N, H, W, seed=9, cov_scale=2.0)
+    render = fit.forward()["render"]
+    tb = fit.tile_bounds
+    xys, depths, radii, conics, nth = project_gaussians_2d_covariance(fit._xyz, fit._cov2d + fit.cholesky_bound, H, W, tb)
+    out = rasterize_gaussians_plus(xys, depths, radii, conics, nth, fit._features_dc, torch.ones(N, 1, device=DEV), H, W)
+    expect = torch.clamp(out, 0, 1).view(-1, H, W, 3).permute(0, 3, 1, 2).contiguous()
+    assert torch.equal(render, expect)
+
+
+@pytest.mark.parametrize("N,H,W,scale,graph", [(400, 96, 128, 1.0, False), (2500, 512, 768, 1.0, True),
+                                                (5000, 512, 768, 3.0, False)])
+def test_fit_step_matches_oracle(oracle, N, H, W, scale, graph):
+    fit, (xyz, cov, bound, rgb, gt) = make_fitter(N, H, W, seed=21, cov_scale=scale, use_graph=graph)
+    ref = oracle.FitState(xyz, cov, bound, rgb, gt)
+    mse_ref, img_ref = ref.train_iter(want_image=True)
+    fit.train_iter()
+    st = fit.stats()
+    assert st["step"] == 1 and st["num_intersects"] == ref.num_intersects
+    img = N_(fit.out_hwc)
+    bad = np.abs(img - img_ref) > 1e-4 * np.abs(img_ref) + 1e-5
+    assert bad.mean() < 1e-5, bad.sum()          # a handful of pixels may sit on the 1/255 threshold
+    assert abs(st["mse"] - mse_ref) <= 1e-5 * mse_ref
+    assert abs(st["lr"] - 0.018) < 1e-9
+    # step 1 of Adam moves every parameter by lr * sign(g): compare where the gradient is not ~0
+    for name, a, b0, b in (("xyz", fit._xyz, xyz, ref.xyz), ("cov", fit._cov2d, cov, ref.cov),
+                           ("rgb", fit._features_dc, rgb, ref.rgb)):
+        d = np.abs(N_(a) - b)
+        assert np.quantile(d, 0.995) < 1e-5, (name, np.quantile(d, 0.995))
+        moved = np.abs(b - b0) > 1e-3
+        assert moved.mean() > 0.3, name
+
+
+def test_fit_trajectory_tracks_oracle(oracle):
+    """PSNR trajectory of the fused path vs the oracle's train_iter restatement at equal iterations."""
+    N, H, W = 1500, 128, 192
+    fit, (xyz, cov, bound, rgb, gt) = make_fitter(N, H, W, seed=33, colors="zeros", use_graph=True)
+    ref = oracle.FitState(xyz, cov, bound, rgb, gt)
+    iters = 300
+    for _ in range(iters):
+        fit.train_iter()
+        mse_ref = ref.train_iter()
+    st = fit.stats()
+    psnr_ref = 10 * np.log10(1.0 / mse_ref)
+    assert st["step"] == iters
+    assert st["psnr"] > 18.0, st
+    assert abs(st["psnr"] - psnr_ref) < 0.25, (st["psnr"], psnr_ref)   # north_star: >= 90% of the trajectory
+
+
+def test_fit_graph_equals_eager():
+    a, _ = make_fitter(2500, 512, 768, seed=4, colors="zeros", use_graph=True)
+    b, _ = make_fitter(2500, 512, 768, seed=4, colors="zeros", use_graph=False)
+    for _ in range(5):
+        a.train_iter()
+        b.train_iter()
+    sa, sb = a.stats(), b.stats()
+    assert sa["step"] == sb["step"] == 5 and sa["num_intersects"] == sb["num_intersects"]
+    # float atomics reorder sums: equal to fp32 noise
+    assert abs(sa["mse"] - sb["mse"]) <= 1e-4 * sb["mse"]
+
+
+def test_capacity_overflow_is_detected_and_recovered():
+    fit, _ = make_fitter(5000, 512, 768, seed=2, isect_capacity=4096)
+    fit.train_iter()
+    st = fit.stats()
+    assert st["overflow"] and st["num_intersects"] > 4096
+    x0 = fit._xyz.clone()
+    assert fit.ensure_capacity()
+    assert torch.equal(x0, fit._xyz)  # the overflowing step did not touch the parameters
+    fit.train_iter()
+    st = fit.stats()
+    assert not st["overflow"] and st["step"] == 1
+
+
+def test_prune_and_densify_keep_state_consistent():
+    fit, _ = make_fitter(2000, 256, 384, seed=6, colors="zeros", use_graph=True)
+    for _ in range(20):
+        fit.train_iter()
+    fit._cov2d[:7, 0] = -1000.0  # make 7 Gaussians indefinite
+    n_bad, n_now = fit.non_semi_definite_prune()
+    assert n_bad == 7 and n_now == 1993 and fit.exp_avg["xyz"].shape[0] == 1993
+    added = fit.add_sample_positions(max_num_points=2300, base_num_samples=200)
+    assert added == 200 and fit.cur_num_points == 2193 and fit.cholesky_bound.shape[0] == 2193
+    p0 = fit.psnr()
+    for _ in range(50):
+        fit.train_iter()
+    st = fit.stats()
+    assert st["step"] == 70 and np.isfinite(st["psnr"]) and st["psnr"] > p0 - 3
+
+
+# --------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("name", ["kodak_5000", "div2k_20000"])
+def test_full_size_properties(name):
+    """Size-independent invariants at BASELINE.json sizes: keys strictly ascending; tile ranges partition
+    [0, I) in tile order; per-tile ids ascending; rendering is linear in the colours; the analytic
+    colour gradient equals a directional finite difference."""
+    H, W, N = synth.CONFIGS[name]
+    fit, (xyz, cov, bound, rgb, gt) = make_fitter(N, H, W, seed=12, cov_scale=2.0)
+    r1 = fit.forward()["render"].clone()
+    st = fit.stats()
+    I = st["num_intersects"]
+    keys = fit.sorted_keys[:I]
+    assert bool((keys[1:] > keys[:-1]).all())
+    bins = fit.tile_bins
+    cnt = bins[:, 1] - bins[:, 0]
+    assert int(cnt.sum()) == I and bool((cnt >= 0).all())
+    nz = bins[cnt > 0]
+    assert bool((nz[1:, 0] == nz[:-1, 1]).all()) and int(nz[0, 0]) == 0 and int(nz[-1, 1]) == I
+    tiles_of_keys = (keys >> 32)
+    assert bool((torch.bincount(tiles_of_keys, minlength=bins.shape[0]) == cnt).all())
+    # linearity in colour (no clamping active: scale colours down)
+    base = fit._features_dc.clone()
+    fit._features_dc.copy_(base * 0.01)
+    ra = fit.forward()["render"].clone()
+    fit._features_dc.copy_(base * 0.02)
+    rb = fit.forward()["render"].clone()
+    assert torch.allclose(rb, 2 * ra, rtol=1e-5, atol=1e-7)
+    # directional derivative of the loss w.r.t. colours vs the analytic gradient of the fused backward
+    fit._features_dc.copy_(base * 0.3)
+    fit.params.lr0 = 0.0  # freeze parameters: Adam with lr=0
+    fit.train_iter()
+    g = fit.grads[:, 5:8].clone()
+    mse0 = fit.stats()["mse"]
+    d = torch.randn_like(base)
+    eps = 1e-2
+    fit._features_dc.copy_(base * 0.3 + eps * d)
+    fit.train_iter()
+    mse1 = fit.stats()["mse"]
+    fit._features_dc.copy_(base * 0.3 - eps * d)
+    fit.train_iter()
+    mse2 = fit.stats()["mse"]
+    fd = (mse1 - mse2) / (2 * eps)
+    an = float((g.double() * d.double()).sum())
+    assert abs(fd - an) <= 2e-2 * abs(an) + 1e-9, (fd, an, mse0)

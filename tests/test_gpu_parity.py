@@ -1,0 +1,308 @@
+"""GPU parity tests: every C-ABI entry point of libgi2d against the CPU oracle on identical
+seeded inputs.  Bars (BASELINE.json north_star): integers (radii, tile counts, keys, sorted ids,
+tile ranges) BIT-EXACT; images and gradients within 1e-4 relative (fp32).
+
+Tolerance for floating point, spelled out:
+  |gpu - oracle| <= 1e-4 * |oracle| + noise + slack
+    noise = 4e-6 * (sum of |terms|)   float32 summation-order noise of the GPU's atomics, measured
+                                      against the oracle's sum of absolute contributions (`mag`)
+    slack = contribution of pairs whose accept/reject test (sigma<0, alpha<1/255) is within
+            ~1e-5 of flipping: ex2.approx on the GPU vs exp2f on the CPU may decide them differently.
+"""
+import numpy as np
+import pytest
+import torch
+
+from gaussianimage_plus_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+RTOL = 1e-4
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def N_(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def B():
+    from gaussianimage_plus_b200 import binding
+
+    return binding
+
+
+def scene(N, H, W, seed=0, colors="rand", cov_scale=1.0):
+    xyz, cov, bound, rgb = synth.init_covariance_model(N, H, W, seed=seed, colors=colors, cov_scale=cov_scale)
+    return xyz, (cov + bound).astype(np.float32), rgb
+
+
+# --------------------------------------------------------------------------- projection
+@pytest.mark.parametrize("N,H,W", [(1, 16, 16), (257, 100, 130), (5000, 512, 768), (20000, 1356, 2040)])
+def test_project_cov_fwd_bit_exact(B, oracle, N, H, W):
+    xyz, cov, _ = scene(N, H, W, seed=N)
+    rng = np.random.default_rng(N)
+    # sprinkle the quirk cases: det == 0, det < 0, off-screen, tiny, huge
+    if N > 50:
+        cov[0] = (4, 2, 1); cov[1] = (1, 3, 1); xyz[2] = (-500, -500); cov[3] = (0.01, 0, 0.01)
+        cov[4] = (1e6, 0, 1e6); xyz[5] = (-7.5, 3.0); cov[6] = (np.nan, 0, 1); xyz[7] = (W + 3, H + 3)
+        xyz[8:40] = rng.uniform(-20, 0, (32, 2))
+    tb = oracle.tile_bounds(H, W)
+    ref = oracle.project_cov_fwd(xyz, cov, H, W, tb)
+    got = B.project_gaussians_2d_covariance_forward(N, 3.0, T(xyz), T(cov), H, W, tb, 0.01, 1.0, False)
+    names = ("xys", "depths", "radii", "conics", "num_tiles_hit")
+    for nme, r, g in zip(names, ref, got):
+        np.testing.assert_array_equal(N_(g), r, err_msg=nme)  # floats too: same IEEE ops in the same order
+
+
+def test_project_chol_fwd_bit_exact(B, oracle):
+    N, H, W = 2500, 512, 768
+    means, L, _ = synth.cholesky_inputs(N, H, W)
+    tb = oracle.tile_bounds(H, W)
+    ref = oracle.project_chol_fwd(means, L, H, W, tb)
+    got = B.project_gaussians_2d_forward(N, 3.0, T(means), T(L), H, W, tb, 0.01, 1.0, False)
+    for r, g in zip(ref, got):
+        np.testing.assert_array_equal(N_(g), r)
+
+
+def test_project_rs_fwd(B, oracle):
+    N, H, W = 3000, 512, 768
+    means, scales, rot, _ = synth.scale_rot_inputs(N, H, W)
+    tb = oracle.tile_bounds(H, W)
+    ref = oracle.project_rs_fwd(means, scales, rot, H, W, tb)
+    got = B.project_gaussians_2d_scale_rot_forward(N, 3.0, T(means), T(scales), T(rot), H, W, tb, 0.01, 1.0, False)
+    # sinf/cosf differ by <= 2 ulp between libdevice and glibc: floats to 1e-5, integers equal except
+    # where a radius sits on a ceil() boundary (bit-exactness for this kernel is pinned against the
+    # reference's own CUDA build in test_ref_cuda_parity.py)
+    np.testing.assert_allclose(N_(got[0]), ref[0], rtol=1e-6)
+    np.testing.assert_allclose(N_(got[3]), ref[3], rtol=2e-5, atol=1e-9)
+    assert (N_(got[2]) != ref[2]).mean() < 2e-3
+    assert (N_(got[4]) != ref[4]).mean() < 2e-3
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_project_bwd(B, oracle, mode):
+    N, H, W = 4097, 512, 768
+    rng = np.random.default_rng(mode)
+    v_xy = rng.normal(size=(N, 2)).astype(np.float32)
+    v_conic = rng.normal(size=(N, 3)).astype(np.float32)
+    tb = oracle.tile_bounds(H, W)
+    if mode == 0:
+        xyz, cov, _ = scene(N, H, W)
+        cov[:10] = 0  # culled rows
+        _, _, radii, conics, _ = oracle.project_cov_fwd(xyz, cov, H, W, tb)
+        ref = oracle.project_bwd(0, None, None, H, W, radii, conics, v_xy, v_conic)
+        got = B.project_gaussians_2d_covariance_backward(N, T(xyz), T(cov), H, W, T(radii), T(conics), T(v_xy), None,
+                                                         T(v_conic))
+    elif mode == 1:
+        means, L, _ = synth.cholesky_inputs(N, H, W)
+        _, _, radii, conics, _ = oracle.project_chol_fwd(means, L, H, W, tb)
+        ref = oracle.project_bwd(1, L, None, H, W, radii, conics, v_xy, v_conic)
+        got = B.project_gaussians_2d_backward(N, T(means), T(L), H, W, T(radii), T(conics), T(v_xy), None, T(v_conic))
+    else:
+        means, scales, rot, _ = synth.scale_rot_inputs(N, H, W)
+        _, _, radii, conics, _ = oracle.project_rs_fwd(means, scales, rot, H, W, tb)
+        ref = oracle.project_bwd(2, scales, rot, H, W, radii, conics, v_xy, v_conic)
+        got = B.project_gaussians_2d_scale_rot_backward(N, T(means), T(scales), T(rot), H, W, T(radii), T(conics),
+                                                        T(v_xy), None, T(v_conic))
+    for r, g in zip(ref, got):
+        if r is None:
+            continue
+        g = N_(g).reshape(r.shape)
+        scale = np.abs(r).max() + 1e-30
+        np.testing.assert_allclose(g, r, rtol=RTOL, atol=1e-6 * scale)
+
+
+# --------------------------------------------------------------------------- binning
+@pytest.mark.parametrize("n", [0, 1, 5, 2048, 2049, 100000, 1 << 21])
+def test_cumsum_exact(B, n):
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 50, n).astype(np.int32)
+    if n == 0:
+        return  # nothing to scan; the wrapper path for empty inputs is covered by the rasterize test
+    cum, total = B.cumsum_i32(T(a))
+    np.testing.assert_array_equal(N_(cum), np.cumsum(a, dtype=np.int32))
+    assert int(total.item()) == int(a.sum())
+
+
+def test_map_and_edges_on_reference_fixture(B, oracle, golden_dir):
+    """The fixture of gsplat/tests/test_map_gaussians.py / test_get_tile_bin_edges.py."""
+    import os
+
+    g = np.load(os.path.join(golden_dir, "binning_seed42.npz"))
+    tb = tuple(int(v) for v in g["tile_bounds"])
+    I = int(g["num_intersects"])
+    ids_o, gids_o = oracle.map_gaussian_to_intersects(I, g["xys"], g["depths"], g["radii"], g["cum_tiles_hit"], tb)
+    ids, gids = B.map_gaussian_to_intersects(int(g["num_points"]), I, T(g["xys"]), T(g["depths"]), T(g["radii"]),
+                                             T(g["cum_tiles_hit"]), tb)
+    np.testing.assert_array_equal(N_(ids), ids_o)
+    np.testing.assert_array_equal(N_(gids), gids_o)
+    # depths are real here -> full 64-bit signed sort
+    ks, vs = B.sort_pairs_i64(T(g["isect_ids"]), T(g["gaussian_ids"]))
+    np.testing.assert_array_equal(N_(ks), g["isect_ids_sorted"])
+    np.testing.assert_array_equal(N_(vs), g["gaussian_ids_sorted"])
+    bins = B.get_tile_bin_edges(I, T(g["isect_ids_sorted"]))
+    np.testing.assert_array_equal(N_(bins), g["tile_bins"])
+
+
+@pytest.mark.parametrize("n", [1, 33, 2048, 2049, 70001, 1 << 20])
+def test_radix_sort_stable_signed(B, oracle, n):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(-(1 << 62), 1 << 62, n, dtype=np.int64)
+    keys[rng.integers(0, n, n // 3)] = keys[0]          # many ties: stability matters
+    keys[rng.integers(0, n, max(1, n // 50))] = -1
+    vals = np.arange(n, dtype=np.int32)
+    ko, vo = oracle.sort_pairs(keys, vals)
+    ks, vs = B.sort_pairs_i64(T(keys), T(vals))
+    np.testing.assert_array_equal(N_(ks), ko)
+    np.testing.assert_array_equal(N_(vs), vo)
+    # restricted bit range == stable sort on those bits only
+    ks2, vs2 = B.sort_pairs_i64(T(keys), T(vals), 32, 43)
+    order = np.argsort((keys >> 32) & 0x7FF, kind="stable")
+    np.testing.assert_array_equal(N_(vs2), vals[order])
+
+
+@pytest.mark.parametrize("N,H,W,scale", [(300, 96, 128, 1.0), (5000, 512, 768, 1.0), (5000, 512, 768, 4.0),
+                                          (20000, 1356, 2040, 1.0)])
+def test_bin_and_sort_composed_exact(B, oracle, N, H, W, scale):
+    from gaussianimage_plus_b200.gsplat import bin_and_sort_gaussians, compute_cumulative_intersects
+
+    xyz, cov, _ = scene(N, H, W, seed=3, cov_scale=scale)
+    tb = oracle.tile_bounds(H, W)
+    xys, depths, radii, conics, nth = oracle.project_cov_fwd(xyz, cov, H, W, tb)
+    total, cum, ids, gids, ids_s, gids_s, bins = oracle.bin_and_sort(xys, depths, radii, nth, tb)
+    I, cum_g = compute_cumulative_intersects(T(nth))
+    assert I == total
+    np.testing.assert_array_equal(N_(cum_g), cum)
+    out = bin_and_sort_gaussians(N, I, T(xys), T(depths), T(radii), cum_g, tb)
+    for g, r, nme in zip(out, (ids, gids, ids_s, gids_s), ("ids", "gids", "ids_sorted", "gids_sorted")):
+        np.testing.assert_array_equal(N_(g), r, err_msg=nme)
+    np.testing.assert_array_equal(N_(out[4])[: tb[0] * tb[1]], bins)
+
+
+# --------------------------------------------------------------------------- rasterize
+def _raster_inputs(oracle, N, H, W, seed, scale=1.0, opac=False):
+    xyz, cov, rgb = scene(N, H, W, seed=seed, cov_scale=scale)
+    if N > 20:
+        cov[1] = (1, 3, 1)  # indefinite conic: sigma changes sign across the tile (Q4)
+    tb = oracle.tile_bounds(H, W)
+    xys, depths, radii, conics, nth = oracle.project_cov_fwd(xyz, cov, H, W, tb)
+    total, cum, ids, gids, ids_s, gids_s, bins = oracle.bin_and_sort(xys, depths, radii, nth, tb)
+    opacity = (np.random.default_rng(seed).uniform(0.3, 1.5, (N, 1)).astype(np.float32) if opac
+               else np.ones((N, 1), np.float32))
+    return dict(tb=tb, xys=xys, conics=conics, rgb=rgb, gids_s=gids_s, bins=bins, opacity=opacity, total=total)
+
+
+@pytest.mark.parametrize("N,H,W,scale,opac", [(40, 33, 47, 1.0, False), (600, 100, 130, 1.0, True),
+                                               (5000, 512, 768, 1.0, False), (5000, 512, 768, 4.0, True),
+                                               (3000, 64, 64, 3.0, False)])  # last: > 256 per tile (Q1)
+def test_rasterize_fwd(B, oracle, N, H, W, scale, opac):
+    s = _raster_inputs(oracle, N, H, W, seed=N + H, scale=scale, opac=opac)
+    ref_img, ref_Ts, ref_idx, slack = oracle.rasterize_sum_fwd(H, W, s["gids_s"], s["bins"], s["xys"], s["conics"],
+                                                               s["rgb"], s["opacity"], with_slack=True)
+    img, Ts, fidx = B.rasterize_sum_plus_forward(s["tb"], (16, 16, 1), (W, H, 1), T(s["gids_s"]), T(s["bins"]),
+                                                 T(s["xys"]), T(s["conics"]), T(s["rgb"]), T(s["opacity"]))
+    img, Ts, fidx = N_(img), N_(Ts), N_(fidx)
+    if N == 3000:
+        cnt = s["bins"][:, 1] - s["bins"][:, 0]
+        assert cnt.max() > 256, "case must exercise the 256-per-tile truncation"
+    tol = RTOL * np.abs(ref_img) + 1e-6 + slack[..., None]
+    assert (np.abs(img - ref_img) <= tol).all(), np.abs(img - ref_img).max()
+    assert (Ts == 1.0).all()
+    firm = slack == 0
+    np.testing.assert_array_equal(fidx[firm], ref_idx[firm])
+    assert firm.mean() > 0.99
+
+
+@pytest.mark.parametrize("N,H,W,scale,opac", [(40, 33, 47, 1.0, False), (600, 100, 130, 1.0, True),
+                                               (5000, 512, 768, 1.0, False), (5000, 512, 768, 4.0, True),
+                                               (3000, 64, 64, 3.0, False)])
+def test_rasterize_bwd(B, oracle, N, H, W, scale, opac):
+    s = _raster_inputs(oracle, N, H, W, seed=N + H, scale=scale, opac=opac)
+    v_out = np.random.default_rng(1).normal(size=(H, W, 3)).astype(np.float32)
+    ref = oracle.rasterize_sum_bwd(H, W, s["gids_s"], s["bins"], s["xys"], s["conics"], s["rgb"], s["opacity"],
+                                   v_out, with_slack=True)
+    slack, mag = ref[4], ref[5]
+    fidx = torch.zeros(H, W, dtype=torch.int32, device=DEV)
+    got = B.rasterize_sum_plus_backward(H, W, 16, 16, T(s["gids_s"]), T(s["bins"]), T(s["xys"]), T(s["conics"]),
+                                        T(s["rgb"]), T(s["opacity"]), None, None, fidx, T(v_out), None)
+    cols = (slice(0, 2), slice(2, 5), slice(5, 8), slice(8, 9))
+    for nme, r, g, c in zip(("v_xy", "v_conic", "v_colors", "v_opacity"), ref[:4], got, cols):
+        g = N_(g).reshape(r.shape)
+        tol = RTOL * np.abs(r) + 4e-6 * mag[:, c].reshape(r.shape) + slack[:, c].reshape(r.shape) + 1e-12
+        bad = np.abs(g - r) > tol
+        assert not bad.any(), (nme, int(bad.sum()), np.abs(g - r)[bad].max())
+
+
+def test_rasterize_empty_and_ragged(B):
+    """No intersections at all, and a tile_bins with fewer rows than tiles."""
+    H, W = 40, 70
+    tb = ((W + 15) // 16, (H + 15) // 16, 1)
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=DEV)
+    img, Ts, fidx = B.rasterize_sum_plus_forward(tb, (16, 16, 1), (W, H, 1), z(0, dt=torch.int32),
+                                                 z(0, 2, dt=torch.int32), z(1, 2), z(1, 3), z(1, 3), z(1, 1))
+    assert float(img.abs().max()) == 0.0 and img.shape == (H, W, 3)
+    with pytest.raises(ValueError):
+        B.rasterize_sum_plus_forward(tb, (8, 8, 1), (W, H, 1), z(0, dt=torch.int32), z(0, 2, dt=torch.int32),
+                                     z(1, 2), z(1, 3), z(1, 3), z(1, 1))
+    with pytest.raises(RuntimeError):
+        B.rasterize_sum_plus_forward(tb, (16, 16, 1), (W, H, 1), z(0, dt=torch.int32).cpu(),
+                                     z(0, 2, dt=torch.int32), z(1, 2), z(1, 3), z(1, 3), z(1, 1))
+
+
+# --------------------------------------------------------------------------- autograd operators
+def test_gsplat_operators_autograd_vs_oracle(oracle):
+    """The reference-facing Python API end to end: project_gaussians_2d_covariance ->
+    rasterize_gaussians_plus -> clamp/permute/mse -> backward, against the oracle chain."""
+    import gaussianimage_plus_b200 as pkg
+
+    pkg.install_as_gsplat()
+    from gsplat.project_gaussians_2d_covariance import project_gaussians_2d_covariance
+    from gsplat.rasterize_sum_plus import rasterize_gaussians_plus
+
+    N, H, W = 2500, 256, 384
+    xyz, cov, rgb = scene(N, H, W, seed=11)
+    gt = synth.target_image(H, W, seed=11)
+    tb = oracle.tile_bounds(H, W)
+    p_xyz, p_cov, p_rgb = (T(a).requires_grad_(True) for a in (xyz, cov, rgb))
+    xys, depths, radii, conics, nth = project_gaussians_2d_covariance(p_xyz, p_cov, H, W, tb)
+    out = rasterize_gaussians_plus(xys, depths, radii, conics, nth, p_rgb, torch.ones(N, 1, device=DEV), H, W, 16, 16,
+                                   background=torch.ones(3, device=DEV))
+    render = torch.clamp(out, 0, 1).view(-1, H, W, 3).permute(0, 3, 1, 2).contiguous()
+    loss = torch.nn.functional.mse_loss(render, T(gt).permute(2, 0, 1).unsqueeze(0))
+    loss.backward()
+    # oracle chain
+    o_xys, o_depths, o_radii, o_conics, o_nth = oracle.project_cov_fwd(xyz, cov, H, W, tb)
+    total, cum, ids, gids, ids_s, gids_s, bins = oracle.bin_and_sort(o_xys, o_depths, o_radii, o_nth, tb)
+    img, _, _, slack = oracle.rasterize_sum_fwd(H, W, gids_s, bins, o_xys, o_conics, rgb, None, with_slack=True)
+    c = np.clip(img, 0, 1)
+    o_loss = float(((c - gt) ** 2).mean())
+    assert abs(float(loss) - o_loss) <= 1e-5 * o_loss + 1e-9
+    v_out = (2.0 / c.size * (c - gt) * ((img >= 0) & (img <= 1))).astype(np.float32)
+    v_xy, v_conic, v_col, _, sl, mag = oracle.rasterize_sum_bwd(H, W, gids_s, bins, o_xys, o_conics, rgb, None, v_out,
+                                                                with_slack=True)
+    _, v_mean, v_L, _ = oracle.project_bwd(0, None, None, H, W, o_radii, o_conics, v_xy, v_conic)
+    np.testing.assert_allclose(N_(p_rgb.grad), v_col, rtol=RTOL, atol=float(4e-6 * mag[:, 5:8].max() + sl.max() + 1e-12))
+    np.testing.assert_allclose(N_(p_xyz.grad), v_mean, rtol=RTOL, atol=float(4e-6 * mag[:, 0:2].max() + sl.max() + 1e-12))
+    gs = np.abs(v_L).max()
+    np.testing.assert_allclose(N_(p_cov.grad), v_L, rtol=1e-3, atol=1e-4 * gs)
+
+
+def test_stale_rasterize_gaussians_sum_forms():
+    from gaussianimage_plus_b200.gsplat import project_gaussians_2d, rasterize_gaussians_sum
+
+    N, H, W = 500, 64, 96
+    means, L, colors = synth.cholesky_inputs(N, H, W)
+    tb = ((W + 15) // 16, (H + 15) // 16, 1)
+    xys, depths, radii, conics, nth = project_gaussians_2d(T(means), T(L), H, W, tb)
+    op = torch.ones(N, 1, device=DEV)
+    clean = rasterize_gaussians_sum(xys, depths, radii, conics, nth, T(colors), op, H, W, 16, 16)
+    ssp = torch.zeros(N, 4, device=DEV)
+    stale = rasterize_gaussians_sum(xys, ssp, depths, radii, conics, nth, T(colors), op, H, W, 16, 16,
+                                    torch.ones(3, device=DEV), False, False)
+    assert isinstance(stale, tuple) and len(stale) == 3
+    assert torch.equal(stale[0], clean) and stale[1].shape == (H, W) and stale[2] is ssp
