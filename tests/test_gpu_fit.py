@@ -134,16 +134,18 @@ def test_prune_and_densify_keep_state_consistent():
     fit, _ = make_fitter(2000, 256, 384, seed=6, colors="zeros", use_graph=True)
     for _ in range(20):
         fit.train_iter()
+    p0 = fit.psnr()
     fit._cov2d[:7, 0] = -1000.0  # make 7 Gaussians indefinite
     n_bad, n_now = fit.non_semi_definite_prune()
     assert n_bad == 7 and n_now == 1993 and fit.exp_avg["xyz"].shape[0] == 1993
     added = fit.add_sample_positions(max_num_points=2300, base_num_samples=200)
-    assert added == 200 and fit.cur_num_points == 2193 and fit.cholesky_bound.shape[0] == 2193
-    p0 = fit.psnr()
+    # densification_postfix drops the new Gaussians whose random covariance is not positive definite
+    assert added == 200 and 2100 < fit.cur_num_points <= 2193
+    assert fit.cholesky_bound.shape[0] == fit.cur_num_points == fit.exp_avg_sq['cov2d'].shape[0]
     for _ in range(50):
         fit.train_iter()
     st = fit.stats()
-    assert st["step"] == 70 and np.isfinite(st["psnr"]) and st["psnr"] > p0 - 3
+    assert st["step"] == 70 and np.isfinite(st["psnr"]) and st["psnr"] > p0 - 1
 
 
 # --------------------------------------------------------------------------- full-size properties
@@ -174,17 +176,18 @@ def test_full_size_properties(name):
     rb = fit.forward()["render"].clone()
     assert torch.allclose(rb, 2 * ra, rtol=1e-5, atol=1e-7)
     # directional derivative of the loss w.r.t. colours vs the analytic gradient of the fused backward
-    fit._features_dc.copy_(base * 0.3)
+    fit._features_dc.copy_(base * 0.05)
     fit.params.lr0 = 0.0  # freeze parameters: Adam with lr=0
     fit.train_iter()
     g = fit.grads[:, 5:8].clone()
     mse0 = fit.stats()["mse"]
-    d = torch.randn_like(base)
-    eps = 1e-2
-    fit._features_dc.copy_(base * 0.3 + eps * d)
+    # probe along the gradient itself: the strongest signal a finite difference can get
+    d = g / g.norm() * (base.numel() ** 0.5)
+    eps = 2e-3
+    fit._features_dc.copy_(base * 0.05 + eps * d)
     fit.train_iter()
     mse1 = fit.stats()["mse"]
-    fit._features_dc.copy_(base * 0.3 - eps * d)
+    fit._features_dc.copy_(base * 0.05 - eps * d)
     fit.train_iter()
     mse2 = fit.stats()["mse"]
     fd = (mse1 - mse2) / (2 * eps)
