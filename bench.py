@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+metric   : fit iterations / s (forward + L2 loss + backward + Adam; one "step" = one train_iter of
+           models/gaussianimage_covariance.py:249-259) at 768x512 with 5000 Gaussians (BASELINE.json
+           `metric`, configs[1]); render FPS and PSNR ride along in the same JSON line.
+value    : whole-job it/s with everything resident in HBM, timed with CUDA events per step, L2 flushed
+           between timed steps (config.l2); `value_l2_warm` is the same loop run back to back.
+e2e      : the same metric through the public API with HOST buffers: every step copies the target image
+           host->device from pinned memory and reads the step's squared error back.
+roofline : the dominant kernel (rasterize fwd+bwd, FP32-issue bound): algorithmic FLOPs (65 per
+           pixel x Gaussian pair) / its event-timed duration, against the FP32 FMA peak measured in
+           this run (MEASURED_PEAKS.json has no FP32 figure) -- plus the HBM fraction of the step.
+cpu_baseline / --impl reference: the oracle's C port of the reference train_iter on the host cores.
+ref_cuda : (extra) the UNMODIFIED reference CUDA extension (oracle/_ref) running the reference's
+           train_iter protocol on the same GPU -- the number the >=5x target is stated against.
+
+Multi-GPU (torchrun, --gpus N): independent images sharded one per rank, no collective on the data
+path (weak scaling); `--mode tilerow` instead splits ONE image by tile rows with an NCCL all-reduce
+of the packed per-Gaussian gradients each iteration (BASELINE.json configs[4]).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FWD_FLOP, BWD_FLOP = 22, 43  # per pixel x Gaussian pair, SURVEY 8(d)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kodak_5000")
+    ap.add_argument("--mode", default="images", choices=["images", "tilerow"])
+    ap.add_argument("--cov-scale", type=float, default=1.0, help=">1 emulates a mid-training state")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=1)
+
+    def summary(self):
+        sm, reasons, mx = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_rate(H, W, N, seconds, cov_scale=1.0, max_steps=None, warmup=1):
+    """it/s of the oracle's C port of the reference train_iter on the host cores (OpenMP)."""
+    from gaussianimage_plus_b200 import synth
+    from oracle import cpu_oracle as O
+
+    xyz, cov, bound, rgb = synth.init_covariance_model(N, H, W, colors="zeros", cov_scale=cov_scale)
+    gt = synth.target_image(H, W)
+    st = O.FitState(xyz, cov, bound, rgb, gt)
+    for _ in range(warmup):
+        st.train_iter()
+    t0, n = time.perf_counter(), 0
+    while True:
+        st.train_iter()
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or (max_steps and n >= max_steps):
+            break
+    return n / el, n, el
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path.  The reference ships none for
+    the accumulate-sum rasterizer, so this is the oracle port (`kind: port`) using every
+    host thread OpenMP gives it.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from gaussianimage_plus_b200 import synth
+
+    H, W, N = synth.CONFIGS[args.workload]
+    cores = os.cpu_count()
+    budget = 150.0
+    rate, n, el = cpu_port_rate(H, W, N, seconds=budget, cov_scale=args.cov_scale, max_steps=args.steps,
+                                warmup=min(args.warmup, 3))
+    line = {
+        "impl": "reference", "metric": "fit_iters_per_s", "value": rate, "unit": "it/s", "n_gpus": args.gpus,
+        "steps": n, "warmup": min(args.warmup, 3), "ms_per_step": 1000.0 / rate, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {W}x{H}, {N} Gaussians, covariance model, L2, Adam",
+                   "cov_scale": args.cov_scale},
+        "cpu_baseline": {"value": rate, "unit": "it/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} full train_iter steps of the same workload ({el:.1f} s)"},
+        "e2e": {"value": rate, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def count_pairs(fit):
+    """algorithmic pixel x Gaussian pairs of one forward: sum over tiles of min(cnt,256) * in-image pixels."""
+    import torch
+
+    tb = fit.tile_bounds
+    bins = fit.tile_bins
+    cnt = (bins[:, 1] - bins[:, 0]).clamp(min=0, max=256).view(tb[1], tb[0]).double()
+    wx = torch.full((tb[0],), 16.0, dtype=torch.float64, device=bins.device)
+    wy = torch.full((tb[1],), 16.0, dtype=torch.float64, device=bins.device)
+    if fit.W % 16:
+        wx[-1] = fit.W % 16
+    if fit.H % 16:
+        wy[-1] = fit.H % 16
+    return float((cnt * wy[:, None] * wx[None, :]).sum())
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from gaussianimage_plus_b200 import _lib, synth
+    from gaussianimage_plus_b200.fit import GaussianImageFitter
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; see --impl reference)")
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, W, N = synth.CONFIGS[args.workload]
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    grad_hook, tile_rows = None, None
+    if args.mode == "tilerow" and world > 1:
+        from gaussianimage_plus_b200.parallel import TileRowPartition
+
+        part = TileRowPartition((H + 15) // 16, world)
+        tile_rows = part.band(rank)
+        grad_hook = part.make_grad_hook()
+    seed = 3047 if args.mode == "tilerow" else 3047 + rank  # image sets: a different image per rank
+    xyz, cov, bound, rgb = synth.init_covariance_model(N, H, W, seed=3047, colors="zeros", cov_scale=args.cov_scale)
+    gt = synth.target_image(H, W, seed=seed)
+    fit = GaussianImageFitter(N, H, W, device=dev, use_graph=(grad_hook is None), tile_rows=tile_rows, grad_hook=grad_hook)
+    for dst, src in ((fit._xyz, xyz), (fit._cov2d, cov), (fit.cholesky_bound, bound), (fit._features_dc, rgb)):
+        dst.copy_(torch.from_numpy(src))
+    gt_pinned = torch.from_numpy(gt).pin_memory()
+    fit.set_target(gt_pinned)
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- warm-up (also lets the Gaussians leave their initial state)
+    for _ in range(Wm):
+        fit.train_iter()
+    torch.cuda.synchronize(dev)
+    fit.ensure_capacity()
+
+    # ---------------- L2-warm, back-to-back (what a fit loop actually looks like)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        fit.train_iter()
+    ev1.record()
+    barrier()
+    warm_ms = ev0.elapsed_time(ev1) / K
+
+    # ---------------- timed region of record: per-step events, L2 flushed between steps
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            starts[i].record()
+            fit.train_iter()
+            stops[i].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = sorted(s.elapsed_time(e) for s, e in zip(starts, stops))
+    total_ms = sum(step_ms)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    stats = fit.stats()
+    units = K * (world if args.mode == "images" else 1)
+    value = units / (total_ms * 1e-3)
+
+    # ---------------- e2e: host buffers in, scalar out, every step
+    sse_host = torch.zeros(72, dtype=torch.float64).pin_memory()
+    Ke = min(K, 2000)
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(Ke):
+        fit.set_target(gt_pinned)                      # H2D of the step's input (pinned -> device)
+        fit.train_iter()
+        sse_host.copy_(fit.stats_buf, non_blocking=False)  # D2H of the step's result (synchronises)
+    barrier()
+    te = time.perf_counter() - te0
+    te_t = torch.tensor([te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+    e2e_value = Ke * (world if args.mode == "images" else 1) / float(te_t.item())
+
+    # ---------------- render FPS (train.py:178-191 protocol: 100 forwards between syncs)
+    fit.forward()
+    barrier()
+    ev0.record()
+    for _ in range(100):
+        fit.forward()
+    ev1.record()
+    barrier()
+    fps = 100.0 / (ev0.elapsed_time(ev1) * 1e-3)
+
+    line = None
+    if rank == 0:
+        # ---------------- per-kernel profile (events between kernels), L2 flushed before each sample
+        import ctypes as C
+
+        ms = (C.c_float * 8)()
+        acc = [0.0] * 5
+        reps = 30
+        st_ptr = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        fit._bind()
+        for i in range(reps + 3):
+            flush.fill_(i & 0xFF)
+            _lib.check(lib.gi2d_fit_profile(C.byref(fit.params), C.byref(fit.buffers), ms, st_ptr), "profile")
+            if i >= 3:
+                for k in range(5):
+                    acc[k] += ms[k] / reps
+        pairs = count_pairs(fit)
+        peak = C.c_float(0)
+        _lib.check(lib.gi2d_measure_fp32_peak(C.byref(peak), st_ptr), "fp32 peak")
+        raster_s = acc[3] * 1e-3
+        achieved_tf = pairs * (FWD_FLOP + BWD_FLOP) / raster_s / 1e12 if raster_s > 0 else 0.0
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        # algorithmic HBM bytes of one step: params+moments+grads, records, keys, images
+        I = stats["num_intersects"]
+        step_bytes = N * (52 + 32 + 8) + I * 8 * 2 + H * W * 24 + N * (32 + 32 + 224)
+        roofline = {
+            "kernel": "fit_raster_kernel<Fit> (rasterize fwd + L2 grad + bwd)", "bound": "fp32",
+            "achieved": achieved_tf, "peak": float(peak.value), "unit": "TFLOP/s",
+            "frac": achieved_tf / float(peak.value) if peak.value else None, "traffic": None,
+            "peak_source": "FP32 FMA microbenchmark in this run (gi2d_measure_fp32_peak); nominal 74.4",
+            "pairs_per_launch": pairs, "flop_per_pair": FWD_FLOP + BWD_FLOP, "kernel_ms": acc[3],
+            "step_kernel_ms": {"project": acc[0], "scan": acc[1], "scatter": acc[2], "raster": acc[3], "adam": acc[4]},
+            "raster_share_of_step": acc[3] / sum(acc) if sum(acc) > 0 else None,
+            "hbm": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (sum(acc) * 1e-3) / 1e9,
+                    "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, n, el = cpu_port_rate(H, W, N, args.cpu_seconds, cov_scale=args.cov_scale)
+            cpu = {"value": rate, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"{n} full train_iter steps of the same workload in {el:.1f} s (oracle C port, OpenMP)"}
+        ref_cuda = None
+        if world == 1 and not args.no_ref_cuda:
+            ref_cuda = bench_ref_cuda(torch, dev, xyz, cov, bound, rgb, gt, H, W)
+        line = {
+            "metric": "fit_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak" if args.mode == "images" else "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {W}x{H}, {N} Gaussians, covariance model, L2, Adam(eps=1e-15)+StepLR",
+                       "mode": args.mode, "cov_scale": args.cov_scale,
+                       "l2": "flushed between timed steps (256 MiB fill); value_l2_warm = back-to-back replay",
+                       "parallelism": "one image per GPU, no collective" if args.mode == "images"
+                       else "tile-row split + NCCL all-reduce of [N,8] gradients"},
+            "value_l2_warm": (K * (world if args.mode == "images" else 1)) / (warm_ms * K * 1e-3),
+            "ms_per_step_l2_warm": warm_ms,
+            "ms_per_step_p50": step_ms[len(step_ms) // 2], "wall_s_timed_region": t_wall,
+            "render_fps": fps, "psnr": stats["psnr"], "train_step": stats["step"], "num_intersects": I,
+            "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": int(gt_pinned.numel() * 4),
+                    "d2h_bytes_per_step": int(sse_host.numel() * 8), "steps": Ke},
+            "gpu_launches": fit.launches_per_iter() * K,
+            "launches_per_step": fit.launches_per_iter(),
+            "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "ref_cuda": ref_cuda,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_ref_cuda(torch, dev, xyz, cov, bound, rgb, gt, H, W, iters=300, warm=30):
+    """The reference's own extension + its train_iter protocol (train.py:126-155, :178-191) on this GPU."""
+    out = {}
+    try:
+        from oracle import ref_cuda
+    except Exception as e:
+        return {"unavailable": str(e)}
+    gt_chw = torch.from_numpy(gt).to(dev).permute(2, 0, 1).unsqueeze(0).contiguous()
+    for variant in ("fastmath", "o3"):
+        if not ref_cuda.available(variant):
+            out[variant] = {"unavailable": "oracle/_ref not built"}
+            continue
+        try:
+            tr = ref_cuda.RefTrainer(variant, *(torch.from_numpy(a) for a in (xyz, cov, bound, rgb)), gt_chw)
+            for _ in range(warm):
+                tr.train_iter()
+            torch.cuda.synchronize(dev)
+            t0 = time.time()
+            for _ in range(iters):
+                _, psnr = tr.train_iter()
+            torch.cuda.synchronize(dev)
+            dt = time.time() - t0
+            with torch.no_grad():
+                tr.forward()
+                torch.cuda.synchronize(dev)
+                t1 = time.time()
+                for _ in range(100):
+                    tr.forward()
+                torch.cuda.synchronize(dev)
+                fps = 100.0 / (time.time() - t1)
+            out[variant] = {"fit_it_s": iters / dt, "render_fps": fps, "psnr_after": psnr, "iters": iters + warm,
+                            "flags": "-O3 --use_fast_math (setup.py)" if variant == "fastmath" else "-O3 (JIT)"}
+        except Exception as e:  # never let the comparison leg break the bench line
+            out[variant] = {"error": repr(e)[:200]}
+    return out
+
+
+if __name__ == "__main__":
+    main()

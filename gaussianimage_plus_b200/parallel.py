@@ -1,0 +1,99 @@
+"""Multi-GPU partitioning of the hot path.  One process per GPU, torch.distributed for
+the plumbing; the reference itself is single-GPU (`train.py:39`), so both modes are new design.
+
+1. Image sets (Kodak-24, DIV2K-100): images are independent units -> `shard_images` deals image i to
+   rank i mod world; NO collective on the data path; `gather_metrics` collects the per-image scalars
+   once at the end (the averages of train.py:327-340).
+
+2. One very large image: `TileRowPartition` gives rank r a contiguous band of tile rows.  Parameters
+   and Adam state are replicated; each rank projects every Gaussian, bins/rasterizes only its band
+   (gi2d_fit_params.tile_row_begin/end) and accumulates partial per-Gaussian gradients; ONE
+   all-reduce(SUM) of the packed f32[N,8] gradient buffer (+ the 64 squared-error partials) per
+   iteration makes them identical everywhere, after which the replicated Adam step is bitwise the
+   same on every rank.  The all-reduce runs on the stream the kernels run on, directly on the buffer
+   the backward kernel accumulated into (no staging copy).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+
+def shard_images(num_images: int, world_size: int, rank: int) -> List[int]:
+    """Indices of the images rank `rank` fits (round-robin keeps 768x512 / 512x768 mixes balanced)."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    return list(range(rank, num_images, world_size))
+
+
+def gather_metrics(local: Sequence[Tuple[int, float, float]], group=None):
+    """All ranks contribute [(image_index, psnr, seconds), ...]; every rank gets the full sorted list."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return sorted(local)
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, list(local), group=group)
+    return sorted(x for part in out for x in part)
+
+
+class TileRowPartition:
+    """Contiguous, near-equal bands of tile rows; optionally weighted by a per-row load histogram
+    (adaptive densification concentrates Gaussians, SURVEY 8e 'load balance caveat')."""
+
+    def __init__(self, tiles_y: int, world_size: int, row_load: Sequence[float] = None):
+        if world_size < 1 or tiles_y < 0:
+            raise ValueError("bad partition")
+        self.tiles_y, self.world_size = tiles_y, world_size
+        if row_load is None:
+            base, rem = divmod(tiles_y, world_size)
+            sizes = [base + (1 if r < rem else 0) for r in range(world_size)]
+            edges = [0]
+            for s in sizes:
+                edges.append(edges[-1] + s)
+        else:
+            if len(row_load) != tiles_y:
+                raise ValueError("row_load must have one entry per tile row")
+            total = float(sum(row_load)) or 1.0
+            edges, acc, r = [0], 0.0, 1
+            for y, w in enumerate(row_load):
+                acc += w
+                while r < world_size and acc >= total * r / world_size:
+                    edges.append(y + 1)
+                    r += 1
+            while len(edges) < world_size:
+                edges.append(tiles_y)
+            edges.append(tiles_y)
+            edges = [min(e, tiles_y) for e in edges]
+        self.edges = edges
+
+    def band(self, rank: int) -> Tuple[int, int]:
+        return self.edges[rank], self.edges[rank + 1]
+
+    def owner_of_row(self, tile_row: int) -> int:
+        for r in range(self.world_size):
+            if self.edges[r] <= tile_row < self.edges[r + 1]:
+                return r
+        raise ValueError(tile_row)
+
+    def make_grad_hook(self, group=None):
+        """Hook for GaussianImageFitter(grad_hook=...): all-reduce the packed gradients and the SSE."""
+        import torch.distributed as dist
+
+        from .fit import STAT_SSE, STAT_SSE_SLOTS
+
+        def hook(fit):
+            dist.all_reduce(fit.grads, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(fit.stats_buf[STAT_SSE:STAT_SSE + STAT_SSE_SLOTS], op=dist.ReduceOp.SUM, group=group)
+
+        return hook
+
+
+def allreduce_packed_gradients(v_xy, v_conic, v_colors, group=None):
+    """Host-side reference of the exchange step for the operator path: pack [N,2]+[N,3]+[N,3] into one
+    [N,8] buffer, one all-reduce, unpack.  (The fused path accumulates straight into the packed buffer.)"""
+    import torch
+    import torch.distributed as dist
+
+    packed = torch.cat((v_xy, v_conic, v_colors), dim=1).contiguous()
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed[:, 0:2], packed[:, 2:5], packed[:, 5:8]
