@@ -70,7 +70,7 @@ SIGNATURES = {
     "gi2d_fit_launch_count": (_I, [C.POINTER(FitParams), _I]),
     "gi2d_fit_profile": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), C.POINTER(C.c_float), _P]),
     "gi2d_measure_fp32_peak": (_I, [C.POINTER(C.c_float), _P]),
-    "gi2d_fit_reset": (_I, [C.POINTER(FitBuffers), _I, _P]),
+    "gi2d_fit_reset": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _P]),
 }
 
 _lib = None

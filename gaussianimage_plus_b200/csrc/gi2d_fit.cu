@@ -1,17 +1,19 @@
 // gi2d_fit.cu -- the fused, synchronisation-free fit step: everything one
 // `train_iter` of models/gaussianimage_covariance.py:249-259 does on the device, in 5 launches
-// for images of up to 2048 tiles (768x512) and 8 beyond, with no host round trip, no allocation
-// and a device-side step counter, so the whole iteration replays from one CUDA graph.
+// for images of up to 2048 tiles (768x512) and a few more beyond, with no host round trip, no
+// allocation and a device-side step counter, so the whole iteration replays from one CUDA graph.
 //
 //   K1 fit_project_kernel   projection (R1) + colour activation + packed 32-B record per
 //                           Gaussian + zeroing of the gradient rows + per-CTA digit histogram of
-//                           the tile ids the Gaussian touches                       [HBM/latency]
+//                           the tile ids the Gaussian touches + step/lr bookkeeping  [HBM/latency]
 //   K2 fit_scan_kernel      prefix sum over the per-tile (digit) overlap counts -> scatter
 //                           offsets, tile ranges, num_intersects                    [latency]
 //   K3 fit_scatter_kernel   stable counting-sort scatter of 64-bit (tile<<32|gaussian) keys:
 //                           one LSD radix pass of up to 11 bits, ranks by warp match_any over a
-//                           load-balanced expansion of the tile boxes               [HBM/latency]
-//      (+ gi2d radix pass + tile edges for images with more than 2048 tiles)
+//                           load-balanced expansion of the tile boxes; also gathers the 32-B
+//                           record of every intersection into sorted order so the rasterizer
+//                           reads its tile's Gaussians as ONE contiguous block      [HBM/latency]
+//      (+ 8-bit radix passes + tile edges + record gather for images with > 2048 tiles)
 //   K4 fit_raster_kernel    per 16x16 tile: rasterize-sum forward (R5), L2 loss gradient and
 //                           squared error, rasterize-sum backward (R6) with register
 //                           accumulation + transposed warp reduction + one red.global per
@@ -41,6 +43,11 @@ constexpr int kProjThreads = 256;
 constexpr int kScatterWarps = 4;
 constexpr int kScatterThreads = kScatterWarps * 32;
 constexpr int kRasterThreads = 256;
+constexpr int kRasterWarps = kRasterThreads / 32;
+
+// private slots of the stats block (beyond the public GI2D_STAT_* ones)
+constexpr int kStatB1Pow = 4;  // beta1^step
+constexpr int kStatB2Pow = 5;  // beta2^step
 
 struct Plan {
     int tile_bits;     // bits needed for a tile id
@@ -59,7 +66,7 @@ Plan make_plan(const gi2d_fit_params &p) {
     pl.bits0 = tb < kMaxDigitBits ? tb : kMaxDigitBits;
     pl.extra_passes = (tb - pl.bits0 + 7) / 8;
     // keep the count matrix (nblocks x 2^bits0) scannable by one CTA: <= ~1184 CTAs
-    int gpb = kScatterThreads;
+    int gpb = kScatterWarps * 16;
     while ((long long)gpb * 1184 < p.num_points) gpb *= 2;
     pl.gpb = gpb;
     pl.nblocks = p.num_points > 0 ? cdiv(p.num_points, gpb) : 1;
@@ -70,9 +77,10 @@ size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct Workspace {
     int32_t *counts;      // [nblocks][D] per-CTA digit counts -> per-CTA exclusive offsets
-    int32_t *digit_base;  // [D]
+    int32_t *totals;      // [D] column totals of counts (= size of every digit bucket)
     ushort4 *boxes;       // [N] clipped tile box per Gaussian
     int32_t *n_isect;     // [1] device copy of num_intersects (clamped to capacity)
+    float4 *records;      // [capacity][2] projected record of every intersection, sorted order
     uint64_t *keys_tmp;   // [capacity] ping-pong buffer for multi-pass sorts
     void *radix_ws;
     size_t radix_ws_bytes;
@@ -85,9 +93,10 @@ Workspace carve(const gi2d_fit_params &p, const Plan &pl, void *base) {
     size_t off = 0;
     const size_t D = (size_t)1 << pl.bits0;
     w.counts = (int32_t *)(c + off);      off += align_up((size_t)pl.nblocks * D * 4);
-    w.digit_base = (int32_t *)(c + off);  off += align_up(D * 4);
+    w.totals = (int32_t *)(c + off);      off += align_up(D * 4);
     w.boxes = (ushort4 *)(c + off);       off += align_up((size_t)(p.num_points > 0 ? p.num_points : 1) * 8);
     w.n_isect = (int32_t *)(c + off);     off += 256;
+    w.records = (float4 *)(c + off);      off += align_up((size_t)p.isect_capacity * 32);
     w.keys_tmp = nullptr;
     w.radix_ws = nullptr;
     w.radix_ws_bytes = 0;
@@ -117,7 +126,16 @@ fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, const float *__restric
     if (blockIdx.x == 0 && threadIdx.x < GI2D_STAT_SSE_SLOTS) stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         stats[GI2D_STAT_OVERFLOW] = 0.0;
-        if (with_backward) stats[GI2D_STAT_STEP] += 1.0;
+        if (with_backward) {
+            // step counter, bias-correction powers and the StepLR schedule live on the device:
+            // torch evaluates beta^step / gamma^floor((step-1)/size) in double precision as well
+            const double step = stats[GI2D_STAT_STEP] + 1.0;
+            stats[GI2D_STAT_STEP] = step;
+            stats[kStatB1Pow] *= (double)p.beta1;
+            stats[kStatB2Pow] *= (double)p.beta2;
+            const long long k = (long long)step - 1;
+            if (k > 0 && p.lr_step_size > 0 && k % p.lr_step_size == 0) stats[GI2D_STAT_LR] *= (double)p.lr_gamma;
+        }
     }
     __syncthreads();
     const int g0 = blockIdx.x * gpb;
@@ -154,57 +172,53 @@ fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, const float *__restric
 }
 
 // ------------------------------------------------------------------------------------ K2
-// One CTA.  counts[b][d] -> exclusive prefix over b (in place); digit_base[d] = exclusive prefix
-// over d of the column totals.  With a single pass (D covers every tile id) the tile ranges
-// fall out directly.
-__global__ void __launch_bounds__(1024)
-fit_scan_kernel(int nblocks, int bits0, int num_tiles, int single_pass, int capacity,
-                int32_t *__restrict__ counts, int32_t *__restrict__ digit_base,
-                int32_t *__restrict__ tile_bins, int32_t *__restrict__ n_isect,
-                double *__restrict__ stats) {
-    __shared__ int s_tot[1 << kMaxDigitBits];
-    __shared__ int s_warp[32];
-    const int D = 1 << bits0;
-    for (int d = threadIdx.x; d < D; d += 1024) {
-        int run = 0;
-        int32_t *col = counts + d;
-#pragma unroll 8
-        for (int b = 0; b < nblocks; ++b) {
-            const int c = col[(size_t)b * D];
-            col[(size_t)b * D] = run;
-            run += c;
+// Prefix sum over the per-tile (digit) overlap counts, step 1: one THREAD per digit column walks
+// the per-CTA counts of K1 top to bottom, turning counts[b][d] into the exclusive prefix over b
+// (in place) and leaving the column total in totals[d].  D/256 CTAs; the loads of a column are
+// issued 8 at a time ahead of the dependent adds/stores (the loop is otherwise one exposed L2
+// round trip per row).  Step 2 (exclusive scan over d of the totals = start of every digit/tile)
+// is 8 KiB of work and is redone by every CTA of K3 in its prologue instead of costing a launch.
+constexpr int kScanThreads = 256;
+
+__global__ void __launch_bounds__(kScanThreads)
+fit_scan_kernel(int nblocks, int D, int32_t *__restrict__ counts, int32_t *__restrict__ totals) {
+    const int d = blockIdx.x * kScanThreads + threadIdx.x;
+    if (d >= D) return;
+    int run = 0;
+    int32_t *col = counts + d;
+    for (int b0 = 0; b0 < nblocks; b0 += 8) {
+        int c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = (b0 + j < nblocks) ? __ldcg(col + (size_t)(b0 + j) * D) : 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (b0 + j < nblocks) col[(size_t)(b0 + j) * D] = run;
+            run += c[j];
         }
-        s_tot[d] = run;
     }
-    __syncthreads();
-    // exclusive scan of s_tot[0..D): each thread owns a contiguous pair (D <= 2048)
-    const int per = (D + 1023) / 1024;  // 1 or 2
-    int v0 = 0, v1 = 0;
+    totals[d] = run;
+}
+
+// Step 2, run by every CTA of K3 (and by the tile-range writer): exclusive scan of totals[0..D)
+// into shared memory.  D <= 2048, kThreads * kPer >= D.
+template <int kThreads>
+__device__ __forceinline__ int scan_totals_to_smem(const int32_t *__restrict__ totals, int D, int *s_base,
+                                                   int *s_warp) {
+    const int per = (D + kThreads - 1) / kThreads;
     const int i0 = threadIdx.x * per;
-    if (i0 < D) v0 = s_tot[i0];
-    if (per == 2 && i0 + 1 < D) v1 = s_tot[i0 + 1];
+    int sum = 0;
+    for (int k = 0; k < per; ++k)
+        if (i0 + k < D) sum += __ldcg(totals + i0 + k);
     int total;
-    const int incl = block_scan_inclusive<1024>(v0 + v1, s_warp, &total);
-    const int excl = incl - (v0 + v1);
-    if (i0 < D) {
-        digit_base[i0] = excl;
-        if (single_pass && i0 < num_tiles) {
-            tile_bins[2 * i0] = excl;
-            tile_bins[2 * i0 + 1] = excl + v0;
+    const int incl = block_scan_inclusive<kThreads>(sum, s_warp, &total);
+    int run = incl - sum;
+    for (int k = 0; k < per; ++k)
+        if (i0 + k < D) {
+            s_base[i0 + k] = run;
+            run += __ldcg(totals + i0 + k);
         }
-    }
-    if (per == 2 && i0 + 1 < D) {
-        digit_base[i0 + 1] = excl + v0;
-        if (single_pass && i0 + 1 < num_tiles) {
-            tile_bins[2 * (i0 + 1)] = excl + v0;
-            tile_bins[2 * (i0 + 1) + 1] = excl + v0 + v1;
-        }
-    }
-    if (threadIdx.x == 0) {
-        stats[GI2D_STAT_ISECTS] = (double)total;
-        if (total > capacity) stats[GI2D_STAT_OVERFLOW] = 1.0;
-        *n_isect = total > capacity ? capacity : total;
-    }
+    __syncthreads();
+    return total;
 }
 
 // ------------------------------------------------------------------------------------ K3
@@ -252,34 +266,50 @@ __device__ __forceinline__ void walk_intersections(int g_begin, int g_end, int t
 }
 
 __global__ void __launch_bounds__(kScatterThreads)
-fit_scatter_kernel(int num_points, int gpb, int bits0, int tiles_x, int capacity,
-                   const ushort4 *__restrict__ boxes, const int32_t *__restrict__ counts,
-                   const int32_t *__restrict__ digit_base, uint64_t *__restrict__ keys_out) {
-    extern __shared__ int s_cnt[];  // [kScatterWarps][D]
+fit_scatter_kernel(int num_points, int gpb, int bits0, int tiles_x, int num_tiles, int single_pass,
+                   int capacity, const ushort4 *__restrict__ boxes, const int32_t *__restrict__ counts,
+                   const int32_t *__restrict__ totals, uint64_t *__restrict__ keys_out,
+                   const float4 *__restrict__ proj, float4 *__restrict__ records,
+                   int32_t *__restrict__ tile_bins, int32_t *__restrict__ n_isect,
+                   double *__restrict__ stats) {
+    extern __shared__ int s_dyn[];  // [kScatterWarps][D] per-warp counters, then [D] digit bases
+    __shared__ int s_warp[kScatterWarps];
     const int D = 1 << bits0;
     const int mask = D - 1;
+    int *s_cnt = s_dyn;
+    int *s_base = s_dyn + kScatterWarps * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < kScatterWarps * D; i += kScatterThreads) s_cnt[i] = 0;
-    __syncthreads();
+    {
+        int4 *z = reinterpret_cast<int4 *>(s_cnt);
+        for (int i = threadIdx.x; i < kScatterWarps * D / 4; i += kScatterThreads) z[i] = make_int4(0, 0, 0, 0);
+    }
+    // start of every digit (== tile, when one pass covers the tile id) in the sorted order
+    const int total = scan_totals_to_smem<kScatterThreads>(totals, D, s_base, s_warp);
+    if (blockIdx.x == 0) {
+        if (single_pass)
+            for (int t = threadIdx.x; t < num_tiles; t += kScatterThreads)
+                reinterpret_cast<int2 *>(tile_bins)[t] = make_int2(s_base[t], s_base[t] + __ldcg(totals + t));
+        if (threadIdx.x == 0) {
+            stats[GI2D_STAT_ISECTS] = (double)total;
+            if (total > capacity) stats[GI2D_STAT_OVERFLOW] = 1.0;
+            *n_isect = total > capacity ? capacity : total;
+        }
+    }
     const int gpw = gpb / kScatterWarps;
     const int g_begin = min(num_points, blockIdx.x * gpb + warp * gpw);
     const int g_end = min(num_points, g_begin + gpw);
     int *my_cnt = s_cnt + warp * D;
     const unsigned lt_mask = (1u << lane) - 1u;
-    // phase A: per-warp digit counts
-    walk_intersections(g_begin, g_end, tiles_x, boxes, [&](bool valid, int tile, int) {
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const int d = tile & mask;
-            const unsigned peers = __match_any_sync(act, d);
-            if (lane == __ffs(peers) - 1) my_cnt[d] += __popc(peers);
-        }
-        __syncwarp();
-    });
+    // phase A: per-warp digit counts (order is irrelevant here: lane = Gaussian, shared atomics)
+    for (int g = g_begin + lane; g < g_end; g += 32) {
+        const ushort4 bx = boxes[g];
+        for (int ty = bx.y; ty < bx.w; ++ty)
+            for (int tx = bx.x; tx < bx.z; ++tx) atomicAdd(&my_cnt[(ty * tiles_x + tx) & mask], 1);
+    }
     __syncthreads();
     // phase B: per digit, exclusive scan over the warps on top of the global offset of (CTA, digit)
     for (int d = threadIdx.x; d < D; d += kScatterThreads) {
-        int run = counts[(size_t)blockIdx.x * D + d] + digit_base[d];
+        int run = __ldcg(counts + (size_t)blockIdx.x * D + d) + s_base[d];
 #pragma unroll
         for (int w = 0; w < kScatterWarps; ++w) {
             const int c = s_cnt[w * D + d];
@@ -288,7 +318,7 @@ fit_scatter_kernel(int num_points, int gpb, int bits0, int tiles_x, int capacity
         }
     }
     __syncthreads();
-    // phase C: same walk, now ranking and writing
+    // phase C: ordered walk, ranking and writing (keys always; records when this is the only pass)
     walk_intersections(g_begin, g_end, tiles_x, boxes, [&](bool valid, int tile, int g) {
         const unsigned act = __ballot_sync(0xffffffffu, valid);
         if (valid) {
@@ -302,48 +332,74 @@ fit_scatter_kernel(int num_points, int gpb, int bits0, int tiles_x, int capacity
             }
             old = __shfl_sync(peers, old, leader);
             const int pos = old + __popc(peers & lt_mask);
-            if (pos < capacity) keys_out[pos] = ((uint64_t)(uint32_t)tile << 32) | (uint32_t)g;
+            if (pos < capacity) {
+                keys_out[pos] = ((uint64_t)(uint32_t)tile << 32) | (uint32_t)g;
+                if (records) {
+                    records[2 * (size_t)pos] = __ldg(proj + 2 * g);
+                    records[2 * (size_t)pos + 1] = __ldg(proj + 2 * g + 1);
+                }
+            }
         }
         __syncwarp();
     });
+}
+
+// multi-pass images: gather the records once the keys are fully sorted
+__global__ void __launch_bounds__(256)
+fit_gather_records_kernel(int capacity, const int32_t *__restrict__ n_dev, const uint64_t *__restrict__ keys,
+                          const float4 *__restrict__ proj, float4 *__restrict__ records) {
+    const int n = min(capacity, *n_dev);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int g = (int)(uint32_t)keys[i];
+    records[2 * (size_t)i] = __ldg(proj + 2 * g);
+    records[2 * (size_t)i + 1] = __ldg(proj + 2 * g + 1);
 }
 
 // ------------------------------------------------------------------------------------ K4
 enum class RasterMode { Render, Fit };
 
 template <RasterMode kMode>
-__global__ void __launch_bounds__(kRasterThreads)
+__global__ void __launch_bounds__(kRasterThreads, kMode == RasterMode::Fit ? 4 : 6)
 fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
-                  const int32_t *__restrict__ tile_bins, const float4 *__restrict__ proj,
+                  const int32_t *__restrict__ tile_bins, const float4 *__restrict__ records,
                   const float *__restrict__ gt, float *__restrict__ out_img,
                   float *__restrict__ grads, double *__restrict__ stats) {
     __shared__ TileRecords sg;
+    __shared__ TileGrad tg;
     __shared__ int s_ids[kMaxPerTile];
-    __shared__ float s_v[3][kTilePixels];
-    __shared__ float s_red[kRasterThreads / 32];
+    __shared__ float s_red[kRasterWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_y = p.tile_row_begin + blockIdx.y;
     const int tile_id = tile_y * p.tiles_x + blockIdx.x;
-    const int2 range = __ldg(reinterpret_cast<const int2 *>(tile_bins) + tile_id);
-    const int cnt = max(0, min(kMaxPerTile, min(range.y, p.isect_capacity) - range.x));
-    if (tid < cnt) {
-        const int g = (int)(uint32_t)__ldg(sorted_keys + range.x + tid);
-        s_ids[tid] = g;
-        sg.xyab[tid] = __ldg(proj + 2 * g);
-        sg.crgb[tid] = __ldg(proj + 2 * g + 1);
-    }
-    __syncthreads();
-    // ---- forward: thread = pixel
     const int j = blockIdx.x * kTile + (tid & 15);
     const int i = tile_y * kTile + (tid >> 4);
     const bool inside = i < p.img_height && j < p.img_width;
+    const size_t pix = (size_t)i * p.img_width + j;
+    // issue every load that does not depend on the tile range first: target pixel, scene flag
+    float tr = 0.f, tgc = 0.f, tb = 0.f;
+    if (kMode == RasterMode::Fit && inside) {
+        tr = __ldg(gt + 3 * pix);
+        tgc = __ldg(gt + 3 * pix + 1);
+        tb = __ldg(gt + 3 * pix + 2);
+    }
+    const double n_isect = stats[GI2D_STAT_ISECTS];
+    const int2 range = __ldg(reinterpret_cast<const int2 *>(tile_bins) + tile_id);
+    const int cnt = max(0, min(kMaxPerTile, min(range.y, p.isect_capacity) - range.x));
+    if (tid < cnt) {
+        // one contiguous block of cnt x 32 B (gathered into sorted order by K3)
+        sg.xyab[tid] = __ldg(records + 2 * (size_t)(range.x + tid));
+        sg.crgb[tid] = __ldg(records + 2 * (size_t)(range.x + tid) + 1);
+        if (kMode == RasterMode::Fit) s_ids[tid] = (int)(uint32_t)__ldg(sorted_keys + range.x + tid);
+    }
+    __syncthreads();
+    // ---- forward: thread = pixel
     float r = 0.f, g = 0.f, b = 0.f;
     int last = -1;
     if (inside) forward_sweep(sg, cnt, (float)j, (float)i, r, g, b, last);
     // no intersection at all: the reference returns ones * background (== 1) and no gradient
     // (rasterize_sum_plus.py:110-118)
-    if (stats[GI2D_STAT_ISECTS] == 0.0) r = g = b = 1.f;
-    const size_t pix = (size_t)i * p.img_width + j;
+    if (n_isect == 0.0) r = g = b = 1.f;
     if (kMode == RasterMode::Render) {
         // the model's `render`: clamp to [0,1], CHW planar (gaussianimage_covariance.py:210-211)
         if (inside && out_img) {
@@ -358,9 +414,8 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
     //      backward mask), squared error of the clamped render for PSNR
     float se = 0.f, vr = 0.f, vg = 0.f, vb = 0.f;
     if (inside) {
-        const float tr = __ldg(gt + 3 * pix), tg = __ldg(gt + 3 * pix + 1), tb = __ldg(gt + 3 * pix + 2);
         const float dr = fminf(fmaxf(r, 0.f), 1.f) - tr;
-        const float dg = fminf(fmaxf(g, 0.f), 1.f) - tg;
+        const float dg = fminf(fmaxf(g, 0.f), 1.f) - tgc;
         const float db = fminf(fmaxf(b, 0.f), 1.f) - tb;
         se = dr * dr + dg * dg + db * db;
         vr = (r >= 0.f && r <= 1.f) ? p.loss_scale * dr : 0.f;
@@ -372,53 +427,24 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
             out_img[3 * pix + 2] = b;
         }
     }
-    s_v[0][tid] = vr;
-    s_v[1][tid] = vg;
-    s_v[2][tid] = vb;
+    tg.v[0][tid] = vr;
+    tg.v[1][tid] = vg;
+    tg.v[2][tid] = vb;
     se = warp_sum(se);
     if (lane == 0) s_red[warp] = se;
     __syncthreads();
     if (tid == 0) {
         float tot = 0.f;
 #pragma unroll
-        for (int w = 0; w < kRasterThreads / 32; ++w) tot += s_red[w];
+        for (int w = 0; w < kRasterWarps; ++w) tot += s_red[w];
         atomicAdd(stats + GI2D_STAT_SSE + (tile_id & (GI2D_STAT_SSE_SLOTS - 1)), (double)tot);
     }
     if (cnt == 0) return;
-    // ---- backward: warp = Gaussian (4 at a time), lane = 8 pixels (column lane&15, rows
-    //      (lane>>4)+2s)
-    LanePixels lp;
-    {
-        const int px = blockIdx.x * kTile + (lane & 15);
-        const int py0 = tile_y * kTile + (lane >> 4);
-        lp.px = (float)px;
-        lp.py0 = (float)py0;
-        lp.inside = 0;
-#pragma unroll
-        for (int st = 0; st < 8; ++st) {
-            const int lp_idx = ((lane >> 4) + 2 * st) * kTile + (lane & 15);
-            lp.vr[st] = s_v[0][lp_idx];
-            lp.vg[st] = s_v[1][lp_idx];
-            lp.vb[st] = s_v[2][lp_idx];
-            if (px < p.img_width && py0 + 2 * st < p.img_height) lp.inside |= 1u << st;
-        }
-    }
-    for (int q = warp; 4 * q < cnt; q += kRasterThreads / 32) {
-        float v[32];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int t = 4 * q + jj;
-            if (t < cnt) {
-                backward_accumulate<false>(sg, t, lp, &v[8 * jj], nullptr);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[8 * jj + k] = 0.f;
-            }
-        }
-        const float total = warp_reduce_scatter32(v);
-        const int t = 4 * q + (lane >> 3);
-        if (t < cnt && total != 0.f) atomicAdd(grads + 8 * (size_t)s_ids[t] + (lane & 7), total);
-    }
+    // ---- backward: warp = Gaussian, lane = 8 pixels
+    const LanePixels lp = lane_pixels(blockIdx.x, tile_y, p.img_width, p.img_height);
+    backward_tile<false, kRasterWarps>(sg, s_ids, cnt, lp, tg,
+                                       [&](int gid, int k) -> float * { return grads + 8 * (size_t)gid + k; },
+                                       nullptr);
 }
 
 // ------------------------------------------------------------------------------------ K5
@@ -427,59 +453,73 @@ fit_adam_kernel(gi2d_fit_params p, float *__restrict__ xyz, float *__restrict__ 
                 float *__restrict__ rgb, float *__restrict__ m_xyz, float *__restrict__ v_xyz,
                 float *__restrict__ m_cov, float *__restrict__ v_cov, float *__restrict__ m_rgb,
                 float *__restrict__ v_rgb, const float4 *__restrict__ proj,
-                const float4 *__restrict__ grads, double *__restrict__ stats) {
-    __shared__ float s_h[4];  // step_size, 1/sqrt(bias2), 1-b1, 1-b2
-    if (threadIdx.x == 0) {
-        // torch/optim/adam.py (_single_tensor_adam) evaluates these in double precision;
-        // StepLR.step() runs after optimizer.step(), so step k uses gamma^floor((k-1)/size)
-        const double step = stats[GI2D_STAT_STEP];
-        const double lr = (double)p.lr0 * pow((double)p.lr_gamma, floor((step - 1.0) / (double)p.lr_step_size));
-        const double bc1 = 1.0 - pow((double)p.beta1, step);
-        const double bc2 = 1.0 - pow((double)p.beta2, step);
-        s_h[0] = (float)(lr / bc1);
-        s_h[1] = (float)sqrt(bc2);
-        s_h[2] = (float)(1.0 - (double)p.beta1);
-        s_h[3] = (float)(1.0 - (double)p.beta2);
-        if (blockIdx.x == 0) stats[GI2D_STAT_LR] = lr;
-    }
-    __syncthreads();
+                const float4 *__restrict__ grads, const double *__restrict__ stats) {
     if (stats[GI2D_STAT_OVERFLOW] != 0.0) return;  // capacity exceeded: the host re-runs the step
     const int g = blockIdx.x * 256 + threadIdx.x;
     if (g >= p.num_points) return;
-    const float step_size = s_h[0], bc2_sqrt = s_h[1], w1 = s_h[2], w2 = s_h[3];
+    // torch/optim/adam.py (_single_tensor_adam): step_size = lr / (1 - beta1^t),
+    // denom = sqrt(v) / sqrt(1 - beta2^t) + eps -- scalars in double, tensors in float
+    const double lr = stats[GI2D_STAT_LR];
+    const float step_size = (float)(lr / (1.0 - stats[kStatB1Pow]));
+    const float bc2_sqrt = (float)sqrt(1.0 - stats[kStatB2Pow]);
+    const float w1 = (float)(1.0 - (double)p.beta1), w2 = (float)(1.0 - (double)p.beta2);
     const float4 p0 = proj[2 * g], p1 = proj[2 * g + 1];
     const float4 g0 = grads[2 * g], g1 = grads[2 * g + 1];
+    // every parameter / moment load is issued before the first dependent store (the three arrays of a
+    // group alias-analyse as one object otherwise and the updates serialise into 8 L2 round trips)
+    float2 x = reinterpret_cast<float2 *>(xyz)[g];
+    float2 mx = reinterpret_cast<float2 *>(m_xyz)[g], vx = reinterpret_cast<float2 *>(v_xyz)[g];
+    float c[3], mc[3], vc[3], q[3], mq[3], vq[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        c[k] = cov[3 * g + k];  mc[k] = m_cov[3 * g + k];  vc[k] = v_cov[3 * g + k];
+        q[k] = rgb[3 * g + k];  mq[k] = m_rgb[3 * g + k];  vq[k] = v_rgb[3 * g + k];
+    }
     // R7, backward2d.cu:157-214: v_cov = -X G X (off-diagonal summed), v_mean = v_xy.
     // For culled Gaussians (radii<=0) conic == 0 and the incoming gradients are 0: same zeros.
-    float gc0, gc1, gc2;
-    conic_vjp(p0.z, p0.w, p1.x, g0.z, g0.w, g1.x, gc0, gc1, gc2);
-    float gr = g1.y, gg = g1.z, gb = g1.w;
+    float gc[3];
+    conic_vjp(p0.z, p0.w, p1.x, g0.z, g0.w, g1.x, gc[0], gc[1], gc[2]);
+    float gq[3] = {g1.y, g1.z, g1.w};
     if (p.color_sigmoid) {
-        gr *= p1.y * (1.f - p1.y);
-        gg *= p1.z * (1.f - p1.z);
-        gb *= p1.w * (1.f - p1.w);
+        gq[0] *= p1.y * (1.f - p1.y);
+        gq[1] *= p1.z * (1.f - p1.z);
+        gq[2] *= p1.w * (1.f - p1.w);
     }
-    auto adam = [&](float *param, float *m, float *v, float grad) {
-        const float mm = *m + (grad - *m) * w1;                 // exp_avg.lerp_(grad, 1-beta1)
-        const float vv = *v * p.beta2 + w2 * grad * grad;       // mul_(beta2).addcmul_(grad, grad, 1-beta2)
-        const float denom = sqrtf(vv) / bc2_sqrt + p.eps;
-        *m = mm;
-        *v = vv;
-        *param = *param - step_size * (mm / denom);             // addcdiv_(exp_avg, denom, -step_size)
+    auto adam = [&](float &param, float &m, float &v, float grad) {
+        m = m + (grad - m) * w1;                                // exp_avg.lerp_(grad, 1-beta1)
+        v = v * p.beta2 + w2 * grad * grad;                     // mul_(beta2).addcmul_(grad, grad, 1-beta2)
+        const float denom = sqrtf(v) / bc2_sqrt + p.eps;
+        param = param - step_size * (m / denom);                // addcdiv_(exp_avg, denom, -step_size)
     };
-    adam(xyz + 2 * g, m_xyz + 2 * g, v_xyz + 2 * g, g0.x);
-    adam(xyz + 2 * g + 1, m_xyz + 2 * g + 1, v_xyz + 2 * g + 1, g0.y);
-    adam(cov + 3 * g, m_cov + 3 * g, v_cov + 3 * g, gc0);
-    adam(cov + 3 * g + 1, m_cov + 3 * g + 1, v_cov + 3 * g + 1, gc1);
-    adam(cov + 3 * g + 2, m_cov + 3 * g + 2, v_cov + 3 * g + 2, gc2);
-    adam(rgb + 3 * g, m_rgb + 3 * g, v_rgb + 3 * g, gr);
-    adam(rgb + 3 * g + 1, m_rgb + 3 * g + 1, v_rgb + 3 * g + 1, gg);
-    adam(rgb + 3 * g + 2, m_rgb + 3 * g + 2, v_rgb + 3 * g + 2, gb);
+    adam(x.x, mx.x, vx.x, g0.x);
+    adam(x.y, mx.y, vx.y, g0.y);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        adam(c[k], mc[k], vc[k], gc[k]);
+        adam(q[k], mq[k], vq[k], gq[k]);
+    }
+    reinterpret_cast<float2 *>(xyz)[g] = x;
+    reinterpret_cast<float2 *>(m_xyz)[g] = mx;
+    reinterpret_cast<float2 *>(v_xyz)[g] = vx;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        cov[3 * g + k] = c[k];  m_cov[3 * g + k] = mc[k];  v_cov[3 * g + k] = vc[k];
+        rgb[3 * g + k] = q[k];  m_rgb[3 * g + k] = mq[k];  v_rgb[3 * g + k] = vq[k];
+    }
 }
 
-__global__ void fit_reset_kernel(double *stats, int step) {
+__global__ void fit_reset_kernel(gi2d_fit_params p, double *stats, int step) {
     const int i = threadIdx.x;
-    if (i < GI2D_STAT_COUNT) stats[i] = i == GI2D_STAT_STEP ? (double)step : 0.0;
+    if (i >= GI2D_STAT_COUNT) return;
+    double v = 0.0;
+    if (i == GI2D_STAT_STEP) v = (double)step;
+    if (i == kStatB1Pow) v = pow((double)p.beta1, (double)step);
+    if (i == kStatB2Pow) v = pow((double)p.beta2, (double)step);
+    // lr the NEXT step will start from: lr0 * gamma^floor((step-1)/size) for step >= 1
+    if (i == GI2D_STAT_LR)
+        v = (double)p.lr0 * pow((double)p.lr_gamma,
+                                (step >= 1 && p.lr_step_size > 0) ? floor((double)(step - 1) / p.lr_step_size) : 0.0);
+    stats[i] = v;
 }
 
 int validate(const gi2d_fit_params *p, const gi2d_fit_buffers *b) {
@@ -493,6 +533,84 @@ int validate(const gi2d_fit_params *p, const gi2d_fit_buffers *b) {
     GI2D_REQUIRE(p->isect_capacity > 0, "isect_capacity must be positive");
     GI2D_REQUIRE(b->stats && b->workspace && b->proj && b->sorted_keys && b->tile_bins, "null buffer");
     return GI2D_OK;
+}
+
+struct Marks {            // optional per-kernel timing marks (gi2d_fit_profile)
+    cudaEvent_t ev[8];
+    int n = 0;
+    bool on = false;
+    void mark(cudaStream_t st) { if (on && n < 8) cudaEventRecord(ev[n++], st); }
+};
+
+int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int with_backward,
+                              cudaStream_t st, Marks *mk) {
+    const int rc = validate(p, b);
+    if (rc != GI2D_OK) return rc;
+    GI2D_REQUIRE(p->num_points == 0 || (b->xyz && b->cov && b->cov_bound && b->rgb), "null parameter buffer");
+    GI2D_REQUIRE(!with_backward || (b->grads && b->gt_hwc), "fit needs grads and gt_hwc");
+    const Plan pl = make_plan(*p);
+    const Workspace w = carve(*p, pl, b->workspace);
+    if (b->workspace_bytes < w.total) {
+        set_error("gi2d_fit_forward_backward: workspace too small (%zu < %zu)", b->workspace_bytes, w.total);
+        return GI2D_ERR_WORKSPACE;
+    }
+    const int D = 1 << pl.bits0;
+    const int num_tiles = p->tiles_x * p->tiles_y;
+    const bool single = pl.extra_passes == 0;
+    if (mk) mk->mark(st);
+    fit_project_kernel<<<pl.nblocks, kProjThreads, D * sizeof(int), st>>>(
+        *p, pl.gpb, pl.bits0, b->xyz, b->cov, b->cov_bound, b->rgb, (float4 *)b->proj, (float4 *)b->grads,
+        w.boxes, w.counts, b->stats, with_backward);
+    if (mk) mk->mark(st);
+    fit_scan_kernel<<<cdiv(D, kScanThreads), kScanThreads, 0, st>>>(pl.nblocks, D, w.counts, w.totals);
+    if (mk) mk->mark(st);
+    // pass 0 lands in sorted_keys when the number of remaining passes is even
+    uint64_t *dst0 = (pl.extra_passes % 2 == 0) ? b->sorted_keys : w.keys_tmp;
+    const size_t scatter_smem = (size_t)(kScatterWarps + 1) * D * sizeof(int);  // <= 40 KiB
+    fit_scatter_kernel<<<pl.nblocks, kScatterThreads, scatter_smem, st>>>(
+        p->num_points, pl.gpb, pl.bits0, p->tiles_x, num_tiles, single ? 1 : 0, p->isect_capacity, w.boxes,
+        w.counts, w.totals, dst0, (const float4 *)b->proj, single ? w.records : nullptr, b->tile_bins, w.n_isect,
+        b->stats);
+    if (!single) {
+        uint64_t *src = dst0;
+        for (int e = 0; e < pl.extra_passes; ++e) {
+            uint64_t *dst = (src == b->sorted_keys) ? w.keys_tmp : b->sorted_keys;
+            const int shift = 32 + pl.bits0 + 8 * e;
+            const int bits = min(8, pl.tile_bits - pl.bits0 - 8 * e);
+            const int r2 = radix_pass_keys_u64(p->isect_capacity, w.n_isect, src, dst, shift, bits, w.radix_ws,
+                                               w.radix_ws_bytes, st);
+            if (r2 != GI2D_OK) return r2;
+            src = dst;
+        }
+        const int r3 = tile_edges_from_keys_u64(p->isect_capacity, w.n_isect, b->sorted_keys, b->tile_bins,
+                                                num_tiles, st);
+        if (r3 != GI2D_OK) return r3;
+        fit_gather_records_kernel<<<cdiv(p->isect_capacity, 256), 256, 0, st>>>(
+            p->isect_capacity, w.n_isect, b->sorted_keys, (const float4 *)b->proj, w.records);
+    }
+    if (mk) mk->mark(st);
+    const int band = p->tile_row_end - p->tile_row_begin;
+    if (band > 0) {
+        dim3 grid(p->tiles_x, band);
+        if (with_backward)
+            fit_raster_kernel<RasterMode::Fit><<<grid, kRasterThreads, 0, st>>>(
+                *p, b->sorted_keys, b->tile_bins, w.records, b->gt_hwc, b->out_img, b->grads, b->stats);
+        else
+            fit_raster_kernel<RasterMode::Render><<<grid, kRasterThreads, 0, st>>>(
+                *p, b->sorted_keys, b->tile_bins, w.records, nullptr, b->out_img, nullptr, b->stats);
+    }
+    if (mk) mk->mark(st);
+    return check_launch("gi2d_fit_forward_backward");
+}
+
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters) {
+    float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;
 }
 
 }  // namespace
@@ -514,94 +632,35 @@ extern "C" int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward
         const int nb = cdiv(p->isect_capacity, 2048);
         const int cumsum_nb = cdiv(nb * 256, 2048);
         n += pl.extra_passes * (2 + (cumsum_nb > 1 ? 3 : 1));  // hist + cumsum + scatter per pass
-        n += 1;                                                 // tile edges (the memset is not a kernel)
+        n += 2;                                                 // tile edges + record gather (memset is no kernel)
     }
     return n + (with_backward ? 1 : 0);  // + adam
 }
 
-extern "C" int gi2d_fit_reset(const gi2d_fit_buffers *b, int step, gi2d_stream_t stream) {
-    GI2D_REQUIRE(b && b->stats, "null stats");
-    fit_reset_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(b->stats, step);
+extern "C" int gi2d_fit_reset(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int step,
+                              gi2d_stream_t stream) {
+    GI2D_REQUIRE(p && b && b->stats, "null stats");
+    fit_reset_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(*p, b->stats, step);
     return check_launch(__func__);
 }
-
-namespace gi2d { namespace {
-struct Marks {            // optional per-kernel timing marks (gi2d_fit_profile)
-    cudaEvent_t ev[8];
-    int n = 0;
-    bool on = false;
-    void mark(cudaStream_t st) { if (on && n < 8) cudaEventRecord(ev[n++], st); }
-};
-int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int with_backward,
-                              cudaStream_t st, Marks *mk);
-} }  // namespace gi2d::<anon>
 
 extern "C" int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fit_buffers *b,
                                          int with_backward, gi2d_stream_t stream) {
     return fit_forward_backward_impl(p, b, with_backward, (cudaStream_t)stream, nullptr);
 }
 
-namespace gi2d { namespace {
-int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int with_backward,
-                              cudaStream_t st, Marks *mk) {
+extern "C" int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, gi2d_stream_t stream) {
     const int rc = validate(p, b);
     if (rc != GI2D_OK) return rc;
-    GI2D_REQUIRE(p->num_points == 0 || (b->xyz && b->cov && b->cov_bound && b->rgb), "null parameter buffer");
-    GI2D_REQUIRE(!with_backward || (b->grads && b->gt_hwc), "fit needs grads and gt_hwc");
-    const Plan pl = make_plan(*p);
-    const Workspace w = carve(*p, pl, b->workspace);
-    if (b->workspace_bytes < w.total) {
-        set_error("%s: workspace too small (%zu < %zu)", __func__, b->workspace_bytes, w.total);
-        return GI2D_ERR_WORKSPACE;
-    }
-    const int D = 1 << pl.bits0;
-    const int num_tiles = p->tiles_x * p->tiles_y;
-    const bool single = pl.extra_passes == 0;
-    if (mk) mk->mark(st);
-    fit_project_kernel<<<pl.nblocks, kProjThreads, D * sizeof(int), st>>>(
-        *p, pl.gpb, pl.bits0, b->xyz, b->cov, b->cov_bound, b->rgb, (float4 *)b->proj, (float4 *)b->grads,
-        w.boxes, w.counts, b->stats, with_backward);
-    if (mk) mk->mark(st);
-    fit_scan_kernel<<<1, 1024, 0, st>>>(pl.nblocks, pl.bits0, num_tiles, single ? 1 : 0, p->isect_capacity,
-                                        w.counts, w.digit_base, b->tile_bins, w.n_isect, b->stats);
-    if (mk) mk->mark(st);
-    // pass 0 lands in sorted_keys when the number of remaining passes is even
-    uint64_t *dst0 = (pl.extra_passes % 2 == 0) ? b->sorted_keys : w.keys_tmp;
-    const size_t scatter_smem = (size_t)kScatterWarps * D * sizeof(int);  // <= 32 KiB
-    fit_scatter_kernel<<<pl.nblocks, kScatterThreads, scatter_smem, st>>>(
-        p->num_points, pl.gpb, pl.bits0, p->tiles_x, p->isect_capacity, w.boxes, w.counts, w.digit_base, dst0);
-    if (!single) {
-        uint64_t *src = dst0;
-        for (int e = 0; e < pl.extra_passes; ++e) {
-            uint64_t *dst = (src == b->sorted_keys) ? w.keys_tmp : b->sorted_keys;
-            const int shift = 32 + pl.bits0 + 8 * e;
-            const int bits = min(8, pl.tile_bits - pl.bits0 - 8 * e);
-            const int r2 = radix_pass_keys_u64(p->isect_capacity, w.n_isect, src, dst, shift, bits, w.radix_ws,
-                                               w.radix_ws_bytes, st);
-            if (r2 != GI2D_OK) return r2;
-            src = dst;
-        }
-        const int r3 = tile_edges_from_keys_u64(p->isect_capacity, w.n_isect, b->sorted_keys, b->tile_bins,
-                                                num_tiles, st);
-        if (r3 != GI2D_OK) return r3;
-    }
-    if (mk) mk->mark(st);
-    const int band = p->tile_row_end - p->tile_row_begin;
-    if (band > 0) {
-        dim3 grid(p->tiles_x, band);
-        if (with_backward)
-            fit_raster_kernel<RasterMode::Fit><<<grid, kRasterThreads, 0, st>>>(
-                *p, b->sorted_keys, b->tile_bins, (const float4 *)b->proj, b->gt_hwc, b->out_img, b->grads,
-                b->stats);
-        else
-            fit_raster_kernel<RasterMode::Render><<<grid, kRasterThreads, 0, st>>>(
-                *p, b->sorted_keys, b->tile_bins, (const float4 *)b->proj, nullptr, b->out_img, nullptr,
-                b->stats);
-    }
-    if (mk) mk->mark(st);
-    return check_launch("gi2d_fit_forward_backward");
+    if (p->num_points == 0) return GI2D_OK;
+    GI2D_REQUIRE(b->xyz && b->cov && b->rgb && b->m_xyz && b->v_xyz && b->m_cov && b->v_cov && b->m_rgb &&
+                     b->v_rgb && b->grads,
+                 "null buffer");
+    fit_adam_kernel<<<cdiv(p->num_points, 256), 256, 0, (cudaStream_t)stream>>>(
+        *p, b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb,
+        (const float4 *)b->proj, (const float4 *)b->grads, b->stats);
+    return check_launch(__func__);
 }
-} }  // namespace gi2d::<anon>
 
 // Measurement utility (bench.py): one full fit step with a CUDA event between the kernels, on
 // `stream`; SYNCHRONISES.  ms[0..4] = project, scan, scatter(+extra passes+edges), raster, adam.
@@ -626,18 +685,6 @@ extern "C" int gi2d_fit_profile(const gi2d_fit_params *p, const gi2d_fit_buffers
 
 // Measurement utility: FP32 FMA issue peak of this GPU (the roofline denominator of the raster
 // kernels; MEASURED_PEAKS.json only carries HBM and bf16 tensor figures).  Returns TFLOP/s.
-namespace gi2d { namespace {
-__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters) {
-    float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    const float m = 1.0000001f, c = 1e-7f;
-    for (int i = 0; i < iters; ++i) {
-        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
-        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
-    }
-    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;
-}
-} }  // namespace gi2d::<anon>
-
 extern "C" int gi2d_measure_fp32_peak(float *tflops_host, gi2d_stream_t stream) {
     GI2D_REQUIRE(tflops_host, "null output");
     cudaStream_t st = (cudaStream_t)stream;
@@ -665,18 +712,5 @@ extern "C" int gi2d_measure_fp32_peak(float *tflops_host, gi2d_stream_t stream) 
     cudaEventDestroy(e1);
     cudaFree(d);
     *tflops_host = best;
-    return check_launch(__func__);
-}
-
-extern "C" int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, gi2d_stream_t stream) {
-    const int rc = validate(p, b);
-    if (rc != GI2D_OK) return rc;
-    if (p->num_points == 0) return GI2D_OK;
-    GI2D_REQUIRE(b->xyz && b->cov && b->rgb && b->m_xyz && b->v_xyz && b->m_cov && b->v_cov && b->m_rgb &&
-                     b->v_rgb && b->grads,
-                 "null buffer");
-    fit_adam_kernel<<<cdiv(p->num_points, 256), 256, 0, (cudaStream_t)stream>>>(
-        *p, b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb,
-        (const float4 *)b->proj, (const float4 *)b->grads, b->stats);
     return check_launch(__func__);
 }

@@ -44,77 +44,48 @@ raster_fwd_kernel(int tiles_x, int img_w, int img_h, const int32_t *__restrict__
 }
 
 template <int kWarps, bool kOpacity>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 4)
 raster_bwd_kernel(int tiles_x, int img_w, int img_h, const int32_t *__restrict__ gids,
                   const int32_t *__restrict__ tile_bins, int rows, const float *__restrict__ xys,
                   const float *__restrict__ conics, const float *__restrict__ colors,
                   const float *__restrict__ opacities, const float *__restrict__ v_output,
                   float *__restrict__ v_xy, float *__restrict__ v_conic,
                   float *__restrict__ v_colors, float *__restrict__ v_opacity) {
+    static_assert(kWarps * 32 == kTilePixels, "one thread per pixel stages v_out");
     __shared__ TileGaussians sg;
+    __shared__ TileGrad tg;
     __shared__ int s_ids[kMaxPerTile];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int tile_id = blockIdx.y * tiles_x + blockIdx.x;
     const int2 range = load_range(tile_bins, tile_id, rows);
     const int cnt = max(0, min(kMaxPerTile, range.y - range.x));
     if (cnt == 0) return;
-    for (int slot = tid; slot < cnt; slot += kWarps * 32) {
-        const int g = __ldg(gids + range.x + slot);
-        s_ids[slot] = g;
-        stage_gaussian(sg, slot, g, xys, conics, colors, opacities);
-    }
-    LanePixels lp;
-    {
-        const int px = blockIdx.x * kTile + (lane & 15);
-        const int py0 = blockIdx.y * kTile + (lane >> 4);
-        lp.px = (float)px;
-        lp.py0 = (float)py0;
-        lp.inside = 0;
-#pragma unroll
-        for (int st = 0; st < 8; ++st) {
-            const int py = py0 + 2 * st;
-            const bool in = px < img_w && py < img_h;
-            lp.vr[st] = lp.vg[st] = lp.vb[st] = 0.f;
-            if (in) {
-                const size_t pix = (size_t)py * img_w + px;
-                lp.vr[st] = __ldg(v_output + 3 * pix);
-                lp.vg[st] = __ldg(v_output + 3 * pix + 1);
-                lp.vb[st] = __ldg(v_output + 3 * pix + 2);
-                lp.inside |= 1u << st;
-            }
+    {   // stage dL/d(out) of this tile (0 outside the image)
+        const int j = blockIdx.x * kTile + (tid & 15), i = blockIdx.y * kTile + (tid >> 4);
+        float vr = 0.f, vg = 0.f, vb = 0.f;
+        if (i < img_h && j < img_w) {
+            const size_t pix = (size_t)i * img_w + j;
+            vr = __ldg(v_output + 3 * pix);
+            vg = __ldg(v_output + 3 * pix + 1);
+            vb = __ldg(v_output + 3 * pix + 2);
         }
+        tg.v[0][tid] = vr;
+        tg.v[1][tid] = vg;
+        tg.v[2][tid] = vb;
+    }
+    if (tid < cnt) {
+        const int g = __ldg(gids + range.x + tid);
+        s_ids[tid] = g;
+        stage_gaussian(sg, tid, g, xys, conics, colors, opacities);
     }
     __syncthreads();
-    for (int q = warp; 4 * q < cnt; q += kWarps) {
-        float v[32];
-        float op[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int t = 4 * q + jj;
-            op[jj] = 0.f;
-            if (t < cnt) {
-                backward_accumulate<kOpacity>(sg, t, lp, &v[8 * jj], &op[jj]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[8 * jj + k] = 0.f;
-            }
-        }
-        const float total = warp_reduce_scatter32(v);
-        const int t = 4 * q + (lane >> 3);
-        if (t < cnt && total != 0.f) {
-            const int g = s_ids[t];
-            const int k = lane & 7;
-            float *dst = k < 2 ? v_xy + 2 * g + k : (k < 5 ? v_conic + 3 * g + (k - 2) : v_colors + 3 * g + (k - 5));
-            atomicAdd(dst, total);
-        }
-        if (kOpacity) {
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const float o = warp_sum(op[jj]);
-                if (lane == 0 && 4 * q + jj < cnt && o != 0.f) atomicAdd(v_opacity + s_ids[4 * q + jj], o);
-            }
-        }
-    }
+    const LanePixels lp = lane_pixels(blockIdx.x, blockIdx.y, img_w, img_h);
+    backward_tile<kOpacity, kWarps>(sg, s_ids, cnt, lp, tg,
+                                    [&](int g, int k) -> float * {
+                                        return k < 2 ? v_xy + 2 * g + k
+                                                     : (k < 5 ? v_conic + 3 * g + (k - 2) : v_colors + 3 * g + (k - 5));
+                                    },
+                                    v_opacity);
 }
 
 }  // namespace

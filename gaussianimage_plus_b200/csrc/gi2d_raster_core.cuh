@@ -7,14 +7,13 @@
 //            Accumulation runs in ascending sorted order, exactly like the reference, so the
 //            image is bit-reproducible.
 // Backward : Gaussian-parallel.  Each warp owns whole Gaussians (round-robin over the tile's
-//            list); its 32 lanes hold 8 pixels each of the tile's v_out in REGISTERS, sweep the
-//            256 pixels in 8 steps accumulating the 8 (9) gradient components in registers, and
-//            only then reduce across lanes -- once per (tile, Gaussian) instead of once per
-//            (warp, Gaussian) as csrc/backward.cu:1322-1345 does.  Four Gaussians are reduced
-//            together with a transposed (reduce-scatter) butterfly: 31 shuffles per 4x8 values
-//            instead of 160, after which lane L holds component L%8 of Gaussian L/8 and issues
-//            ONE red.global.add: 8 atomics per (tile, Gaussian) versus the reference's
-//            9 per (warp, Gaussian) = 72.
+//            list); its 32 lanes own 8 pixels each of the tile (v_out staged planar in shared
+//            memory), sweep the 256 pixels in 8 steps accumulating the 8 (9) gradient components
+//            in registers, and only then reduce across lanes -- once per (tile, Gaussian)
+//            instead of once per (warp, Gaussian) as csrc/backward.cu:1322-1345 does -- with a
+//            transposed (reduce-scatter) butterfly: 9 shuffles for the 8 components instead of
+//            40, after which 8 lanes each issue ONE red.global.add: 8 atomics per
+//            (tile, Gaussian) versus the reference's 9 per (warp, Gaussian) = 72.
 #pragma once
 #include "gi2d_common.cuh"
 
@@ -82,20 +81,25 @@ __device__ __forceinline__ void forward_sweep(const Store &s, int cnt, float px,
     }
 }
 
-// Transposed butterfly: every lane holds v[0..31]; on return lane L holds sum over lanes of v[L].
-__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32]) {
+// Reduce-scatter of 8 per-lane values over the warp in 9 shuffles (4+2+1 transposed steps over
+// lane bits 4,3,2, then a 2-step butterfly over bits 1,0): on return EVERY lane holds the warp
+// total of component (lane >> 2).  A plain butterfly would take 8 x 5 = 40.
+__device__ __forceinline__ float warp_reduce_scatter8(float (&v)[8]) {
     const unsigned lane = threadIdx.x & 31u;
 #pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
-        const bool upper = (lane & half) != 0;
+    for (int half = 4; half >= 1; half >>= 1) {
+        const bool upper = (lane & (half << 2)) != 0;
 #pragma unroll
         for (int i = 0; i < half; ++i) {
             const float send = upper ? v[i] : v[i + half];
             const float keep = upper ? v[i + half] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half << 2);
         }
     }
-    return v[0];
+    float r = v[0];
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -104,20 +108,42 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Pixel ownership of a lane in the backward sweep: column = lane & 15, rows (lane>>4) + 2*s.
-struct LanePixels {
-    float vr[8], vg[8], vb[8];  // dL/d(out) for the lane's 8 pixels (0 outside the image)
-    unsigned inside;            // bit s set when pixel s is inside the image
-    float px, py0;              // pixel x, and y of step 0 (y of step s = py0 + 2 s)
+// dL/d(out) of the tile's 256 pixels, planar in shared memory: v[c][row*16 + col]; pixels outside
+// the image hold 0 and are flagged in the lane's `inside` mask.
+struct TileGrad {
+    float v[3][kTilePixels];
 };
 
+// Pixel ownership of a lane in the backward sweep: column = lane & 15, rows (lane>>4) + 2*s, s=0..7.
+// Consecutive lanes read consecutive shared-memory words: conflict free.
+struct LanePixels {
+    unsigned inside;   // bit s set when pixel s is inside the image
+    float px, py0;     // pixel x, and y of step 0 (y of step s = py0 + 2 s)
+    int base;          // (lane>>4)*16 + (lane&15): index of the step-0 pixel in TileGrad
+};
+
+__device__ __forceinline__ LanePixels lane_pixels(int tile_x, int tile_y, int img_w, int img_h) {
+    const int lane = threadIdx.x & 31;
+    const int px = tile_x * kTile + (lane & 15);
+    const int py0 = tile_y * kTile + (lane >> 4);
+    LanePixels lp;
+    lp.px = (float)px;
+    lp.py0 = (float)py0;
+    lp.base = (lane >> 4) * kTile + (lane & 15);
+    lp.inside = 0;
+#pragma unroll
+    for (int st = 0; st < 8; ++st)
+        if (px < img_w && py0 + 2 * st < img_h) lp.inside |= 1u << st;
+    return lp;
+}
+
 // Accumulate the gradient of ONE staged Gaussian over the lane's 8 pixels into acc[0..8):
-//   acc = { v_x, v_y, v_a, v_b, v_c, v_r, v_g, v_b }  (+ *acc_op for opacity when non-null)
+//   acc = { v_x, v_y, v_a, v_b, v_c, v_r, v_g, v_b }  (+ *acc_op for opacity when kOpacity)
 // Same validity rule as backward.cu:1273-1283 (sigma>=0, alpha>=1/255); the `<= final_idx`
 // condition of the reference is implied by the 256-per-tile cap.
 template <bool kOpacity, class Store>
 __device__ __forceinline__ void backward_accumulate(const Store &s, int t, const LanePixels &lp,
-                                                    float *acc, float *acc_op) {
+                                                    const TileGrad &tg, float (&acc)[8], float *acc_op) {
     const GaussRec q = s.get(t);
     const float dx = __fsub_rn(q.x, lp.px);
     // dx-only subexpressions are shared by the 8 rows (bit-identical to recomputing them)
@@ -135,7 +161,8 @@ __device__ __forceinline__ void backward_accumulate(const Store &s, int t, const
         const bool valid = ((lp.inside >> st) & 1u) && !(sigma < 0.f || alpha < kAlphaMin);
         if (!__any_sync(0xffffffffu, valid)) continue;
         if (valid) {
-            const float vr = lp.vr[st], vg = lp.vg[st], vb = lp.vb[st];
+            const int pi = lp.base + 2 * kTile * st;
+            const float vr = tg.v[0][pi], vg = tg.v[1][pi], vb = tg.v[2][pi];
             ar = fmaf(alpha, vr, ar);
             ag = fmaf(alpha, vg, ag);
             abl = fmaf(alpha, vb, abl);
@@ -160,6 +187,26 @@ __device__ __forceinline__ void backward_accumulate(const Store &s, int t, const
     acc[6] = ag;
     acc[7] = abl;
     if (kOpacity) *acc_op = ao;
+}
+
+// Backward of one tile: warps take the staged Gaussians round-robin, one at a time.  After the
+// reduce-scatter lane L holds component L>>2; lanes with (L&3)==0 issue the red.global.add.
+// grad_of(g, k) returns the address of component k (0..7) of Gaussian g.
+template <bool kOpacity, int kWarps, class Store, class GradAddr>
+__device__ __forceinline__ void backward_tile(const Store &s, const int *s_ids, int cnt, const LanePixels &lp,
+                                              const TileGrad &tg, GradAddr grad_of, float *v_opacity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = warp; t < cnt; t += kWarps) {
+        float acc[8];
+        float op = 0.f;
+        backward_accumulate<kOpacity>(s, t, lp, tg, acc, &op);
+        const float total = warp_reduce_scatter8(acc);
+        if ((lane & 3) == 0 && total != 0.f) atomicAdd(grad_of(s_ids[t], lane >> 2), total);
+        if (kOpacity) {
+            op = warp_sum(op);
+            if (lane == 0 && op != 0.f) atomicAdd(v_opacity + s_ids[t], op);
+        }
+    }
 }
 
 }  // namespace gi2d

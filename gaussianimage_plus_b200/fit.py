@@ -111,7 +111,7 @@ class GaussianImageFitter:
 
     def reset_stats(self, step: int = 0):
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.gi2d_fit_reset(C.byref(self.buffers), int(step), _stream(self.device)), "fit_reset")
+            _lib.check(self.lib.gi2d_fit_reset(C.byref(self.params), C.byref(self.buffers), int(step), _stream(self.device)), "fit_reset")
 
     # ------------------------------------------------------------------ target
     def set_target(self, gt_image: torch.Tensor):

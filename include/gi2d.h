@@ -222,7 +222,7 @@ size_t gi2d_fit_workspace_size(const gi2d_fit_params *p);
 int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward);
 
 /* Zero the stats block (and set the step counter): call once before the first step. */
-int gi2d_fit_reset(const gi2d_fit_buffers *b, int step, gi2d_stream_t stream);
+int gi2d_fit_reset(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int step, gi2d_stream_t stream);
 
 /* project + bin + rasterize; with_backward != 0 also computes the L2 loss gradient and the
  * rasterize backward into b->grads and advances the step counter. */
