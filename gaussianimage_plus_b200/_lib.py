@@ -41,7 +41,7 @@ class FitBuffers(C.Structure):
         ("m_xyz", _P), ("v_xyz", _P), ("m_cov", _P), ("v_cov", _P), ("m_rgb", _P), ("v_rgb", _P),
         ("gt_hwc", _P), ("out_img", _P),
         ("grads", _P), ("proj", _P), ("sorted_keys", _P), ("tile_bins", _P), ("stats", _P),
-        ("workspace", _P), ("workspace_bytes", _SZ),
+        ("workspace", _P), ("workspace_bytes", _SZ), ("gt_u8_hwc", _P),
     ]
 
 

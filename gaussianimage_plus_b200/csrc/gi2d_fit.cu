@@ -48,6 +48,8 @@ constexpr int kRasterWarps = kRasterThreads / 32;
 // private slots of the stats block (beyond the public GI2D_STAT_* ones)
 constexpr int kStatB1Pow = 4;  // beta1^step
 constexpr int kStatB2Pow = 5;  // beta2^step
+constexpr int kStatStepSize = 6;  // lr / (1 - beta1^step)   of the step in flight
+constexpr int kStatBc2Sqrt = 7;   // sqrt(1 - beta2^step)
 
 struct Plan {
     int tile_bits;     // bits needed for a tile id
@@ -135,6 +137,8 @@ fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, const float *__restric
             stats[kStatB2Pow] *= (double)p.beta2;
             const long long k = (long long)step - 1;
             if (k > 0 && p.lr_step_size > 0 && k % p.lr_step_size == 0) stats[GI2D_STAT_LR] *= (double)p.lr_gamma;
+            stats[kStatStepSize] = stats[GI2D_STAT_LR] / (1.0 - stats[kStatB1Pow]);
+            stats[kStatBc2Sqrt] = sqrt(1.0 - stats[kStatB2Pow]);
         }
     }
     __syncthreads();
@@ -172,51 +176,82 @@ fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, const float *__restric
 }
 
 // ------------------------------------------------------------------------------------ K2
-// Prefix sum over the per-tile (digit) overlap counts, step 1: one THREAD per digit column walks
-// the per-CTA counts of K1 top to bottom, turning counts[b][d] into the exclusive prefix over b
-// (in place) and leaving the column total in totals[d].  D/256 CTAs; the loads of a column are
-// issued 8 at a time ahead of the dependent adds/stores (the loop is otherwise one exposed L2
-// round trip per row).  Step 2 (exclusive scan over d of the totals = start of every digit/tile)
-// is 8 KiB of work and is redone by every CTA of K3 in its prologue instead of costing a launch.
-constexpr int kScanThreads = 256;
+// Prefix sum over the per-tile (digit) overlap counts, step 1: turn the per-CTA counts of K1,
+// counts[b][d], into the exclusive prefix over b (in place) and leave the column total in
+// totals[d].  A CTA owns 32 digit columns; its 8 warps split the rows into 8 contiguous segments
+// (a warp reads 128 contiguous bytes per row), scan their segment with all loads in flight at
+// once, exchange the 8 segment sums through shared memory and write back.  D/32 CTAs: the whole
+// matrix is in flight at once instead of one exposed L2 round trip per row.
+// Step 2 (exclusive scan over d of the totals = start of every digit/tile) is 8 KiB of work and
+// is redone by every CTA of K3 in its prologue instead of costing a launch.
+constexpr int kScanCols = 32;
+constexpr int kScanSegs = 8;
+constexpr int kScanThreads = kScanCols * kScanSegs;
+constexpr int kScanMaxRows = 16;  // rows per segment held in registers per trip
 
 __global__ void __launch_bounds__(kScanThreads)
 fit_scan_kernel(int nblocks, int D, int32_t *__restrict__ counts, int32_t *__restrict__ totals) {
-    const int d = blockIdx.x * kScanThreads + threadIdx.x;
-    if (d >= D) return;
-    int run = 0;
+    __shared__ int s_seg[kScanSegs][kScanCols];
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int d = blockIdx.x * kScanCols + lane;
+    const int rows_per_seg = (nblocks + kScanSegs - 1) / kScanSegs;
+    const int r0 = min(nblocks, seg * rows_per_seg), r1 = min(nblocks, r0 + rows_per_seg);
     int32_t *col = counts + d;
-    for (int b0 = 0; b0 < nblocks; b0 += 8) {
-        int c[8];
+    const bool ok = d < D;
+    // pass 1: segment sum
+    int sum = 0;
+    for (int r = r0; r < r1; r += kScanMaxRows) {
+        int c[kScanMaxRows];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) c[j] = (b0 + j < nblocks) ? __ldcg(col + (size_t)(b0 + j) * D) : 0;
+        for (int j = 0; j < kScanMaxRows; ++j) c[j] = (ok && r + j < r1) ? __ldcg(col + (size_t)(r + j) * D) : 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (b0 + j < nblocks) col[(size_t)(b0 + j) * D] = run;
+        for (int j = 0; j < kScanMaxRows; ++j) sum += c[j];
+    }
+    s_seg[seg][lane] = sum;
+    __syncthreads();
+    int run = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < kScanSegs; ++k) {
+        const int v = s_seg[k][lane];
+        if (k < seg) run += v;
+        total += v;
+    }
+    if (seg == 0 && ok) totals[d] = total;
+    // pass 2: exclusive prefix within the segment on top of the preceding segments (L2 hits)
+    for (int r = r0; r < r1; r += kScanMaxRows) {
+        int c[kScanMaxRows];
+#pragma unroll
+        for (int j = 0; j < kScanMaxRows; ++j) c[j] = (ok && r + j < r1) ? __ldcg(col + (size_t)(r + j) * D) : 0;
+#pragma unroll
+        for (int j = 0; j < kScanMaxRows; ++j) {
+            if (ok && r + j < r1) col[(size_t)(r + j) * D] = run;
             run += c[j];
         }
     }
-    totals[d] = run;
 }
 
-// Step 2, run by every CTA of K3 (and by the tile-range writer): exclusive scan of totals[0..D)
-// into shared memory.  D <= 2048, kThreads * kPer >= D.
+// Step 2, run by every CTA of K3: exclusive scan of totals[0..D) into shared memory.
+// D <= 2048 = kThreads * 16.
 template <int kThreads>
 __device__ __forceinline__ int scan_totals_to_smem(const int32_t *__restrict__ totals, int D, int *s_base,
                                                    int *s_warp) {
-    const int per = (D + kThreads - 1) / kThreads;
-    const int i0 = threadIdx.x * per;
+    constexpr int kPer = (1 << kMaxDigitBits) / kThreads;
+    const int i0 = threadIdx.x * kPer;
+    int v[kPer];
     int sum = 0;
-    for (int k = 0; k < per; ++k)
-        if (i0 + k < D) sum += __ldcg(totals + i0 + k);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        v[k] = (i0 + k < D) ? __ldcg(totals + i0 + k) : 0;
+        sum += v[k];
+    }
     int total;
     const int incl = block_scan_inclusive<kThreads>(sum, s_warp, &total);
     int run = incl - sum;
-    for (int k = 0; k < per; ++k)
-        if (i0 + k < D) {
-            s_base[i0 + k] = run;
-            run += __ldcg(totals + i0 + k);
-        }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        if (i0 + k < D) s_base[i0 + k] = run;
+        run += v[k];
+    }
     __syncthreads();
     return total;
 }
@@ -308,13 +343,25 @@ fit_scatter_kernel(int num_points, int gpb, int bits0, int tiles_x, int num_tile
     }
     __syncthreads();
     // phase B: per digit, exclusive scan over the warps on top of the global offset of (CTA, digit)
-    for (int d = threadIdx.x; d < D; d += kScatterThreads) {
-        int run = __ldcg(counts + (size_t)blockIdx.x * D + d) + s_base[d];
+    for (int d0 = threadIdx.x; d0 < D; d0 += 4 * kScatterThreads) {
+        int off[4];
 #pragma unroll
-        for (int w = 0; w < kScatterWarps; ++w) {
-            const int c = s_cnt[w * D + d];
-            s_cnt[w * D + d] = run;
-            run += c;
+        for (int j = 0; j < 4; ++j) {
+            const int d = d0 + j * kScatterThreads;
+            off[j] = d < D ? __ldcg(counts + (size_t)blockIdx.x * D + d) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int d = d0 + j * kScatterThreads;
+            if (d < D) {
+                int run = off[j] + s_base[d];
+#pragma unroll
+                for (int w = 0; w < kScatterWarps; ++w) {
+                    const int c = s_cnt[w * D + d];
+                    s_cnt[w * D + d] = run;
+                    run += c;
+                }
+            }
         }
     }
     __syncthreads();
@@ -363,8 +410,8 @@ template <RasterMode kMode>
 __global__ void __launch_bounds__(kRasterThreads, kMode == RasterMode::Fit ? 4 : 6)
 fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
                   const int32_t *__restrict__ tile_bins, const float4 *__restrict__ records,
-                  const float *__restrict__ gt, float *__restrict__ out_img,
-                  float *__restrict__ grads, double *__restrict__ stats) {
+                  const float *__restrict__ gt, const uint8_t *__restrict__ gt_u8,
+                  float *__restrict__ out_img, float *__restrict__ grads, double *__restrict__ stats) {
     __shared__ TileRecords sg;
     __shared__ TileGrad tg;
     __shared__ int s_ids[kMaxPerTile];
@@ -372,31 +419,41 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_y = p.tile_row_begin + blockIdx.y;
     const int tile_id = tile_y * p.tiles_x + blockIdx.x;
-    const int j = blockIdx.x * kTile + (tid & 15);
-    const int i = tile_y * kTile + (tid >> 4);
+    const int blk = warp;  // forward: warp <-> 8x4 sub-block
+    const int lx = blk_x(blk, lane), ly = blk_y(blk, lane);
+    const int j = blockIdx.x * kTile + lx;
+    const int i = tile_y * kTile + ly;
     const bool inside = i < p.img_height && j < p.img_width;
     const size_t pix = (size_t)i * p.img_width + j;
     // issue every load that does not depend on the tile range first: target pixel, scene flag
     float tr = 0.f, tgc = 0.f, tb = 0.f;
     if (kMode == RasterMode::Fit && inside) {
-        tr = __ldg(gt + 3 * pix);
-        tgc = __ldg(gt + 3 * pix + 1);
-        tb = __ldg(gt + 3 * pix + 2);
+        if (gt) {
+            tr = __ldg(gt + 3 * pix);
+            tgc = __ldg(gt + 3 * pix + 1);
+            tb = __ldg(gt + 3 * pix + 2);
+        } else {
+            // 8-bit target: the value torchvision's ToTensor produces, u8 / 255 (IEEE division)
+            tr = __fdiv_rn((float)__ldg(gt_u8 + 3 * pix), 255.f);
+            tgc = __fdiv_rn((float)__ldg(gt_u8 + 3 * pix + 1), 255.f);
+            tb = __fdiv_rn((float)__ldg(gt_u8 + 3 * pix + 2), 255.f);
+        }
     }
     const double n_isect = stats[GI2D_STAT_ISECTS];
     const int2 range = __ldg(reinterpret_cast<const int2 *>(tile_bins) + tile_id);
     const int cnt = max(0, min(kMaxPerTile, min(range.y, p.isect_capacity) - range.x));
     if (tid < cnt) {
         // one contiguous block of cnt x 32 B (gathered into sorted order by K3)
-        sg.xyab[tid] = __ldg(records + 2 * (size_t)(range.x + tid));
-        sg.crgb[tid] = __ldg(records + 2 * (size_t)(range.x + tid) + 1);
+        stage_record(sg, tid, __ldg(records + 2 * (size_t)(range.x + tid)),
+                     __ldg(records + 2 * (size_t)(range.x + tid) + 1), (float)(blockIdx.x * kTile),
+                     (float)(tile_y * kTile));
         if (kMode == RasterMode::Fit) s_ids[tid] = (int)(uint32_t)__ldg(sorted_keys + range.x + tid);
     }
     __syncthreads();
     // ---- forward: thread = pixel
     float r = 0.f, g = 0.f, b = 0.f;
     int last = -1;
-    if (inside) forward_sweep(sg, cnt, (float)j, (float)i, r, g, b, last);
+    forward_sweep(sg, cnt, blk, inside, (float)j, (float)i, r, g, b, last);
     // no intersection at all: the reference returns ones * background (== 1) and no gradient
     // (rasterize_sum_plus.py:110-118)
     if (n_isect == 0.0) r = g = b = 1.f;
@@ -427,9 +484,10 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
             out_img[3 * pix + 2] = b;
         }
     }
-    tg.v[0][tid] = vr;
-    tg.v[1][tid] = vg;
-    tg.v[2][tid] = vb;
+    const int gi = grad_index(lx, ly);
+    tg.v[0][gi] = vr;
+    tg.v[1][gi] = vg;
+    tg.v[2][gi] = vb;
     se = warp_sum(se);
     if (lane == 0) s_red[warp] = se;
     __syncthreads();
@@ -454,14 +512,15 @@ fit_adam_kernel(gi2d_fit_params p, float *__restrict__ xyz, float *__restrict__ 
                 float *__restrict__ m_cov, float *__restrict__ v_cov, float *__restrict__ m_rgb,
                 float *__restrict__ v_rgb, const float4 *__restrict__ proj,
                 const float4 *__restrict__ grads, const double *__restrict__ stats) {
-    if (stats[GI2D_STAT_OVERFLOW] != 0.0) return;  // capacity exceeded: the host re-runs the step
     const int g = blockIdx.x * 256 + threadIdx.x;
     if (g >= p.num_points) return;
+    // capacity exceeded: nothing is stored and the host re-runs the step.  (Tested at the stores, not
+    // here, so that every load below is issued before the first dependent instruction.)
+    const bool skip = stats[GI2D_STAT_OVERFLOW] != 0.0;
     // torch/optim/adam.py (_single_tensor_adam): step_size = lr / (1 - beta1^t),
-    // denom = sqrt(v) / sqrt(1 - beta2^t) + eps -- scalars in double, tensors in float
-    const double lr = stats[GI2D_STAT_LR];
-    const float step_size = (float)(lr / (1.0 - stats[kStatB1Pow]));
-    const float bc2_sqrt = (float)sqrt(1.0 - stats[kStatB2Pow]);
+    // denom = sqrt(v) / sqrt(1 - beta2^t) + eps -- scalars in double (K1 did that once), tensors in float
+    const float step_size = (float)stats[kStatStepSize];
+    const float bc2_sqrt = (float)stats[kStatBc2Sqrt];
     const float w1 = (float)(1.0 - (double)p.beta1), w2 = (float)(1.0 - (double)p.beta2);
     const float4 p0 = proj[2 * g], p1 = proj[2 * g + 1];
     const float4 g0 = grads[2 * g], g1 = grads[2 * g + 1];
@@ -485,11 +544,17 @@ fit_adam_kernel(gi2d_fit_params p, float *__restrict__ xyz, float *__restrict__ 
         gq[1] *= p1.z * (1.f - p1.z);
         gq[2] *= p1.w * (1.f - p1.w);
     }
+    // sqrt / divide through the SFU (sqrt.approx, div.approx: 1-2 ulp): the IEEE versions branch into
+    // slow paths on the denormal second moments Adam produces with eps = 1e-15 and made this kernel
+    // 3x longer; 2 ulp is far inside the 1e-4 budget of the parameters.
+    const float inv_bc2 = 1.f / bc2_sqrt;
     auto adam = [&](float &param, float &m, float &v, float grad) {
         m = m + (grad - m) * w1;                                // exp_avg.lerp_(grad, 1-beta1)
         v = v * p.beta2 + w2 * grad * grad;                     // mul_(beta2).addcmul_(grad, grad, 1-beta2)
-        const float denom = sqrtf(v) / bc2_sqrt + p.eps;
-        param = param - step_size * (m / denom);                // addcdiv_(exp_avg, denom, -step_size)
+        float sq;
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
+        const float denom = fmaf(sq, inv_bc2, p.eps);
+        param = param - step_size * __fdividef(m, denom);       // addcdiv_(exp_avg, denom, -step_size)
     };
     adam(x.x, mx.x, vx.x, g0.x);
     adam(x.y, mx.y, vx.y, g0.y);
@@ -498,6 +563,7 @@ fit_adam_kernel(gi2d_fit_params p, float *__restrict__ xyz, float *__restrict__ 
         adam(c[k], mc[k], vc[k], gc[k]);
         adam(q[k], mq[k], vq[k], gq[k]);
     }
+    if (skip) return;
     reinterpret_cast<float2 *>(xyz)[g] = x;
     reinterpret_cast<float2 *>(m_xyz)[g] = mx;
     reinterpret_cast<float2 *>(v_xyz)[g] = vx;
@@ -547,7 +613,7 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     const int rc = validate(p, b);
     if (rc != GI2D_OK) return rc;
     GI2D_REQUIRE(p->num_points == 0 || (b->xyz && b->cov && b->cov_bound && b->rgb), "null parameter buffer");
-    GI2D_REQUIRE(!with_backward || (b->grads && b->gt_hwc), "fit needs grads and gt_hwc");
+    GI2D_REQUIRE(!with_backward || (b->grads && (b->gt_hwc || b->gt_u8_hwc)), "fit needs grads and a target image");
     const Plan pl = make_plan(*p);
     const Workspace w = carve(*p, pl, b->workspace);
     if (b->workspace_bytes < w.total) {
@@ -562,7 +628,7 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
         *p, pl.gpb, pl.bits0, b->xyz, b->cov, b->cov_bound, b->rgb, (float4 *)b->proj, (float4 *)b->grads,
         w.boxes, w.counts, b->stats, with_backward);
     if (mk) mk->mark(st);
-    fit_scan_kernel<<<cdiv(D, kScanThreads), kScanThreads, 0, st>>>(pl.nblocks, D, w.counts, w.totals);
+    fit_scan_kernel<<<cdiv(D, kScanCols), kScanThreads, 0, st>>>(pl.nblocks, D, w.counts, w.totals);
     if (mk) mk->mark(st);
     // pass 0 lands in sorted_keys when the number of remaining passes is even
     uint64_t *dst0 = (pl.extra_passes % 2 == 0) ? b->sorted_keys : w.keys_tmp;
@@ -594,10 +660,10 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
         dim3 grid(p->tiles_x, band);
         if (with_backward)
             fit_raster_kernel<RasterMode::Fit><<<grid, kRasterThreads, 0, st>>>(
-                *p, b->sorted_keys, b->tile_bins, w.records, b->gt_hwc, b->out_img, b->grads, b->stats);
+                *p, b->sorted_keys, b->tile_bins, w.records, b->gt_hwc, b->gt_u8_hwc, b->out_img, b->grads, b->stats);
         else
             fit_raster_kernel<RasterMode::Render><<<grid, kRasterThreads, 0, st>>>(
-                *p, b->sorted_keys, b->tile_bins, w.records, nullptr, b->out_img, nullptr, b->stats);
+                *p, b->sorted_keys, b->tile_bins, w.records, nullptr, nullptr, b->out_img, nullptr, b->stats);
     }
     if (mk) mk->mark(st);
     return check_launch("gi2d_fit_forward_backward");

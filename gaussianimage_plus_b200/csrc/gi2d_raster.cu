@@ -23,17 +23,21 @@ raster_fwd_kernel(int tiles_x, int img_w, int img_h, const int32_t *__restrict__
     __shared__ TileGaussians sg;
     const int tid = threadIdx.x;
     const int tile_id = blockIdx.y * tiles_x + blockIdx.x;
-    const int j = blockIdx.x * kTile + (tid & (kTile - 1));
-    const int i = blockIdx.y * kTile + (tid >> 4);
+    const int blk = tid >> 5;  // warp <-> 8x4 sub-block
+    const int j = blockIdx.x * kTile + blk_x(blk, tid & 31);
+    const int i = blockIdx.y * kTile + blk_y(blk, tid & 31);
     const int2 range = load_range(tile_bins, tile_id, rows);
     // forward.cu:673 -- only the first 256-batch is ever processed
     const int cnt = max(0, min(kMaxPerTile, range.y - range.x));
-    if (tid < cnt) stage_gaussian(sg, tid, __ldg(gids + range.x + tid), xys, conics, colors, opacities);
+    if (tid < cnt)
+        stage_gaussian(sg, tid, __ldg(gids + range.x + tid), (float)(blockIdx.x * kTile),
+                       (float)(blockIdx.y * kTile), xys, conics, colors, opacities);
     __syncthreads();
-    if (i < img_h && j < img_w) {
-        float r = 0.f, g = 0.f, b = 0.f;
-        int last = -1;
-        forward_sweep(sg, cnt, (float)j, (float)i, r, g, b, last);
+    const bool inside = i < img_h && j < img_w;
+    float r = 0.f, g = 0.f, b = 0.f;
+    int last = -1;
+    forward_sweep(sg, cnt, blk, inside, (float)j, (float)i, r, g, b, last);
+    if (inside) {
         const size_t pix = (size_t)i * img_w + j;
         out_img[3 * pix] = r;
         out_img[3 * pix + 1] = g;
@@ -69,14 +73,16 @@ raster_bwd_kernel(int tiles_x, int img_w, int img_h, const int32_t *__restrict__
             vg = __ldg(v_output + 3 * pix + 1);
             vb = __ldg(v_output + 3 * pix + 2);
         }
-        tg.v[0][tid] = vr;
-        tg.v[1][tid] = vg;
-        tg.v[2][tid] = vb;
+        const int gi = grad_index(tid & 15, tid >> 4);
+        tg.v[0][gi] = vr;
+        tg.v[1][gi] = vg;
+        tg.v[2][gi] = vb;
     }
     if (tid < cnt) {
         const int g = __ldg(gids + range.x + tid);
         s_ids[tid] = g;
-        stage_gaussian(sg, tid, g, xys, conics, colors, opacities);
+        stage_gaussian(sg, tid, g, (float)(blockIdx.x * kTile), (float)(blockIdx.y * kTile), xys, conics, colors,
+                       opacities);
     }
     __syncthreads();
     const LanePixels lp = lane_pixels(blockIdx.x, blockIdx.y, img_w, img_h);

@@ -105,9 +105,10 @@ class GaussianImageFitter:
             self._xyz.data_ptr(), self._cov2d.data_ptr(), self.cholesky_bound.data_ptr(),
             self._features_dc.data_ptr(), m["xyz"].data_ptr(), v["xyz"].data_ptr(), m["cov2d"].data_ptr(),
             v["cov2d"].data_ptr(), m["f_dc"].data_ptr(), v["f_dc"].data_ptr(),
-            self.gt_hwc.data_ptr() if self.gt_hwc is not None else None,
+            self.gt_hwc.data_ptr() if (self.gt_hwc is not None and self.gt_hwc.dtype == torch.float32) else None,
             out_img, self.grads.data_ptr(), self.proj.data_ptr(), self.sorted_keys.data_ptr(),
-            self.tile_bins.data_ptr(), self.stats_buf.data_ptr(), self.workspace.data_ptr(), self.workspace.numel())
+            self.tile_bins.data_ptr(), self.stats_buf.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(),
+            self.gt_hwc.data_ptr() if (self.gt_hwc is not None and self.gt_hwc.dtype == torch.uint8) else None)
 
     def reset_stats(self, step: int = 0):
         with torch.cuda.device(self.device):
@@ -115,18 +116,24 @@ class GaussianImageFitter:
 
     # ------------------------------------------------------------------ target
     def set_target(self, gt_image: torch.Tensor):
-        """gt_image: [1,3,H,W] (the reference's layout, utils.py:21-27) or [H,W,3]; copied to HWC on device."""
+        """gt_image: float32 [1,3,H,W] (the reference's layout, utils.py:21-27) or [H,W,3]; or uint8 [H,W,3]
+        -- the image as stored: the kernels then use u8/255, the value ToTensor would have produced, and
+        the host->device copy is 4x smaller.  Copied (asynchronously from pinned memory) to HWC on device."""
         if gt_image.dim() == 4:
             gt_image = gt_image[0].permute(1, 2, 0)
         assert gt_image.shape == (self.H, self.W, 3), gt_image.shape
-        if self.gt_hwc is None:
-            self.gt_hwc = torch.empty(self.H, self.W, 3, dtype=torch.float32, device=self.device)
+        assert gt_image.dtype in (torch.float32, torch.uint8), gt_image.dtype
+        if self.gt_hwc is None or self.gt_hwc.dtype != gt_image.dtype:
+            first = self.gt_hwc is None
+            self.gt_hwc = torch.empty(self.H, self.W, 3, dtype=gt_image.dtype, device=self.device)
             self._graph = None
+            self._eager_left = max(self._eager_left, 0)
             self.gt_hwc.copy_(gt_image, non_blocking=True)
             self._bind()
-            self.reset_stats(self._step0)
-        else:
-            self.gt_hwc.copy_(gt_image, non_blocking=True)
+            if first:
+                self.reset_stats(self._step0)
+            return
+        self.gt_hwc.copy_(gt_image, non_blocking=True)
 
     # ------------------------------------------------------------------ one iteration
     def _enqueue_step(self):
@@ -188,6 +195,17 @@ class GaussianImageFitter:
     def psnr(self) -> float:
         return self.stats()["psnr"]
 
+    def stats_async(self, host_slot: torch.Tensor, event: "torch.cuda.Event"):
+        """Enqueue a device->host copy of the stats block of the step just issued into pinned `host_slot`
+        (f64[STAT_COUNT]) and record `event` after it; the caller waits on the event when it wants the
+        numbers.  Lets a driver read EVERY step's result without stalling the GPU between steps."""
+        host_slot.copy_(self.stats_buf, non_blocking=True)
+        event.record(torch.cuda.current_stream(self.device))
+
+    @staticmethod
+    def mse_from_stats(host_slot: torch.Tensor, H: int, W: int) -> float:
+        return float(host_slot[STAT_SSE:STAT_SSE + STAT_SSE_SLOTS].sum()) / (3.0 * H * W)
+
     def ensure_capacity(self) -> bool:
         """Host check of the overflow flag; grows the intersection buffers when it tripped.
         Returns True when a regrow happened (the overflowing step was skipped by the Adam kernel)."""
@@ -247,6 +265,8 @@ class GaussianImageFitter:
         """train.py:85-118: new Gaussians at the pixels of largest L1 error of the current render."""
         render = self.forward()["render"]
         gt = self.gt_hwc.permute(2, 0, 1).unsqueeze(0)
+        if gt.dtype == torch.uint8:
+            gt = gt.float() / 255
         errors = torch.abs(render - gt).sum(dim=1)
         p_flat = (errors / torch.sum(errors)).view(-1)
         room = max(0, max_num_points - self.cur_num_points)

@@ -214,6 +214,8 @@ typedef struct gi2d_fit_buffers {
     double *stats;         /* f64[GI2D_STAT_COUNT] */
     void *workspace;
     size_t workspace_bytes;
+    const uint8_t *gt_u8_hwc; /* u8[H,W,3] target as stored (PNG bytes); used when gt_hwc is NULL: the
+                                 kernel computes u8/255 exactly like torchvision's ToTensor (utils.py:21-27) */
 } gi2d_fit_buffers;
 
 size_t gi2d_fit_workspace_size(const gi2d_fit_params *p);

@@ -193,3 +193,22 @@ def test_full_size_properties(name):
     fd = (mse1 - mse2) / (2 * eps)
     an = float((g.double() * d.double()).sum())
     assert abs(fd - an) <= 4e-2 * abs(an) + 1e-9, (fd, an, mse0)
+
+
+def test_u8_target_equals_float_target():
+    """An 8-bit target handed over as bytes gives bit-identical results to the float image u8/255."""
+    N, H, W = 2500, 200, 300
+    fa, (xyz, cov, bound, rgb, gt) = make_fitter(N, H, W, seed=8, colors="zeros")
+    fb, _ = make_fitter(N, H, W, seed=8, colors="zeros")
+    gt_u8 = np.round(gt * 255).astype(np.uint8)
+    fa.set_target(torch.from_numpy(gt_u8.astype(np.float32) / np.float32(255)))
+    fb.set_target(torch.from_numpy(gt_u8))
+    fa.train_iter()
+    fb.train_iter()
+    assert torch.equal(fa.out_hwc, fb.out_hwc)
+    sa, sb = fa.stats()["sse"], fb.stats()["sse"]
+    assert abs(sa - sb) <= 1e-12 * sa      # identical per-tile partials, summed by double atomics
+    # one more step: the gradients (and so the parameters) agree to float-atomic noise
+    fa.train_iter()
+    fb.train_iter()
+    assert abs(fa.stats()["mse"] - fb.stats()["mse"]) <= 1e-5 * fa.stats()["mse"]
