@@ -180,6 +180,9 @@ def main():
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     H, W, N = synth.CONFIGS[args.workload]
     K, Wm = args.steps, max(args.warmup, 3)
@@ -367,7 +370,8 @@ def main():
             "launches_per_step": fit.launches_per_iter(),
             "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "ref_cuda": ref_cuda,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
