@@ -100,4 +100,33 @@ __device__ __forceinline__ float fast_exp_neg(float sigma) {
 
 constexpr float kAlphaMin = 1.f / 255.f;
 
+// ---- programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may start while
+// its predecessor on the stream is still draining; everything before pdl_wait() (index math, shared
+// memory zeroing, loads of data no predecessor writes) overlaps the predecessor's tail.  pdl_wait()
+// returns once the predecessor grid has completed and its writes are visible.  Every thread calls it
+// before touching dependent data (and before any early return, which keeps the chain transitive).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    // Inside a CUDA-graph capture the programmatic edges made replays SLOWER on this driver (580.159:
+    // 42.9 vs 37.5 us per 5-kernel step, measured), so captured launches keep full serialisation and
+    // only eager launches (render loop, un-graphed steps) overlap their prologues.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    cfg.numAttrs = cap == cudaStreamCaptureStatusNone ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace gi2d

@@ -124,7 +124,9 @@ fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, const float *__restric
     extern __shared__ int s_hist[];
     const int D = 1 << bits0;
     const int mask = D - 1;
+    pdl_launch_dependents();
     for (int d = threadIdx.x; d < D; d += kProjThreads) s_hist[d] = 0;
+    pdl_wait();  // the previous step's Adam wrote the parameters, its rasterizer read grads / proj
     if (blockIdx.x == 0 && threadIdx.x < GI2D_STAT_SSE_SLOTS) stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         stats[GI2D_STAT_OVERFLOW] = 0.0;
@@ -192,6 +194,8 @@ constexpr int kScanMaxRows = 16;  // rows per segment held in registers per trip
 __global__ void __launch_bounds__(kScanThreads)
 fit_scan_kernel(int nblocks, int D, int32_t *__restrict__ counts, int32_t *__restrict__ totals) {
     __shared__ int s_seg[kScanSegs][kScanCols];
+    pdl_launch_dependents();
+    pdl_wait();
     const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
     const int d = blockIdx.x * kScanCols + lane;
     const int rows_per_seg = (nblocks + kScanSegs - 1) / kScanSegs;
@@ -314,10 +318,12 @@ fit_scatter_kernel(int num_points, int gpb, int bits0, int tiles_x, int num_tile
     int *s_cnt = s_dyn;
     int *s_base = s_dyn + kScatterWarps * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_launch_dependents();
     {
         int4 *z = reinterpret_cast<int4 *>(s_cnt);
         for (int i = threadIdx.x; i < kScatterWarps * D / 4; i += kScatterThreads) z[i] = make_int4(0, 0, 0, 0);
     }
+    pdl_wait();
     // start of every digit (== tile, when one pass covers the tile id) in the sorted order
     const int total = scan_totals_to_smem<kScatterThreads>(totals, D, s_base, s_warp);
     if (blockIdx.x == 0) {
@@ -419,6 +425,7 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_y = p.tile_row_begin + blockIdx.y;
     const int tile_id = tile_y * p.tiles_x + blockIdx.x;
+    pdl_launch_dependents();
     const int blk = warp;  // forward: warp <-> 8x4 sub-block
     const int lx = blk_x(blk, lane), ly = blk_y(blk, lane);
     const int j = blockIdx.x * kTile + lx;
@@ -439,6 +446,7 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
             tb = __fdiv_rn((float)__ldg(gt_u8 + 3 * pix + 2), 255.f);
         }
     }
+    pdl_wait();  // the target image above is written by no kernel of the step; everything below is
     const double n_isect = stats[GI2D_STAT_ISECTS];
     const int2 range = __ldg(reinterpret_cast<const int2 *>(tile_bins) + tile_id);
     const int cnt = max(0, min(kMaxPerTile, min(range.y, p.isect_capacity) - range.x));
@@ -512,6 +520,8 @@ fit_adam_kernel(gi2d_fit_params p, float *__restrict__ xyz, float *__restrict__ 
                 float *__restrict__ m_cov, float *__restrict__ v_cov, float *__restrict__ m_rgb,
                 float *__restrict__ v_rgb, const float4 *__restrict__ proj,
                 const float4 *__restrict__ grads, const double *__restrict__ stats) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int g = blockIdx.x * 256 + threadIdx.x;
     if (g >= p.num_points) return;
     // capacity exceeded: nothing is stored and the host re-runs the step.  (Tested at the stores, not
@@ -624,16 +634,17 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     const int num_tiles = p->tiles_x * p->tiles_y;
     const bool single = pl.extra_passes == 0;
     if (mk) mk->mark(st);
-    fit_project_kernel<<<pl.nblocks, kProjThreads, D * sizeof(int), st>>>(
+    launch_pdl(fit_project_kernel, dim3(pl.nblocks), dim3(kProjThreads), D * sizeof(int), st,
         *p, pl.gpb, pl.bits0, b->xyz, b->cov, b->cov_bound, b->rgb, (float4 *)b->proj, (float4 *)b->grads,
         w.boxes, w.counts, b->stats, with_backward);
     if (mk) mk->mark(st);
-    fit_scan_kernel<<<cdiv(D, kScanCols), kScanThreads, 0, st>>>(pl.nblocks, D, w.counts, w.totals);
+    launch_pdl(fit_scan_kernel, dim3(cdiv(D, kScanCols)), dim3(kScanThreads), 0, st, pl.nblocks, D, w.counts,
+               w.totals);
     if (mk) mk->mark(st);
     // pass 0 lands in sorted_keys when the number of remaining passes is even
     uint64_t *dst0 = (pl.extra_passes % 2 == 0) ? b->sorted_keys : w.keys_tmp;
     const size_t scatter_smem = (size_t)(kScatterWarps + 1) * D * sizeof(int);  // <= 40 KiB
-    fit_scatter_kernel<<<pl.nblocks, kScatterThreads, scatter_smem, st>>>(
+    launch_pdl(fit_scatter_kernel, dim3(pl.nblocks), dim3(kScatterThreads), scatter_smem, st,
         p->num_points, pl.gpb, pl.bits0, p->tiles_x, num_tiles, single ? 1 : 0, p->isect_capacity, w.boxes,
         w.counts, w.totals, dst0, (const float4 *)b->proj, single ? w.records : nullptr, b->tile_bins, w.n_isect,
         b->stats);
@@ -659,10 +670,10 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     if (band > 0) {
         dim3 grid(p->tiles_x, band);
         if (with_backward)
-            fit_raster_kernel<RasterMode::Fit><<<grid, kRasterThreads, 0, st>>>(
+            launch_pdl(fit_raster_kernel<RasterMode::Fit>, grid, dim3(kRasterThreads), 0, st,
                 *p, b->sorted_keys, b->tile_bins, w.records, b->gt_hwc, b->gt_u8_hwc, b->out_img, b->grads, b->stats);
         else
-            fit_raster_kernel<RasterMode::Render><<<grid, kRasterThreads, 0, st>>>(
+            launch_pdl(fit_raster_kernel<RasterMode::Render>, grid, dim3(kRasterThreads), 0, st,
                 *p, b->sorted_keys, b->tile_bins, w.records, nullptr, nullptr, b->out_img, nullptr, b->stats);
     }
     if (mk) mk->mark(st);
@@ -722,7 +733,7 @@ extern "C" int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b
     GI2D_REQUIRE(b->xyz && b->cov && b->rgb && b->m_xyz && b->v_xyz && b->m_cov && b->v_cov && b->m_rgb &&
                      b->v_rgb && b->grads,
                  "null buffer");
-    fit_adam_kernel<<<cdiv(p->num_points, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(fit_adam_kernel, dim3(cdiv(p->num_points, 256)), dim3(256), 0, (cudaStream_t)stream,
         *p, b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb,
         (const float4 *)b->proj, (const float4 *)b->grads, b->stats);
     return check_launch(__func__);
