@@ -50,6 +50,8 @@ constexpr int kStatB1Pow = 4;  // beta1^step
 constexpr int kStatB2Pow = 5;  // beta2^step
 constexpr int kStatStepSize = 6;  // lr / (1 - beta1^step)   of the step in flight
 constexpr int kStatBc2Sqrt = 7;   // sqrt(1 - beta2^step)
+constexpr int kStatPending = 8;   // != 0: grads of the last step have not been applied yet (Adam is folded
+                                  // into the NEXT step's projection kernel, or flushed by gi2d_fit_adam)
 
 struct Plan {
     int tile_bits;     // bits needed for a tile id
@@ -114,45 +116,107 @@ Workspace carve(const gi2d_fit_params &p, const Plan &pl, void *base) {
 
 __device__ __forceinline__ float sigmoidf(float v) { return 1.f / (1.f + expf(-v)); }
 
+// ------------------------------------------------------------------------- Adam (shared)
+struct AdamPtrs {
+    float *xyz, *cov, *rgb, *m_xyz, *v_xyz, *m_cov, *v_cov, *m_rgb, *v_rgb;
+};
+
+// Projection backward (R7, backward2d.cu:157-214: v_cov = -X G X with the off-diagonal summed,
+// v_mean = v_xy; for culled Gaussians conic == 0 and the incoming gradients are 0, the same zeros
+// the reference's early return leaves) followed by torch.optim.Adam's update
+// (torch/optim/adam.py _single_tensor_adam: step_size = lr/(1-beta1^t), denom = sqrt(v)/sqrt(1-beta2^t)+eps;
+// the scalars were evaluated in double by the bookkeeping thread, tensors are float) for ONE Gaussian.
+// Every load is issued before the first dependent store.  sqrt / divide go through the SFU
+// (sqrt.approx, div.approx: 1-2 ulp): the IEEE versions branch into slow paths on the denormal second
+// moments Adam produces with eps = 1e-15; 2 ulp is far inside the 1e-4 budget of the parameters.
+// Returns the updated parameters in (x, c, q) so the caller can go on projecting them.
+__device__ __forceinline__ void adam_update_gaussian(const gi2d_fit_params &p, const AdamPtrs &a, int g,
+                                                     float4 p0, float4 p1, float4 g0, float4 g1,
+                                                     const double *__restrict__ stats, bool skip,
+                                                     float2 &x, float (&c)[3], float (&q)[3]) {
+    const float step_size = (float)stats[kStatStepSize];
+    const float bc2_sqrt = (float)stats[kStatBc2Sqrt];
+    const float w1 = (float)(1.0 - (double)p.beta1), w2 = (float)(1.0 - (double)p.beta2);
+    x = reinterpret_cast<float2 *>(a.xyz)[g];
+    float2 mx = reinterpret_cast<float2 *>(a.m_xyz)[g], vx = reinterpret_cast<float2 *>(a.v_xyz)[g];
+    float mc[3], vc[3], mq[3], vq[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        c[k] = a.cov[3 * g + k];  mc[k] = a.m_cov[3 * g + k];  vc[k] = a.v_cov[3 * g + k];
+        q[k] = a.rgb[3 * g + k];  mq[k] = a.m_rgb[3 * g + k];  vq[k] = a.v_rgb[3 * g + k];
+    }
+    if (skip) return;  // (values loaded above are returned unchanged)
+    float gc[3];
+    conic_vjp(p0.z, p0.w, p1.x, g0.z, g0.w, g1.x, gc[0], gc[1], gc[2]);
+    float gq[3] = {g1.y, g1.z, g1.w};
+    if (p.color_sigmoid) {
+        gq[0] *= p1.y * (1.f - p1.y);
+        gq[1] *= p1.z * (1.f - p1.z);
+        gq[2] *= p1.w * (1.f - p1.w);
+    }
+    const float inv_bc2 = 1.f / bc2_sqrt;
+    auto adam = [&](float &param, float &m, float &v, float grad) {
+        m = m + (grad - m) * w1;                                // exp_avg.lerp_(grad, 1-beta1)
+        v = v * p.beta2 + w2 * grad * grad;                     // mul_(beta2).addcmul_(grad, grad, 1-beta2)
+        float sq;
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
+        const float denom = fmaf(sq, inv_bc2, p.eps);
+        param = param - step_size * __fdividef(m, denom);       // addcdiv_(exp_avg, denom, -step_size)
+    };
+    adam(x.x, mx.x, vx.x, g0.x);
+    adam(x.y, mx.y, vx.y, g0.y);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        adam(c[k], mc[k], vc[k], gc[k]);
+        adam(q[k], mq[k], vq[k], gq[k]);
+    }
+    reinterpret_cast<float2 *>(a.xyz)[g] = x;
+    reinterpret_cast<float2 *>(a.m_xyz)[g] = mx;
+    reinterpret_cast<float2 *>(a.v_xyz)[g] = vx;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        a.cov[3 * g + k] = c[k];  a.m_cov[3 * g + k] = mc[k];  a.v_cov[3 * g + k] = vc[k];
+        a.rgb[3 * g + k] = q[k];  a.m_rgb[3 * g + k] = mq[k];  a.v_rgb[3 * g + k] = vq[k];
+    }
+}
+
 // ------------------------------------------------------------------------------------ K1
+// Optimiser of the PREVIOUS step + projection of THIS step, per Gaussian, in one launch: the thread
+// that owns Gaussian g first applies projection-backward + Adam to it when a gradient is pending
+// (stats[kStatPending]; the overflow flag of that step vetoes it), then projects the fresh parameters,
+// writes the 32-B record, zeroes the gradient row for the coming backward and counts the tiles.
+// This kernel only READS the stats block; the bookkeeping for the step in flight is done by K2.
 __global__ void __launch_bounds__(kProjThreads)
-fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, const float *__restrict__ xyz,
-                   const float *__restrict__ cov, const float *__restrict__ cov_bound,
-                   const float *__restrict__ rgb, float4 *__restrict__ proj,
-                   float4 *__restrict__ grads, ushort4 *__restrict__ boxes,
-                   int32_t *__restrict__ counts, double *__restrict__ stats, int with_backward) {
+fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, AdamPtrs a, const float *__restrict__ cov_bound,
+                   float4 *__restrict__ proj, float4 *__restrict__ grads, ushort4 *__restrict__ boxes,
+                   int32_t *__restrict__ counts, const double *__restrict__ stats, int with_backward) {
     extern __shared__ int s_hist[];
     const int D = 1 << bits0;
     const int mask = D - 1;
     pdl_launch_dependents();
     for (int d = threadIdx.x; d < D; d += kProjThreads) s_hist[d] = 0;
-    pdl_wait();  // the previous step's Adam wrote the parameters, its rasterizer read grads / proj
-    if (blockIdx.x == 0 && threadIdx.x < GI2D_STAT_SSE_SLOTS) stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        stats[GI2D_STAT_OVERFLOW] = 0.0;
-        if (with_backward) {
-            // step counter, bias-correction powers and the StepLR schedule live on the device:
-            // torch evaluates beta^step / gamma^floor((step-1)/size) in double precision as well
-            const double step = stats[GI2D_STAT_STEP] + 1.0;
-            stats[GI2D_STAT_STEP] = step;
-            stats[kStatB1Pow] *= (double)p.beta1;
-            stats[kStatB2Pow] *= (double)p.beta2;
-            const long long k = (long long)step - 1;
-            if (k > 0 && p.lr_step_size > 0 && k % p.lr_step_size == 0) stats[GI2D_STAT_LR] *= (double)p.lr_gamma;
-            stats[kStatStepSize] = stats[GI2D_STAT_LR] / (1.0 - stats[kStatB1Pow]);
-            stats[kStatBc2Sqrt] = sqrt(1.0 - stats[kStatB2Pow]);
-        }
-    }
+    pdl_wait();  // the previous step's rasterizer wrote grads (and read proj)
+    const bool pending = a.m_xyz != nullptr && stats[kStatPending] != 0.0;
+    const bool veto = stats[GI2D_STAT_OVERFLOW] != 0.0;  // that step overflowed: the host re-runs it
     __syncthreads();
     const int g0 = blockIdx.x * gpb;
     const int g1 = min(p.num_points, g0 + gpb);
     for (int g = g0 + threadIdx.x; g < g1; g += kProjThreads) {
-        const float2 m = __ldg(reinterpret_cast<const float2 *>(xyz) + g);
+        float2 m;
+        float c[3], q[3];
+        if (pending) {
+            adam_update_gaussian(p, a, g, proj[2 * g], proj[2 * g + 1], grads[2 * g], grads[2 * g + 1], stats, veto,
+                                 m, c, q);
+        } else {
+            m = reinterpret_cast<const float2 *>(a.xyz)[g];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { c[k] = a.cov[3 * g + k]; q[k] = a.rgb[3 * g + k]; }
+        }
         // get_cov2d_elements = _cov2d + cholesky_bound (gaussianimage_covariance.py:169)
-        const float sx = __fadd_rn(__ldg(cov + 3 * g), __ldg(cov_bound + 3 * g));
-        const float sxy = __fadd_rn(__ldg(cov + 3 * g + 1), __ldg(cov_bound + 3 * g + 1));
-        const float sy = __fadd_rn(__ldg(cov + 3 * g + 2), __ldg(cov_bound + 3 * g + 2));
-        float cr = __ldg(rgb + 3 * g), cg = __ldg(rgb + 3 * g + 1), cb = __ldg(rgb + 3 * g + 2);
+        const float sx = __fadd_rn(c[0], __ldg(cov_bound + 3 * g));
+        const float sxy = __fadd_rn(c[1], __ldg(cov_bound + 3 * g + 1));
+        const float sy = __fadd_rn(c[2], __ldg(cov_bound + 3 * g + 2));
+        float cr = q[0], cg = q[1], cb = q[2];
         if (p.color_sigmoid) { cr = sigmoidf(cr); cg = sigmoidf(cg); cb = sigmoidf(cb); }
         const Projected pr = project_cov(m.x, m.y, sx, sxy, sy, p.clip_coe, p.radius_clip, p.tiles_x, p.tiles_y);
         proj[2 * g] = make_float4(pr.x, pr.y, pr.a, pr.b);
@@ -192,10 +256,30 @@ constexpr int kScanThreads = kScanCols * kScanSegs;
 constexpr int kScanMaxRows = 16;  // rows per segment held in registers per trip
 
 __global__ void __launch_bounds__(kScanThreads)
-fit_scan_kernel(int nblocks, int D, int32_t *__restrict__ counts, int32_t *__restrict__ totals) {
+fit_scan_kernel(gi2d_fit_params p, int with_backward, double *__restrict__ stats, int nblocks, int D,
+                int32_t *__restrict__ counts, int32_t *__restrict__ totals) {
     __shared__ int s_seg[kScanSegs][kScanCols];
     pdl_launch_dependents();
     pdl_wait();
+    // Bookkeeping of the step in flight (K1 has already consumed the previous step's values): zero the
+    // SSE partials and the overflow flag, and -- for a training step -- advance the step counter, the
+    // bias-correction powers and the StepLR schedule.  torch evaluates beta^t and gamma^floor((t-1)/size)
+    // in double precision as well.  The Adam that uses them runs inside the NEXT K1 (or gi2d_fit_adam).
+    if (blockIdx.x == 0 && threadIdx.x < GI2D_STAT_SSE_SLOTS) stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        stats[GI2D_STAT_OVERFLOW] = 0.0;
+        stats[kStatPending] = with_backward ? 1.0 : 0.0;
+        if (with_backward) {
+            const double step = stats[GI2D_STAT_STEP] + 1.0;
+            stats[GI2D_STAT_STEP] = step;
+            stats[kStatB1Pow] *= (double)p.beta1;
+            stats[kStatB2Pow] *= (double)p.beta2;
+            const long long k = (long long)step - 1;
+            if (k > 0 && p.lr_step_size > 0 && k % p.lr_step_size == 0) stats[GI2D_STAT_LR] *= (double)p.lr_gamma;
+            stats[kStatStepSize] = stats[GI2D_STAT_LR] / (1.0 - stats[kStatB1Pow]);
+            stats[kStatBc2Sqrt] = sqrt(1.0 - stats[kStatB2Pow]);
+        }
+    }
     const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
     const int d = blockIdx.x * kScanCols + lane;
     const int rows_per_seg = (nblocks + kScanSegs - 1) / kScanSegs;
@@ -514,75 +598,26 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
 }
 
 // ------------------------------------------------------------------------------------ K5
+// Stand-alone optimiser launch: applies a pending gradient NOW (before the host reads or edits the
+// parameters, renders, or all the steps are done).  In the steady state it is never launched: the
+// next step's K1 does the same work.
 __global__ void __launch_bounds__(256)
-fit_adam_kernel(gi2d_fit_params p, float *__restrict__ xyz, float *__restrict__ cov,
-                float *__restrict__ rgb, float *__restrict__ m_xyz, float *__restrict__ v_xyz,
-                float *__restrict__ m_cov, float *__restrict__ v_cov, float *__restrict__ m_rgb,
-                float *__restrict__ v_rgb, const float4 *__restrict__ proj,
+fit_adam_kernel(gi2d_fit_params p, AdamPtrs a, const float4 *__restrict__ proj,
                 const float4 *__restrict__ grads, const double *__restrict__ stats) {
     pdl_launch_dependents();
     pdl_wait();
     const int g = blockIdx.x * 256 + threadIdx.x;
-    if (g >= p.num_points) return;
-    // capacity exceeded: nothing is stored and the host re-runs the step.  (Tested at the stores, not
-    // here, so that every load below is issued before the first dependent instruction.)
-    const bool skip = stats[GI2D_STAT_OVERFLOW] != 0.0;
-    // torch/optim/adam.py (_single_tensor_adam): step_size = lr / (1 - beta1^t),
-    // denom = sqrt(v) / sqrt(1 - beta2^t) + eps -- scalars in double (K1 did that once), tensors in float
-    const float step_size = (float)stats[kStatStepSize];
-    const float bc2_sqrt = (float)stats[kStatBc2Sqrt];
-    const float w1 = (float)(1.0 - (double)p.beta1), w2 = (float)(1.0 - (double)p.beta2);
-    const float4 p0 = proj[2 * g], p1 = proj[2 * g + 1];
-    const float4 g0 = grads[2 * g], g1 = grads[2 * g + 1];
-    // every parameter / moment load is issued before the first dependent store (the three arrays of a
-    // group alias-analyse as one object otherwise and the updates serialise into 8 L2 round trips)
-    float2 x = reinterpret_cast<float2 *>(xyz)[g];
-    float2 mx = reinterpret_cast<float2 *>(m_xyz)[g], vx = reinterpret_cast<float2 *>(v_xyz)[g];
-    float c[3], mc[3], vc[3], q[3], mq[3], vq[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        c[k] = cov[3 * g + k];  mc[k] = m_cov[3 * g + k];  vc[k] = v_cov[3 * g + k];
-        q[k] = rgb[3 * g + k];  mq[k] = m_rgb[3 * g + k];  vq[k] = v_rgb[3 * g + k];
-    }
-    // R7, backward2d.cu:157-214: v_cov = -X G X (off-diagonal summed), v_mean = v_xy.
-    // For culled Gaussians (radii<=0) conic == 0 and the incoming gradients are 0: same zeros.
-    float gc[3];
-    conic_vjp(p0.z, p0.w, p1.x, g0.z, g0.w, g1.x, gc[0], gc[1], gc[2]);
-    float gq[3] = {g1.y, g1.z, g1.w};
-    if (p.color_sigmoid) {
-        gq[0] *= p1.y * (1.f - p1.y);
-        gq[1] *= p1.z * (1.f - p1.z);
-        gq[2] *= p1.w * (1.f - p1.w);
-    }
-    // sqrt / divide through the SFU (sqrt.approx, div.approx: 1-2 ulp): the IEEE versions branch into
-    // slow paths on the denormal second moments Adam produces with eps = 1e-15 and made this kernel
-    // 3x longer; 2 ulp is far inside the 1e-4 budget of the parameters.
-    const float inv_bc2 = 1.f / bc2_sqrt;
-    auto adam = [&](float &param, float &m, float &v, float grad) {
-        m = m + (grad - m) * w1;                                // exp_avg.lerp_(grad, 1-beta1)
-        v = v * p.beta2 + w2 * grad * grad;                     // mul_(beta2).addcmul_(grad, grad, 1-beta2)
-        float sq;
-        asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
-        const float denom = fmaf(sq, inv_bc2, p.eps);
-        param = param - step_size * __fdividef(m, denom);       // addcdiv_(exp_avg, denom, -step_size)
-    };
-    adam(x.x, mx.x, vx.x, g0.x);
-    adam(x.y, mx.y, vx.y, g0.y);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        adam(c[k], mc[k], vc[k], gc[k]);
-        adam(q[k], mq[k], vq[k], gq[k]);
-    }
-    if (skip) return;
-    reinterpret_cast<float2 *>(xyz)[g] = x;
-    reinterpret_cast<float2 *>(m_xyz)[g] = mx;
-    reinterpret_cast<float2 *>(v_xyz)[g] = vx;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        cov[3 * g + k] = c[k];  m_cov[3 * g + k] = mc[k];  v_cov[3 * g + k] = vc[k];
-        rgb[3 * g + k] = q[k];  m_rgb[3 * g + k] = mq[k];  v_rgb[3 * g + k] = vq[k];
+    const bool pending = stats[kStatPending] != 0.0;
+    const bool veto = stats[GI2D_STAT_OVERFLOW] != 0.0;
+    if (g < p.num_points && pending) {
+        float2 x;
+        float c[3], q[3];
+        adam_update_gaussian(p, a, g, proj[2 * g], proj[2 * g + 1], grads[2 * g], grads[2 * g + 1], stats, veto, x, c, q);
     }
 }
+
+// second half of the flush: only after EVERY CTA of fit_adam_kernel has read the flag may it be cleared
+__global__ void fit_clear_pending_kernel(double *__restrict__ stats) { stats[kStatPending] = 0.0; }
 
 __global__ void fit_reset_kernel(gi2d_fit_params p, double *stats, int step) {
     const int i = threadIdx.x;
@@ -623,6 +658,8 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     const int rc = validate(p, b);
     if (rc != GI2D_OK) return rc;
     GI2D_REQUIRE(p->num_points == 0 || (b->xyz && b->cov && b->cov_bound && b->rgb), "null parameter buffer");
+    GI2D_REQUIRE(!with_backward || (b->m_xyz && b->v_xyz && b->m_cov && b->v_cov && b->m_rgb && b->v_rgb),
+                 "a training step needs the Adam moment buffers");
     GI2D_REQUIRE(!with_backward || (b->grads && (b->gt_hwc || b->gt_u8_hwc)), "fit needs grads and a target image");
     const Plan pl = make_plan(*p);
     const Workspace w = carve(*p, pl, b->workspace);
@@ -634,12 +671,13 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     const int num_tiles = p->tiles_x * p->tiles_y;
     const bool single = pl.extra_passes == 0;
     if (mk) mk->mark(st);
+    const AdamPtrs ap{b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
     launch_pdl(fit_project_kernel, dim3(pl.nblocks), dim3(kProjThreads), D * sizeof(int), st,
-        *p, pl.gpb, pl.bits0, b->xyz, b->cov, b->cov_bound, b->rgb, (float4 *)b->proj, (float4 *)b->grads,
+        *p, pl.gpb, pl.bits0, ap, b->cov_bound, (float4 *)b->proj, (float4 *)b->grads,
         w.boxes, w.counts, b->stats, with_backward);
     if (mk) mk->mark(st);
-    launch_pdl(fit_scan_kernel, dim3(cdiv(D, kScanCols)), dim3(kScanThreads), 0, st, pl.nblocks, D, w.counts,
-               w.totals);
+    launch_pdl(fit_scan_kernel, dim3(cdiv(D, kScanCols)), dim3(kScanThreads), 0, st, *p, with_backward, b->stats,
+               pl.nblocks, D, w.counts, w.totals);
     if (mk) mk->mark(st);
     // pass 0 lands in sorted_keys when the number of remaining passes is even
     uint64_t *dst0 = (pl.extra_passes % 2 == 0) ? b->sorted_keys : w.keys_tmp;
@@ -711,7 +749,8 @@ extern "C" int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward
         n += pl.extra_passes * (2 + (cumsum_nb > 1 ? 3 : 1));  // hist + cumsum + scatter per pass
         n += 2;                                                 // tile edges + record gather (memset is no kernel)
     }
-    return n + (with_backward ? 1 : 0);  // + adam
+    (void)with_backward;  // the optimiser rides in the next step's projection kernel
+    return n;
 }
 
 extern "C" int gi2d_fit_reset(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int step,
@@ -733,14 +772,15 @@ extern "C" int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b
     GI2D_REQUIRE(b->xyz && b->cov && b->rgb && b->m_xyz && b->v_xyz && b->m_cov && b->v_cov && b->m_rgb &&
                      b->v_rgb && b->grads,
                  "null buffer");
-    launch_pdl(fit_adam_kernel, dim3(cdiv(p->num_points, 256)), dim3(256), 0, (cudaStream_t)stream,
-        *p, b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb,
-        (const float4 *)b->proj, (const float4 *)b->grads, b->stats);
+    const AdamPtrs ap{b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
+    launch_pdl(fit_adam_kernel, dim3(cdiv(p->num_points, 256)), dim3(256), 0, (cudaStream_t)stream, *p, ap,
+               (const float4 *)b->proj, (const float4 *)b->grads, b->stats);
+    fit_clear_pending_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(b->stats);
     return check_launch(__func__);
 }
 
 // Measurement utility (bench.py): one full fit step with a CUDA event between the kernels, on
-// `stream`; SYNCHRONISES.  ms[0..4] = project, scan, scatter(+extra passes+edges), raster, adam.
+// `stream`; SYNCHRONISES.  ms[0..4] = adam(prev)+project, scan, scatter(+extra passes+edges), raster, 0.
 extern "C" int gi2d_fit_profile(const gi2d_fit_params *p, const gi2d_fit_buffers *b, float *ms_host,
                                 gi2d_stream_t stream) {
     GI2D_REQUIRE(ms_host, "null ms_host");
@@ -749,7 +789,6 @@ extern "C" int gi2d_fit_profile(const gi2d_fit_params *p, const gi2d_fit_buffers
     mk.on = true;
     for (int i = 0; i < 8; ++i) cudaEventCreate(&mk.ev[i]);
     int rc = fit_forward_backward_impl(p, b, 1, st, &mk);
-    if (rc == GI2D_OK) rc = gi2d_fit_adam(p, b, stream);
     mk.mark(st);
     cudaStreamSynchronize(st);
     for (int i = 0; i < 5; ++i) {

@@ -3,12 +3,19 @@
 `GaussianImageFitter` keeps the reference model's vocabulary (models/gaussianimage_covariance.py):
 `_xyz`, `_cov2d`, `_features_dc`, `cholesky_bound`, `forward()`, `train_iter()`,
 `densification_postfix()`, `non_semi_definite_prune()` -- but one `train_iter` is a single CUDA
-graph replay of 5 kernels (gi2d_fit.cu) instead of ~70 launches and two host syncs
+graph replay of 4 kernels (gi2d_fit.cu) instead of ~70 launches and two host syncs
 (SURVEY 3.1).  Nothing here computes on the CPU; without libgi2d.so it raises.
 
-PSNR is not read back every iteration: `train_iter()` only enqueues work; `psnr()` /
-`stats()` synchronise when the caller wants the number (the reference's per-iteration
-`.item()` at gaussianimage_covariance.py:257 is exactly the sync this removes).
+Two things differ from a literal transcription, both invisible in the results:
+
+* PSNR is not read back every iteration: `train_iter()` only enqueues work; `psnr()` / `stats()`
+  synchronise when the caller wants the number (the reference's per-iteration `.item()` at
+  gaussianimage_covariance.py:257 is exactly the sync this removes).
+* The optimiser step of iteration k is applied by the first kernel of iteration k+1 (the thread that
+  projects Gaussian g first applies Adam to it).  Until then the gradient is *pending*; any host
+  access to the parameters (`_xyz`, `_cov2d`, `_features_dc`, `exp_avg*`), `forward()`, pruning and
+  densification flush it first, so the host always observes the reference's post-`optimizer.step()`
+  values.
 """
 from __future__ import annotations
 
@@ -19,10 +26,11 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from .binding import TILE, _p, _stream
+from .binding import TILE, _stream
 
-STAT_STEP, STAT_ISECTS, STAT_OVERFLOW, STAT_LR, STAT_SSE, STAT_SSE_SLOTS = 0, 1, 2, 3, 8, 64
+STAT_STEP, STAT_ISECTS, STAT_OVERFLOW, STAT_LR, STAT_SSE, STAT_SSE_SLOTS = 0, 1, 2, 3, 16, 64
 STAT_COUNT = STAT_SSE + STAT_SSE_SLOTS
+_NAMES = ("xyz", "cov2d", "f_dc")  # the reference's optimiser group names (gaussianimage_covariance.py:93-96)
 
 
 def slv_bound(H: int, W: int, num_points: int) -> float:
@@ -30,7 +38,25 @@ def slv_bound(H: int, W: int, num_points: int) -> float:
     return min(H * W / (9 * math.pi * num_points), 300)
 
 
+def _flushed(attr):
+    """Property over a private attribute whose getter first applies a pending optimiser step."""
+    def get(self):
+        self.sync_params()
+        return getattr(self, attr)
+
+    def set_(self, value):
+        setattr(self, attr, value)
+
+    return property(get, set_)
+
+
 class GaussianImageFitter:
+    _xyz = _flushed("_t_xyz")                # f32[N,2] pixel coordinates
+    _cov2d = _flushed("_t_cov2d")            # f32[N,3] covariance parameters (before the SLV bound)
+    _features_dc = _flushed("_t_f_dc")       # f32[N,3] colours
+    exp_avg = _flushed("_t_m")               # Adam first moments, dict keyed like the reference's groups
+    exp_avg_sq = _flushed("_t_v")            # Adam second moments
+
     def __init__(self, num_points: int, H: int, W: int, device="cuda:0", lr: float = 0.018,
                  clip_coe: float = 3.0, radius_clip: float = 1.0, color_norm: bool = False,
                  SLV_init: bool = True, tile_rows: Optional[Tuple[int, int]] = None,
@@ -46,15 +72,17 @@ class GaussianImageFitter:
         self.lr, self.clip_coe, self.radius_clip = lr, clip_coe, radius_clip
         self.color_norm, self.SLV = bool(color_norm), bool(SLV_init)
         self.use_graph = use_graph
-        self.grad_hook = grad_hook  # called between backward and Adam (multi-GPU all-reduce)
+        self.grad_hook = grad_hook  # called right after the backward of every step (multi-GPU all-reduce)
         self._capacity_hint = isect_capacity
+        self._dirty = False         # a gradient is pending on the device
+        self.keep_render = False    # tests: also store the unclamped [H,W,3] render of every train_iter
         f = dict(dtype=torch.float32, device=self.device)
         # reference init, gaussianimage_covariance.py:52-66
         w_init = torch.rand(num_points, 1, **f) * self.W
         h_init = torch.rand(num_points, 1, **f) * self.H
-        self._xyz = torch.cat((w_init, h_init), dim=1).contiguous()
-        self._cov2d = torch.rand((num_points, 3), **f)
-        self._features_dc = torch.zeros(num_points, 3, **f)
+        self._t_xyz = torch.cat((w_init, h_init), dim=1).contiguous()
+        self._t_cov2d = torch.rand((num_points, 3), **f)
+        self._t_f_dc = torch.zeros(num_points, 3, **f)
         lp = slv_bound(self.H, self.W, num_points) if self.SLV else 0.5
         self.cholesky_bound = torch.tensor([lp, 0, lp], **f).view(1, 3).repeat(num_points, 1).contiguous()
         self.gt_hwc = None
@@ -64,14 +92,17 @@ class GaussianImageFitter:
     # ------------------------------------------------------------------ buffers
     @property
     def cur_num_points(self) -> int:
-        return self._xyz.shape[0]
+        return self._t_xyz.shape[0]
+
+    def _raw_params(self):
+        return {"xyz": self._t_xyz, "cov2d": self._t_cov2d, "f_dc": self._t_f_dc}
 
     def _alloc_state(self, zero_moments: bool):
         n = self.cur_num_points
         f = dict(dtype=torch.float32, device=self.device)
         if zero_moments:
-            self.exp_avg = {k: torch.zeros_like(t) for k, t in self._named_params()}
-            self.exp_avg_sq = {k: torch.zeros_like(t) for k, t in self._named_params()}
+            self._t_m = {k: torch.zeros_like(t) for k, t in self._raw_params().items()}
+            self._t_v = {k: torch.zeros_like(t) for k, t in self._raw_params().items()}
         tiles = self.tile_bounds[0] * self.tile_bounds[1]
         cap = self._capacity_hint or max(1 << 16, 32 * n)
         self.isect_capacity = int(min(cap, max(n, 1) * tiles, 2 ** 31 - 1024))
@@ -91,28 +122,37 @@ class GaussianImageFitter:
         self.workspace = torch.zeros(max(ws_bytes, 256), dtype=torch.uint8, device=self.device)
         self._graph = None
         self._eager_left = 1
-        self.keep_render = getattr(self, "keep_render", False)
+        self._dirty = False
         self._bind()
 
-    def _named_params(self):
-        return (("xyz", self._xyz), ("cov2d", self._cov2d), ("f_dc", self._features_dc))
-
     def _bind(self, out_img=None):
-        m, v = self.exp_avg, self.exp_avg_sq
+        m, v = self._t_m, self._t_v
         if out_img is None and self.keep_render:
-            out_img = self.out_hwc.data_ptr()  # unclamped [H,W,3] render of every train_iter (tests)
+            out_img = self.out_hwc.data_ptr()
+        gt = self.gt_hwc
         self.buffers = _lib.FitBuffers(
-            self._xyz.data_ptr(), self._cov2d.data_ptr(), self.cholesky_bound.data_ptr(),
-            self._features_dc.data_ptr(), m["xyz"].data_ptr(), v["xyz"].data_ptr(), m["cov2d"].data_ptr(),
-            v["cov2d"].data_ptr(), m["f_dc"].data_ptr(), v["f_dc"].data_ptr(),
-            self.gt_hwc.data_ptr() if (self.gt_hwc is not None and self.gt_hwc.dtype == torch.float32) else None,
+            self._t_xyz.data_ptr(), self._t_cov2d.data_ptr(), self.cholesky_bound.data_ptr(), self._t_f_dc.data_ptr(),
+            m["xyz"].data_ptr(), v["xyz"].data_ptr(), m["cov2d"].data_ptr(), v["cov2d"].data_ptr(),
+            m["f_dc"].data_ptr(), v["f_dc"].data_ptr(),
+            gt.data_ptr() if (gt is not None and gt.dtype == torch.float32) else None,
             out_img, self.grads.data_ptr(), self.proj.data_ptr(), self.sorted_keys.data_ptr(),
             self.tile_bins.data_ptr(), self.stats_buf.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(),
-            self.gt_hwc.data_ptr() if (self.gt_hwc is not None and self.gt_hwc.dtype == torch.uint8) else None)
+            gt.data_ptr() if (gt is not None and gt.dtype == torch.uint8) else None)
 
     def reset_stats(self, step: int = 0):
+        """Zero the device-side statistics (drops a pending gradient) and set the Adam step counter."""
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.gi2d_fit_reset(C.byref(self.params), C.byref(self.buffers), int(step), _stream(self.device)), "fit_reset")
+            _lib.check(self.lib.gi2d_fit_reset(C.byref(self.params), C.byref(self.buffers), int(step),
+                                               _stream(self.device)), "fit_reset")
+        self._dirty = False
+
+    def sync_params(self):
+        """Apply a pending optimiser step now (asynchronous; no-op when nothing is pending)."""
+        if self._dirty:
+            self._dirty = False
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.gi2d_fit_adam(C.byref(self.params), C.byref(self.buffers), _stream(self.device)),
+                           "fit_adam")
 
     # ------------------------------------------------------------------ target
     def set_target(self, gt_image: torch.Tensor):
@@ -127,7 +167,6 @@ class GaussianImageFitter:
             first = self.gt_hwc is None
             self.gt_hwc = torch.empty(self.H, self.W, 3, dtype=gt_image.dtype, device=self.device)
             self._graph = None
-            self._eager_left = max(self._eager_left, 0)
             self.gt_hwc.copy_(gt_image, non_blocking=True)
             self._bind()
             if first:
@@ -142,12 +181,12 @@ class GaussianImageFitter:
                    "fit_forward_backward")
         if self.grad_hook is not None:
             self.grad_hook(self)
-        _lib.check(self.lib.gi2d_fit_adam(C.byref(self.params), C.byref(self.buffers), st), "fit_adam")
 
     def train_iter(self):
         """One fit iteration (gaussianimage_covariance.py:249-259), asynchronous."""
         if self.gt_hwc is None:
             raise RuntimeError("set_target() first")
+        self._dirty = True
         with torch.cuda.device(self.device):
             if not self.use_graph or self._eager_left > 0:
                 # the first step after (re)allocation runs eagerly: it loads the kernels (CUDA lazy
@@ -156,6 +195,7 @@ class GaussianImageFitter:
                 self._enqueue_step()
                 return
             if self._graph is None:
+                self._bind()
                 self._graph = torch.cuda.CUDAGraph()
                 s = torch.cuda.Stream(device=self.device)
                 s.wait_stream(torch.cuda.current_stream(self.device))
@@ -171,12 +211,14 @@ class GaussianImageFitter:
 
     # ------------------------------------------------------------------ render / metrics
     def forward(self) -> dict:
-        """The model's forward (gaussianimage_covariance.py:187-218): {'render': [1,3,H,W] clamped}."""
+        """The model's forward (gaussianimage_covariance.py:187-218): {'render': [1,3,H,W] clamped}.
+        A pending optimiser step is applied by the same launch before projecting."""
         with torch.cuda.device(self.device):
             self._bind(out_img=self.render_chw.data_ptr())
             _lib.check(self.lib.gi2d_fit_forward_backward(C.byref(self.params), C.byref(self.buffers), 0,
                                                           _stream(self.device)), "fit_forward (render)")
             self._bind(out_img=None)
+        self._dirty = False
         return {"render": self.render_chw.view(1, 3, self.H, self.W)}
 
     __call__ = forward
@@ -185,11 +227,10 @@ class GaussianImageFitter:
         """Synchronises.  mse/psnr refer to the render of the LAST train_iter (before its Adam update),
         like the reference's per-iteration psnr (gaussianimage_covariance.py:256-257)."""
         s = self.stats_buf.cpu()
-        band_rows = self.tile_rows[1] - self.tile_rows[0]
         sse = float(s[STAT_SSE:STAT_SSE + STAT_SSE_SLOTS].sum())
         mse = sse / (3.0 * self.H * self.W)
         return {"step": int(s[STAT_STEP]), "num_intersects": int(s[STAT_ISECTS]), "overflow": bool(s[STAT_OVERFLOW]),
-                "lr": float(s[STAT_LR]), "sse": sse, "mse": mse, "band_rows": band_rows,
+                "lr": float(s[STAT_LR]), "sse": sse, "mse": mse,
                 "psnr": 10 * math.log10(1.0 / mse) if mse > 0 else float("inf")}
 
     def psnr(self) -> float:
@@ -208,7 +249,7 @@ class GaussianImageFitter:
 
     def ensure_capacity(self) -> bool:
         """Host check of the overflow flag; grows the intersection buffers when it tripped.
-        Returns True when a regrow happened (the overflowing step was skipped by the Adam kernel)."""
+        Returns True when a regrow happened (the overflowing step's gradient is dropped, not applied)."""
         st = self.stats()
         if not st["overflow"]:
             return False
@@ -227,9 +268,9 @@ class GaussianImageFitter:
 
     def _replace(self, xyz, cov, rgb, bound, m, v):
         step = self.stats()["step"]
-        self._xyz, self._cov2d, self._features_dc, self.cholesky_bound = (
+        self._t_xyz, self._t_cov2d, self._t_f_dc, self.cholesky_bound = (
             t.contiguous() for t in (xyz, cov, rgb, bound))
-        self.exp_avg, self.exp_avg_sq = m, v
+        self._t_m, self._t_v = m, v
         self._step0 = step
         self._alloc_state(zero_moments=False)
         self.reset_stats(step)
@@ -237,7 +278,7 @@ class GaussianImageFitter:
     def non_semi_definite_prune(self):
         """gaussianimage_covariance.py:354-371: drop Gaussians whose covariance is not positive definite
         (parameters, Adam moments and SLV bounds are masked together)."""
-        n_bad, valid = self.check_non_semi_definite()
+        n_bad, valid = self.check_non_semi_definite()      # (flushes a pending step first)
         if n_bad and self.cur_num_points - n_bad > 0:
             m = {k: t[valid].contiguous() for k, t in self.exp_avg.items()}
             v = {k: t[valid].contiguous() for k, t in self.exp_avg_sq.items()}

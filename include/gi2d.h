@@ -190,7 +190,7 @@ typedef struct gi2d_fit_params {
 #define GI2D_STAT_ISECTS 1      /* num_intersects of the last forward */
 #define GI2D_STAT_OVERFLOW 2    /* != 0: num_intersects exceeded isect_capacity (step skipped) */
 #define GI2D_STAT_LR 3          /* lr used by the last Adam step */
-#define GI2D_STAT_SSE 8         /* 64 partial sums of squared error of the clamped render */
+#define GI2D_STAT_SSE 16        /* 64 partial sums of squared error of the clamped render */
 #define GI2D_STAT_SSE_SLOTS 64
 #define GI2D_STAT_COUNT (GI2D_STAT_SSE + GI2D_STAT_SSE_SLOTS)
 
@@ -226,12 +226,15 @@ int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward);
 /* Zero the stats block (and set the step counter): call once before the first step. */
 int gi2d_fit_reset(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int step, gi2d_stream_t stream);
 
-/* project + bin + rasterize; with_backward != 0 also computes the L2 loss gradient and the
- * rasterize backward into b->grads and advances the step counter. */
+/* One step: [Adam of the previous step, if its gradient is still pending] + project + bin + rasterize.
+ * with_backward != 0 also computes the L2 loss gradient and the rasterize backward into b->grads,
+ * advances the step counter and leaves that gradient PENDING: projection backward + Adam are folded
+ * into the first kernel of the next call (same per-Gaussian thread, no extra launch).  A multi-GPU
+ * caller all-reduces b->grads between two calls.  Call gi2d_fit_adam to apply a pending gradient now. */
 int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fit_buffers *b,
                               int with_backward, gi2d_stream_t stream);
-/* projection backward + Adam on xyz/cov/rgb from b->grads.  Separate from the call above so a
- * multi-GPU caller can all-reduce b->grads (and the SSE) in between. */
+/* Flush: projection backward + Adam on xyz/cov/rgb from a pending b->grads (no-op when nothing is
+ * pending).  Needed before the host reads or edits parameters, and after the last step. */
 int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, gi2d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
