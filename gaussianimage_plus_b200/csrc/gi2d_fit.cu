@@ -46,6 +46,9 @@ constexpr int kRasterThreads = 256;
 constexpr int kRasterWarps = kRasterThreads / 32;
 
 // private slots of the stats block (beyond the public GI2D_STAT_* ones)
+constexpr int kPass1ChunkBits = 11;               // the second pass works on chunks of 2048 keys
+constexpr int kPass1Bits = 9;                     // and up to 9 more tile bits
+constexpr int kPass1Radix = 1 << kPass1Bits;
 constexpr int kStatB1Pow = 4;  // beta1^step
 constexpr int kStatB2Pow = 5;  // beta2^step
 constexpr int kStatStepSize = 6;  // lr / (1 - beta1^step)   of the step in flight
@@ -67,11 +70,24 @@ Plan make_plan(const gi2d_fit_params &p) {
     int tb = 1;
     while ((1 << tb) < tiles) ++tb;
     pl.tile_bits = tb;
-    pl.bits0 = tb < kMaxDigitBits ? tb : kMaxDigitBits;
-    pl.extra_passes = (tb - pl.bits0 + 7) / 8;
-    // keep the count matrix (nblocks x 2^bits0) scannable by one CTA: <= ~1184 CTAs
-    int gpb = kScatterWarps * 16;
-    while ((long long)gpb * 1184 < p.num_points) gpb *= 2;
+    if (tb <= kMaxDigitBits) {
+        pl.bits0 = tb;          // one pass: digit == tile id
+        pl.extra_passes = 0;
+    } else if (tb <= kMaxDigitBits + kPass1Bits) {
+        // two passes: give the second (chunked, perfectly balanced, 512-bin) pass as many bits as it can
+        // take; the first pass then has a SMALL digit, so every per-CTA cost that scales with the number
+        // of bins (histogram zeroing, offset tables, the count matrix) shrinks with it
+        pl.bits0 = tb - kPass1Bits;
+        pl.extra_passes = 1;
+    } else {
+        pl.bits0 = kMaxDigitBits;  // > 2^20 tiles: generic 8-bit passes over the remaining bits
+        pl.extra_passes = (tb - pl.bits0 + 7) / 8;
+    }
+    // keep the count matrix (nblocks x 2^bits0 ints) around 10 MB
+    constexpr int gpw = 16;  // Gaussians per warp of K3: measured best of {8,16,32,64} at 768x512 / 5000
+    const long long max_rows = 1184LL * (2048 >> pl.bits0 > 0 ? (2048 >> pl.bits0) : 1);
+    int gpb = kScatterWarps * gpw;
+    while ((long long)gpb * max_rows < p.num_points) gpb *= 2;
     pl.gpb = gpb;
     pl.nblocks = p.num_points > 0 ? cdiv(p.num_points, gpb) : 1;
     return pl;
@@ -86,6 +102,8 @@ struct Workspace {
     int32_t *n_isect;     // [1] device copy of num_intersects (clamped to capacity)
     float4 *records;      // [capacity][2] projected record of every intersection, sorted order
     uint64_t *keys_tmp;   // [capacity] ping-pong buffer for multi-pass sorts
+    int32_t *counts1;     // [capacity/2048][256] second-pass histogram (kept zero between iterations)
+    int32_t *totals1;     // [256]
     void *radix_ws;
     size_t radix_ws_bytes;
     size_t total;
@@ -102,10 +120,15 @@ Workspace carve(const gi2d_fit_params &p, const Plan &pl, void *base) {
     w.n_isect = (int32_t *)(c + off);     off += 256;
     w.records = (float4 *)(c + off);      off += align_up((size_t)p.isect_capacity * 32);
     w.keys_tmp = nullptr;
+    w.counts1 = nullptr;
+    w.totals1 = nullptr;
     w.radix_ws = nullptr;
     w.radix_ws_bytes = 0;
     if (pl.extra_passes > 0) {
         w.keys_tmp = (uint64_t *)(c + off);  off += align_up((size_t)p.isect_capacity * 8);
+        w.counts1 = (int32_t *)(c + off);
+        off += align_up((size_t)cdiv(p.isect_capacity, 1 << kPass1ChunkBits) * kPass1Radix * 4);
+        w.totals1 = (int32_t *)(c + off);    off += align_up(kPass1Radix * 4);
         w.radix_ws = (void *)(c + off);
         w.radix_ws_bytes = radix_pass_workspace_size(p.isect_capacity);
         off += align_up(w.radix_ws_bytes);
@@ -257,7 +280,8 @@ constexpr int kScanMaxRows = 16;  // rows per segment held in registers per trip
 
 __global__ void __launch_bounds__(kScanThreads)
 fit_scan_kernel(gi2d_fit_params p, int with_backward, double *__restrict__ stats, int nblocks, int D,
-                int32_t *__restrict__ counts, int32_t *__restrict__ totals) {
+                int32_t *__restrict__ counts, int32_t *__restrict__ totals, const int32_t *__restrict__ n_items,
+                int items_per_row) {
     __shared__ int s_seg[kScanSegs][kScanCols];
     pdl_launch_dependents();
     pdl_wait();
@@ -265,8 +289,12 @@ fit_scan_kernel(gi2d_fit_params p, int with_backward, double *__restrict__ stats
     // SSE partials and the overflow flag, and -- for a training step -- advance the step counter, the
     // bias-correction powers and the StepLR schedule.  torch evaluates beta^t and gamma^floor((t-1)/size)
     // in double precision as well.  The Adam that uses them runs inside the NEXT K1 (or gi2d_fit_adam).
-    if (blockIdx.x == 0 && threadIdx.x < GI2D_STAT_SSE_SLOTS) stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // (with_backward < 0: this launch scans the second pass' matrix and does no bookkeeping; its row count
+    //  is the number of 2048-key chunks actually in use, known only on the device)
+    if (n_items) nblocks = min(nblocks, (*n_items + items_per_row - 1) / items_per_row);
+    if (with_backward >= 0 && blockIdx.x == 0 && threadIdx.x < GI2D_STAT_SSE_SLOTS)
+        stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
+    if (with_backward >= 0 && blockIdx.x == 0 && threadIdx.x == 0) {
         stats[GI2D_STAT_OVERFLOW] = 0.0;
         stats[kStatPending] = with_backward ? 1.0 : 0.0;
         if (with_backward) {
@@ -394,7 +422,7 @@ fit_scatter_kernel(int num_points, int gpb, int bits0, int tiles_x, int num_tile
                    const int32_t *__restrict__ totals, uint64_t *__restrict__ keys_out,
                    const float4 *__restrict__ proj, float4 *__restrict__ records,
                    int32_t *__restrict__ tile_bins, int32_t *__restrict__ n_isect,
-                   double *__restrict__ stats) {
+                   double *__restrict__ stats, int32_t *__restrict__ counts1, int bits1) {
     extern __shared__ int s_dyn[];  // [kScatterWarps][D] per-warp counters, then [D] digit bases
     __shared__ int s_warp[kScatterWarps];
     const int D = 1 << bits0;
@@ -471,6 +499,10 @@ fit_scatter_kernel(int num_points, int gpb, int bits0, int tiles_x, int num_tile
             const int pos = old + __popc(peers & lt_mask);
             if (pos < capacity) {
                 keys_out[pos] = ((uint64_t)(uint32_t)tile << 32) | (uint32_t)g;
+                // second pass ahead: its per-chunk digit histogram is accumulated right here
+                if (counts1)
+                    atomicAdd(counts1 + (size_t)(pos >> kPass1ChunkBits) * kPass1Radix +
+                                  ((tile >> bits0) & ((1 << bits1) - 1)), 1);
                 if (records) {
                     records[2 * (size_t)pos] = __ldg(proj + 2 * g);
                     records[2 * (size_t)pos + 1] = __ldg(proj + 2 * g + 1);
@@ -489,6 +521,109 @@ fit_gather_records_kernel(int capacity, const int32_t *__restrict__ n_dev, const
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const int g = (int)(uint32_t)keys[i];
+    records[2 * (size_t)i] = __ldg(proj + 2 * g);
+    records[2 * (size_t)i + 1] = __ldg(proj + 2 * g + 1);
+}
+
+// ---- second pass for images with more than 2048 tiles (up to 2^19): stable scatter by the high
+// tile bits.  Chunk c = keys [2048 c, 2048 c + 2048) of the pass-0 output; its digit histogram was
+// accumulated by K3 (counts1[c][d]), turned into exclusive per-chunk offsets + totals by a second
+// launch of fit_scan_kernel.  Ranking inside the chunk: warp-striped rounds of 32 consecutive keys,
+// match_any, per-warp digit counters, exclusive scan across warps (same scheme as gi2d_binning.cu).
+__global__ void __launch_bounds__(256)
+fit_scatter1_kernel(int capacity, const int32_t *__restrict__ n_dev, const uint64_t *__restrict__ keys_in,
+                    uint64_t *__restrict__ keys_out, int shift, int bits, const int32_t *__restrict__ counts1,
+                    const int32_t *__restrict__ totals1) {
+    constexpr int kWarps = 8, kItems = 8;
+    __shared__ int s_cnt[kWarps][kPass1Radix];
+    __shared__ int s_base[kPass1Radix];
+    __shared__ int s_warp[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(capacity, *n_dev);
+    if (blockIdx.x * (1 << kPass1ChunkBits) >= n) return;  // (whole CTA)
+    for (int i = tid; i < kWarps * kPass1Radix; i += 256) (&s_cnt[0][0])[i] = 0;
+    {   // exclusive scan of the digit totals (2 per thread) + this chunk's exclusive offsets
+        static_assert(kPass1Radix == 512, "two digits per thread");
+        const int v0 = __ldcg(totals1 + 2 * tid), v1 = __ldcg(totals1 + 2 * tid + 1);
+        const int incl = block_scan_inclusive<256>(v0 + v1, s_warp, nullptr);
+        const int32_t *off = counts1 + (size_t)blockIdx.x * kPass1Radix;
+        s_base[2 * tid] = incl - v0 - v1 + __ldcg(off + 2 * tid);
+        s_base[2 * tid + 1] = incl - v1 + __ldcg(off + 2 * tid + 1);
+    }
+    __syncthreads();
+    const int wbase = blockIdx.x * (1 << kPass1ChunkBits) + warp * (kItems * 32);
+    uint64_t key[kItems];
+    int rank[kItems], dig[kItems];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int dmask = (1 << bits) - 1;
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+        const int i = wbase + r * 32 + lane;
+        const bool valid = i < n;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        rank[r] = 0;
+        dig[r] = 0;
+        key[r] = 0;
+        if (valid) {
+            key[r] = keys_in[i];
+            const int d = (int)(key[r] >> shift) & dmask;
+            dig[r] = d;
+            const unsigned peers = __match_any_sync(act, d);
+            const int leader = __ffs(peers) - 1;
+            int old = 0;
+            if (lane == leader) {
+                old = s_cnt[warp][d];
+                s_cnt[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(peers, old, leader);
+            rank[r] = old + __popc(peers & lt_mask);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int d = tid; d < kPass1Radix; d += 256) {
+        int run = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const int c = s_cnt[w][d];
+            s_cnt[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+        const int i = wbase + r * 32 + lane;
+        if (i < n) keys_out[s_base[dig[r]] + s_cnt[warp][dig[r]] + rank[r]] = key[r];
+    }
+}
+
+// After the last pass: tile ranges from the key boundaries (forward.cu:211-233; tile_bins was zeroed by
+// a memset node), the 32-B records gathered into sorted order, and the second-pass histogram handed
+// back zeroed for the next iteration.
+__global__ void __launch_bounds__(256)
+fit_finalize_kernel(int capacity, const int32_t *__restrict__ n_dev, const uint64_t *__restrict__ keys,
+                    const float4 *__restrict__ proj, float4 *__restrict__ records,
+                    int32_t *__restrict__ tile_bins, int num_tiles, int32_t *__restrict__ counts1) {
+    const int n = min(capacity, *n_dev);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int used = ((n + (1 << kPass1ChunkBits) - 1) >> kPass1ChunkBits) * kPass1Radix;
+    if (i < used) counts1[i] = 0;
+    if (i >= n) return;
+    const uint64_t key = keys[i];
+    const int cur = (int)(key >> 32);
+    if (cur < num_tiles) {
+        if (i == 0) tile_bins[2 * cur] = 0;
+        if (i == n - 1) tile_bins[2 * cur + 1] = n;
+    }
+    if (i > 0) {
+        const int prev = (int)(keys[i - 1] >> 32);
+        if (prev != cur) {
+            if (prev < num_tiles) tile_bins[2 * prev + 1] = i;
+            if (cur < num_tiles) tile_bins[2 * cur] = i;
+        }
+    }
+    const int g = (int)(uint32_t)key;
     records[2 * (size_t)i] = __ldg(proj + 2 * g);
     records[2 * (size_t)i + 1] = __ldg(proj + 2 * g + 1);
 }
@@ -677,16 +812,29 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
         w.boxes, w.counts, b->stats, with_backward);
     if (mk) mk->mark(st);
     launch_pdl(fit_scan_kernel, dim3(cdiv(D, kScanCols)), dim3(kScanThreads), 0, st, *p, with_backward, b->stats,
-               pl.nblocks, D, w.counts, w.totals);
+               pl.nblocks, D, w.counts, w.totals, (const int32_t *)nullptr, 1);
     if (mk) mk->mark(st);
     // pass 0 lands in sorted_keys when the number of remaining passes is even
     uint64_t *dst0 = (pl.extra_passes % 2 == 0) ? b->sorted_keys : w.keys_tmp;
     const size_t scatter_smem = (size_t)(kScatterWarps + 1) * D * sizeof(int);  // <= 40 KiB
+    const bool fast2 = pl.extra_passes == 1;  // <= 2^19 tiles: streamlined second pass
+    const int bits1 = pl.tile_bits - pl.bits0;
     launch_pdl(fit_scatter_kernel, dim3(pl.nblocks), dim3(kScatterThreads), scatter_smem, st,
         p->num_points, pl.gpb, pl.bits0, p->tiles_x, num_tiles, single ? 1 : 0, p->isect_capacity, w.boxes,
         w.counts, w.totals, dst0, (const float4 *)b->proj, single ? w.records : nullptr, b->tile_bins, w.n_isect,
-        b->stats);
-    if (!single) {
+        b->stats, fast2 ? w.counts1 : nullptr, bits1);
+    if (fast2) {
+        const int chunks = cdiv(p->isect_capacity, 1 << kPass1ChunkBits);
+        fit_scan_kernel<<<cdiv(kPass1Radix, kScanCols), kScanThreads, 0, st>>>(
+            *p, -1, b->stats, chunks, kPass1Radix, w.counts1, w.totals1, w.n_isect, 1 << kPass1ChunkBits);
+        fit_scatter1_kernel<<<chunks, 256, 0, st>>>(p->isect_capacity, w.n_isect, dst0, b->sorted_keys,
+                                                    32 + pl.bits0, bits1, w.counts1, w.totals1);
+        cudaMemsetAsync(b->tile_bins, 0, (size_t)num_tiles * 2 * sizeof(int32_t), st);
+        const int fin = max(p->isect_capacity, chunks * kPass1Radix);
+        fit_finalize_kernel<<<cdiv(fin, 256), 256, 0, st>>>(p->isect_capacity, w.n_isect, b->sorted_keys,
+                                                            (const float4 *)b->proj, w.records, b->tile_bins,
+                                                            num_tiles, w.counts1);
+    } else if (!single) {
         uint64_t *src = dst0;
         for (int e = 0; e < pl.extra_passes; ++e) {
             uint64_t *dst = (src == b->sorted_keys) ? w.keys_tmp : b->sorted_keys;
@@ -743,7 +891,9 @@ extern "C" int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward
     if (!p) return 0;
     const Plan pl = make_plan(*p);
     int n = 4;  // project, scan, scatter, raster
-    if (pl.extra_passes > 0) {
+    if (pl.extra_passes == 1) {
+        n += 3;  // second-pass scan, scatter, finalize (tile ranges + record gather); the memset is no kernel
+    } else if (pl.extra_passes > 1) {
         const int nb = cdiv(p->isect_capacity, 2048);
         const int cumsum_nb = cdiv(nb * 256, 2048);
         n += pl.extra_passes * (2 + (cumsum_nb > 1 ? 3 : 1));  // hist + cumsum + scatter per pass

@@ -30,7 +30,8 @@ def make_fitter(N, H, W, seed, colors="rand", cov_scale=1.0, use_graph=False, ke
 
 
 @pytest.mark.parametrize("N,H,W,scale", [(400, 96, 128, 1.0), (5000, 512, 768, 1.0), (5000, 512, 768, 4.0),
-                                          (20000, 1356, 2040, 1.0), (3000, 64, 64, 3.0)])
+                                          (20000, 1356, 2040, 1.0), (3000, 64, 64, 3.0),
+                                          (1000000, 8192, 8192, 1.0)])   # BASELINE configs[4], 2^18 tiles
 def test_fit_binning_bit_exact(oracle, N, H, W, scale):
     """sorted (tile|gaussian) keys, tile ranges and num_intersects of the fused path == oracle
     (== the reference's cumsum + map + sort + gather + edges), including the multi-pass case
