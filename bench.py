@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kodak_5000")
     ap.add_argument("--mode", default="images", choices=["images", "tilerow"])
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="tilerow mode: fused peer-memory reduce-scatter+Adam+all-gather kernel, or NCCL all-reduce")
     ap.add_argument("--cov-scale", type=float, default=1.0, help=">1 emulates a mid-training state")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -193,7 +195,7 @@ def main():
 
         part = TileRowPartition((H + 15) // 16, world)
         tile_rows = part.band(rank)
-        grad_hook = part.make_grad_hook()
+        grad_hook = part.make_grad_hook() if args.exchange == "nccl" else None
     seed = 3047 if args.mode == "tilerow" else 3047 + rank  # image sets: a different image per rank
     xyz, cov, bound, rgb = synth.init_covariance_model(N, H, W, seed=3047, colors="zeros", cov_scale=args.cov_scale)
     # the target as an image file would hold it: 8-bit RGB; every arm (ours, CPU port, reference CUDA
@@ -202,9 +204,15 @@ def main():
 
     gt_u8 = np.round(synth.target_image(H, W, seed=seed) * 255.0).astype(np.uint8)
     gt = (gt_u8.astype(np.float32) / np.float32(255.0)).astype(np.float32)
-    fit = GaussianImageFitter(N, H, W, device=dev, use_graph=(grad_hook is None), tile_rows=tile_rows, grad_hook=grad_hook)
+    tilerow = args.mode == "tilerow" and world > 1
+    fit = GaussianImageFitter(N, H, W, device=dev, use_graph=not tilerow, tile_rows=tile_rows, grad_hook=grad_hook)
     for dst, src in ((fit._xyz, xyz), (fit._cov2d, cov), (fit.cholesky_bound, bound), (fit._features_dc, rgb)):
         dst.copy_(torch.from_numpy(src))
+    exchange = None
+    if tilerow and args.exchange == "fused":
+        from gaussianimage_plus_b200.parallel import FusedTileRowExchange
+
+        exchange = FusedTileRowExchange(fit)
     gt_pinned = torch.from_numpy(gt).pin_memory()
     gt_u8_pinned = torch.from_numpy(gt_u8).pin_memory()
     fit.set_target(gt_pinned)
@@ -251,7 +259,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    stats = fit.stats()
+    stats = exchange.global_stats() if exchange is not None else fit.stats()
     units = K * (world if args.mode == "images" else 1)
     value = units / (total_ms * 1e-3)
 
@@ -361,7 +369,8 @@ def main():
                        "mode": args.mode, "cov_scale": args.cov_scale,
                        "l2": "flushed between timed steps (256 MiB fill); value_l2_warm = back-to-back replay",
                        "parallelism": "one image per GPU, no collective" if args.mode == "images"
-                       else "tile-row split + NCCL all-reduce of [N,8] gradients"},
+                       else ("tile-row split + NCCL all-reduce of [N,8] gradients" if args.exchange == "nccl" else
+                             "tile-row split + fused peer-memory reduce-scatter/Adam/all-gather kernel")},
             "value_l2_warm": (K * (world if args.mode == "images" else 1)) / (warm_ms * K * 1e-3),
             "ms_per_step_l2_warm": warm_ms,
             "ms_per_step_p50": step_ms[len(step_ms) // 2], "wall_s_timed_region": t_wall,

@@ -30,7 +30,7 @@ class FitParams(C.Structure):
         ("clip_coe", C.c_float), ("radius_clip", C.c_float),
         ("lr0", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("lr_step_size", C.c_int32), ("lr_gamma", C.c_float),
-        ("color_sigmoid", C.c_int32), ("loss_scale", C.c_float),
+        ("color_sigmoid", C.c_int32), ("loss_scale", C.c_float), ("external_optimizer", C.c_int32),
     ]
 
 
@@ -42,6 +42,7 @@ class FitBuffers(C.Structure):
         ("gt_hwc", _P), ("out_img", _P),
         ("grads", _P), ("proj", _P), ("sorted_keys", _P), ("tile_bins", _P), ("stats", _P),
         ("workspace", _P), ("workspace_bytes", _SZ), ("gt_u8_hwc", _P),
+        ("best", _P), ("err_map", _P),
     ]
 
 
@@ -70,6 +71,8 @@ SIGNATURES = {
     "gi2d_fit_launch_count": (_I, [C.POINTER(FitParams), _I]),
     "gi2d_fit_profile": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), C.POINTER(C.c_float), _P]),
     "gi2d_measure_fp32_peak": (_I, [C.POINTER(C.c_float), _P]),
+    "gi2d_fit_exchange_adam": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _I, C.POINTER(_P),
+                                   C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P]),
     "gi2d_fit_reset": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _P]),
 }
 

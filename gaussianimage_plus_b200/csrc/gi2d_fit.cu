@@ -56,6 +56,37 @@ constexpr int kStatBc2Sqrt = 7;   // sqrt(1 - beta2^step)
 constexpr int kStatPending = 8;   // != 0: grads of the last step have not been applied yet (Adam is folded
                                   // into the NEXT step's projection kernel, or flushed by gi2d_fit_adam)
 
+constexpr int kStatNonPsdAcc = 12;  // accumulator behind GI2D_STAT_NON_PSD (moved + zeroed by the clear kernel)
+
+// Squared error of the last training step: the 64 partials summed by ONE warp in a fixed order, so that
+// every CTA of the optimiser kernel and the bookkeeping thread take the same best-so-far decision.
+__device__ __forceinline__ double sse_total_warp(const double *__restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    double v = stats[GI2D_STAT_SSE + lane] + stats[GI2D_STAT_SSE + 32 + lane];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// Was the step whose gradient is pending a new best (train.py:132: `if best_psnr < psnr`)?  Warp 0 of the
+// CTA evaluates, everybody reads s_flag after the caller's __syncthreads().
+__device__ __forceinline__ void best_flag_warp0(const double *__restrict__ stats, bool candidate, int *s_flag) {
+    if (threadIdx.x < 32) {
+        const double tot = sse_total_warp(stats);
+        if (threadIdx.x == 0) *s_flag = (candidate && tot < stats[GI2D_STAT_BEST_SSE]) ? 1 : 0;
+    }
+}
+
+// Bookkeeping half of the same decision, by warp 0 of ONE CTA after every optimiser thread has read it.
+__device__ __forceinline__ void best_commit_warp0(double *__restrict__ stats) {
+    const double tot = sse_total_warp(stats);
+    if ((threadIdx.x & 31) == 0 && stats[kStatPending] != 0.0 && stats[GI2D_STAT_OVERFLOW] == 0.0 &&
+        tot < stats[GI2D_STAT_BEST_SSE]) {
+        stats[GI2D_STAT_BEST_SSE] = tot;
+        stats[GI2D_STAT_BEST_STEP] = stats[GI2D_STAT_STEP];
+    }
+}
+
 struct Plan {
     int tile_bits;     // bits needed for a tile id
     int bits0;         // digit width of the in-kernel pass
@@ -212,8 +243,10 @@ __device__ __forceinline__ void adam_update_gaussian(const gi2d_fit_params &p, c
 __global__ void __launch_bounds__(kProjThreads)
 fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, AdamPtrs a, const float *__restrict__ cov_bound,
                    float4 *__restrict__ proj, float4 *__restrict__ grads, ushort4 *__restrict__ boxes,
-                   int32_t *__restrict__ counts, const double *__restrict__ stats, int with_backward) {
+                   int32_t *__restrict__ counts, const double *__restrict__ stats, int with_backward,
+                   float4 *__restrict__ best) {
     extern __shared__ int s_hist[];
+    __shared__ int s_best;
     const int D = 1 << bits0;
     const int mask = D - 1;
     pdl_launch_dependents();
@@ -221,7 +254,9 @@ fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, AdamPtrs a, const floa
     pdl_wait();  // the previous step's rasterizer wrote grads (and read proj)
     const bool pending = a.m_xyz != nullptr && stats[kStatPending] != 0.0;
     const bool veto = stats[GI2D_STAT_OVERFLOW] != 0.0;  // that step overflowed: the host re-runs it
+    best_flag_warp0(stats, best != nullptr && pending && !veto, &s_best);
     __syncthreads();
+    const bool snapshot = s_best != 0;
     const int g0 = blockIdx.x * gpb;
     const int g1 = min(p.num_points, g0 + gpb);
     for (int g = g0 + threadIdx.x; g < g1; g += kProjThreads) {
@@ -230,6 +265,10 @@ fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, AdamPtrs a, const floa
         if (pending) {
             adam_update_gaussian(p, a, g, proj[2 * g], proj[2 * g + 1], grads[2 * g], grads[2 * g + 1], stats, veto,
                                  m, c, q);
+            if (snapshot) {  // the state dict right after optimizer.step() of the best iteration (train.py:132-137)
+                best[2 * g] = make_float4(m.x, m.y, c[0], c[1]);
+                best[2 * g + 1] = make_float4(c[2], q[0], q[1], q[2]);
+            }
         } else {
             m = reinterpret_cast<const float2 *>(a.xyz)[g];
 #pragma unroll
@@ -292,11 +331,16 @@ fit_scan_kernel(gi2d_fit_params p, int with_backward, double *__restrict__ stats
     // (with_backward < 0: this launch scans the second pass' matrix and does no bookkeeping; its row count
     //  is the number of 2048-key chunks actually in use, known only on the device)
     if (n_items) nblocks = min(nblocks, (*n_items + items_per_row - 1) / items_per_row);
-    if (with_backward >= 0 && blockIdx.x == 0 && threadIdx.x < GI2D_STAT_SSE_SLOTS)
+    if (with_backward >= 0 && blockIdx.x == 0 && threadIdx.x < 32) {
+        best_commit_warp0(stats);  // (the optimiser threads of K1 took the same decision for their snapshot)
+        __syncwarp();
         stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
+        stats[GI2D_STAT_SSE + 32 + threadIdx.x] = 0.0;
+        __syncwarp();
+    }
     if (with_backward >= 0 && blockIdx.x == 0 && threadIdx.x == 0) {
         stats[GI2D_STAT_OVERFLOW] = 0.0;
-        stats[kStatPending] = with_backward ? 1.0 : 0.0;
+        stats[kStatPending] = (with_backward && !p.external_optimizer) ? 1.0 : 0.0;
         if (with_backward) {
             const double step = stats[GI2D_STAT_STEP] + 1.0;
             stats[GI2D_STAT_STEP] = step;
@@ -636,7 +680,8 @@ __global__ void __launch_bounds__(kRasterThreads, kMode == RasterMode::Fit ? 4 :
 fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
                   const int32_t *__restrict__ tile_bins, const float4 *__restrict__ records,
                   const float *__restrict__ gt, const uint8_t *__restrict__ gt_u8,
-                  float *__restrict__ out_img, float *__restrict__ grads, double *__restrict__ stats) {
+                  float *__restrict__ out_img, float *__restrict__ grads, double *__restrict__ stats,
+                  float *__restrict__ err_map) {
     __shared__ TileRecords sg;
     __shared__ TileGrad tg;
     __shared__ int s_ids[kMaxPerTile];
@@ -710,6 +755,8 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
             out_img[3 * pix + 1] = g;
             out_img[3 * pix + 2] = b;
         }
+        // torch.abs(render - gt).sum(dim=1) of train.py:87, channel order r,g,b
+        if (err_map) err_map[pix] = __fadd_rn(__fadd_rn(fabsf(dr), fabsf(dg)), fabsf(db));
     }
     const int gi = grad_index(lx, ly);
     tg.v[0][gi] = vr;
@@ -737,28 +784,106 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
 // parameters, renders, or all the steps are done).  In the steady state it is never launched: the
 // next step's K1 does the same work.
 __global__ void __launch_bounds__(256)
-fit_adam_kernel(gi2d_fit_params p, AdamPtrs a, const float4 *__restrict__ proj,
-                const float4 *__restrict__ grads, const double *__restrict__ stats) {
+fit_adam_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bound, const float4 *__restrict__ proj,
+                const float4 *__restrict__ grads, double *__restrict__ stats, float4 *__restrict__ best) {
+    __shared__ int s_best;
     pdl_launch_dependents();
     pdl_wait();
     const int g = blockIdx.x * 256 + threadIdx.x;
     const bool pending = stats[kStatPending] != 0.0;
     const bool veto = stats[GI2D_STAT_OVERFLOW] != 0.0;
-    if (g < p.num_points && pending) {
-        float2 x;
-        float c[3], q[3];
-        adam_update_gaussian(p, a, g, proj[2 * g], proj[2 * g + 1], grads[2 * g], grads[2 * g + 1], stats, veto, x, c, q);
+    best_flag_warp0(stats, best != nullptr && pending && !veto, &s_best);
+    __syncthreads();
+    bool bad = false;
+    if (g < p.num_points) {
+        float c[3];
+        if (pending) {
+            float2 x;
+            float q[3];
+            adam_update_gaussian(p, a, g, proj[2 * g], proj[2 * g + 1], grads[2 * g], grads[2 * g + 1], stats, veto,
+                                 x, c, q);
+            if (s_best) {
+                best[2 * g] = make_float4(x.x, x.y, c[0], c[1]);
+                best[2 * g + 1] = make_float4(c[2], q[0], q[1], q[2]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) c[k] = a.cov[3 * g + k];
+        }
+        // check_non_semi_definite (gaussianimage_covariance.py:373-382) on cov + bound, torch's op order
+        const float sx = __fadd_rn(c[0], cov_bound[3 * g]), sxy = __fadd_rn(c[1], cov_bound[3 * g + 1]);
+        const float sy = __fadd_rn(c[2], cov_bound[3 * g + 2]);
+        const float det = __fsub_rn(__fmul_rn(sx, sy), __fmul_rn(sxy, sxy));
+        bad = !((det > 0.f) && (sx > 0.f) && (sy > 0.f));
+    }
+    const int nbad = __syncthreads_count(bad);
+    if (threadIdx.x == 0 && nbad) atomicAdd(stats + kStatNonPsdAcc, (double)nbad);
+}
+
+// second half of the flush: only after EVERY CTA of fit_adam_kernel has read the flags may they change
+__global__ void fit_clear_pending_kernel(double *__restrict__ stats) {
+    best_commit_warp0(stats);
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        stats[kStatPending] = 0.0;
+        stats[GI2D_STAT_NON_PSD] = stats[kStatNonPsdAcc];
+        stats[kStatNonPsdAcc] = 0.0;
     }
 }
 
-// second half of the flush: only after EVERY CTA of fit_adam_kernel has read the flag may it be cleared
-__global__ void fit_clear_pending_kernel(double *__restrict__ stats) { stats[kStatPending] = 0.0; }
+// --------------------------------------------------------------------- multi-GPU exchange
+// Tile-row split of ONE image over `world` GPUs: every rank rasterized a band and holds
+// PARTIAL per-Gaussian gradients in its own grads[N,8].  Instead of "all-reduce, then a replicated
+// optimiser step", one kernel per rank does the exchange and the math together over NVLink peer
+// memory (symmetric allocations, raw peer pointers):
+//   reduce-scatter : the rank owns the Gaussians [g0,g1); for each it LOADS that row of every peer's
+//                    gradient buffer (P2P LDG.128) and sums them in rank order (same order on every
+//                    rank => the parameters stay bitwise identical everywhere);
+//   optimiser      : projection backward + Adam with the moments of the owned slice only (the
+//                    optimiser state is sharded: 1/world of the moment traffic per GPU);
+//   all-gather     : the 8 updated parameters are STORED into every rank's xyz / cov / rgb (P2P STG).
+// Bytes over NVLink per rank and step: (world-1)/world * N * (32 in + 32 out) -- versus
+// 2 (world-1)/world * N * 32 for a ring all-reduce, plus a full-size replicated Adam.
+// Cross-GPU ordering (peers finished their backward / their stores) is the caller's barrier on the
+// symmetric-memory signal pads before and after this launch.
+struct PeerPtrs {
+    const float4 *grads[8];
+    float *xyz[8], *cov[8], *rgb[8];
+};
+
+__global__ void __launch_bounds__(256)
+fit_exchange_adam_kernel(gi2d_fit_params p, AdamPtrs local, PeerPtrs peers, int rank, int world, int g0, int g1,
+                         const float4 *__restrict__ proj, const double *__restrict__ stats) {
+    const int g = g0 + blockIdx.x * 256 + threadIdx.x;
+    if (g >= g1) return;
+    const bool veto = stats[GI2D_STAT_OVERFLOW] != 0.0;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    for (int q = 0; q < world; ++q) {  // fixed order: identical sums on every rank
+        const float4 a0 = __ldcg(peers.grads[q] + 2 * g), a1 = __ldcg(peers.grads[q] + 2 * g + 1);
+        s0.x += a0.x; s0.y += a0.y; s0.z += a0.z; s0.w += a0.w;
+        s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
+    }
+    float2 x;
+    float c[3], col[3];
+    adam_update_gaussian(p, local, g, proj[2 * g], proj[2 * g + 1], s0, s1, stats, veto, x, c, col);
+    if (veto) return;
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) continue;  // the local copy was written by adam_update_gaussian
+        reinterpret_cast<float2 *>(peers.xyz[q])[g] = x;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            peers.cov[q][3 * g + k] = c[k];
+            peers.rgb[q][3 * g + k] = col[k];
+        }
+    }
+}
 
 __global__ void fit_reset_kernel(gi2d_fit_params p, double *stats, int step) {
     const int i = threadIdx.x;
     if (i >= GI2D_STAT_COUNT) return;
     double v = 0.0;
     if (i == GI2D_STAT_STEP) v = (double)step;
+    if (i == GI2D_STAT_BEST_SSE) v = __longlong_as_double(0x7ff0000000000000LL);  // +inf: nothing seen yet
     if (i == kStatB1Pow) v = pow((double)p.beta1, (double)step);
     if (i == kStatB2Pow) v = pow((double)p.beta2, (double)step);
     // lr the NEXT step will start from: lr0 * gamma^floor((step-1)/size) for step >= 1
@@ -809,7 +934,7 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     const AdamPtrs ap{b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
     launch_pdl(fit_project_kernel, dim3(pl.nblocks), dim3(kProjThreads), D * sizeof(int), st,
         *p, pl.gpb, pl.bits0, ap, b->cov_bound, (float4 *)b->proj, (float4 *)b->grads,
-        w.boxes, w.counts, b->stats, with_backward);
+        w.boxes, w.counts, b->stats, with_backward, (float4 *)b->best);
     if (mk) mk->mark(st);
     launch_pdl(fit_scan_kernel, dim3(cdiv(D, kScanCols)), dim3(kScanThreads), 0, st, *p, with_backward, b->stats,
                pl.nblocks, D, w.counts, w.totals, (const int32_t *)nullptr, 1);
@@ -857,10 +982,12 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
         dim3 grid(p->tiles_x, band);
         if (with_backward)
             launch_pdl(fit_raster_kernel<RasterMode::Fit>, grid, dim3(kRasterThreads), 0, st,
-                *p, b->sorted_keys, b->tile_bins, w.records, b->gt_hwc, b->gt_u8_hwc, b->out_img, b->grads, b->stats);
+                *p, b->sorted_keys, b->tile_bins, w.records, b->gt_hwc, b->gt_u8_hwc, b->out_img, b->grads, b->stats,
+                b->err_map);
         else
             launch_pdl(fit_raster_kernel<RasterMode::Render>, grid, dim3(kRasterThreads), 0, st,
-                *p, b->sorted_keys, b->tile_bins, w.records, nullptr, nullptr, b->out_img, nullptr, b->stats);
+                *p, b->sorted_keys, b->tile_bins, w.records, nullptr, nullptr, b->out_img, nullptr, b->stats,
+                nullptr);
     }
     if (mk) mk->mark(st);
     return check_launch("gi2d_fit_forward_backward");
@@ -919,13 +1046,14 @@ extern "C" int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b
     const int rc = validate(p, b);
     if (rc != GI2D_OK) return rc;
     if (p->num_points == 0) return GI2D_OK;
-    GI2D_REQUIRE(b->xyz && b->cov && b->rgb && b->m_xyz && b->v_xyz && b->m_cov && b->v_cov && b->m_rgb &&
-                     b->v_rgb && b->grads,
+    GI2D_REQUIRE(b->xyz && b->cov && b->cov_bound && b->rgb && b->m_xyz && b->v_xyz && b->m_cov && b->v_cov &&
+                     b->m_rgb && b->v_rgb && b->grads,
                  "null buffer");
     const AdamPtrs ap{b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
     launch_pdl(fit_adam_kernel, dim3(cdiv(p->num_points, 256)), dim3(256), 0, (cudaStream_t)stream, *p, ap,
-               (const float4 *)b->proj, (const float4 *)b->grads, b->stats);
-    fit_clear_pending_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(b->stats);
+               (const float *)b->cov_bound, (const float4 *)b->proj, (const float4 *)b->grads, b->stats,
+               (float4 *)b->best);
+    fit_clear_pending_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(b->stats);
     return check_launch(__func__);
 }
 
@@ -978,5 +1106,36 @@ extern "C" int gi2d_measure_fp32_peak(float *tflops_host, gi2d_stream_t stream) 
     cudaEventDestroy(e1);
     cudaFree(d);
     *tflops_host = best;
+    return check_launch(__func__);
+}
+
+// Fused reduce-scatter + optimiser + all-gather over peer memory (see fit_exchange_adam_kernel).
+// peer_* are HOST arrays of `world` device pointers (this rank's own buffer at index `rank`); the
+// caller guarantees, with a cross-GPU barrier on the stream before and after this call, that every
+// peer finished its backward before and sees the stores after.  p->external_optimizer must be 1.
+extern "C" int gi2d_fit_exchange_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int rank, int world,
+                                      const void *const *peer_grads, void *const *peer_xyz, void *const *peer_cov,
+                                      void *const *peer_rgb, gi2d_stream_t stream) {
+    const int rc = validate(p, b);
+    if (rc != GI2D_OK) return rc;
+    GI2D_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad rank/world (<= 8 GPUs of one box)");
+    GI2D_REQUIRE(p->external_optimizer, "set external_optimizer so that the step leaves its gradient to this call");
+    GI2D_REQUIRE(peer_grads && peer_xyz && peer_cov && peer_rgb, "null peer pointer table");
+    GI2D_REQUIRE(b->m_xyz && b->v_xyz && b->m_cov && b->v_cov && b->m_rgb && b->v_rgb, "null moment buffer");
+    if (p->num_points == 0) return GI2D_OK;
+    PeerPtrs pp{};
+    for (int q = 0; q < world; ++q) {
+        pp.grads[q] = (const float4 *)peer_grads[q];
+        pp.xyz[q] = (float *)peer_xyz[q];
+        pp.cov[q] = (float *)peer_cov[q];
+        pp.rgb[q] = (float *)peer_rgb[q];
+        GI2D_REQUIRE(pp.grads[q] && pp.xyz[q] && pp.cov[q] && pp.rgb[q], "null peer pointer");
+    }
+    const int per = cdiv(p->num_points, world);
+    const int g0 = min(p->num_points, rank * per), g1 = min(p->num_points, g0 + per);
+    if (g1 <= g0) return GI2D_OK;
+    const AdamPtrs ap{b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
+    fit_exchange_adam_kernel<<<cdiv(g1 - g0, 256), 256, 0, (cudaStream_t)stream>>>(
+        *p, ap, pp, rank, world, g0, g1, (const float4 *)b->proj, b->stats);
     return check_launch(__func__);
 }

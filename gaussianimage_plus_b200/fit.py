@@ -75,6 +75,7 @@ class GaussianImageFitter:
         self.grad_hook = grad_hook  # called right after the backward of every step (multi-GPU all-reduce)
         self._capacity_hint = isect_capacity
         self._dirty = False         # a gradient is pending on the device
+        self.external_optimizer = False  # True: grad_hook applies the gradients itself (parallel.FusedTileRowExchange)
         self.keep_render = False    # tests: also store the unclamped [H,W,3] render of every train_iter
         f = dict(dtype=torch.float32, device=self.device)
         # reference init, gaussianimage_covariance.py:52-66
@@ -117,7 +118,7 @@ class GaussianImageFitter:
         self.params = _lib.FitParams(
             n, self.W, self.H, self.tile_bounds[0], self.tile_bounds[1], self.tile_rows[0], self.tile_rows[1],
             self.isect_capacity, self.clip_coe, self.radius_clip, self.lr, 0.9, 0.999, 1e-15, 20000, 0.5,
-            int(self.color_norm), 2.0 / (3.0 * self.H * self.W))
+            int(self.color_norm), 2.0 / (3.0 * self.H * self.W), 1 if self.external_optimizer else 0)
         ws_bytes = self.lib.gi2d_fit_workspace_size(C.byref(self.params))
         self.workspace = torch.zeros(max(ws_bytes, 256), dtype=torch.uint8, device=self.device)
         self._graph = None
@@ -186,7 +187,7 @@ class GaussianImageFitter:
         """One fit iteration (gaussianimage_covariance.py:249-259), asynchronous."""
         if self.gt_hwc is None:
             raise RuntimeError("set_target() first")
-        self._dirty = True
+        self._dirty = not self.external_optimizer
         with torch.cuda.device(self.device):
             if not self.use_graph or self._eager_left > 0:
                 # the first step after (re)allocation runs eagerly: it loads the kernels (CUDA lazy

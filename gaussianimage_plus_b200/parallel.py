@@ -97,3 +97,83 @@ def allreduce_packed_gradients(v_xy, v_conic, v_colors, group=None):
     packed = torch.cat((v_xy, v_conic, v_colors), dim=1).contiguous()
     dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
     return packed[:, 0:2], packed[:, 2:5], packed[:, 5:8]
+
+
+class FusedTileRowExchange:
+    """Tile-row split with the exchange step fused into ONE kernel over NVLink peer memory.
+
+    Replaces `TileRowPartition.make_grad_hook()` (NCCL all-reduce of grads + replicated Adam) by
+    `gi2d_fit_exchange_adam`: reduce-scatter of the partial gradients by P2P loads, projection backward
+    + Adam on the owned 1/world slice (sharded optimiser state), all-gather of the updated parameters
+    by P2P stores.  The fitter's xyz / cov / rgb / grads are re-homed in symmetric memory
+    (torch.distributed._symmetric_memory: same allocation on every rank, peer pointers exchanged once);
+    the only per-step synchronisation is the signal-pad barrier before and after the kernel.
+    The squared-error partials are NOT exchanged per step: `stats()` all-reduces them when asked.
+    """
+
+    def __init__(self, fit, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+
+        self.fit, self.group = fit, group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise ValueError("peer-memory exchange is for the GPUs of one NVSwitch box (<= 8)")
+        name = self.group.group_name
+        symm_mem.enable_symm_mem_for_group(name)
+        fit.sync_params()
+        n = fit.cur_num_points
+        src = {"xyz": fit._t_xyz, "cov": fit._t_cov2d, "rgb": fit._t_f_dc, "grads": fit.grads}
+        self.tensors, self.handles, self.tables = {}, {}, {}
+        for key, t in src.items():
+            s = symm_mem.empty(*t.shape, dtype=torch.float32, device=fit.device)
+            s.copy_(t)
+            self.tensors[key] = s
+            self.handles[key] = symm_mem.rendezvous(s, name)
+            ptrs = [int(p) for p in self.handles[key].buffer_ptrs]
+            assert ptrs[self.rank] == s.data_ptr()
+            self.tables[key] = (C.c_void_p * self.world)(*ptrs)
+        fit._t_xyz, fit._t_cov2d, fit._t_f_dc = self.tensors["xyz"], self.tensors["cov"], self.tensors["rgb"]
+        fit.grads = self.tensors["grads"]
+        fit.external_optimizer = True
+        fit.params.external_optimizer = 1
+        fit.use_graph = False
+        fit._graph = None
+        fit._bind()
+        fit.grad_hook = self
+        self._lib, self._C = _lib, C
+        dist.barrier(self.group)
+        torch.cuda.synchronize(fit.device)
+
+    def __call__(self, fit):
+        import torch
+
+        h = self.handles["grads"]
+        h.barrier(channel=0)        # every peer has finished the backward of this step
+        st = self._C.c_void_p(torch.cuda.current_stream(fit.device).cuda_stream)
+        self._lib.check(fit.lib.gi2d_fit_exchange_adam(
+            self._C.byref(fit.params), self._C.byref(fit.buffers), self.rank, self.world, self.tables["grads"],
+            self.tables["xyz"], self.tables["cov"], self.tables["rgb"], st), "fit_exchange_adam")
+        h.barrier(channel=1)        # every peer's stores into my parameters have landed
+
+    def global_stats(self):
+        """fit.stats() with the squared error summed over the bands (one small all-reduce, on demand)."""
+        import math
+
+        import torch
+        import torch.distributed as dist
+
+        from .fit import STAT_SSE, STAT_SSE_SLOTS
+
+        st = self.fit.stats()
+        sse = torch.tensor([st["sse"]], dtype=torch.float64, device=self.fit.device)
+        dist.all_reduce(sse, group=self.group)
+        st["sse"] = float(sse.item())
+        st["mse"] = st["sse"] / (3.0 * self.fit.H * self.fit.W)
+        st["psnr"] = 10 * math.log10(1.0 / st["mse"]) if st["mse"] > 0 else float("inf")
+        return st

@@ -182,6 +182,8 @@ typedef struct gi2d_fit_params {
     float lr_gamma;
     int32_t color_sigmoid;      /* 1: colours = sigmoid(features) (the reference's color_norm) */
     float loss_scale;           /* dL/d(out) = loss_scale * (clamp(out) - gt); 2/(3*H*W) for mse */
+    int32_t external_optimizer; /* 1: a training step leaves b->grads alone (nothing pending); the caller applies
+                                   them with gi2d_fit_exchange_adam (multi-GPU tile-row split) */
 } gi2d_fit_params;
 
 /* stats layout (f64): the device-side step counter makes the step graph-replayable with no
@@ -190,6 +192,9 @@ typedef struct gi2d_fit_params {
 #define GI2D_STAT_ISECTS 1      /* num_intersects of the last forward */
 #define GI2D_STAT_OVERFLOW 2    /* != 0: num_intersects exceeded isect_capacity (step skipped) */
 #define GI2D_STAT_LR 3          /* lr used by the last Adam step */
+#define GI2D_STAT_BEST_SSE 9    /* smallest squared error of any training step so far (+inf before the first) */
+#define GI2D_STAT_BEST_STEP 10  /* the step (1-based) that achieved it; b->best holds the parameters AFTER its update */
+#define GI2D_STAT_NON_PSD 11    /* Gaussians whose covariance is not positive definite, counted by gi2d_fit_adam */
 #define GI2D_STAT_SSE 16        /* 64 partial sums of squared error of the clamped render */
 #define GI2D_STAT_SSE_SLOTS 64
 #define GI2D_STAT_COUNT (GI2D_STAT_SSE + GI2D_STAT_SSE_SLOTS)
@@ -216,6 +221,12 @@ typedef struct gi2d_fit_buffers {
     size_t workspace_bytes;
     const uint8_t *gt_u8_hwc; /* u8[H,W,3] target as stored (PNG bytes); used when gt_hwc is NULL: the
                                  kernel computes u8/255 exactly like torchvision's ToTensor (utils.py:21-27) */
+    float *best;    /* nullable f32[N,8] = xyz(2) cov(3) rgb(3): best-state snapshot.  train.py:132-137 deep-copies
+                       the state dict whenever the step's PSNR beats the best so far; here the kernel that applies
+                       a step's Adam update also stores the updated parameters when that step's squared error was
+                       a new minimum (GI2D_STAT_BEST_SSE / _STEP) -- no host round trip, no extra launch */
+    float *err_map; /* nullable f32[H,W]: a training step also writes the per-pixel L1 error of its clamped
+                       render, sum_c |clamp(out)-gt| (the `errors` map of train.py:87 that drives densification) */
 } gi2d_fit_buffers;
 
 size_t gi2d_fit_workspace_size(const gi2d_fit_params *p);
@@ -233,9 +244,20 @@ int gi2d_fit_reset(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int step
  * caller all-reduces b->grads between two calls.  Call gi2d_fit_adam to apply a pending gradient now. */
 int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fit_buffers *b,
                               int with_backward, gi2d_stream_t stream);
-/* Flush: projection backward + Adam on xyz/cov/rgb from a pending b->grads (no-op when nothing is
- * pending).  Needed before the host reads or edits parameters, and after the last step. */
+/* Flush: projection backward + Adam on xyz/cov/rgb from a pending b->grads (no update when nothing is
+ * pending).  Needed before the host reads or edits parameters, and after the last step.  Also counts the
+ * Gaussians whose covariance cov+cov_bound is not positive definite into GI2D_STAT_NON_PSD (the test of
+ * gaussianimage_covariance.py:373-382), so the prune decision costs no extra launch. */
 int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, gi2d_stream_t stream);
+
+/* Multi-GPU tile-row split: fused reduce-scatter of the partial gradients + projection
+ * backward + Adam on the owned slice (sharded optimiser state) + all-gather of the updated parameters,
+ * ONE kernel over NVLink peer memory.  peer_* are HOST arrays of `world` device pointers to every
+ * rank's grads f32[N,8] / xyz / cov / rgb (symmetric allocations; own buffers at index `rank`).
+ * The caller brackets the call with a cross-GPU barrier on `stream`.  Requires external_optimizer. */
+int gi2d_fit_exchange_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int rank, int world,
+                           const void *const *peer_grads, void *const *peer_xyz, void *const *peer_cov,
+                           void *const *peer_rgb, gi2d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement utilities for bench.py (these two SYNCHRONISE; never call them while capturing).

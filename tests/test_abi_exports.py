@@ -41,8 +41,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     from gaussianimage_plus_b200 import _lib
 
-    assert ctypes.sizeof(_lib.FitParams) == 18 * 4
-    assert ctypes.sizeof(_lib.FitBuffers) == 20 * 8
+    assert ctypes.sizeof(_lib.FitParams) == 19 * 4
+    assert ctypes.sizeof(_lib.FitBuffers) == 22 * 8
 
 
 def test_no_cpu_fallback_in_product():
