@@ -31,6 +31,7 @@ class FitParams(C.Structure):
         ("lr0", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("lr_step_size", C.c_int32), ("lr_gamma", C.c_float),
         ("color_sigmoid", C.c_int32), ("loss_scale", C.c_float), ("external_optimizer", C.c_int32),
+        ("loss_l1_scale", C.c_float), ("loss_ssim_weight", C.c_float),
     ]
 
 
@@ -73,6 +74,8 @@ SIGNATURES = {
     "gi2d_measure_fp32_peak": (_I, [C.POINTER(C.c_float), _P]),
     "gi2d_fit_exchange_adam": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _I, C.POINTER(_P),
                                    C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P]),
+    "gi2d_ssim_workspace_size": (_SZ, [_I, _I]),
+    "gi2d_image_loss_grad": (_I, [_I, _I, _P, _P, _P, _F, _F, _F, _P, _P, _P, _SZ, _P]),
     "gi2d_fit_reset": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _P]),
 }
 

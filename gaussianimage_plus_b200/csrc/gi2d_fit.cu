@@ -36,6 +36,10 @@ size_t radix_pass_workspace_size(int n_capacity);
 int tile_edges_from_keys_u64(int n_capacity, const int32_t *n_dev, const uint64_t *keys, int32_t *tile_bins,
                              int rows, cudaStream_t st);
 
+int ssim_grad_launch(int H, int W, const float *render, const float *gt, const uint8_t *gt_u8, float *dm_ws,
+                     float ssim_weight, float l2_scale, float l1_scale, float *v_out, double *ssim_sum,
+                     cudaStream_t st);  // gi2d_loss.cu
+
 namespace {
 
 constexpr int kMaxDigitBits = 11;                 // 2048 bins: a 768x512 image sorts in ONE pass
@@ -137,6 +141,9 @@ struct Workspace {
     int32_t *totals1;     // [256]
     void *radix_ws;
     size_t radix_ws_bytes;
+    float *loss_render;   // [H,W,3] unclamped render   } only with loss_ssim_weight != 0:
+    float *loss_dm;       // [9][H,W] SSIM partials      } the rasterize launch is split around
+    float *loss_vout;     // [H,W,3] dL/d(out)           } the SSIM gradient kernels
     size_t total;
 };
 
@@ -163,6 +170,13 @@ Workspace carve(const gi2d_fit_params &p, const Plan &pl, void *base) {
         w.radix_ws = (void *)(c + off);
         w.radix_ws_bytes = radix_pass_workspace_size(p.isect_capacity);
         off += align_up(w.radix_ws_bytes);
+    }
+    w.loss_render = w.loss_dm = w.loss_vout = nullptr;
+    if (p.loss_ssim_weight != 0.f) {
+        const size_t px = (size_t)p.img_width * p.img_height;
+        w.loss_render = (float *)(c + off);  off += align_up(px * 3 * 4);
+        w.loss_dm = (float *)(c + off);      off += align_up(px * 9 * 4);
+        w.loss_vout = (float *)(c + off);    off += align_up(px * 3 * 4);
     }
     w.total = off;
     return w;
@@ -340,6 +354,8 @@ fit_scan_kernel(gi2d_fit_params p, int with_backward, double *__restrict__ stats
     }
     if (with_backward >= 0 && blockIdx.x == 0 && threadIdx.x == 0) {
         stats[GI2D_STAT_OVERFLOW] = 0.0;
+        stats[GI2D_STAT_SSIM_SUM] = 0.0;
+        stats[GI2D_STAT_ABS_SUM] = 0.0;
         stats[kStatPending] = (with_backward && !p.external_optimizer) ? 1.0 : 0.0;
         if (with_backward) {
             const double step = stats[GI2D_STAT_STEP] + 1.0;
@@ -673,19 +689,26 @@ fit_finalize_kernel(int capacity, const int32_t *__restrict__ n_dev, const uint6
 }
 
 // ------------------------------------------------------------------------------------ K4
-enum class RasterMode { Render, Fit };
+// Render      : forward, clamped CHW `render` tensor out
+// Fit         : forward + pointwise loss gradient (mse / l1) + backward, one launch
+// FitForward  : forward + squared error + unclamped HWC image out      } the split used when the loss has an
+// FitBackward : backward from a dL/d(out) image (v_out, f32[H,W,3])    } SSIM term (needs neighbouring tiles)
+enum class RasterMode { Render, Fit, FitForward, FitBackward };
 
 template <RasterMode kMode>
-__global__ void __launch_bounds__(kRasterThreads, kMode == RasterMode::Fit ? 4 : 6)
+__global__ void __launch_bounds__(kRasterThreads, (kMode == RasterMode::Fit || kMode == RasterMode::FitBackward) ? 4 : 6)
 fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
                   const int32_t *__restrict__ tile_bins, const float4 *__restrict__ records,
                   const float *__restrict__ gt, const uint8_t *__restrict__ gt_u8,
                   float *__restrict__ out_img, float *__restrict__ grads, double *__restrict__ stats,
-                  float *__restrict__ err_map) {
+                  float *__restrict__ err_map, const float *__restrict__ v_out) {
+    constexpr bool kHasFwd = kMode != RasterMode::FitBackward;
+    constexpr bool kHasLoss = kMode == RasterMode::Fit || kMode == RasterMode::FitForward;
+    constexpr bool kHasBwd = kMode == RasterMode::Fit || kMode == RasterMode::FitBackward;
     __shared__ TileRecords sg;
     __shared__ TileGrad tg;
     __shared__ int s_ids[kMaxPerTile];
-    __shared__ float s_red[kRasterWarps];
+    __shared__ float s_red[2][kRasterWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_y = p.tile_row_begin + blockIdx.y;
     const int tile_id = tile_y * p.tiles_x + blockIdx.x;
@@ -698,7 +721,7 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
     const size_t pix = (size_t)i * p.img_width + j;
     // issue every load that does not depend on the tile range first: target pixel, scene flag
     float tr = 0.f, tgc = 0.f, tb = 0.f;
-    if (kMode == RasterMode::Fit && inside) {
+    if (kHasLoss && inside) {
         if (gt) {
             tr = __ldg(gt + 3 * pix);
             tgc = __ldg(gt + 3 * pix + 1);
@@ -719,13 +742,19 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
         stage_record(sg, tid, __ldg(records + 2 * (size_t)(range.x + tid)),
                      __ldg(records + 2 * (size_t)(range.x + tid) + 1), (float)(blockIdx.x * kTile),
                      (float)(tile_y * kTile));
-        if (kMode == RasterMode::Fit) s_ids[tid] = (int)(uint32_t)__ldg(sorted_keys + range.x + tid);
+        if (kHasBwd) s_ids[tid] = (int)(uint32_t)__ldg(sorted_keys + range.x + tid);
+    }
+    if (kMode == RasterMode::FitBackward) {
+        // dL/d(out) of this tile, computed by the loss kernels between the two halves
+        const int gi = grad_index(lx, ly);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tg.v[c][gi] = (inside && n_isect != 0.0) ? __ldg(v_out + 3 * pix + c) : 0.f;
     }
     __syncthreads();
     // ---- forward: thread = pixel
     float r = 0.f, g = 0.f, b = 0.f;
     int last = -1;
-    forward_sweep(sg, cnt, blk, inside, (float)j, (float)i, r, g, b, last);
+    if (kHasFwd) forward_sweep(sg, cnt, blk, inside, (float)j, (float)i, r, g, b, last);
     // no intersection at all: the reference returns ones * background (== 1) and no gradient
     // (rasterize_sum_plus.py:110-118)
     if (n_isect == 0.0) r = g = b = 1.f;
@@ -739,17 +768,21 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
         }
         return;
     }
-    // ---- L2 loss: d/d out = loss_scale * (clamp(out) - gt) where 0 <= out <= 1 (torch.clamp
-    //      backward mask), squared error of the clamped render for PSNR
-    float se = 0.f, vr = 0.f, vg = 0.f, vb = 0.f;
+    if (kHasLoss) {
+    // ---- pointwise loss (mse and/or l1, models/utils.py:64-67,74-75):
+    //      d/d out = loss_scale * d + loss_l1_scale * sign(d), d = clamp(out) - gt, where 0 <= out <= 1
+    //      (torch.clamp backward mask); squared error of the clamped render for PSNR
+    float se = 0.f, ae = 0.f, vr = 0.f, vg = 0.f, vb = 0.f;
     if (inside) {
         const float dr = fminf(fmaxf(r, 0.f), 1.f) - tr;
         const float dg = fminf(fmaxf(g, 0.f), 1.f) - tgc;
         const float db = fminf(fmaxf(b, 0.f), 1.f) - tb;
         se = dr * dr + dg * dg + db * db;
-        vr = (r >= 0.f && r <= 1.f) ? p.loss_scale * dr : 0.f;
-        vg = (g >= 0.f && g <= 1.f) ? p.loss_scale * dg : 0.f;
-        vb = (b >= 0.f && b <= 1.f) ? p.loss_scale * db : 0.f;
+        ae = fabsf(dr) + fabsf(dg) + fabsf(db);
+        const float l1 = p.loss_l1_scale;
+        vr = (r >= 0.f && r <= 1.f) ? fmaf(l1, (float)((dr > 0.f) - (dr < 0.f)), p.loss_scale * dr) : 0.f;
+        vg = (g >= 0.f && g <= 1.f) ? fmaf(l1, (float)((dg > 0.f) - (dg < 0.f)), p.loss_scale * dg) : 0.f;
+        vb = (b >= 0.f && b <= 1.f) ? fmaf(l1, (float)((db > 0.f) - (db < 0.f)), p.loss_scale * db) : 0.f;
         if (out_img) {
             out_img[3 * pix] = r;
             out_img[3 * pix + 1] = g;
@@ -763,15 +796,18 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
     tg.v[1][gi] = vg;
     tg.v[2][gi] = vb;
     se = warp_sum(se);
-    if (lane == 0) s_red[warp] = se;
+    if (p.loss_l1_scale != 0.f) ae = warp_sum(ae);
+    if (lane == 0) { s_red[0][warp] = se; s_red[1][warp] = ae; }
     __syncthreads();
     if (tid == 0) {
-        float tot = 0.f;
+        float tot = 0.f, tot1 = 0.f;
 #pragma unroll
-        for (int w = 0; w < kRasterWarps; ++w) tot += s_red[w];
+        for (int w = 0; w < kRasterWarps; ++w) { tot += s_red[0][w]; tot1 += s_red[1][w]; }
         atomicAdd(stats + GI2D_STAT_SSE + (tile_id & (GI2D_STAT_SSE_SLOTS - 1)), (double)tot);
+        if (p.loss_l1_scale != 0.f) atomicAdd(stats + GI2D_STAT_ABS_SUM, (double)tot1);
     }
-    if (cnt == 0) return;
+    }  // kHasLoss
+    if (!kHasBwd || cnt == 0) return;
     // ---- backward: warp = Gaussian, lane = 8 pixels
     const LanePixels lp = lane_pixels(blockIdx.x, tile_y, p.img_width, p.img_height);
     backward_tile<false, kRasterWarps>(sg, s_ids, cnt, lp, tg,
@@ -902,6 +938,10 @@ int validate(const gi2d_fit_params *p, const gi2d_fit_buffers *b) {
     GI2D_REQUIRE(0 <= p->tile_row_begin && p->tile_row_begin <= p->tile_row_end && p->tile_row_end <= p->tiles_y,
                  "bad tile row band");
     GI2D_REQUIRE(p->isect_capacity > 0, "isect_capacity must be positive");
+    GI2D_REQUIRE(p->loss_ssim_weight == 0.f || (p->img_width >= 11 && p->img_height >= 11),
+                 "the SSIM window needs an image of at least 11x11 pixels");
+    GI2D_REQUIRE(p->loss_ssim_weight == 0.f || (p->tile_row_begin == 0 && p->tile_row_end == p->tiles_y),
+                 "SSIM losses are not available for a tile-row band (the window crosses band borders)");
     GI2D_REQUIRE(b->stats && b->workspace && b->proj && b->sorted_keys && b->tile_bins, "null buffer");
     return GI2D_OK;
 }
@@ -980,14 +1020,29 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     const int band = p->tile_row_end - p->tile_row_begin;
     if (band > 0) {
         dim3 grid(p->tiles_x, band);
-        if (with_backward)
+        if (with_backward && p->loss_ssim_weight != 0.f) {
+            // SSIM couples pixels across tile borders: forward everywhere, then the loss gradient image, then
+            // the backward half.  (Band-split multi-GPU runs would need a halo exchange of the render.)
+            fit_raster_kernel<RasterMode::FitForward><<<grid, kRasterThreads, 0, st>>>(
+                *p, b->sorted_keys, b->tile_bins, w.records, b->gt_hwc, b->gt_u8_hwc, w.loss_render, nullptr, b->stats,
+                b->err_map, nullptr);
+            if (b->out_img)
+                cudaMemcpyAsync(b->out_img, w.loss_render, (size_t)p->img_width * p->img_height * 12,
+                                cudaMemcpyDeviceToDevice, st);
+            ssim_grad_launch(p->img_height, p->img_width, w.loss_render, b->gt_hwc, b->gt_u8_hwc, w.loss_dm,
+                             p->loss_ssim_weight, p->loss_scale, p->loss_l1_scale, w.loss_vout,
+                             b->stats + GI2D_STAT_SSIM_SUM, st);
+            fit_raster_kernel<RasterMode::FitBackward><<<grid, kRasterThreads, 0, st>>>(
+                *p, b->sorted_keys, b->tile_bins, w.records, nullptr, nullptr, nullptr, b->grads, b->stats, nullptr,
+                w.loss_vout);
+        } else if (with_backward)
             launch_pdl(fit_raster_kernel<RasterMode::Fit>, grid, dim3(kRasterThreads), 0, st,
                 *p, b->sorted_keys, b->tile_bins, w.records, b->gt_hwc, b->gt_u8_hwc, b->out_img, b->grads, b->stats,
-                b->err_map);
+                b->err_map, (const float *)nullptr);
         else
             launch_pdl(fit_raster_kernel<RasterMode::Render>, grid, dim3(kRasterThreads), 0, st,
                 *p, b->sorted_keys, b->tile_bins, w.records, nullptr, nullptr, b->out_img, nullptr, b->stats,
-                nullptr);
+                nullptr, (const float *)nullptr);
     }
     if (mk) mk->mark(st);
     return check_launch("gi2d_fit_forward_backward");
@@ -1026,7 +1081,7 @@ extern "C" int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward
         n += pl.extra_passes * (2 + (cumsum_nb > 1 ? 3 : 1));  // hist + cumsum + scatter per pass
         n += 2;                                                 // tile edges + record gather (memset is no kernel)
     }
-    (void)with_backward;  // the optimiser rides in the next step's projection kernel
+    if (with_backward && p->loss_ssim_weight != 0.f) n += 3;  // forward / SSIM stats / SSIM gradient / backward
     return n;
 }
 

@@ -1,0 +1,233 @@
+// gi2d_loss.cu -- gradient of the SSIM-family image losses of models/utils.py:60-80
+// (`SSIM`, `Fusion1` = 0.7 mse + 0.3 (1-ssim), `Fusion2` = 0.7 l1 + 0.3 (1-ssim)) with respect to the
+// UNCLAMPED rasterizer output, i.e. everything autograd does between `out_img` and the loss in
+// gaussianimage_covariance.py:210,252-253: torch.clamp(0,1) -> pytorch_msssim.ssim(data_range=1,
+// size_average=True) / mse / l1 -> backward.  The pointwise losses (L2, L1, Fusion3) never come here:
+// the rasterizer evaluates them inline (gi2d_fit.cu, K4).
+//
+// pytorch_msssim is a third-party dependency that is NOT vendored in /root/reference and is unpinned
+// (requirements.txt: "pytorch-msssim"); the algorithm restated here is the one of its `ssim()` as
+// published (v1.0.0, pytorch_msssim/ssim.py `_fspecial_gauss_1d`, `gaussian_filter`, `_ssim`):
+//   window  : 11 taps, sigma 1.5, exp(-(k-5)^2 / (2 sigma^2)) normalised in float32;
+//   filter  : separable, VALID (no padding): the SSIM map has (H-10) x (W-10) entries per channel;
+//   moments : mu1 = g*X, mu2 = g*Y, s1 = g*X^2 - mu1^2, s2 = g*Y^2 - mu2^2, s12 = g*XY - mu1 mu2;
+//   map     : ((2 mu1 mu2 + C1) / (mu1^2 + mu2^2 + C1)) * ((2 s12 + C2) / (s1 + s2 + C2)),
+//             C1 = 0.01^2, C2 = 0.03^2;  ssim = mean over channels of the spatial means.
+//
+// Two kernels, both per 16x16 tile with a 5-pixel halo staged in shared memory (HBM-bound: the image,
+// the target and three derivative planes per channel are each read once plus halo, 2.6x):
+//   S1 ssim_stats_kernel : the 5 filtered moments -> SSIM map value (summed into the stats block)
+//                          and its partials  M = d map/d mu1 (total, through s1 and s12 as well),
+//                          S = d map/d s1,  T = d map/d s12  at every valid window, 0 elsewhere;
+//   S2 ssim_grad_kernel  : d loss/d X[p] = coef * sum_w g[w-p] (M[w] + 2 X[p] S[w] + Y[p] T[w])
+//                          (the transpose of the three filters), plus the pointwise mse / l1 terms,
+//                          times the clamp mask (0 <= out <= 1); written as v_out f32[H,W,3].
+#include "gi2d_common.cuh"
+
+namespace gi2d {
+namespace {
+
+constexpr int kWin = 11;
+constexpr int kHalo = kWin / 2;
+constexpr int kLT = 16;                 // output tile edge
+constexpr int kLIn = kLT + 2 * kHalo;   // staged edge: 26
+constexpr int kLPad = kLIn + 1;
+
+// float32 values of torch: g = exp(-(arange(11)-5)^2 / (2*1.5^2)); g /= g.sum()
+__constant__ float c_win[kWin] = {
+    0.0010283803567290306f, 0.0075987582094967365f, 0.036000773310661316f, 0.10936068743467331f,
+    0.21300552785396576f,   0.26601171493530273f,   0.21300552785396576f,  0.10936068743467331f,
+    0.036000773310661316f,  0.0075987582094967365f, 0.0010283803567290306f};
+
+constexpr float kC1 = 0.01f * 0.01f, kC2 = 0.03f * 0.03f;
+
+__device__ __forceinline__ float target_at(const float *gt, const uint8_t *gt_u8, size_t idx) {
+    return gt ? __ldg(gt + idx) : __fdiv_rn((float)__ldg(gt_u8 + idx), 255.f);
+}
+
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+// S1.  dm: 9 planes f32[H*W], plane 3*c+q for channel c and q in {M,S,T}.
+__global__ void __launch_bounds__(256)
+ssim_stats_kernel(int H, int W, const float *__restrict__ render, const float *__restrict__ gt,
+                  const uint8_t *__restrict__ gt_u8, float *__restrict__ dm, double *__restrict__ ssim_sum) {
+    __shared__ float sx[kLIn][kLPad], sy[kLIn][kLPad];
+    __shared__ float sh[5][kLIn][kLT];
+    __shared__ float s_red[8];
+    const int tid = threadIdx.x, lx = tid & 15, ly = tid >> 4;
+    const int x0 = blockIdx.x * kLT, y0 = blockIdx.y * kLT;
+    const int px = x0 + lx, py = y0 + ly;
+    const size_t plane = (size_t)H * W;
+    // a window is valid when all of its 11x11 pixels are inside the image
+    const bool valid = px >= kHalo && px < W - kHalo && py >= kHalo && py < H - kHalo;
+    float acc = 0.f;
+    for (int c = 0; c < 3; ++c) {
+        for (int i = tid; i < kLIn * kLIn; i += 256) {
+            const int r = i / kLIn, q = i - r * kLIn;
+            const int yy = y0 - kHalo + r, xx = x0 - kHalo + q;
+            float a = 0.f, b = 0.f;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const size_t idx = 3 * ((size_t)yy * W + xx) + c;
+                a = clamp01(__ldg(render + idx));
+                b = target_at(gt, gt_u8, idx);
+            }
+            sx[r][q] = a;
+            sy[r][q] = b;
+        }
+        __syncthreads();
+        // horizontal pass: 26 rows x 16 columns x 5 moments
+        for (int i = tid; i < kLIn * kLT; i += 256) {
+            const int r = i >> 4, q = i & 15;
+            float m1 = 0.f, m2 = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+#pragma unroll
+            for (int k = 0; k < kWin; ++k) {
+                const float w = c_win[k], a = sx[r][q + k], b = sy[r][q + k];
+                m1 = fmaf(w, a, m1);
+                m2 = fmaf(w, b, m2);
+                xx = fmaf(w, a * a, xx);
+                yy = fmaf(w, b * b, yy);
+                xy = fmaf(w, a * b, xy);
+            }
+            sh[0][r][q] = m1; sh[1][r][q] = m2; sh[2][r][q] = xx; sh[3][r][q] = yy; sh[4][r][q] = xy;
+        }
+        __syncthreads();
+        float m1 = 0.f, m2 = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) {
+            const float w = c_win[k];
+            m1 = fmaf(w, sh[0][ly + k][lx], m1);
+            m2 = fmaf(w, sh[1][ly + k][lx], m2);
+            xx = fmaf(w, sh[2][ly + k][lx], xx);
+            yy = fmaf(w, sh[3][ly + k][lx], yy);
+            xy = fmaf(w, sh[4][ly + k][lx], xy);
+        }
+        float M = 0.f, S = 0.f, T = 0.f;
+        if (valid) {
+            const float s1 = xx - m1 * m1, s2 = yy - m2 * m2, s12 = xy - m1 * m2;
+            const float A1 = fmaf(2.f * m1, m2, kC1), A2 = fmaf(2.f, s12, kC2);
+            const float B1 = fmaf(m1, m1, fmaf(m2, m2, kC1)), B2 = s1 + s2 + kC2;
+            const float iB1 = 1.f / B1, iB2 = 1.f / B2;
+            const float lum = A1 * iB1, cs = A2 * iB2;
+            acc += lum * cs;
+            // partials at fixed (s1, s12), then the chain through s1 = E[x^2] - mu1^2, s12 = E[xy] - mu1 mu2
+            S = -lum * cs * iB2;
+            T = 2.f * lum * iB2;
+            const float dmu = 2.f * (m2 - m1 * lum) * iB1 * cs;
+            M = dmu - 2.f * m1 * S - m2 * T;
+        }
+        if (px < W && py < H) {
+            const size_t pix = (size_t)py * W + px;
+            dm[(3 * c + 0) * plane + pix] = M;
+            dm[(3 * c + 1) * plane + pix] = S;
+            dm[(3 * c + 2) * plane + pix] = T;
+        }
+        __syncthreads();  // sx/sy/sh are rewritten by the next channel
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((tid & 31) == 0) s_red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        if (ssim_sum) atomicAdd(ssim_sum, (double)t);
+    }
+}
+
+// S2.  v_out f32[H,W,3] = mask * (ssim_coef * filter^T(M,S,T) + l2_scale * d + l1_scale * sign(d)),
+// d = clamp(out) - gt.
+__global__ void __launch_bounds__(256)
+ssim_grad_kernel(int H, int W, const float *__restrict__ render, const float *__restrict__ gt,
+                 const uint8_t *__restrict__ gt_u8, const float *__restrict__ dm, float ssim_coef,
+                 float l2_scale, float l1_scale, float *__restrict__ v_out) {
+    __shared__ float sd[3][kLIn][kLPad];
+    __shared__ float sh[3][kLIn][kLT];
+    const int tid = threadIdx.x, lx = tid & 15, ly = tid >> 4;
+    const int x0 = blockIdx.x * kLT, y0 = blockIdx.y * kLT;
+    const int px = x0 + lx, py = y0 + ly;
+    const size_t plane = (size_t)H * W;
+    const bool inside = px < W && py < H;
+    for (int c = 0; c < 3; ++c) {
+        for (int i = tid; i < kLIn * kLIn; i += 256) {
+            const int r = i / kLIn, q = i - r * kLIn;
+            const int yy = y0 - kHalo + r, xx = x0 - kHalo + q;
+            const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const size_t pix = ok ? (size_t)yy * W + xx : 0;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) sd[m][r][q] = ok ? __ldg(dm + (3 * c + m) * plane + pix) : 0.f;
+        }
+        __syncthreads();
+        for (int i = tid; i < kLIn * kLT; i += 256) {
+            const int r = i >> 4, q = i & 15;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < kWin; ++k) {
+                const float w = c_win[k];
+                a0 = fmaf(w, sd[0][r][q + k], a0);
+                a1 = fmaf(w, sd[1][r][q + k], a1);
+                a2 = fmaf(w, sd[2][r][q + k], a2);
+            }
+            sh[0][r][q] = a0; sh[1][r][q] = a1; sh[2][r][q] = a2;
+        }
+        __syncthreads();
+        float fM = 0.f, fS = 0.f, fT = 0.f;
+#pragma unroll
+        for (int k = 0; k < kWin; ++k) {
+            const float w = c_win[k];
+            fM = fmaf(w, sh[0][ly + k][lx], fM);
+            fS = fmaf(w, sh[1][ly + k][lx], fS);
+            fT = fmaf(w, sh[2][ly + k][lx], fT);
+        }
+        if (inside) {
+            const size_t idx = 3 * ((size_t)py * W + px) + c;
+            const float o = __ldg(render + idx);
+            const float x = clamp01(o), y = target_at(gt, gt_u8, idx);
+            const float d = x - y;
+            float v = ssim_coef * fmaf(2.f * x, fS, fmaf(y, fT, fM));
+            v = fmaf(l2_scale, d, v);
+            v = fmaf(l1_scale, (float)((d > 0.f) - (d < 0.f)), v);
+            v_out[idx] = (o >= 0.f && o <= 1.f) ? v : 0.f;  // torch.clamp backward
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+// Internal launcher shared with the fused fit step.  dm_ws: 9 * H * W floats.
+int ssim_grad_launch(int H, int W, const float *render, const float *gt, const uint8_t *gt_u8, float *dm_ws,
+                     float ssim_weight, float l2_scale, float l1_scale, float *v_out, double *ssim_sum,
+                     cudaStream_t st) {
+    const dim3 grid(cdiv(W, kLT), cdiv(H, kLT));
+    ssim_stats_kernel<<<grid, 256, 0, st>>>(H, W, render, gt, gt_u8, dm_ws, ssim_sum);
+    // loss term = ssim_weight * (1 - mean(map)), mean over 3 channels x (H-10)(W-10) windows
+    const float coef = -ssim_weight / (3.f * (float)(H - 2 * kHalo) * (float)(W - 2 * kHalo));
+    ssim_grad_kernel<<<grid, 256, 0, st>>>(H, W, render, gt, gt_u8, dm_ws, coef, l2_scale, l1_scale, v_out);
+    return GI2D_OK;
+}
+
+}  // namespace gi2d
+
+using namespace gi2d;
+
+extern "C" size_t gi2d_ssim_workspace_size(int img_height, int img_width) {
+    return (size_t)9 * img_height * img_width * sizeof(float);
+}
+
+extern "C" int gi2d_image_loss_grad(int img_height, int img_width, const float *render_hwc, const float *gt_hwc,
+                                    const uint8_t *gt_u8_hwc, float ssim_weight, float l2_scale, float l1_scale,
+                                    float *v_out_hwc, double *ssim_sum, void *workspace, size_t workspace_bytes,
+                                    gi2d_stream_t stream) {
+    GI2D_REQUIRE(img_height >= kWin && img_width >= kWin, "SSIM needs an image of at least 11x11 pixels");
+    GI2D_REQUIRE(render_hwc && (gt_hwc || gt_u8_hwc) && v_out_hwc && workspace, "null buffer");
+    if (workspace_bytes < gi2d_ssim_workspace_size(img_height, img_width)) {
+        set_error("gi2d_image_loss_grad: workspace too small");
+        return GI2D_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ssim_sum) cudaMemsetAsync(ssim_sum, 0, sizeof(double), st);
+    ssim_grad_launch(img_height, img_width, render_hwc, gt_hwc, gt_u8_hwc, (float *)workspace, ssim_weight, l2_scale,
+                     l1_scale, v_out_hwc, ssim_sum, st);
+    return check_launch(__func__);
+}

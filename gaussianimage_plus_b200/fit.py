@@ -29,6 +29,7 @@ from . import _lib
 from .binding import TILE, _stream
 
 STAT_STEP, STAT_ISECTS, STAT_OVERFLOW, STAT_LR, STAT_SSE, STAT_SSE_SLOTS = 0, 1, 2, 3, 16, 64
+STAT_BEST_SSE, STAT_BEST_STEP, STAT_NON_PSD, STAT_SSIM_SUM, STAT_ABS_SUM = 9, 10, 11, 13, 14
 STAT_COUNT = STAT_SSE + STAT_SSE_SLOTS
 _NAMES = ("xyz", "cov2d", "f_dc")  # the reference's optimiser group names (gaussianimage_covariance.py:93-96)
 
@@ -36,6 +37,29 @@ _NAMES = ("xyz", "cov2d", "f_dc")  # the reference's optimiser group names (gaus
 def slv_bound(H: int, W: int, num_points: int) -> float:
     """SLV low-pass bound of the reference init: min(HW / (9 pi N), 300) (gaussianimage_covariance.py:61)."""
     return min(H * W / (9 * math.pi * num_points), 300)
+
+
+# loss_fn of models/utils.py:60-80 as (w_mse, w_l1, w_ssim); lambda_value = 0.7 at both call sites
+# (gaussianimage_covariance.py:222,252).  The MS-SSIM variants (Fusion4, Fusion_hinerv) are not built.
+def loss_weights(loss_type: str, lambda_value: float = 0.7) -> Tuple[float, float, float]:
+    lam = float(lambda_value)
+    table = {"L2": (1.0, 0.0, 0.0), "L1": (0.0, 1.0, 0.0), "SSIM": (0.0, 0.0, 1.0),
+             "Fusion1": (lam, 0.0, 1.0 - lam), "Fusion2": (0.0, lam, 1.0 - lam), "Fusion3": (lam, 1.0 - lam, 0.0)}
+    if loss_type not in table:
+        raise ValueError(f"loss_type {loss_type!r} is not supported (have {sorted(table)}; the MS-SSIM losses "
+                         "Fusion4 / Fusion_hinerv are out of scope)")
+    return table[loss_type]
+
+
+def _sse_total(s) -> float:
+    """Sum of the 64 squared-error partials in the order the kernels use for their best-so-far decision
+    (sse_total_warp in gi2d_fit.cu: slot i + slot 32+i, then an xor butterfly), so that the `sse` of the best
+    step and `best_sse` are the same double."""
+    t = s[STAT_SSE:STAT_SSE + STAT_SSE_SLOTS].tolist()
+    v = [t[i] + t[32 + i] for i in range(32)]
+    for d in (16, 8, 4, 2, 1):
+        v = [v[i] + v[i ^ d] for i in range(d)]   # only lanes < d feed lane 0
+    return v[0]
 
 
 def _flushed(attr):
@@ -61,7 +85,7 @@ class GaussianImageFitter:
                  clip_coe: float = 3.0, radius_clip: float = 1.0, color_norm: bool = False,
                  SLV_init: bool = True, tile_rows: Optional[Tuple[int, int]] = None,
                  isect_capacity: Optional[int] = None, use_graph: bool = True,
-                 grad_hook=None):
+                 grad_hook=None, loss_type: str = "L2", lambda_value: float = 0.7):
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -72,11 +96,14 @@ class GaussianImageFitter:
         self.lr, self.clip_coe, self.radius_clip = lr, clip_coe, radius_clip
         self.color_norm, self.SLV = bool(color_norm), bool(SLV_init)
         self.use_graph = use_graph
+        self.loss_type, self.loss_w = loss_type, loss_weights(loss_type, lambda_value)
         self.grad_hook = grad_hook  # called right after the backward of every step (multi-GPU all-reduce)
         self._capacity_hint = isect_capacity
         self._dirty = False         # a gradient is pending on the device
         self.external_optimizer = False  # True: grad_hook applies the gradients itself (parallel.FusedTileRowExchange)
         self.keep_render = False    # tests: also store the unclamped [H,W,3] render of every train_iter
+        self.track_best = True      # keep the parameters of the best-PSNR step on the device (train.py:132-137)
+        self._best_frozen = None    # best state of an EARLIER Gaussian count (prune/densify happened since)
         f = dict(dtype=torch.float32, device=self.device)
         # reference init, gaussianimage_covariance.py:52-66
         w_init = torch.rand(num_points, 1, **f) * self.W
@@ -109,6 +136,10 @@ class GaussianImageFitter:
         self.isect_capacity = int(min(cap, max(n, 1) * tiles, 2 ** 31 - 1024))
         self.grads = torch.zeros(n, 8, **f)
         self.proj = torch.zeros(n, 8, **f)
+        if getattr(self, "best", None) is None or self.best.shape[0] != n:
+            self.best = torch.zeros(n, 8, **f)   # device-side best-state snapshot (train.py:132-137)
+        if not hasattr(self, "err_map"):
+            self.err_map = torch.zeros(self.H, self.W, **f)
         self.sorted_keys = torch.zeros(self.isect_capacity, dtype=torch.int64, device=self.device)
         self.tile_bins = torch.zeros(tiles, 2, dtype=torch.int32, device=self.device)
         if not hasattr(self, "stats_buf"):
@@ -118,7 +149,8 @@ class GaussianImageFitter:
         self.params = _lib.FitParams(
             n, self.W, self.H, self.tile_bounds[0], self.tile_bounds[1], self.tile_rows[0], self.tile_rows[1],
             self.isect_capacity, self.clip_coe, self.radius_clip, self.lr, 0.9, 0.999, 1e-15, 20000, 0.5,
-            int(self.color_norm), 2.0 / (3.0 * self.H * self.W), 1 if self.external_optimizer else 0)
+            int(self.color_norm), 2.0 * self.loss_w[0] / (3.0 * self.H * self.W),
+            1 if self.external_optimizer else 0, self.loss_w[1] / (3.0 * self.H * self.W), self.loss_w[2])
         ws_bytes = self.lib.gi2d_fit_workspace_size(C.byref(self.params))
         self.workspace = torch.zeros(max(ws_bytes, 256), dtype=torch.uint8, device=self.device)
         self._graph = None
@@ -126,7 +158,7 @@ class GaussianImageFitter:
         self._dirty = False
         self._bind()
 
-    def _bind(self, out_img=None):
+    def _bind(self, out_img=None, err_map=False):
         m, v = self._t_m, self._t_v
         if out_img is None and self.keep_render:
             out_img = self.out_hwc.data_ptr()
@@ -138,7 +170,9 @@ class GaussianImageFitter:
             gt.data_ptr() if (gt is not None and gt.dtype == torch.float32) else None,
             out_img, self.grads.data_ptr(), self.proj.data_ptr(), self.sorted_keys.data_ptr(),
             self.tile_bins.data_ptr(), self.stats_buf.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(),
-            gt.data_ptr() if (gt is not None and gt.dtype == torch.uint8) else None)
+            gt.data_ptr() if (gt is not None and gt.dtype == torch.uint8) else None,
+            self.best.data_ptr() if self.track_best else None,
+            self.err_map.data_ptr() if err_map else None)
 
     def reset_stats(self, step: int = 0):
         """Zero the device-side statistics (drops a pending gradient) and set the Adam step counter."""
@@ -147,9 +181,10 @@ class GaussianImageFitter:
                                                _stream(self.device)), "fit_reset")
         self._dirty = False
 
-    def sync_params(self):
-        """Apply a pending optimiser step now (asynchronous; no-op when nothing is pending)."""
-        if self._dirty:
+    def sync_params(self, force: bool = False):
+        """Apply a pending optimiser step now (asynchronous; no-op when nothing is pending).  `force`
+        launches the flush kernel regardless, for its non-positive-definite count (stats()['non_psd'])."""
+        if self._dirty or force:
             self._dirty = False
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.gi2d_fit_adam(C.byref(self.params), C.byref(self.buffers), _stream(self.device)),
@@ -183,12 +218,18 @@ class GaussianImageFitter:
         if self.grad_hook is not None:
             self.grad_hook(self)
 
-    def train_iter(self):
-        """One fit iteration (gaussianimage_covariance.py:249-259), asynchronous."""
+    def train_iter(self, want_error_map: bool = False):
+        """One fit iteration (gaussianimage_covariance.py:249-259), asynchronous.  `want_error_map` also
+        leaves the per-pixel L1 error of this iteration's render in `self.err_map` (train.py:87)."""
         if self.gt_hwc is None:
             raise RuntimeError("set_target() first")
         self._dirty = not self.external_optimizer
         with torch.cuda.device(self.device):
+            if want_error_map:
+                self._bind(err_map=True)
+                self._enqueue_step()
+                self._bind()
+                return
             if not self.use_graph or self._eager_left > 0:
                 # the first step after (re)allocation runs eagerly: it loads the kernels (CUDA lazy
                 # module loading is not capturable) and is an ordinary step in every other respect
@@ -228,11 +269,22 @@ class GaussianImageFitter:
         """Synchronises.  mse/psnr refer to the render of the LAST train_iter (before its Adam update),
         like the reference's per-iteration psnr (gaussianimage_covariance.py:256-257)."""
         s = self.stats_buf.cpu()
-        sse = float(s[STAT_SSE:STAT_SSE + STAT_SSE_SLOTS].sum())
+        sse = _sse_total(s)
         mse = sse / (3.0 * self.H * self.W)
+        best_mse = float(s[STAT_BEST_SSE]) / (3.0 * self.H * self.W)
+        w2, w1, ws = self.loss_w
+        loss = w2 * mse
+        if w1:
+            loss += w1 * float(s[STAT_ABS_SUM]) / (3.0 * self.H * self.W)
+        if ws:
+            loss += ws * (1.0 - float(s[STAT_SSIM_SUM]) / (3.0 * (self.H - 10) * (self.W - 10)))
         return {"step": int(s[STAT_STEP]), "num_intersects": int(s[STAT_ISECTS]), "overflow": bool(s[STAT_OVERFLOW]),
-                "lr": float(s[STAT_LR]), "sse": sse, "mse": mse,
-                "psnr": 10 * math.log10(1.0 / mse) if mse > 0 else float("inf")}
+                "lr": float(s[STAT_LR]), "sse": sse, "mse": mse, "loss": loss,
+                "psnr": 10 * math.log10(1.0 / mse) if mse > 0 else float("inf"),
+                "best_sse": float(s[STAT_BEST_SSE]), "best_step": int(s[STAT_BEST_STEP]),
+                "best_psnr": (10 * math.log10(1.0 / best_mse) if 0 < best_mse < float("inf") else
+                              (0.0 if best_mse > 0 else float("inf"))),
+                "non_psd": int(s[STAT_NON_PSD])}
 
     def psnr(self) -> float:
         return self.stats()["psnr"]
@@ -246,7 +298,7 @@ class GaussianImageFitter:
 
     @staticmethod
     def mse_from_stats(host_slot: torch.Tensor, H: int, W: int) -> float:
-        return float(host_slot[STAT_SSE:STAT_SSE + STAT_SSE_SLOTS].sum()) / (3.0 * H * W)
+        return _sse_total(host_slot) / (3.0 * H * W)
 
     def ensure_capacity(self) -> bool:
         """Host check of the overflow flag; grows the intersection buffers when it tripped.
@@ -257,8 +309,42 @@ class GaussianImageFitter:
         self._capacity_hint = int(st["num_intersects"] * 2)
         self._step0 = st["step"] - 1  # the overflowing step did not update the parameters
         self._alloc_state(zero_moments=False)
-        self.reset_stats(self._step0)
+        self._reset_keep_best(self._step0, st)
         return True
+
+    def _reset_keep_best(self, step: int, st: dict):
+        """reset_stats() that carries the best-so-far squared error / step over (the snapshot stays valid)."""
+        self.reset_stats(step)
+        self.stats_buf[STAT_BEST_SSE:STAT_BEST_STEP + 1] = torch.tensor(
+            [st["best_sse"], float(st["best_step"])], dtype=torch.float64, device=self.device)
+
+    def best_state(self) -> dict:
+        """The reference's `best_model_dict` + `slv_bound` (train.py:132-137,159-164): parameters right after
+        the optimiser step of the best-PSNR iteration, and the SLV bound of that moment.  Synchronises."""
+        self.sync_params()
+        st = self.stats()
+        fr = self._best_frozen
+        if fr is not None and fr["best_step"] >= st["best_step"]:
+            return dict(fr)
+        if st["best_step"] == 0:
+            raise RuntimeError("no training step has completed yet")
+        b = self.best
+        return {"_xyz": b[:, 0:2].clone(), "_cov2d": b[:, 2:5].clone(), "_features_dc": b[:, 5:8].clone(),
+                "cholesky_bound": self.cholesky_bound.clone(), "best_step": st["best_step"],
+                "best_psnr": st["best_psnr"]}
+
+    def load_best_state(self):
+        """train.py:158-164: continue (evaluate) from the best state."""
+        bs = self.best_state()
+        st = self.stats()
+        n = bs["_xyz"].shape[0]
+        zeros = lambda t: torch.zeros_like(t)
+        self._best_frozen = bs
+        self._replace(bs["_xyz"], bs["_cov2d"], bs["_features_dc"], bs["cholesky_bound"],
+                      {"xyz": zeros(bs["_xyz"]), "cov2d": zeros(bs["_cov2d"]), "f_dc": zeros(bs["_features_dc"])},
+                      {"xyz": zeros(bs["_xyz"]), "cov2d": zeros(bs["_cov2d"]), "f_dc": zeros(bs["_features_dc"])},
+                      _stats=st)
+        return n
 
     # ------------------------------------------------------------------ N-changing operations
     def check_non_semi_definite(self, cov2d=None):
@@ -267,19 +353,31 @@ class GaussianImageFitter:
         valid = (c[:, 0] * c[:, 2] - c[:, 1] ** 2 > 0) & (c[:, 0] > 0) & (c[:, 2] > 0)
         return int((~valid).sum().item()), valid
 
-    def _replace(self, xyz, cov, rgb, bound, m, v):
-        step = self.stats()["step"]
+    def _replace(self, xyz, cov, rgb, bound, m, v, _stats=None):
+        """Swap in parameter/moment tensors of a different Gaussian count.  The best-state snapshot of the old
+        count is frozen first (the reference keeps its deep copy across prune/densify the same way)."""
+        self.sync_params()
+        st = _stats or self.stats()
+        step = st["step"]
+        if self.track_best and st["best_step"] > 0 and (
+                self._best_frozen is None or self._best_frozen["best_step"] < st["best_step"]):
+            self._best_frozen = self.best_state()
         self._t_xyz, self._t_cov2d, self._t_f_dc, self.cholesky_bound = (
             t.contiguous() for t in (xyz, cov, rgb, bound))
         self._t_m, self._t_v = m, v
         self._step0 = step
         self._alloc_state(zero_moments=False)
-        self.reset_stats(step)
+        self._reset_keep_best(step, st)
 
     def non_semi_definite_prune(self):
         """gaussianimage_covariance.py:354-371: drop Gaussians whose covariance is not positive definite
         (parameters, Adam moments and SLV bounds are masked together)."""
-        n_bad, valid = self.check_non_semi_definite()      # (flushes a pending step first)
+        # the flush kernel counts the non-PSD Gaussians while it applies the pending step: the common
+        # "nothing to prune" outcome costs that launch + one small read-back, no torch ops
+        self.sync_params(force=True)
+        if self.stats()["non_psd"] == 0:
+            return 0, self.cur_num_points
+        n_bad, valid = self.check_non_semi_definite()
         if n_bad and self.cur_num_points - n_bad > 0:
             m = {k: t[valid].contiguous() for k, t in self.exp_avg.items()}
             v = {k: t[valid].contiguous() for k, t in self.exp_avg_sq.items()}
@@ -303,13 +401,17 @@ class GaussianImageFitter:
                       cat(self.cholesky_bound, new_bound), m, v)
         return n_new, n_bad
 
-    def add_sample_positions(self, max_num_points: int, base_num_samples: int = 1000, last: bool = False):
-        """train.py:85-118: new Gaussians at the pixels of largest L1 error of the current render."""
-        render = self.forward()["render"]
-        gt = self.gt_hwc.permute(2, 0, 1).unsqueeze(0)
-        if gt.dtype == torch.uint8:
-            gt = gt.float() / 255
-        errors = torch.abs(render - gt).sum(dim=1)
+    def add_sample_positions(self, max_num_points: int, base_num_samples: int = 1000, last: bool = False,
+                             errors: Optional[torch.Tensor] = None):
+        """train.py:85-118: new Gaussians at the pixels of largest L1 error.  `errors` f32[H,W] is the map a
+        `train_iter(want_error_map=True)` left behind (the reference passes that iteration's render); without
+        it the current parameters are rendered first."""
+        if errors is None:
+            render = self.forward()["render"]
+            gt = self.gt_hwc.permute(2, 0, 1).unsqueeze(0)
+            if gt.dtype == torch.uint8:
+                gt = gt.float() / 255
+            errors = torch.abs(render - gt).sum(dim=1)
         p_flat = (errors / torch.sum(errors)).view(-1)
         room = max(0, max_num_points - self.cur_num_points)
         k = room if last else min(base_num_samples, room)
@@ -318,6 +420,28 @@ class GaussianImageFitter:
         _, idx = torch.topk(p_flat, k)
         xyz = torch.stack([idx % self.W, idx // self.W], dim=1).float()
         color = torch.zeros(k, 3, device=self.device)
-        cov = torch.rand(k, 3, device=self.device) + torch.tensor([0.5, 0, 0.5], device=self.device)
+        # the reference draws on the CPU generator and moves the sample over (train.py:110-112)
+        cov = torch.rand(k, 3).to(self.device) + torch.tensor([0.5, 0, 0.5], device=self.device)
         self.densification_postfix(xyz, color, cov)
         return k
+
+    # ------------------------------------------------------------------ the training loop
+    def fit(self, iterations: int, max_num_points: Optional[int] = None, prune_iter: int = 100,
+            grow_iter: int = 5000, adaptive_add: bool = True, prune: bool = True, callback=None) -> dict:
+        """`SimpleTrainer2d.train` (train.py:120-176) without its per-iteration host work: every iteration is
+        one graph replay; the best state is snapshotted by the kernels; the host looks at the device only
+        every `prune_iter` iterations (non-PSD count, one small read-back) and every `grow_iter` iterations
+        (densification).  Returns the final stats (incl. best_psnr / best_step); `best_state()` has the
+        parameters.  `callback(iteration, self)` runs after every iteration when given (tests, logging)."""
+        max_num_points = max_num_points if max_num_points is not None else self.cur_num_points
+        for it in range(1, iterations + 1):
+            grow = adaptive_add and it % grow_iter == 0 and it < iterations
+            self.train_iter(want_error_map=grow)
+            if prune and it % prune_iter == 0:
+                self.non_semi_definite_prune()
+            if grow:
+                self.add_sample_positions(max_num_points, last=(it == iterations - grow_iter), errors=self.err_map)
+            if callback is not None:
+                callback(it, self)
+        self.sync_params()
+        return self.stats()

@@ -184,6 +184,13 @@ typedef struct gi2d_fit_params {
     float loss_scale;           /* dL/d(out) = loss_scale * (clamp(out) - gt); 2/(3*H*W) for mse */
     int32_t external_optimizer; /* 1: a training step leaves b->grads alone (nothing pending); the caller applies
                                    them with gi2d_fit_exchange_adam (multi-GPU tile-row split) */
+    /* loss_fn of models/utils.py:60-80 as three weights:  loss = w2 * mse + w1 * l1 + ws * (1 - ssim)
+     *   L2 (1,0,0)  L1 (0,1,0)  SSIM (0,0,1)  Fusion1 (l,0,1-l)  Fusion2 (0,l,1-l)  Fusion3 (l,1-l,0),  l = 0.7
+     * loss_scale = 2 w2 / (3HW) (above), loss_l1_scale = w1 / (3HW), loss_ssim_weight = ws.  With ws == 0 the
+     * loss gradient is evaluated inside the rasterize launch; with ws != 0 the launch is split in forward /
+     * SSIM gradient (2 kernels, gi2d_loss.cu) / backward. */
+    float loss_l1_scale;
+    float loss_ssim_weight;
 } gi2d_fit_params;
 
 /* stats layout (f64): the device-side step counter makes the step graph-replayable with no
@@ -195,6 +202,8 @@ typedef struct gi2d_fit_params {
 #define GI2D_STAT_BEST_SSE 9    /* smallest squared error of any training step so far (+inf before the first) */
 #define GI2D_STAT_BEST_STEP 10  /* the step (1-based) that achieved it; b->best holds the parameters AFTER its update */
 #define GI2D_STAT_NON_PSD 11    /* Gaussians whose covariance is not positive definite, counted by gi2d_fit_adam */
+#define GI2D_STAT_SSIM_SUM 13   /* sum of the SSIM map over channels and valid windows of the last step (ws != 0) */
+#define GI2D_STAT_ABS_SUM 14    /* sum |clamp(out)-gt| of the last step (w1 != 0) */
 #define GI2D_STAT_SSE 16        /* 64 partial sums of squared error of the clamped render */
 #define GI2D_STAT_SSE_SLOTS 64
 #define GI2D_STAT_COUNT (GI2D_STAT_SSE + GI2D_STAT_SSE_SLOTS)
@@ -258,6 +267,19 @@ int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, gi2d_stre
 int gi2d_fit_exchange_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int rank, int world,
                            const void *const *peer_grads, void *const *peer_xyz, void *const *peer_cov,
                            void *const *peer_rgb, gi2d_stream_t stream);
+
+/* Stand-alone form of the loss gradient the fit step uses when loss_ssim_weight != 0: everything autograd does
+ * between the rasterizer output and the loss in gaussianimage_covariance.py:210,252-253 --
+ *   v_out = d/d(out) [ ssim_weight * (1 - ssim(clamp(out), gt)) + (l2_scale/2) * sum (clamp(out)-gt)^2
+ *                      + l1_scale * sum |clamp(out)-gt| ]
+ * with pytorch_msssim.ssim(data_range=1, size_average=True) semantics (11-tap sigma-1.5 window, valid
+ * filtering).  render/gt/v_out are f32[H,W,3] (gt alternatively u8); *ssim_sum (nullable, device f64) receives
+ * the sum of the SSIM map (mean = sum / (3 (H-10)(W-10))).  workspace: gi2d_ssim_workspace_size bytes. */
+size_t gi2d_ssim_workspace_size(int img_height, int img_width);
+int gi2d_image_loss_grad(int img_height, int img_width, const float *render_hwc, const float *gt_hwc,
+                         const uint8_t *gt_u8_hwc, float ssim_weight, float l2_scale, float l1_scale,
+                         float *v_out_hwc, double *ssim_sum, void *workspace, size_t workspace_bytes,
+                         gi2d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement utilities for bench.py (these two SYNCHRONISE; never call them while capturing).

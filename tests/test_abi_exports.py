@@ -41,7 +41,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     from gaussianimage_plus_b200 import _lib
 
-    assert ctypes.sizeof(_lib.FitParams) == 19 * 4
+    assert ctypes.sizeof(_lib.FitParams) == 21 * 4
     assert ctypes.sizeof(_lib.FitBuffers) == 22 * 8
 
 

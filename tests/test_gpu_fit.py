@@ -149,6 +149,79 @@ def test_prune_and_densify_keep_state_consistent():
     assert st["step"] == 70 and np.isfinite(st["psnr"]) and st["psnr"] > p0 - 1
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_best_state_snapshot_matches_host_tracking(graph):
+    """train.py:132-137 (`if best_psnr < psnr: deepcopy(state_dict)`): the device-side snapshot taken by the
+    kernel that applies a step's update == what a host that watched every step would have copied.  The host
+    watcher works one step behind and without flushing: after step k+1 was issued the raw parameter tensors
+    hold the values right after the update of step k."""
+    fit, (_, _, _, _, gt) = make_fitter(1500, 192, 256, seed=21, colors="zeros", use_graph=graph, keep_render=False)
+    raw = lambda: torch.cat((fit._t_xyz, fit._t_cov2d, fit._t_f_dc), dim=1).clone()
+    best = {"sse": float("inf"), "step": 0, "params": None}
+    prev = None          # (sse of step k, k) waiting for the parameters that step k+1's first kernel produces
+    fit.lr = 0.5         # (params struct already built: set it there as well) big steps => PSNR goes up AND down
+    fit.params.lr0 = 0.5
+    fit.reset_stats(0)
+    worse = 0
+    for it in range(1, 61):
+        if it == 41:                           # swap the target: the error jumps, the best stays behind at <= 40
+            fit.set_target(torch.from_numpy(1.0 - gt))
+        fit.train_iter()
+        st = fit.stats()                       # no flush: reads the stats block only
+        if prev is not None:
+            if prev[0] < best["sse"]:
+                best = {"sse": prev[0], "step": prev[1], "params": raw()}
+            else:
+                worse += 1
+        prev = (st["sse"], it)
+    hist_ok = worse >= 3                       # the run must have had a non-monotone PSNR to mean anything
+    fit.sync_params()                          # flush path: step 60's update (+ its snapshot, if a new best)
+    if prev[0] < best["sse"]:
+        best = {"sse": prev[0], "step": prev[1], "params": raw()}
+    st = fit.stats()
+    assert st["best_step"] == best["step"] and st["best_sse"] == best["sse"]
+    bs = fit.best_state()
+    got = torch.cat((bs["_xyz"], bs["_cov2d"], bs["_features_dc"]), dim=1)
+    assert torch.equal(got, best["params"])
+    assert hist_ok, "degenerate test: PSNR was monotone"
+    assert abs(st["best_psnr"] - 10 * np.log10(3.0 * 192 * 256 / best["sse"])) < 1e-9
+    assert st["best_step"] <= 40 < st["step"]
+
+
+def test_fit_loop_prune_densify_schedule():
+    """GaussianImageFitter.fit == train.py:120-152: prune every prune_iter, grow every grow_iter from the L1
+    error map of that iteration's render (the last growth fills up to max_num_points), best state kept
+    across the changes of the Gaussian count."""
+    fit, _ = make_fitter(600, 128, 192, seed=22, colors="zeros", use_graph=True, keep_render=False)
+    seen = []
+    torch.manual_seed(3047)
+    st = fit.fit(900, max_num_points=1500, prune_iter=100, grow_iter=300, callback=lambda it, f: seen.append(f.cur_num_points))
+    assert st["step"] == 900
+    # +min(1000, room)=900 at 300 (minus non-PSD draws and prunes), then the rest at 600 (= iterations - grow_iter)
+    assert seen[298] <= 600 and 600 < seen[299] <= 1500 and seen[-1] <= 1500
+    assert seen[599] > seen[598] - 1
+    assert fit.cholesky_bound.shape[0] == fit.cur_num_points == fit.exp_avg["xyz"].shape[0]
+    # the error map of a step == |clamp(render) - gt| summed over channels, from the same step's render
+    fit.keep_render = True
+    fit.train_iter(want_error_map=True)
+    torch.cuda.synchronize()
+    # (keep_render binds out_hwc only through _bind(); bind both for this check)
+    fit._bind(out_img=fit.out_hwc.data_ptr(), err_map=True)
+    fit._enqueue_step()
+    fit._dirty = True
+    fit._bind()
+    torch.cuda.synchronize()
+    ref = (fit.out_hwc.clamp(0, 1) - fit.gt_hwc).abs().sum(dim=2)
+    assert torch.allclose(fit.err_map, ref, atol=1e-6)
+    bs = fit.best_state()
+    assert bs["_xyz"].shape[0] == bs["cholesky_bound"].shape[0]
+    assert st["best_psnr"] >= st["psnr"] - 1e-9 and st["best_step"] > 0
+    n = fit.load_best_state()
+    assert n == bs["_xyz"].shape[0]
+    psnr_best_render = 10 * np.log10(1.0 / float(((fit.forward()["render"][0].permute(1, 2, 0) - fit.gt_hwc) ** 2).mean()))
+    assert psnr_best_render > st["best_psnr"] - 0.5   # (the snapshot is the state AFTER the best step's update)
+
+
 # --------------------------------------------------------------------------- full-size properties
 @pytest.mark.parametrize("name", ["kodak_5000", "div2k_20000"])
 def test_full_size_properties(name):

@@ -88,3 +88,30 @@ def test_tile_row_bands_sum_to_full_gradient(oracle):
         acc = [a + p for a, p in zip(acc, part)]
     for a, f in zip(acc, full):
         np.testing.assert_allclose(a, f, rtol=1e-5, atol=1e-6)
+
+
+def test_ssim_oracle_anchors():
+    """oracle/ssim_oracle.py restates pytorch_msssim.ssim (absent, unpinned): its closed-form anchors."""
+    import torch
+
+    from oracle import ssim_oracle as S
+
+    win = S.fspecial_gauss_1d()
+    assert win.shape == (11,) and abs(float(win.sum()) - 1) < 1e-6 and torch.equal(win, win.flip(0))
+    assert abs(float(win[5]) - 0.26601171493530273) < 1e-9      # the float32 value the kernels hard-code
+    torch.manual_seed(0)
+    x = torch.rand(1, 3, 40, 52, dtype=torch.float64)
+    y = torch.rand(1, 3, 40, 52, dtype=torch.float64)
+    assert abs(float(S.ssim(x, x)) - 1.0) < 1e-12
+    assert abs(float(S.ssim(x, y)) - float(S.ssim(y, x))) < 1e-12
+    # constant images: sigma = 0 -> ssim = (2 a b + C1) / (a^2 + b^2 + C1)
+    a, b = 0.5, 0.25
+    got = float(S.ssim(torch.full((1, 3, 20, 20), a, dtype=torch.float64), torch.full((1, 3, 20, 20), b, dtype=torch.float64)))
+    assert abs(got - (2 * a * b + 1e-4) / (a * a + b * b + 1e-4)) < 1e-5
+    # valid filtering: an 11x11 image has exactly one window
+    assert S.gaussian_filter(x[..., :11, :11], win).shape[-2:] == (1, 1)
+    # loss_fn weights (models/utils.py:70-75)
+    l2 = float(S.loss_fn(x, y, "L2")); l1 = float(S.loss_fn(x, y, "L1")); ss = float(S.loss_fn(x, y, "SSIM"))
+    assert abs(float(S.loss_fn(x, y, "Fusion1")) - (0.7 * l2 + 0.3 * ss)) < 1e-12
+    assert abs(float(S.loss_fn(x, y, "Fusion2")) - (0.7 * l1 + 0.3 * ss)) < 1e-12
+    assert abs(float(S.loss_fn(x, y, "Fusion3")) - (0.7 * l2 + 0.3 * l1)) < 1e-12
