@@ -95,7 +95,8 @@ def load():
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or `make -C gaussianimage_plus_b200/csrc`.  There is no CPU fallback."
             )
-        lib = C.CDLL(LIB_PATH)
+        # GI2D_LIB: a differently-compiled libgi2d (tools/build_variant.sh) for A/B timing; still no fallback
+        lib = C.CDLL(os.environ.get("GI2D_LIB") or LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res

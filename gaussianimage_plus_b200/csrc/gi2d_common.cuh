@@ -100,6 +100,21 @@ __device__ __forceinline__ float fast_exp_neg(float sigma) {
 
 constexpr float kAlphaMin = 1.f / 255.f;
 
+// ---- 8-bit target sample -> float exactly as torchvision's ToTensor (u8 / 255, IEEE division;
+// utils.py:21-27): one Newton step on x * fl(1/255).  Equal to __fdiv_rn(x, 255.f) for all 256 inputs
+// (checked exhaustively, tests/test_oracle_golden.py) without the divide's special-case branch.
+__device__ __forceinline__ float u8_to_unit(uint8_t v) {
+    const float x = (float)v, r = 0.0039215688593685626984f;
+    const float q = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-q, 255.f, x), r, q);
+}
+
+__device__ __forceinline__ float sqrt_approx(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 // ---- programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may start while
 // its predecessor on the stream is still draining; everything before pdl_wait() (index math, shared
 // memory zeroing, loads of data no predecessor writes) overlaps the predecessor's tail.  pdl_wait()

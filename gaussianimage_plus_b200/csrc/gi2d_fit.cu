@@ -695,8 +695,11 @@ fit_finalize_kernel(int capacity, const int32_t *__restrict__ n_dev, const uint6
 // FitBackward : backward from a dL/d(out) image (v_out, f32[H,W,3])    } SSIM term (needs neighbouring tiles)
 enum class RasterMode { Render, Fit, FitForward, FitBackward };
 
+#ifndef GI2D_FIT_MINBLOCKS
+#define GI2D_FIT_MINBLOCKS 4
+#endif
 template <RasterMode kMode>
-__global__ void __launch_bounds__(kRasterThreads, (kMode == RasterMode::Fit || kMode == RasterMode::FitBackward) ? 4 : 6)
+__global__ void __launch_bounds__(kRasterThreads, (kMode == RasterMode::Fit || kMode == RasterMode::FitBackward) ? GI2D_FIT_MINBLOCKS : 6)
 fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
                   const int32_t *__restrict__ tile_bins, const float4 *__restrict__ records,
                   const float *__restrict__ gt, const uint8_t *__restrict__ gt_u8,
@@ -728,9 +731,9 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
             tb = __ldg(gt + 3 * pix + 2);
         } else {
             // 8-bit target: the value torchvision's ToTensor produces, u8 / 255 (IEEE division)
-            tr = __fdiv_rn((float)__ldg(gt_u8 + 3 * pix), 255.f);
-            tgc = __fdiv_rn((float)__ldg(gt_u8 + 3 * pix + 1), 255.f);
-            tb = __fdiv_rn((float)__ldg(gt_u8 + 3 * pix + 2), 255.f);
+            tr = u8_to_unit(__ldg(gt_u8 + 3 * pix));
+            tgc = u8_to_unit(__ldg(gt_u8 + 3 * pix + 1));
+            tb = u8_to_unit(__ldg(gt_u8 + 3 * pix + 2));
         }
     }
     pdl_wait();  // the target image above is written by no kernel of the step; everything below is
@@ -810,9 +813,12 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
     if (!kHasBwd || cnt == 0) return;
     // ---- backward: warp = Gaussian, lane = 8 pixels
     const LanePixels lp = lane_pixels(blockIdx.x, tile_y, p.img_width, p.img_height);
-    backward_tile<false, kRasterWarps>(sg, s_ids, cnt, lp, tg,
-                                       [&](int gid, int k) -> float * { return grads + 8 * (size_t)gid + k; },
-                                       nullptr);
+    auto grad_of = [&](int gid, int k) -> float * { return grads + 8 * (size_t)gid + k; };
+    // (CTA-uniform) a tile that lies wholly inside the image needs no per-pixel inside test
+    if ((blockIdx.x + 1) * kTile <= p.img_width && (tile_y + 1) * kTile <= p.img_height)
+        backward_tile<false, kRasterWarps, true>(sg, s_ids, cnt, lp, tg, grad_of, nullptr);
+    else
+        backward_tile<false, kRasterWarps, false>(sg, s_ids, cnt, lp, tg, grad_of, nullptr);
 }
 
 // ------------------------------------------------------------------------------------ K5

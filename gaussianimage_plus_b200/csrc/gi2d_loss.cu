@@ -42,7 +42,7 @@ __constant__ float c_win[kWin] = {
 constexpr float kC1 = 0.01f * 0.01f, kC2 = 0.03f * 0.03f;
 
 __device__ __forceinline__ float target_at(const float *gt, const uint8_t *gt_u8, size_t idx) {
-    return gt ? __ldg(gt + idx) : __fdiv_rn((float)__ldg(gt_u8 + idx), 255.f);
+    return gt ? __ldg(gt + idx) : u8_to_unit(__ldg(gt_u8 + idx));
 }
 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }

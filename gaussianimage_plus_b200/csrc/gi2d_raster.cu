@@ -86,7 +86,7 @@ raster_bwd_kernel(int tiles_x, int img_w, int img_h, const int32_t *__restrict__
     }
     __syncthreads();
     const LanePixels lp = lane_pixels(blockIdx.x, blockIdx.y, img_w, img_h);
-    backward_tile<kOpacity, kWarps>(sg, s_ids, cnt, lp, tg,
+    backward_tile<kOpacity, kWarps, false>(sg, s_ids, cnt, lp, tg,
                                     [&](int g, int k) -> float * {
                                         return k < 2 ? v_xy + 2 * g + k
                                                      : (k < 5 ? v_conic + 3 * g + (k - 2) : v_colors + 3 * g + (k - 5));

@@ -45,9 +45,10 @@ __device__ __forceinline__ unsigned reach_mask(float gx, float gy, float a, floa
     const float L = __logf(255.f * op) * 1.001f + 1e-3f;
     // indefinite / NaN / extremely anisotropic (det would carry cancellation error): no culling
     if (!(det > 1e-3f * a * c && a > 0.f && c > 0.f && L > 0.f && L < 1e30f)) return 0xFFu;
-    const float k = 2.f * L / det;
-    const float hx = sqrtf(k * c) * 1.001f + 1e-3f;
-    const float hy = sqrtf(k * a) * 1.001f + 1e-3f;
+    // (approximate divide / sqrt, <= 2 ulp each: far inside the 0.1 % + 1e-3 px inflation)
+    const float k = __fdividef(2.f * L, det);
+    const float hx = sqrt_approx(k * c) * 1.001f + 1e-3f;
+    const float hy = sqrt_approx(k * a) * 1.001f + 1e-3f;
     if (!(hx < 1e30f && hy < 1e30f)) return 0xFFu;
     const float x0 = gx - hx, x1 = gx + hx, y0 = gy - hy, y1 = gy + hy;
     unsigned m = 0;
@@ -201,7 +202,7 @@ __device__ __forceinline__ LanePixels lane_pixels(int tile_x, int tile_y, int im
 //   acc = { v_x, v_y, v_a, v_b, v_c, v_r, v_g, v_b }  (+ *acc_op for opacity when kOpacity)
 // Same validity rule as backward.cu:1273-1283 (sigma>=0, alpha>=1/255); the `<= final_idx`
 // condition of the reference is implied by the 256-per-tile cap.
-template <bool kOpacity, class Store>
+template <bool kOpacity, bool kFullTile, class Store>
 __device__ __forceinline__ void backward_accumulate(const Store &s, int t, const LanePixels &lp,
                                                     const TileGrad &tg, float (&acc)[8], float *acc_op) {
     const GaussRec q = s.get(t);
@@ -221,7 +222,7 @@ __device__ __forceinline__ void backward_accumulate(const Store &s, int t, const
         const float sigma = __fmaf_rn(dy, bdx, __fmul_rn(qq, 0.5f));
         const float vis = fast_exp_neg(sigma);
         const float alpha = Store::kUnitOpacity ? vis : fminf(1.f, __fmul_rn(q.op, vis));
-        const bool valid = ((lp.inside >> blk) & 1u) && !(sigma < 0.f || alpha < kAlphaMin);
+        const bool valid = (kFullTile || ((lp.inside >> blk) & 1u)) && !(sigma < 0.f || alpha < kAlphaMin);
         if (!__any_sync(0xffffffffu, valid)) continue;
         if (valid) {
             const int pi = lp.base + ((blk & 1) << 3) + ((blk >> 1) << 2) * kGradStride;
@@ -256,7 +257,7 @@ __device__ __forceinline__ void backward_accumulate(const Store &s, int t, const
 // Backward of one tile: warps take the staged Gaussians round-robin, one at a time.  After the
 // reduce-scatter lane L holds component L>>2; lanes with (L&3)==0 issue the red.global.add.
 // grad_of(g, k) returns the address of component k (0..7) of Gaussian g.
-template <bool kOpacity, int kWarps, class Store, class GradAddr>
+template <bool kOpacity, int kWarps, bool kFullTile, class Store, class GradAddr>
 __device__ __forceinline__ void backward_tile(const Store &s, const int *s_ids, int cnt, const LanePixels &lp,
                                               const TileGrad &tg, GradAddr grad_of, float *v_opacity) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -264,7 +265,7 @@ __device__ __forceinline__ void backward_tile(const Store &s, const int *s_ids, 
         if (s.mask[t] == 0) continue;  // the alpha >= 1/255 ellipse misses the tile altogether (warp-uniform)
         float acc[8];
         float op = 0.f;
-        backward_accumulate<kOpacity>(s, t, lp, tg, acc, &op);
+        backward_accumulate<kOpacity, kFullTile>(s, t, lp, tg, acc, &op);
         const float total = warp_reduce_scatter8(acc);
         if ((lane & 3) == 0 && total != 0.f) atomicAdd(grad_of(s_ids[t], lane >> 2), total);
         if (kOpacity) {
