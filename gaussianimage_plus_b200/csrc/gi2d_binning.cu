@@ -255,6 +255,13 @@ int radix_pass_keys_u64(int n_capacity, const int32_t *n_dev, const uint64_t *ke
     return check_launch("radix_pass_keys_u64");
 }
 
+// inclusive prefix sum for the fit step's per-tile overlap counts (gi2d_fit.cu)
+int cumsum_i32_launch(int n, const int32_t *in, int32_t *out, int32_t *total, int32_t *block_sums,
+                      cudaStream_t st) {
+    return launch_cumsum(n, in, out, total, block_sums, st);
+}
+size_t cumsum_i32_workspace(int n) { return gi2d_scan_workspace_size(n); }
+
 int tile_edges_from_keys_u64(int n_capacity, const int32_t *n_dev, const uint64_t *keys, int32_t *tile_bins,
                              int rows, cudaStream_t st) {
     cudaMemsetAsync(tile_bins, 0, (size_t)rows * 2 * sizeof(int32_t), st);

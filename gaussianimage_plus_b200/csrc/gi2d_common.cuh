@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/gi2d.h"
 
 namespace gi2d {
@@ -120,6 +121,11 @@ __device__ __forceinline__ float sqrt_approx(float v) {
 // memory zeroing, loads of data no predecessor writes) overlaps the predecessor's tail.  pdl_wait()
 // returns once the predecessor grid has completed and its writes are visible.  Every thread calls it
 // before touching dependent data (and before any early return, which keeps the chain transitive).
+// RULE: data produced by a predecessor in the chain must be read with COHERENT loads (__ldcg / plain
+// ld.global), never through the read-only path (__ldg, or a `const T *__restrict__` the compiler may turn
+// into ld.global.nc): the kernel's lifetime starts BEFORE those writes, so "read-only for the lifetime of
+// the kernel" does not hold and a stale L1/texture line can be served (seen as a once-in-many-steps glitch
+// whenever the intersection list shifted between two steps).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -140,7 +146,8 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     // only eager launches (render loop, un-graphed steps) overlap their prologues.
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
-    cfg.numAttrs = cap == cudaStreamCaptureStatusNone ? 1 : 0;
+    static const bool no_pdl = getenv("GI2D_NO_PDL") != nullptr;  // debugging aid: fully serialised launches
+    cfg.numAttrs = (cap == cudaStreamCaptureStatusNone && !no_pdl) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -1,40 +1,41 @@
 // gi2d_fit.cu -- the fused, synchronisation-free fit step: everything one
-// `train_iter` of models/gaussianimage_covariance.py:249-259 does on the device, in 5 launches
-// for images of up to 2048 tiles (768x512) and a few more beyond, with no host round trip, no
-// allocation and a device-side step counter, so the whole iteration replays from one CUDA graph.
+// `train_iter` of models/gaussianimage_covariance.py:249-259 does on the device, in 3 launches
+// for images of up to 2048 tiles (768x512) and 6 beyond, with no host round trip, no allocation
+// and a device-side step counter, so the whole iteration replays from one CUDA graph.
 //
-//   K1 fit_project_kernel   projection (R1) + colour activation + packed 32-B record per
-//                           Gaussian + zeroing of the gradient rows + per-CTA digit histogram of
-//                           the tile ids the Gaussian touches + step/lr bookkeeping  [HBM/latency]
-//   K2 fit_scan_kernel      prefix sum over the per-tile (digit) overlap counts -> scatter
-//                           offsets, tile ranges, num_intersects                    [latency]
-//   K3 fit_scatter_kernel   stable counting-sort scatter of 64-bit (tile<<32|gaussian) keys:
-//                           one LSD radix pass of up to 11 bits, ranks by warp match_any over a
-//                           load-balanced expansion of the tile boxes; also gathers the 32-B
-//                           record of every intersection into sorted order so the rasterizer
-//                           reads its tile's Gaussians as ONE contiguous block      [HBM/latency]
-//      (+ 8-bit radix passes + tile edges + record gather for images with > 2048 tiles)
-//   K4 fit_raster_kernel    per 16x16 tile: rasterize-sum forward (R5), L2 loss gradient and
-//                           squared error, rasterize-sum backward (R6) with register
-//                           accumulation + transposed warp reduction + one red.global per
-//                           (tile, Gaussian, component)                             [FP32 issue]
-//   K5 fit_adam_kernel      projection backward (R7) + Adam + StepLR on xyz/cov/rgb [HBM]
+//   K1 fit_project_kernel   [Adam of the previous step] + projection (R1) + colour activation +
+//                           packed 32-B record per Gaussian + zeroing of the gradient row + the
+//                           per-tile overlap COUNT (one red.global per touched tile)   [HBM/latency]
+//   K2 fit_place_kernel     prefix sum over the per-tile overlap counts -> tile ranges and
+//                           num_intersects (redone per CTA in shared memory for <= 2048 tiles; a
+//                           3-launch device-wide scan beyond), then the counting-sort placement of
+//                           every (tile, gaussian) pair: slot = start[tile] + atomic cursor; writes
+//                           the 64-bit key (tile<<32|gaussian) and the 32-B record, so a tile's
+//                           Gaussians are ONE contiguous block; step/lr bookkeeping     [HBM/latency]
+//   K3 fit_raster_kernel    per 16x16 tile: finish the key sort (the placement is ordered by tile
+//                           only: the <= 256 entries of the tile are rank-sorted by gaussian id in
+//                           shared memory while they are staged, and written back sorted);
+//                           rasterize-sum forward (R5), loss gradient and squared error,
+//                           rasterize-sum backward (R6) with register accumulation + transposed
+//                           warp reduction + one red.global per (tile, Gaussian, component) [FP32 issue]
+//   (K5 fit_adam_kernel     stand-alone flush of a pending optimiser step; in steady state K1 does it)
 //
-// Ordering inside a tile is ascending Gaussian id (what the reference's stable sort of
-// (tile<<32|depth=0) keys emitted Gaussian-major yields), so tile ranges, sorted ids and the
-// rendered image are bit-identical to the reference-shaped path in gi2d_binning.cu/gi2d_raster.cu.
+// The 64-bit key sort of the reference (torch.sort of tile<<32|depth-bits, stable, Gaussian-major
+// emission: utils.py:301, forward.cu:187-196) orders by tile, then by ascending Gaussian id.  Here
+// the tile word is sorted by ONE counting pass whose digit is the whole tile id (no limit on the
+// number of tiles, no multi-pass radix), the gaussian word by a comparison-rank sort inside the
+// tile: same keys, same order, bit for bit (tests/test_gpu_fit.py::test_fit_binning_bit_exact).
+// The LSD radix sort of arbitrary 64-bit keys lives in gi2d_binning.cu (gi2d_sort_pairs_i64).
 #include "gi2d_project_core.cuh"
 #include "gi2d_raster_core.cuh"
 #include "gi2d_scan.cuh"
 
 namespace gi2d {
 
-// implemented in gi2d_binning.cu: one 8-bit-digit LSD pass over u64 keys (no payload)
-int radix_pass_keys_u64(int n_capacity, const int32_t *n_dev, const uint64_t *keys_in, uint64_t *keys_out,
-                        int shift, int bits, void *workspace, size_t workspace_bytes, cudaStream_t st);
-size_t radix_pass_workspace_size(int n_capacity);
-int tile_edges_from_keys_u64(int n_capacity, const int32_t *n_dev, const uint64_t *keys, int32_t *tile_bins,
-                             int rows, cudaStream_t st);
+// implemented in gi2d_binning.cu: inclusive prefix sum of n ints (1 launch up to 2048 items, else 3)
+int cumsum_i32_launch(int n, const int32_t *in, int32_t *out, int32_t *total, int32_t *block_sums,
+                      cudaStream_t st);
+size_t cumsum_i32_workspace(int n);
 
 int ssim_grad_launch(int H, int W, const float *render, const float *gt, const uint8_t *gt_u8, float *dm_ws,
                      float ssim_weight, float l2_scale, float l1_scale, float *v_out, double *ssim_sum,
@@ -42,17 +43,16 @@ int ssim_grad_launch(int H, int W, const float *render, const float *gt, const u
 
 namespace {
 
-constexpr int kMaxDigitBits = 11;                 // 2048 bins: a 768x512 image sorts in ONE pass
-constexpr int kProjThreads = 256;
-constexpr int kScatterWarps = 4;
-constexpr int kScatterThreads = kScatterWarps * 32;
+constexpr int kMaxSmemTiles = 2048;               // tile starts are scanned in shared memory up to here
+constexpr int kProjThreads = 256;                   // launch bound; small scenes launch 64-thread CTAs (latency bound:
+                                                    // spread over the SMs), large ones 256
+constexpr int kPlaceWarps = 8;
+constexpr int kPlaceThreads = kPlaceWarps * 32;
+constexpr int kPlaceGpw = 8;                      // Gaussians per warp of K2
 constexpr int kRasterThreads = 256;
 constexpr int kRasterWarps = kRasterThreads / 32;
 
 // private slots of the stats block (beyond the public GI2D_STAT_* ones)
-constexpr int kPass1ChunkBits = 11;               // the second pass works on chunks of 2048 keys
-constexpr int kPass1Bits = 9;                     // and up to 9 more tile bits
-constexpr int kPass1Radix = 1 << kPass1Bits;
 constexpr int kStatB1Pow = 4;  // beta1^step
 constexpr int kStatB2Pow = 5;  // beta2^step
 constexpr int kStatStepSize = 6;  // lr / (1 - beta1^step)   of the step in flight
@@ -66,7 +66,7 @@ constexpr int kStatNonPsdAcc = 12;  // accumulator behind GI2D_STAT_NON_PSD (mov
 // every CTA of the optimiser kernel and the bookkeeping thread take the same best-so-far decision.
 __device__ __forceinline__ double sse_total_warp(const double *__restrict__ stats) {
     const int lane = threadIdx.x & 31;
-    double v = stats[GI2D_STAT_SSE + lane] + stats[GI2D_STAT_SSE + 32 + lane];
+    double v = __ldcg(stats + GI2D_STAT_SSE + lane) + __ldcg(stats + GI2D_STAT_SSE + 32 + lane);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     return v;
@@ -77,7 +77,7 @@ __device__ __forceinline__ double sse_total_warp(const double *__restrict__ stat
 __device__ __forceinline__ void best_flag_warp0(const double *__restrict__ stats, bool candidate, int *s_flag) {
     if (threadIdx.x < 32) {
         const double tot = sse_total_warp(stats);
-        if (threadIdx.x == 0) *s_flag = (candidate && tot < stats[GI2D_STAT_BEST_SSE]) ? 1 : 0;
+        if (threadIdx.x == 0) *s_flag = (candidate && tot < __ldcg(stats + GI2D_STAT_BEST_SSE)) ? 1 : 0;
     }
 }
 
@@ -92,37 +92,19 @@ __device__ __forceinline__ void best_commit_warp0(double *__restrict__ stats) {
 }
 
 struct Plan {
-    int tile_bits;     // bits needed for a tile id
-    int bits0;         // digit width of the in-kernel pass
-    int gpb;           // Gaussians per CTA of K1/K3 (multiple of kScatterThreads)
-    int nblocks;       // CTAs of K1/K3
-    int extra_passes;  // additional 8-bit passes over the high tile bits
+    int num_tiles;
+    bool smem_scan;    // tile starts fit the in-kernel scan
+    int gpb;           // Gaussians per CTA of K2
+    int nblocks;       // CTAs of K2
 };
 
 Plan make_plan(const gi2d_fit_params &p) {
     Plan pl;
-    const int tiles = p.tiles_x * p.tiles_y;
-    int tb = 1;
-    while ((1 << tb) < tiles) ++tb;
-    pl.tile_bits = tb;
-    if (tb <= kMaxDigitBits) {
-        pl.bits0 = tb;          // one pass: digit == tile id
-        pl.extra_passes = 0;
-    } else if (tb <= kMaxDigitBits + kPass1Bits) {
-        // two passes: give the second (chunked, perfectly balanced, 512-bin) pass as many bits as it can
-        // take; the first pass then has a SMALL digit, so every per-CTA cost that scales with the number
-        // of bins (histogram zeroing, offset tables, the count matrix) shrinks with it
-        pl.bits0 = tb - kPass1Bits;
-        pl.extra_passes = 1;
-    } else {
-        pl.bits0 = kMaxDigitBits;  // > 2^20 tiles: generic 8-bit passes over the remaining bits
-        pl.extra_passes = (tb - pl.bits0 + 7) / 8;
-    }
-    // keep the count matrix (nblocks x 2^bits0 ints) around 10 MB
-    constexpr int gpw = 16;  // Gaussians per warp of K3: measured best of {8,16,32,64} at 768x512 / 5000
-    const long long max_rows = 1184LL * (2048 >> pl.bits0 > 0 ? (2048 >> pl.bits0) : 1);
-    int gpb = kScatterWarps * gpw;
-    while ((long long)gpb * max_rows < p.num_points) gpb *= 2;
+    pl.num_tiles = p.tiles_x * p.tiles_y;
+    pl.smem_scan = pl.num_tiles <= kMaxSmemTiles;
+    // at most ~16 CTAs per SM of K2: beyond that, more Gaussians per CTA
+    int gpb = kPlaceWarps * kPlaceGpw;
+    while ((long long)gpb * 2368 < p.num_points) gpb *= 2;
     pl.gpb = gpb;
     pl.nblocks = p.num_points > 0 ? cdiv(p.num_points, gpb) : 1;
     return pl;
@@ -131,16 +113,14 @@ Plan make_plan(const gi2d_fit_params &p) {
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct Workspace {
-    int32_t *counts;      // [nblocks][D] per-CTA digit counts -> per-CTA exclusive offsets
-    int32_t *totals;      // [D] column totals of counts (= size of every digit bucket)
+    int32_t *tile_count;  // [T] overlap count per tile (K1 adds, K3 hands it back zeroed)
+    int32_t *tile_fill;   // [T] placement cursor per tile (K2 adds, K3 hands it back zeroed)
+    int32_t *tile_incl;   // [T] inclusive prefix of tile_count (only beyond kMaxSmemTiles tiles)
+    int32_t *scan_ws;     //     block sums of that scan
     ushort4 *boxes;       // [N] clipped tile box per Gaussian
     int32_t *n_isect;     // [1] device copy of num_intersects (clamped to capacity)
-    float4 *records;      // [capacity][2] projected record of every intersection, sorted order
-    uint64_t *keys_tmp;   // [capacity] ping-pong buffer for multi-pass sorts
-    int32_t *counts1;     // [capacity/2048][256] second-pass histogram (kept zero between iterations)
-    int32_t *totals1;     // [256]
-    void *radix_ws;
-    size_t radix_ws_bytes;
+    float4 *records;      // [capacity][2] projected record of every intersection, tile order
+    uint64_t *keys_tmp;   // [capacity] scratch for tiles with more than 256 entries (full in-tile sort)
     float *loss_render;   // [H,W,3] unclamped render   } only with loss_ssim_weight != 0:
     float *loss_dm;       // [9][H,W] SSIM partials      } the rasterize launch is split around
     float *loss_vout;     // [H,W,3] dL/d(out)           } the SSIM gradient kernels
@@ -151,26 +131,20 @@ Workspace carve(const gi2d_fit_params &p, const Plan &pl, void *base) {
     Workspace w;
     char *c = (char *)base;
     size_t off = 0;
-    const size_t D = (size_t)1 << pl.bits0;
-    w.counts = (int32_t *)(c + off);      off += align_up((size_t)pl.nblocks * D * 4);
-    w.totals = (int32_t *)(c + off);      off += align_up(D * 4);
+    const size_t T = (size_t)(pl.num_tiles > 0 ? pl.num_tiles : 1);
+    // (tile_count and tile_fill are adjacent: one memset zeroes both when the workspace is created)
+    w.tile_count = (int32_t *)(c + off);  off += align_up(T * 4);
+    w.tile_fill = (int32_t *)(c + off);   off += align_up(T * 4);
+    w.tile_incl = nullptr;
+    w.scan_ws = nullptr;
+    if (!pl.smem_scan) {
+        w.tile_incl = (int32_t *)(c + off);  off += align_up(T * 4);
+        w.scan_ws = (int32_t *)(c + off);    off += align_up(cumsum_i32_workspace((int)T));
+    }
     w.boxes = (ushort4 *)(c + off);       off += align_up((size_t)(p.num_points > 0 ? p.num_points : 1) * 8);
     w.n_isect = (int32_t *)(c + off);     off += 256;
     w.records = (float4 *)(c + off);      off += align_up((size_t)p.isect_capacity * 32);
-    w.keys_tmp = nullptr;
-    w.counts1 = nullptr;
-    w.totals1 = nullptr;
-    w.radix_ws = nullptr;
-    w.radix_ws_bytes = 0;
-    if (pl.extra_passes > 0) {
-        w.keys_tmp = (uint64_t *)(c + off);  off += align_up((size_t)p.isect_capacity * 8);
-        w.counts1 = (int32_t *)(c + off);
-        off += align_up((size_t)cdiv(p.isect_capacity, 1 << kPass1ChunkBits) * kPass1Radix * 4);
-        w.totals1 = (int32_t *)(c + off);    off += align_up(kPass1Radix * 4);
-        w.radix_ws = (void *)(c + off);
-        w.radix_ws_bytes = radix_pass_workspace_size(p.isect_capacity);
-        off += align_up(w.radix_ws_bytes);
-    }
+    w.keys_tmp = (uint64_t *)(c + off);   off += align_up((size_t)p.isect_capacity * 8);
     w.loss_render = w.loss_dm = w.loss_vout = nullptr;
     if (p.loss_ssim_weight != 0.f) {
         const size_t px = (size_t)p.img_width * p.img_height;
@@ -181,6 +155,7 @@ Workspace carve(const gi2d_fit_params &p, const Plan &pl, void *base) {
     w.total = off;
     return w;
 }
+
 
 __device__ __forceinline__ float sigmoidf(float v) { return 1.f / (1.f + expf(-v)); }
 
@@ -202,8 +177,8 @@ __device__ __forceinline__ void adam_update_gaussian(const gi2d_fit_params &p, c
                                                      float4 p0, float4 p1, float4 g0, float4 g1,
                                                      const double *__restrict__ stats, bool skip,
                                                      float2 &x, float (&c)[3], float (&q)[3]) {
-    const float step_size = (float)stats[kStatStepSize];
-    const float bc2_sqrt = (float)stats[kStatBc2Sqrt];
+    const float step_size = (float)__ldcg(stats + kStatStepSize);
+    const float bc2_sqrt = (float)__ldcg(stats + kStatBc2Sqrt);
     const float w1 = (float)(1.0 - (double)p.beta1), w2 = (float)(1.0 - (double)p.beta2);
     x = reinterpret_cast<float2 *>(a.xyz)[g];
     float2 mx = reinterpret_cast<float2 *>(a.m_xyz)[g], vx = reinterpret_cast<float2 *>(a.v_xyz)[g];
@@ -252,107 +227,77 @@ __device__ __forceinline__ void adam_update_gaussian(const gi2d_fit_params &p, c
 // Optimiser of the PREVIOUS step + projection of THIS step, per Gaussian, in one launch: the thread
 // that owns Gaussian g first applies projection-backward + Adam to it when a gradient is pending
 // (stats[kStatPending]; the overflow flag of that step vetoes it), then projects the fresh parameters,
-// writes the 32-B record, zeroes the gradient row for the coming backward and counts the tiles.
+// writes the 32-B record, zeroes the gradient row for the coming backward and adds 1 to the overlap
+// count of every tile its box touches ("per-tile overlap counts", one fire-and-forget red.global each).
 // This kernel only READS the stats block; the bookkeeping for the step in flight is done by K2.
 __global__ void __launch_bounds__(kProjThreads)
-fit_project_kernel(gi2d_fit_params p, int gpb, int bits0, AdamPtrs a, const float *__restrict__ cov_bound,
+fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bound,
                    float4 *__restrict__ proj, float4 *__restrict__ grads, ushort4 *__restrict__ boxes,
-                   int32_t *__restrict__ counts, const double *__restrict__ stats, int with_backward,
+                   int32_t *__restrict__ tile_count, const double *__restrict__ stats, int with_backward,
                    float4 *__restrict__ best) {
-    extern __shared__ int s_hist[];
     __shared__ int s_best;
-    const int D = 1 << bits0;
-    const int mask = D - 1;
     pdl_launch_dependents();
-    for (int d = threadIdx.x; d < D; d += kProjThreads) s_hist[d] = 0;
-    pdl_wait();  // the previous step's rasterizer wrote grads (and read proj)
-    const bool pending = a.m_xyz != nullptr && stats[kStatPending] != 0.0;
-    const bool veto = stats[GI2D_STAT_OVERFLOW] != 0.0;  // that step overflowed: the host re-runs it
+    pdl_wait();  // the previous step's rasterizer wrote grads (and read proj, and zeroed tile_count)
+    const bool pending = a.m_xyz != nullptr && __ldcg(stats + kStatPending) != 0.0;
+    const bool veto = __ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0;  // that step overflowed: the host re-runs it
     best_flag_warp0(stats, best != nullptr && pending && !veto, &s_best);
     __syncthreads();
     const bool snapshot = s_best != 0;
-    const int g0 = blockIdx.x * gpb;
-    const int g1 = min(p.num_points, g0 + gpb);
-    for (int g = g0 + threadIdx.x; g < g1; g += kProjThreads) {
-        float2 m;
-        float c[3], q[3];
-        if (pending) {
-            adam_update_gaussian(p, a, g, proj[2 * g], proj[2 * g + 1], grads[2 * g], grads[2 * g + 1], stats, veto,
-                                 m, c, q);
-            if (snapshot) {  // the state dict right after optimizer.step() of the best iteration (train.py:132-137)
-                best[2 * g] = make_float4(m.x, m.y, c[0], c[1]);
-                best[2 * g + 1] = make_float4(c[2], q[0], q[1], q[2]);
-            }
-        } else {
-            m = reinterpret_cast<const float2 *>(a.xyz)[g];
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.num_points) return;
+    float2 m;
+    float c[3], q[3];
+    if (pending) {
+        adam_update_gaussian(p, a, g, __ldcg(proj + 2 * g), __ldcg(proj + 2 * g + 1), __ldcg(grads + 2 * g),
+                             __ldcg(grads + 2 * g + 1), stats, veto, m, c, q);
+        if (snapshot) {  // the state dict right after optimizer.step() of the best iteration (train.py:132-137)
+            best[2 * g] = make_float4(m.x, m.y, c[0], c[1]);
+            best[2 * g + 1] = make_float4(c[2], q[0], q[1], q[2]);
+        }
+    } else {
+        m = reinterpret_cast<const float2 *>(a.xyz)[g];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { c[k] = a.cov[3 * g + k]; q[k] = a.rgb[3 * g + k]; }
-        }
-        // get_cov2d_elements = _cov2d + cholesky_bound (gaussianimage_covariance.py:169)
-        const float sx = __fadd_rn(c[0], __ldg(cov_bound + 3 * g));
-        const float sxy = __fadd_rn(c[1], __ldg(cov_bound + 3 * g + 1));
-        const float sy = __fadd_rn(c[2], __ldg(cov_bound + 3 * g + 2));
-        float cr = q[0], cg = q[1], cb = q[2];
-        if (p.color_sigmoid) { cr = sigmoidf(cr); cg = sigmoidf(cg); cb = sigmoidf(cb); }
-        const Projected pr = project_cov(m.x, m.y, sx, sxy, sy, p.clip_coe, p.radius_clip, p.tiles_x, p.tiles_y);
-        proj[2 * g] = make_float4(pr.x, pr.y, pr.a, pr.b);
-        proj[2 * g + 1] = make_float4(pr.c, cr, cg, cb);
-        if (with_backward) {
-            grads[2 * g] = make_float4(0.f, 0.f, 0.f, 0.f);
-            grads[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        // the map kernel's own cull (forward.cu:161) and the band owned by this rank
-        int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-        if (pr.ntiles > 0 && !((float)pr.radius < p.radius_clip)) {
-            x0 = pr.box.x0; x1 = pr.box.x1;
-            y0 = max(pr.box.y0, p.tile_row_begin);
-            y1 = min(pr.box.y1, p.tile_row_end);
-            if (y1 <= y0) { x0 = x1 = y0 = y1 = 0; }
-        }
-        boxes[g] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
-        for (int ty = y0; ty < y1; ++ty)
-            for (int tx = x0; tx < x1; ++tx) atomicAdd(&s_hist[(ty * p.tiles_x + tx) & mask], 1);
+        for (int k = 0; k < 3; ++k) { c[k] = a.cov[3 * g + k]; q[k] = a.rgb[3 * g + k]; }
     }
-    __syncthreads();
-    for (int d = threadIdx.x; d < D; d += kProjThreads) counts[(size_t)blockIdx.x * D + d] = s_hist[d];
+    // get_cov2d_elements = _cov2d + cholesky_bound (gaussianimage_covariance.py:169)
+    const float sx = __fadd_rn(c[0], __ldg(cov_bound + 3 * g));
+    const float sxy = __fadd_rn(c[1], __ldg(cov_bound + 3 * g + 1));
+    const float sy = __fadd_rn(c[2], __ldg(cov_bound + 3 * g + 2));
+    float cr = q[0], cg = q[1], cb = q[2];
+    if (p.color_sigmoid) { cr = sigmoidf(cr); cg = sigmoidf(cg); cb = sigmoidf(cb); }
+    const Projected pr = project_cov(m.x, m.y, sx, sxy, sy, p.clip_coe, p.radius_clip, p.tiles_x, p.tiles_y);
+    proj[2 * g] = make_float4(pr.x, pr.y, pr.a, pr.b);
+    proj[2 * g + 1] = make_float4(pr.c, cr, cg, cb);
+    if (with_backward) {
+        grads[2 * g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        grads[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // the map kernel's own cull (forward.cu:161) and the band owned by this rank
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    if (pr.ntiles > 0 && !((float)pr.radius < p.radius_clip)) {
+        x0 = pr.box.x0; x1 = pr.box.x1;
+        y0 = max(pr.box.y0, p.tile_row_begin);
+        y1 = min(pr.box.y1, p.tile_row_end);
+        if (y1 <= y0) { x0 = x1 = y0 = y1 = 0; }
+    }
+    boxes[g] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+    for (int ty = y0; ty < y1; ++ty)
+        for (int tx = x0; tx < x1; ++tx) atomicAdd(tile_count + ty * p.tiles_x + tx, 1);
 }
 
-// ------------------------------------------------------------------------------------ K2
-// Prefix sum over the per-tile (digit) overlap counts, step 1: turn the per-CTA counts of K1,
-// counts[b][d], into the exclusive prefix over b (in place) and leave the column total in
-// totals[d].  A CTA owns 32 digit columns; its 8 warps split the rows into 8 contiguous segments
-// (a warp reads 128 contiguous bytes per row), scan their segment with all loads in flight at
-// once, exchange the 8 segment sums through shared memory and write back.  D/32 CTAs: the whole
-// matrix is in flight at once instead of one exposed L2 round trip per row.
-// Step 2 (exclusive scan over d of the totals = start of every digit/tile) is 8 KiB of work and
-// is redone by every CTA of K3 in its prologue instead of costing a launch.
-constexpr int kScanCols = 32;
-constexpr int kScanSegs = 8;
-constexpr int kScanThreads = kScanCols * kScanSegs;
-constexpr int kScanMaxRows = 16;  // rows per segment held in registers per trip
-
-__global__ void __launch_bounds__(kScanThreads)
-fit_scan_kernel(gi2d_fit_params p, int with_backward, double *__restrict__ stats, int nblocks, int D,
-                int32_t *__restrict__ counts, int32_t *__restrict__ totals, const int32_t *__restrict__ n_items,
-                int items_per_row) {
-    __shared__ int s_seg[kScanSegs][kScanCols];
-    pdl_launch_dependents();
-    pdl_wait();
-    // Bookkeeping of the step in flight (K1 has already consumed the previous step's values): zero the
-    // SSE partials and the overflow flag, and -- for a training step -- advance the step counter, the
-    // bias-correction powers and the StepLR schedule.  torch evaluates beta^t and gamma^floor((t-1)/size)
-    // in double precision as well.  The Adam that uses them runs inside the NEXT K1 (or gi2d_fit_adam).
-    // (with_backward < 0: this launch scans the second pass' matrix and does no bookkeeping; its row count
-    //  is the number of 2048-key chunks actually in use, known only on the device)
-    if (n_items) nblocks = min(nblocks, (*n_items + items_per_row - 1) / items_per_row);
-    if (with_backward >= 0 && blockIdx.x == 0 && threadIdx.x < 32) {
-        best_commit_warp0(stats);  // (the optimiser threads of K1 took the same decision for their snapshot)
-        __syncwarp();
-        stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
-        stats[GI2D_STAT_SSE + 32 + threadIdx.x] = 0.0;
-        __syncwarp();
-    }
-    if (with_backward >= 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+// Bookkeeping of the step in flight, by warp 0 of ONE CTA of K2 (K1 has already consumed the previous
+// step's values; K3 has not started): commit the best-so-far decision, zero the loss accumulators and
+// the overflow flag, and -- for a training step -- advance the step counter, the bias-correction powers
+// and the StepLR schedule.  torch evaluates beta^t and gamma^floor((t-1)/size) in double precision as
+// well.  The Adam that uses them runs inside the NEXT K1 (or gi2d_fit_adam).
+__device__ __forceinline__ void step_bookkeeping_warp0(const gi2d_fit_params &p, int with_backward,
+                                                       double *__restrict__ stats) {
+    best_commit_warp0(stats);  // (the optimiser threads of K1 took the same decision for their snapshot)
+    __syncwarp();
+    stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
+    stats[GI2D_STAT_SSE + 32 + threadIdx.x] = 0.0;
+    __syncwarp();
+    if (threadIdx.x == 0) {
         stats[GI2D_STAT_OVERFLOW] = 0.0;
         stats[GI2D_STAT_SSIM_SUM] = 0.0;
         stats[GI2D_STAT_ABS_SUM] = 0.0;
@@ -368,56 +313,19 @@ fit_scan_kernel(gi2d_fit_params p, int with_backward, double *__restrict__ stats
             stats[kStatBc2Sqrt] = sqrt(1.0 - stats[kStatB2Pow]);
         }
     }
-    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
-    const int d = blockIdx.x * kScanCols + lane;
-    const int rows_per_seg = (nblocks + kScanSegs - 1) / kScanSegs;
-    const int r0 = min(nblocks, seg * rows_per_seg), r1 = min(nblocks, r0 + rows_per_seg);
-    int32_t *col = counts + d;
-    const bool ok = d < D;
-    // pass 1: segment sum
-    int sum = 0;
-    for (int r = r0; r < r1; r += kScanMaxRows) {
-        int c[kScanMaxRows];
-#pragma unroll
-        for (int j = 0; j < kScanMaxRows; ++j) c[j] = (ok && r + j < r1) ? __ldcg(col + (size_t)(r + j) * D) : 0;
-#pragma unroll
-        for (int j = 0; j < kScanMaxRows; ++j) sum += c[j];
-    }
-    s_seg[seg][lane] = sum;
-    __syncthreads();
-    int run = 0, total = 0;
-#pragma unroll
-    for (int k = 0; k < kScanSegs; ++k) {
-        const int v = s_seg[k][lane];
-        if (k < seg) run += v;
-        total += v;
-    }
-    if (seg == 0 && ok) totals[d] = total;
-    // pass 2: exclusive prefix within the segment on top of the preceding segments (L2 hits)
-    for (int r = r0; r < r1; r += kScanMaxRows) {
-        int c[kScanMaxRows];
-#pragma unroll
-        for (int j = 0; j < kScanMaxRows; ++j) c[j] = (ok && r + j < r1) ? __ldcg(col + (size_t)(r + j) * D) : 0;
-#pragma unroll
-        for (int j = 0; j < kScanMaxRows; ++j) {
-            if (ok && r + j < r1) col[(size_t)(r + j) * D] = run;
-            run += c[j];
-        }
-    }
 }
 
-// Step 2, run by every CTA of K3: exclusive scan of totals[0..D) into shared memory.
-// D <= 2048 = kThreads * 16.
+// Exclusive scan of count[0..T) into shared memory, T <= kMaxSmemTiles = kThreads * kPer.
 template <int kThreads>
-__device__ __forceinline__ int scan_totals_to_smem(const int32_t *__restrict__ totals, int D, int *s_base,
+__device__ __forceinline__ int scan_counts_to_smem(const int32_t *__restrict__ count, int T, int *s_base,
                                                    int *s_warp) {
-    constexpr int kPer = (1 << kMaxDigitBits) / kThreads;
+    constexpr int kPer = kMaxSmemTiles / kThreads;
     const int i0 = threadIdx.x * kPer;
     int v[kPer];
     int sum = 0;
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
-        v[k] = (i0 + k < D) ? __ldcg(totals + i0 + k) : 0;
+        v[k] = (i0 + k < T) ? __ldcg(count + i0 + k) : 0;
         sum += v[k];
     }
     int total;
@@ -425,18 +333,18 @@ __device__ __forceinline__ int scan_totals_to_smem(const int32_t *__restrict__ t
     int run = incl - sum;
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
-        if (i0 + k < D) s_base[i0 + k] = run;
+        if (i0 + k < T) s_base[i0 + k] = run;
         run += v[k];
     }
     __syncthreads();
     return total;
 }
 
-// ------------------------------------------------------------------------------------ K3
-// Walk the intersections of a warp's Gaussians in emission order (Gaussian-major, tiles
-// row-major: forward.cu:187-196), 32 at a time, load balanced: lane i of a chunk owns Gaussian
-// i, an inclusive scan of the box areas gives every intersection its slot, a 5-step shuffle
-// search gives every slot its owner.  `visit(valid, tile, gaussian)` is called warp-converged.
+// ------------------------------------------------------------------------------------ K2
+// Walk the intersections of a warp's Gaussians (Gaussian-major, tiles row-major: forward.cu:187-196),
+// 32 at a time, load balanced: lane i of a chunk owns Gaussian i, an inclusive scan of the box areas
+// gives every intersection its slot, a 5-step shuffle search gives every slot its owner.
+// `visit(valid, tile, gaussian)` is called warp-converged.
 template <class Visit>
 __device__ __forceinline__ void walk_intersections(int g_begin, int g_end, int tiles_x,
                                                    const ushort4 *__restrict__ boxes, Visit visit) {
@@ -444,7 +352,7 @@ __device__ __forceinline__ void walk_intersections(int g_begin, int g_end, int t
     for (int base = g_begin; base < g_end; base += 32) {
         const int g = base + lane;
         ushort4 bx = make_ushort4(0, 0, 0, 0);
-        if (g < g_end) bx = boxes[g];
+        if (g < g_end) bx = __ldcg(boxes + g);
         const int w = (int)bx.z - (int)bx.x;
         const int n = w * ((int)bx.w - (int)bx.y);
         const int incl = warp_scan_inclusive(n);
@@ -476,216 +384,65 @@ __device__ __forceinline__ void walk_intersections(int g_begin, int g_end, int t
     }
 }
 
-__global__ void __launch_bounds__(kScatterThreads)
-fit_scatter_kernel(int num_points, int gpb, int bits0, int tiles_x, int num_tiles, int single_pass,
-                   int capacity, const ushort4 *__restrict__ boxes, const int32_t *__restrict__ counts,
-                   const int32_t *__restrict__ totals, uint64_t *__restrict__ keys_out,
-                   const float4 *__restrict__ proj, float4 *__restrict__ records,
-                   int32_t *__restrict__ tile_bins, int32_t *__restrict__ n_isect,
-                   double *__restrict__ stats, int32_t *__restrict__ counts1, int bits1) {
-    extern __shared__ int s_dyn[];  // [kScatterWarps][D] per-warp counters, then [D] digit bases
-    __shared__ int s_warp[kScatterWarps];
-    const int D = 1 << bits0;
-    const int mask = D - 1;
-    int *s_cnt = s_dyn;
-    int *s_base = s_dyn + kScatterWarps * D;
+// Prefix sum over the per-tile overlap counts + placement.  The start of a tile's range comes from the
+// in-CTA scan (kSmemScan: every CTA redoes the <= 8 KiB scan instead of paying a launch for it) or from
+// the device-wide inclusive scan tile_incl[] that ran between K1 and this kernel.  An intersection's
+// slot inside its tile's range is handed out by an atomic cursor: the order within a tile is arbitrary
+// here and fixed by the rank sort of K3.  CTA 0 also publishes the tile ranges (forward.cu:211-233;
+// empty tiles keep the reference's (0,0)) and does the bookkeeping.
+template <bool kSmemScan>
+__global__ void __launch_bounds__(kPlaceThreads)
+fit_place_kernel(gi2d_fit_params p, int with_backward, int gpb, int num_tiles,
+                 const ushort4 *__restrict__ boxes, const int32_t *__restrict__ tile_count,
+                 const int32_t *__restrict__ tile_incl, int32_t *__restrict__ tile_fill,
+                 uint64_t *__restrict__ keys_out, const float4 *__restrict__ proj, float4 *__restrict__ records,
+                 int32_t *__restrict__ tile_bins, int32_t *__restrict__ n_isect, double *__restrict__ stats) {
+    __shared__ int s_base[kSmemScan ? kMaxSmemTiles : 1];
+    __shared__ int s_warp[kPlaceWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_launch_dependents();
-    {
-        int4 *z = reinterpret_cast<int4 *>(s_cnt);
-        for (int i = threadIdx.x; i < kScatterWarps * D / 4; i += kScatterThreads) z[i] = make_int4(0, 0, 0, 0);
-    }
     pdl_wait();
-    // start of every digit (== tile, when one pass covers the tile id) in the sorted order
-    const int total = scan_totals_to_smem<kScatterThreads>(totals, D, s_base, s_warp);
-    if (blockIdx.x == 0) {
-        if (single_pass)
-            for (int t = threadIdx.x; t < num_tiles; t += kScatterThreads)
-                reinterpret_cast<int2 *>(tile_bins)[t] = make_int2(s_base[t], s_base[t] + __ldcg(totals + t));
-        if (threadIdx.x == 0) {
+    int total;
+    if (kSmemScan) {
+        total = scan_counts_to_smem<kPlaceThreads>(tile_count, num_tiles, s_base, s_warp);
+    } else {
+        total = num_tiles > 0 ? __ldcg(tile_incl + num_tiles - 1) : 0;
+    }
+    // tile ranges: CTA 0 when they sit in its shared memory, else all CTAs share the tiles
+    if (kSmemScan) {
+        if (blockIdx.x == 0)
+            for (int t = threadIdx.x; t < num_tiles; t += kPlaceThreads) {
+                const int c = __ldcg(tile_count + t);
+                reinterpret_cast<int2 *>(tile_bins)[t] = c ? make_int2(s_base[t], s_base[t] + c) : make_int2(0, 0);
+            }
+    } else {
+        for (int t = blockIdx.x * kPlaceThreads + threadIdx.x; t < num_tiles; t += gridDim.x * kPlaceThreads) {
+            const int e = __ldcg(tile_incl + t), c = __ldcg(tile_count + t);
+            reinterpret_cast<int2 *>(tile_bins)[t] = c ? make_int2(e - c, e) : make_int2(0, 0);
+        }
+    }
+    if (blockIdx.x == 0 && warp == 0) {
+        step_bookkeeping_warp0(p, with_backward, stats);
+        if (lane == 0) {
             stats[GI2D_STAT_ISECTS] = (double)total;
-            if (total > capacity) stats[GI2D_STAT_OVERFLOW] = 1.0;
-            *n_isect = total > capacity ? capacity : total;
+            if (total > p.isect_capacity) stats[GI2D_STAT_OVERFLOW] = 1.0;
+            *n_isect = total > p.isect_capacity ? p.isect_capacity : total;
         }
     }
-    const int gpw = gpb / kScatterWarps;
-    const int g_begin = min(num_points, blockIdx.x * gpb + warp * gpw);
-    const int g_end = min(num_points, g_begin + gpw);
-    int *my_cnt = s_cnt + warp * D;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    // phase A: per-warp digit counts (order is irrelevant here: lane = Gaussian, shared atomics)
-    for (int g = g_begin + lane; g < g_end; g += 32) {
-        const ushort4 bx = boxes[g];
-        for (int ty = bx.y; ty < bx.w; ++ty)
-            for (int tx = bx.x; tx < bx.z; ++tx) atomicAdd(&my_cnt[(ty * tiles_x + tx) & mask], 1);
-    }
-    __syncthreads();
-    // phase B: per digit, exclusive scan over the warps on top of the global offset of (CTA, digit)
-    for (int d0 = threadIdx.x; d0 < D; d0 += 4 * kScatterThreads) {
-        int off[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int d = d0 + j * kScatterThreads;
-            off[j] = d < D ? __ldcg(counts + (size_t)blockIdx.x * D + d) : 0;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int d = d0 + j * kScatterThreads;
-            if (d < D) {
-                int run = off[j] + s_base[d];
-#pragma unroll
-                for (int w = 0; w < kScatterWarps; ++w) {
-                    const int c = s_cnt[w * D + d];
-                    s_cnt[w * D + d] = run;
-                    run += c;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    // phase C: ordered walk, ranking and writing (keys always; records when this is the only pass)
-    walk_intersections(g_begin, g_end, tiles_x, boxes, [&](bool valid, int tile, int g) {
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
+    const int gpw = gpb / kPlaceWarps;
+    const int g_begin = min(p.num_points, blockIdx.x * gpb + warp * gpw);
+    const int g_end = min(p.num_points, g_begin + gpw);
+    walk_intersections(g_begin, g_end, p.tiles_x, boxes, [&](bool valid, int tile, int g) {
         if (valid) {
-            const int d = tile & mask;
-            const unsigned peers = __match_any_sync(act, d);
-            const int leader = __ffs(peers) - 1;
-            int old = 0;
-            if (lane == leader) {
-                old = my_cnt[d];
-                my_cnt[d] = old + __popc(peers);
-            }
-            old = __shfl_sync(peers, old, leader);
-            const int pos = old + __popc(peers & lt_mask);
-            if (pos < capacity) {
+            const int start = kSmemScan ? s_base[tile] : (__ldcg(tile_incl + tile) - __ldcg(tile_count + tile));
+            const int pos = start + atomicAdd(tile_fill + tile, 1);
+            if (pos < p.isect_capacity) {
                 keys_out[pos] = ((uint64_t)(uint32_t)tile << 32) | (uint32_t)g;
-                // second pass ahead: its per-chunk digit histogram is accumulated right here
-                if (counts1)
-                    atomicAdd(counts1 + (size_t)(pos >> kPass1ChunkBits) * kPass1Radix +
-                                  ((tile >> bits0) & ((1 << bits1) - 1)), 1);
-                if (records) {
-                    records[2 * (size_t)pos] = __ldg(proj + 2 * g);
-                    records[2 * (size_t)pos + 1] = __ldg(proj + 2 * g + 1);
-                }
+                records[2 * (size_t)pos] = __ldcg(proj + 2 * g);
+                records[2 * (size_t)pos + 1] = __ldcg(proj + 2 * g + 1);
             }
         }
-        __syncwarp();
     });
-}
-
-// multi-pass images: gather the records once the keys are fully sorted
-__global__ void __launch_bounds__(256)
-fit_gather_records_kernel(int capacity, const int32_t *__restrict__ n_dev, const uint64_t *__restrict__ keys,
-                          const float4 *__restrict__ proj, float4 *__restrict__ records) {
-    const int n = min(capacity, *n_dev);
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const int g = (int)(uint32_t)keys[i];
-    records[2 * (size_t)i] = __ldg(proj + 2 * g);
-    records[2 * (size_t)i + 1] = __ldg(proj + 2 * g + 1);
-}
-
-// ---- second pass for images with more than 2048 tiles (up to 2^19): stable scatter by the high
-// tile bits.  Chunk c = keys [2048 c, 2048 c + 2048) of the pass-0 output; its digit histogram was
-// accumulated by K3 (counts1[c][d]), turned into exclusive per-chunk offsets + totals by a second
-// launch of fit_scan_kernel.  Ranking inside the chunk: warp-striped rounds of 32 consecutive keys,
-// match_any, per-warp digit counters, exclusive scan across warps (same scheme as gi2d_binning.cu).
-__global__ void __launch_bounds__(256)
-fit_scatter1_kernel(int capacity, const int32_t *__restrict__ n_dev, const uint64_t *__restrict__ keys_in,
-                    uint64_t *__restrict__ keys_out, int shift, int bits, const int32_t *__restrict__ counts1,
-                    const int32_t *__restrict__ totals1) {
-    constexpr int kWarps = 8, kItems = 8;
-    __shared__ int s_cnt[kWarps][kPass1Radix];
-    __shared__ int s_base[kPass1Radix];
-    __shared__ int s_warp[kWarps];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = min(capacity, *n_dev);
-    if (blockIdx.x * (1 << kPass1ChunkBits) >= n) return;  // (whole CTA)
-    for (int i = tid; i < kWarps * kPass1Radix; i += 256) (&s_cnt[0][0])[i] = 0;
-    {   // exclusive scan of the digit totals (2 per thread) + this chunk's exclusive offsets
-        static_assert(kPass1Radix == 512, "two digits per thread");
-        const int v0 = __ldcg(totals1 + 2 * tid), v1 = __ldcg(totals1 + 2 * tid + 1);
-        const int incl = block_scan_inclusive<256>(v0 + v1, s_warp, nullptr);
-        const int32_t *off = counts1 + (size_t)blockIdx.x * kPass1Radix;
-        s_base[2 * tid] = incl - v0 - v1 + __ldcg(off + 2 * tid);
-        s_base[2 * tid + 1] = incl - v1 + __ldcg(off + 2 * tid + 1);
-    }
-    __syncthreads();
-    const int wbase = blockIdx.x * (1 << kPass1ChunkBits) + warp * (kItems * 32);
-    uint64_t key[kItems];
-    int rank[kItems], dig[kItems];
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const int dmask = (1 << bits) - 1;
-#pragma unroll
-    for (int r = 0; r < kItems; ++r) {
-        const int i = wbase + r * 32 + lane;
-        const bool valid = i < n;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        rank[r] = 0;
-        dig[r] = 0;
-        key[r] = 0;
-        if (valid) {
-            key[r] = keys_in[i];
-            const int d = (int)(key[r] >> shift) & dmask;
-            dig[r] = d;
-            const unsigned peers = __match_any_sync(act, d);
-            const int leader = __ffs(peers) - 1;
-            int old = 0;
-            if (lane == leader) {
-                old = s_cnt[warp][d];
-                s_cnt[warp][d] = old + __popc(peers);
-            }
-            old = __shfl_sync(peers, old, leader);
-            rank[r] = old + __popc(peers & lt_mask);
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    for (int d = tid; d < kPass1Radix; d += 256) {
-        int run = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const int c = s_cnt[w][d];
-            s_cnt[w][d] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < kItems; ++r) {
-        const int i = wbase + r * 32 + lane;
-        if (i < n) keys_out[s_base[dig[r]] + s_cnt[warp][dig[r]] + rank[r]] = key[r];
-    }
-}
-
-// After the last pass: tile ranges from the key boundaries (forward.cu:211-233; tile_bins was zeroed by
-// a memset node), the 32-B records gathered into sorted order, and the second-pass histogram handed
-// back zeroed for the next iteration.
-__global__ void __launch_bounds__(256)
-fit_finalize_kernel(int capacity, const int32_t *__restrict__ n_dev, const uint64_t *__restrict__ keys,
-                    const float4 *__restrict__ proj, float4 *__restrict__ records,
-                    int32_t *__restrict__ tile_bins, int num_tiles, int32_t *__restrict__ counts1) {
-    const int n = min(capacity, *n_dev);
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const int used = ((n + (1 << kPass1ChunkBits) - 1) >> kPass1ChunkBits) * kPass1Radix;
-    if (i < used) counts1[i] = 0;
-    if (i >= n) return;
-    const uint64_t key = keys[i];
-    const int cur = (int)(key >> 32);
-    if (cur < num_tiles) {
-        if (i == 0) tile_bins[2 * cur] = 0;
-        if (i == n - 1) tile_bins[2 * cur + 1] = n;
-    }
-    if (i > 0) {
-        const int prev = (int)(keys[i - 1] >> 32);
-        if (prev != cur) {
-            if (prev < num_tiles) tile_bins[2 * prev + 1] = i;
-            if (cur < num_tiles) tile_bins[2 * cur] = i;
-        }
-    }
-    const int g = (int)(uint32_t)key;
-    records[2 * (size_t)i] = __ldg(proj + 2 * g);
-    records[2 * (size_t)i + 1] = __ldg(proj + 2 * g + 1);
 }
 
 // ------------------------------------------------------------------------------------ K4
@@ -695,13 +452,16 @@ fit_finalize_kernel(int capacity, const int32_t *__restrict__ n_dev, const uint6
 // FitBackward : backward from a dL/d(out) image (v_out, f32[H,W,3])    } SSIM term (needs neighbouring tiles)
 enum class RasterMode { Render, Fit, FitForward, FitBackward };
 
+// 6 CTAs/SM (40 registers, no spills) measured best on all three workloads: 768x512/5k +4 %, 2040x1356/20k
+// +12 %, 8192^2/1M +18 % over 4 CTAs/SM (48 registers) -- latency hiding beats the few extra registers
 #ifndef GI2D_FIT_MINBLOCKS
-#define GI2D_FIT_MINBLOCKS 4
+#define GI2D_FIT_MINBLOCKS 6
 #endif
 template <RasterMode kMode>
 __global__ void __launch_bounds__(kRasterThreads, (kMode == RasterMode::Fit || kMode == RasterMode::FitBackward) ? GI2D_FIT_MINBLOCKS : 6)
-fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
-                  const int32_t *__restrict__ tile_bins, const float4 *__restrict__ records,
+fit_raster_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_t *__restrict__ keys_tmp,
+                  const int32_t *__restrict__ tile_bins, int32_t *__restrict__ tile_count,
+                  int32_t *__restrict__ tile_fill, const float4 *__restrict__ records,
                   const float *__restrict__ gt, const uint8_t *__restrict__ gt_u8,
                   float *__restrict__ out_img, float *__restrict__ grads, double *__restrict__ stats,
                   float *__restrict__ err_map, const float *__restrict__ v_out) {
@@ -711,6 +471,7 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
     __shared__ TileRecords sg;
     __shared__ TileGrad tg;
     __shared__ int s_ids[kMaxPerTile];
+    __shared__ int s_sort[kMaxPerTile];
     __shared__ float s_red[2][kRasterWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_y = p.tile_row_begin + blockIdx.y;
@@ -737,21 +498,63 @@ fit_raster_kernel(gi2d_fit_params p, const uint64_t *__restrict__ sorted_keys,
         }
     }
     pdl_wait();  // the target image above is written by no kernel of the step; everything below is
-    const double n_isect = stats[GI2D_STAT_ISECTS];
-    const int2 range = __ldg(reinterpret_cast<const int2 *>(tile_bins) + tile_id);
-    const int cnt = max(0, min(kMaxPerTile, min(range.y, p.isect_capacity) - range.x));
-    if (tid < cnt) {
-        // one contiguous block of cnt x 32 B (gathered into sorted order by K3)
-        stage_record(sg, tid, __ldg(records + 2 * (size_t)(range.x + tid)),
-                     __ldg(records + 2 * (size_t)(range.x + tid) + 1), (float)(blockIdx.x * kTile),
-                     (float)(tile_y * kTile));
-        if (kHasBwd) s_ids[tid] = (int)(uint32_t)__ldg(sorted_keys + range.x + tid);
+    const double n_isect = __ldcg(stats + GI2D_STAT_ISECTS);
+    const int2 range = __ldcg(reinterpret_cast<const int2 *>(tile_bins) + tile_id);
+    const int total_cnt = max(0, min(range.y, p.isect_capacity) - range.x);
+    const int cnt = min(kMaxPerTile, total_cnt);
+    // the counters of this tile go back to K1 / K2 of the next step zeroed
+    if (kHasFwd && tid == 0) { tile_count[tile_id] = 0; tile_fill[tile_id] = 0; }
+    // Finish the key sort: K2 placed this tile's entries in arbitrary order.  Rank every entry by its
+    // gaussian id (ids are unique within a tile, so ranks are a permutation) and stage it at its rank:
+    // shared memory then holds the reference's order (ascending id == the stable sort of Gaussian-major
+    // emitted keys), truncated to the first 256 (forward.cu:673).  The sorted keys are written back so that
+    // sorted_keys is the fully sorted 64-bit sequence -- except by the forward half of a split step, whose
+    // backward half must find keys and records still paired.
+    constexpr bool kWriteBack = kMode != RasterMode::FitForward;
+    const float tx0 = (float)(blockIdx.x * kTile), ty0 = (float)(tile_y * kTile);
+    if (total_cnt <= kMaxPerTile) {
+        uint64_t key = 0;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        if (tid < cnt) {
+            // one contiguous block of cnt x (8 + 32) B
+            key = __ldcg(sorted_keys + range.x + tid);
+            r0 = __ldcg(records + 2 * (size_t)(range.x + tid));
+            r1 = __ldcg(records + 2 * (size_t)(range.x + tid) + 1);
+            s_sort[tid] = (int)(uint32_t)key;
+        }
+        __syncthreads();
+        if (tid < cnt) {
+            const int id = (int)(uint32_t)key;
+            int rank = 0;
+            for (int jj = 0; jj < cnt; ++jj) rank += (s_sort[jj] < id) ? 1 : 0;
+            stage_record(sg, rank, r0, r1, tx0, ty0);
+            if (kHasBwd) s_ids[rank] = id;
+            if (kWriteBack && rank != tid) sorted_keys[range.x + rank] = key;
+        }
+    } else {
+        // more than 256 entries (a degenerate scene): full rank sort straight from global memory
+        for (int e = tid; e < total_cnt; e += kRasterThreads) {
+            const uint64_t key = __ldcg(sorted_keys + range.x + e);
+            const int id = (int)(uint32_t)key;
+            int rank = 0;
+            for (int jj = 0; jj < total_cnt; ++jj) rank += ((int)(uint32_t)__ldcg(sorted_keys + range.x + jj) < id) ? 1 : 0;
+            keys_tmp[range.x + rank] = key;
+            if (rank < kMaxPerTile) {
+                stage_record(sg, rank, __ldcg(records + 2 * (size_t)(range.x + e)),
+                             __ldcg(records + 2 * (size_t)(range.x + e) + 1), tx0, ty0);
+                if (kHasBwd) s_ids[rank] = id;
+            }
+        }
+        if (kWriteBack) {
+            __syncthreads();
+            for (int e = tid; e < total_cnt; e += kRasterThreads) sorted_keys[range.x + e] = __ldcg(keys_tmp + range.x + e);
+        }
     }
     if (kMode == RasterMode::FitBackward) {
         // dL/d(out) of this tile, computed by the loss kernels between the two halves
         const int gi = grad_index(lx, ly);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) tg.v[c][gi] = (inside && n_isect != 0.0) ? __ldg(v_out + 3 * pix + c) : 0.f;
+        for (int c = 0; c < 3; ++c) tg.v[c][gi] = (inside && n_isect != 0.0) ? __ldcg(v_out + 3 * pix + c) : 0.f;
     }
     __syncthreads();
     // ---- forward: thread = pixel
@@ -832,8 +635,8 @@ fit_adam_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bou
     pdl_launch_dependents();
     pdl_wait();
     const int g = blockIdx.x * 256 + threadIdx.x;
-    const bool pending = stats[kStatPending] != 0.0;
-    const bool veto = stats[GI2D_STAT_OVERFLOW] != 0.0;
+    const bool pending = __ldcg(stats + kStatPending) != 0.0;
+    const bool veto = __ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0;
     best_flag_warp0(stats, best != nullptr && pending && !veto, &s_best);
     __syncthreads();
     bool bad = false;
@@ -842,8 +645,8 @@ fit_adam_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bou
         if (pending) {
             float2 x;
             float q[3];
-            adam_update_gaussian(p, a, g, proj[2 * g], proj[2 * g + 1], grads[2 * g], grads[2 * g + 1], stats, veto,
-                                 x, c, q);
+            adam_update_gaussian(p, a, g, __ldcg(proj + 2 * g), __ldcg(proj + 2 * g + 1), __ldcg(grads + 2 * g),
+                                 __ldcg(grads + 2 * g + 1), stats, veto, x, c, q);
             if (s_best) {
                 best[2 * g] = make_float4(x.x, x.y, c[0], c[1]);
                 best[2 * g + 1] = make_float4(c[2], q[0], q[1], q[2]);
@@ -898,7 +701,7 @@ fit_exchange_adam_kernel(gi2d_fit_params p, AdamPtrs local, PeerPtrs peers, int 
                          const float4 *__restrict__ proj, const double *__restrict__ stats) {
     const int g = g0 + blockIdx.x * 256 + threadIdx.x;
     if (g >= g1) return;
-    const bool veto = stats[GI2D_STAT_OVERFLOW] != 0.0;
+    const bool veto = __ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0;
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
     for (int q = 0; q < world; ++q) {  // fixed order: identical sums on every rank
         const float4 a0 = __ldcg(peers.grads[q] + 2 * g), a1 = __ldcg(peers.grads[q] + 2 * g + 1);
@@ -907,7 +710,7 @@ fit_exchange_adam_kernel(gi2d_fit_params p, AdamPtrs local, PeerPtrs peers, int 
     }
     float2 x;
     float c[3], col[3];
-    adam_update_gaussian(p, local, g, proj[2 * g], proj[2 * g + 1], s0, s1, stats, veto, x, c, col);
+    adam_update_gaussian(p, local, g, __ldcg(proj + 2 * g), __ldcg(proj + 2 * g + 1), s0, s1, stats, veto, x, c, col);
     if (veto) return;
     for (int q = 0; q < world; ++q) {
         if (q == rank) continue;  // the local copy was written by adam_update_gaussian
@@ -973,55 +776,28 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
         set_error("gi2d_fit_forward_backward: workspace too small (%zu < %zu)", b->workspace_bytes, w.total);
         return GI2D_ERR_WORKSPACE;
     }
-    const int D = 1 << pl.bits0;
-    const int num_tiles = p->tiles_x * p->tiles_y;
-    const bool single = pl.extra_passes == 0;
+    const int num_tiles = pl.num_tiles;
     if (mk) mk->mark(st);
     const AdamPtrs ap{b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
-    launch_pdl(fit_project_kernel, dim3(pl.nblocks), dim3(kProjThreads), D * sizeof(int), st,
-        *p, pl.gpb, pl.bits0, ap, b->cov_bound, (float4 *)b->proj, (float4 *)b->grads,
-        w.boxes, w.counts, b->stats, with_backward, (float4 *)b->best);
+    const int proj_threads = p->num_points <= (1 << 16) ? 64 : kProjThreads;
+    launch_pdl(fit_project_kernel, dim3(max(1, cdiv(p->num_points, proj_threads))), dim3(proj_threads), 0, st,
+        *p, ap, b->cov_bound, (float4 *)b->proj, (float4 *)b->grads, w.boxes, w.tile_count, b->stats, with_backward,
+        (float4 *)b->best);
     if (mk) mk->mark(st);
-    launch_pdl(fit_scan_kernel, dim3(cdiv(D, kScanCols)), dim3(kScanThreads), 0, st, *p, with_backward, b->stats,
-               pl.nblocks, D, w.counts, w.totals, (const int32_t *)nullptr, 1);
-    if (mk) mk->mark(st);
-    // pass 0 lands in sorted_keys when the number of remaining passes is even
-    uint64_t *dst0 = (pl.extra_passes % 2 == 0) ? b->sorted_keys : w.keys_tmp;
-    const size_t scatter_smem = (size_t)(kScatterWarps + 1) * D * sizeof(int);  // <= 40 KiB
-    const bool fast2 = pl.extra_passes == 1;  // <= 2^19 tiles: streamlined second pass
-    const int bits1 = pl.tile_bits - pl.bits0;
-    launch_pdl(fit_scatter_kernel, dim3(pl.nblocks), dim3(kScatterThreads), scatter_smem, st,
-        p->num_points, pl.gpb, pl.bits0, p->tiles_x, num_tiles, single ? 1 : 0, p->isect_capacity, w.boxes,
-        w.counts, w.totals, dst0, (const float4 *)b->proj, single ? w.records : nullptr, b->tile_bins, w.n_isect,
-        b->stats, fast2 ? w.counts1 : nullptr, bits1);
-    if (fast2) {
-        const int chunks = cdiv(p->isect_capacity, 1 << kPass1ChunkBits);
-        fit_scan_kernel<<<cdiv(kPass1Radix, kScanCols), kScanThreads, 0, st>>>(
-            *p, -1, b->stats, chunks, kPass1Radix, w.counts1, w.totals1, w.n_isect, 1 << kPass1ChunkBits);
-        fit_scatter1_kernel<<<chunks, 256, 0, st>>>(p->isect_capacity, w.n_isect, dst0, b->sorted_keys,
-                                                    32 + pl.bits0, bits1, w.counts1, w.totals1);
-        cudaMemsetAsync(b->tile_bins, 0, (size_t)num_tiles * 2 * sizeof(int32_t), st);
-        const int fin = max(p->isect_capacity, chunks * kPass1Radix);
-        fit_finalize_kernel<<<cdiv(fin, 256), 256, 0, st>>>(p->isect_capacity, w.n_isect, b->sorted_keys,
-                                                            (const float4 *)b->proj, w.records, b->tile_bins,
-                                                            num_tiles, w.counts1);
-    } else if (!single) {
-        uint64_t *src = dst0;
-        for (int e = 0; e < pl.extra_passes; ++e) {
-            uint64_t *dst = (src == b->sorted_keys) ? w.keys_tmp : b->sorted_keys;
-            const int shift = 32 + pl.bits0 + 8 * e;
-            const int bits = min(8, pl.tile_bits - pl.bits0 - 8 * e);
-            const int r2 = radix_pass_keys_u64(p->isect_capacity, w.n_isect, src, dst, shift, bits, w.radix_ws,
-                                               w.radix_ws_bytes, st);
-            if (r2 != GI2D_OK) return r2;
-            src = dst;
-        }
-        const int r3 = tile_edges_from_keys_u64(p->isect_capacity, w.n_isect, b->sorted_keys, b->tile_bins,
-                                                num_tiles, st);
-        if (r3 != GI2D_OK) return r3;
-        fit_gather_records_kernel<<<cdiv(p->isect_capacity, 256), 256, 0, st>>>(
-            p->isect_capacity, w.n_isect, b->sorted_keys, (const float4 *)b->proj, w.records);
+    if (!pl.smem_scan) {
+        // more tiles than one CTA scans in shared memory: device-wide inclusive prefix sum of the counts
+        const int r2 = cumsum_i32_launch(num_tiles, w.tile_count, w.tile_incl, nullptr, w.scan_ws, st);
+        if (r2 != GI2D_OK) return r2;
     }
+    if (mk) mk->mark(st);
+    if (pl.smem_scan)
+        launch_pdl(fit_place_kernel<true>, dim3(pl.nblocks), dim3(kPlaceThreads), 0, st,
+            *p, with_backward, pl.gpb, num_tiles, w.boxes, w.tile_count, w.tile_incl, w.tile_fill, b->sorted_keys,
+            (const float4 *)b->proj, w.records, b->tile_bins, w.n_isect, b->stats);
+    else
+        launch_pdl(fit_place_kernel<false>, dim3(pl.nblocks), dim3(kPlaceThreads), 0, st,
+            *p, with_backward, pl.gpb, num_tiles, w.boxes, w.tile_count, w.tile_incl, w.tile_fill, b->sorted_keys,
+            (const float4 *)b->proj, w.records, b->tile_bins, w.n_isect, b->stats);
     if (mk) mk->mark(st);
     const int band = p->tile_row_end - p->tile_row_begin;
     if (band > 0) {
@@ -1030,8 +806,8 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
             // SSIM couples pixels across tile borders: forward everywhere, then the loss gradient image, then
             // the backward half.  (Band-split multi-GPU runs would need a halo exchange of the render.)
             fit_raster_kernel<RasterMode::FitForward><<<grid, kRasterThreads, 0, st>>>(
-                *p, b->sorted_keys, b->tile_bins, w.records, b->gt_hwc, b->gt_u8_hwc, w.loss_render, nullptr, b->stats,
-                b->err_map, nullptr);
+                *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count, w.tile_fill, w.records, b->gt_hwc,
+                b->gt_u8_hwc, w.loss_render, nullptr, b->stats, b->err_map, nullptr);
             if (b->out_img)
                 cudaMemcpyAsync(b->out_img, w.loss_render, (size_t)p->img_width * p->img_height * 12,
                                 cudaMemcpyDeviceToDevice, st);
@@ -1039,16 +815,17 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
                              p->loss_ssim_weight, p->loss_scale, p->loss_l1_scale, w.loss_vout,
                              b->stats + GI2D_STAT_SSIM_SUM, st);
             fit_raster_kernel<RasterMode::FitBackward><<<grid, kRasterThreads, 0, st>>>(
-                *p, b->sorted_keys, b->tile_bins, w.records, nullptr, nullptr, nullptr, b->grads, b->stats, nullptr,
-                w.loss_vout);
+                *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count, w.tile_fill, w.records, nullptr, nullptr,
+                nullptr, b->grads, b->stats, nullptr, w.loss_vout);
         } else if (with_backward)
             launch_pdl(fit_raster_kernel<RasterMode::Fit>, grid, dim3(kRasterThreads), 0, st,
-                *p, b->sorted_keys, b->tile_bins, w.records, b->gt_hwc, b->gt_u8_hwc, b->out_img, b->grads, b->stats,
-                b->err_map, (const float *)nullptr);
+                *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count, w.tile_fill, (const float4 *)w.records,
+                b->gt_hwc, b->gt_u8_hwc, b->out_img, b->grads, b->stats, b->err_map, (const float *)nullptr);
         else
             launch_pdl(fit_raster_kernel<RasterMode::Render>, grid, dim3(kRasterThreads), 0, st,
-                *p, b->sorted_keys, b->tile_bins, w.records, nullptr, nullptr, b->out_img, nullptr, b->stats,
-                nullptr, (const float *)nullptr);
+                *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count, w.tile_fill, (const float4 *)w.records,
+                (const float *)nullptr, (const uint8_t *)nullptr, b->out_img, (float *)nullptr, b->stats,
+                (float *)nullptr, (const float *)nullptr);
     }
     if (mk) mk->mark(st);
     return check_launch("gi2d_fit_forward_backward");
@@ -1078,15 +855,8 @@ extern "C" size_t gi2d_fit_workspace_size(const gi2d_fit_params *p) {
 extern "C" int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward) {
     if (!p) return 0;
     const Plan pl = make_plan(*p);
-    int n = 4;  // project, scan, scatter, raster
-    if (pl.extra_passes == 1) {
-        n += 3;  // second-pass scan, scatter, finalize (tile ranges + record gather); the memset is no kernel
-    } else if (pl.extra_passes > 1) {
-        const int nb = cdiv(p->isect_capacity, 2048);
-        const int cumsum_nb = cdiv(nb * 256, 2048);
-        n += pl.extra_passes * (2 + (cumsum_nb > 1 ? 3 : 1));  // hist + cumsum + scatter per pass
-        n += 2;                                                 // tile edges + record gather (memset is no kernel)
-    }
+    int n = 3;  // project(+Adam), place, raster
+    if (!pl.smem_scan) n += cdiv(pl.num_tiles, 2048) > 1 ? 3 : 1;  // device-wide scan of the tile counts
     if (with_backward && p->loss_ssim_weight != 0.f) n += 3;  // forward / SSIM stats / SSIM gradient / backward
     return n;
 }
@@ -1094,6 +864,13 @@ extern "C" int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward
 extern "C" int gi2d_fit_reset(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int step,
                               gi2d_stream_t stream) {
     GI2D_REQUIRE(p && b && b->stats, "null stats");
+    if (b->workspace) {  // the per-tile counters must start from zero (K3 hands them back zeroed after every step)
+        const Plan pl = make_plan(*p);
+        const Workspace w = carve(*p, pl, b->workspace);
+        if (b->workspace_bytes >= w.total)
+            cudaMemsetAsync(w.tile_count, 0, (char *)w.tile_fill - (char *)w.tile_count + (size_t)pl.num_tiles * 4,
+                            (cudaStream_t)stream);
+    }
     fit_reset_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(*p, b->stats, step);
     return check_launch(__func__);
 }
@@ -1119,7 +896,7 @@ extern "C" int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b
 }
 
 // Measurement utility (bench.py): one full fit step with a CUDA event between the kernels, on
-// `stream`; SYNCHRONISES.  ms[0..4] = adam(prev)+project, scan, scatter(+extra passes+edges), raster, 0.
+// `stream`; SYNCHRONISES.  ms[0..4] = adam(prev)+project, tile-count scan (0 up to 2048 tiles), place, raster, 0.
 extern "C" int gi2d_fit_profile(const gi2d_fit_params *p, const gi2d_fit_buffers *b, float *ms_host,
                                 gi2d_stream_t stream) {
     GI2D_REQUIRE(ms_host, "null ms_host");

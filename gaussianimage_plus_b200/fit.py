@@ -314,9 +314,11 @@ class GaussianImageFitter:
 
     def _reset_keep_best(self, step: int, st: dict):
         """reset_stats() that carries the best-so-far squared error / step over (the snapshot stays valid)."""
+        keep = self.stats_buf[STAT_SSE:STAT_SSE + STAT_SSE_SLOTS].clone()   # the last step's squared error
         self.reset_stats(step)
         self.stats_buf[STAT_BEST_SSE:STAT_BEST_STEP + 1] = torch.tensor(
             [st["best_sse"], float(st["best_step"])], dtype=torch.float64, device=self.device)
+        self.stats_buf[STAT_SSE:STAT_SSE + STAT_SSE_SLOTS] = keep
 
     def best_state(self) -> dict:
         """The reference's `best_model_dict` + `slv_bound` (train.py:132-137,159-164): parameters right after

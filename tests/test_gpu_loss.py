@@ -91,7 +91,7 @@ def test_fit_step_with_loss_type(loss_type, graph):
     grads = fit.grads.clone()
     st = fit.stats()
     assert st["step"] == steps
-    assert fit.launches_per_iter() == (7 if fit.loss_w[2] else 4)
+    assert fit.launches_per_iter() == (6 if fit.loss_w[2] else 3)
     xys, depths, radii, conics, nth = project_gaussians_2d_covariance(p_xyz, p_cov + T(bound), H, W, fit.tile_bounds)
     out = rasterize_gaussians_plus(xys, depths, radii, conics, nth, p_rgb, torch.ones(N, 1, device=DEV), H, W)
     xys.retain_grad(); conics.retain_grad()

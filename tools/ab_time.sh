@@ -3,7 +3,7 @@
 WL=$1; shift
 for n in "$@"; do
   if [ "$n" = "main" ]; then unset GI2D_LIB; else export GI2D_LIB=$PWD/gaussianimage_plus_b200/csrc/build/libgi2d_$n.so; fi
-  python bench.py --workload $WL --steps 1500 --warmup 300 --no-ref-cuda --no-cpu-baseline > gpurun_out/ab_$n.json 2> gpurun_out/ab_$n.err || { echo "$n FAILED"; tail -5 gpurun_out/ab_$n.err; continue; }
+  python bench.py --workload $WL --steps ${STEPS:-1500} --warmup ${WARM:-300} --no-ref-cuda --no-cpu-baseline > gpurun_out/ab_$n.json 2> gpurun_out/ab_$n.err || { echo "$n FAILED"; tail -5 gpurun_out/ab_$n.err; continue; }
   python - "$n" <<'PY'
 import json,sys
 n=sys.argv[1]
