@@ -173,29 +173,38 @@ struct AdamPtrs {
 // (sqrt.approx, div.approx: 1-2 ulp): the IEEE versions branch into slow paths on the denormal second
 // moments Adam produces with eps = 1e-15; 2 ulp is far inside the 1e-4 budget of the parameters.
 // Returns the updated parameters in (x, c, q) so the caller can go on projecting them.
-__device__ __forceinline__ void adam_update_gaussian(const gi2d_fit_params &p, const AdamPtrs &a, int g,
-                                                     float4 p0, float4 p1, float4 g0, float4 g1,
-                                                     const double *__restrict__ stats, bool skip,
-                                                     float2 &x, float (&c)[3], float (&q)[3]) {
+struct AdamRegs {     // everything the optimiser thread of one Gaussian reads
+    float2 x, mx, vx;
+    float c[3], mc[3], vc[3], q[3], mq[3], vq[3];
+    float4 p0, p1, g0, g1;   // projected record and gradient row of the step being applied
+};
+
+__device__ __forceinline__ void adam_load(const AdamPtrs &a, int g, const float4 *proj, const float4 *grads,
+                                          AdamRegs &r) {
+    r.p0 = __ldcg(proj + 2 * g);   r.p1 = __ldcg(proj + 2 * g + 1);
+    r.g0 = __ldcg(grads + 2 * g);  r.g1 = __ldcg(grads + 2 * g + 1);
+    r.x = reinterpret_cast<float2 *>(a.xyz)[g];
+    r.mx = reinterpret_cast<float2 *>(a.m_xyz)[g];
+    r.vx = reinterpret_cast<float2 *>(a.v_xyz)[g];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r.c[k] = a.cov[3 * g + k];  r.mc[k] = a.m_cov[3 * g + k];  r.vc[k] = a.v_cov[3 * g + k];
+        r.q[k] = a.rgb[3 * g + k];  r.mq[k] = a.m_rgb[3 * g + k];  r.vq[k] = a.v_rgb[3 * g + k];
+    }
+}
+
+__device__ __forceinline__ void adam_apply(const gi2d_fit_params &p, const AdamPtrs &a, int g, AdamRegs &r,
+                                           const double *__restrict__ stats) {
     const float step_size = (float)__ldcg(stats + kStatStepSize);
     const float bc2_sqrt = (float)__ldcg(stats + kStatBc2Sqrt);
     const float w1 = (float)(1.0 - (double)p.beta1), w2 = (float)(1.0 - (double)p.beta2);
-    x = reinterpret_cast<float2 *>(a.xyz)[g];
-    float2 mx = reinterpret_cast<float2 *>(a.m_xyz)[g], vx = reinterpret_cast<float2 *>(a.v_xyz)[g];
-    float mc[3], vc[3], mq[3], vq[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        c[k] = a.cov[3 * g + k];  mc[k] = a.m_cov[3 * g + k];  vc[k] = a.v_cov[3 * g + k];
-        q[k] = a.rgb[3 * g + k];  mq[k] = a.m_rgb[3 * g + k];  vq[k] = a.v_rgb[3 * g + k];
-    }
-    if (skip) return;  // (values loaded above are returned unchanged)
     float gc[3];
-    conic_vjp(p0.z, p0.w, p1.x, g0.z, g0.w, g1.x, gc[0], gc[1], gc[2]);
-    float gq[3] = {g1.y, g1.z, g1.w};
+    conic_vjp(r.p0.z, r.p0.w, r.p1.x, r.g0.z, r.g0.w, r.g1.x, gc[0], gc[1], gc[2]);
+    float gq[3] = {r.g1.y, r.g1.z, r.g1.w};
     if (p.color_sigmoid) {
-        gq[0] *= p1.y * (1.f - p1.y);
-        gq[1] *= p1.z * (1.f - p1.z);
-        gq[2] *= p1.w * (1.f - p1.w);
+        gq[0] *= r.p1.y * (1.f - r.p1.y);
+        gq[1] *= r.p1.z * (1.f - r.p1.z);
+        gq[2] *= r.p1.w * (1.f - r.p1.w);
     }
     const float inv_bc2 = 1.f / bc2_sqrt;
     auto adam = [&](float &param, float &m, float &v, float grad) {
@@ -206,21 +215,34 @@ __device__ __forceinline__ void adam_update_gaussian(const gi2d_fit_params &p, c
         const float denom = fmaf(sq, inv_bc2, p.eps);
         param = param - step_size * __fdividef(m, denom);       // addcdiv_(exp_avg, denom, -step_size)
     };
-    adam(x.x, mx.x, vx.x, g0.x);
-    adam(x.y, mx.y, vx.y, g0.y);
+    adam(r.x.x, r.mx.x, r.vx.x, r.g0.x);
+    adam(r.x.y, r.mx.y, r.vx.y, r.g0.y);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        adam(c[k], mc[k], vc[k], gc[k]);
-        adam(q[k], mq[k], vq[k], gq[k]);
+        adam(r.c[k], r.mc[k], r.vc[k], gc[k]);
+        adam(r.q[k], r.mq[k], r.vq[k], gq[k]);
     }
-    reinterpret_cast<float2 *>(a.xyz)[g] = x;
-    reinterpret_cast<float2 *>(a.m_xyz)[g] = mx;
-    reinterpret_cast<float2 *>(a.v_xyz)[g] = vx;
+    reinterpret_cast<float2 *>(a.xyz)[g] = r.x;
+    reinterpret_cast<float2 *>(a.m_xyz)[g] = r.mx;
+    reinterpret_cast<float2 *>(a.v_xyz)[g] = r.vx;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        a.cov[3 * g + k] = c[k];  a.m_cov[3 * g + k] = mc[k];  a.v_cov[3 * g + k] = vc[k];
-        a.rgb[3 * g + k] = q[k];  a.m_rgb[3 * g + k] = mq[k];  a.v_rgb[3 * g + k] = vq[k];
+        a.cov[3 * g + k] = r.c[k];  a.m_cov[3 * g + k] = r.mc[k];  a.v_cov[3 * g + k] = r.vc[k];
+        a.rgb[3 * g + k] = r.q[k];  a.m_rgb[3 * g + k] = r.mq[k];  a.v_rgb[3 * g + k] = r.vq[k];
     }
+}
+
+// load + (unless vetoed) apply; returns the resulting parameters in (x, c, q)
+__device__ __forceinline__ void adam_update_gaussian(const gi2d_fit_params &p, const AdamPtrs &a, int g,
+                                                     const float4 *proj, const float4 *grads,
+                                                     const double *__restrict__ stats, bool skip,
+                                                     float2 &x, float (&c)[3], float (&q)[3]) {
+    AdamRegs r;
+    adam_load(a, g, proj, grads, r);
+    if (!skip) adam_apply(p, a, g, r, stats);
+    x = r.x;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { c[k] = r.c[k]; q[k] = r.q[k]; }
 }
 
 // ------------------------------------------------------------------------------------ K1
@@ -234,26 +256,40 @@ __global__ void __launch_bounds__(kProjThreads)
 fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bound,
                    float4 *__restrict__ proj, float4 *__restrict__ grads, ushort4 *__restrict__ boxes,
                    int32_t *__restrict__ tile_count, const double *__restrict__ stats, int with_backward,
-                   float4 *__restrict__ best) {
+                   float4 *__restrict__ best, int expect_pending) {
     __shared__ int s_best;
     pdl_launch_dependents();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = g < p.num_points;
     pdl_wait();  // the previous step's rasterizer wrote grads (and read proj, and zeroed tile_count)
+    // A training step nearly always finds a gradient pending: issue every load of the optimiser BEFORE the
+    // flags that say so come back (one L2 round trip less on this latency-bound kernel); a render-only call
+    // (expect_pending == 0) loads lazily.
+    const bool early = expect_pending && a.m_xyz != nullptr && mine;
+    AdamRegs r;
+    if (early) adam_load(a, g, proj, grads, r);
     const bool pending = a.m_xyz != nullptr && __ldcg(stats + kStatPending) != 0.0;
     const bool veto = __ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0;  // that step overflowed: the host re-runs it
     best_flag_warp0(stats, best != nullptr && pending && !veto, &s_best);
     __syncthreads();
     const bool snapshot = s_best != 0;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= p.num_points) return;
+    if (!mine) return;
     float2 m;
     float c[3], q[3];
     if (pending) {
-        adam_update_gaussian(p, a, g, __ldcg(proj + 2 * g), __ldcg(proj + 2 * g + 1), __ldcg(grads + 2 * g),
-                             __ldcg(grads + 2 * g + 1), stats, veto, m, c, q);
+        if (!early) adam_load(a, g, proj, grads, r);
+        if (!veto) adam_apply(p, a, g, r, stats);
+        m = r.x;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { c[k] = r.c[k]; q[k] = r.q[k]; }
         if (snapshot) {  // the state dict right after optimizer.step() of the best iteration (train.py:132-137)
             best[2 * g] = make_float4(m.x, m.y, c[0], c[1]);
             best[2 * g + 1] = make_float4(c[2], q[0], q[1], q[2]);
         }
+    } else if (early) {
+        m = r.x;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { c[k] = r.c[k]; q[k] = r.q[k]; }
     } else {
         m = reinterpret_cast<const float2 *>(a.xyz)[g];
 #pragma unroll
@@ -347,12 +383,14 @@ __device__ __forceinline__ int scan_counts_to_smem(const int32_t *__restrict__ c
 // `visit(valid, tile, gaussian)` is called warp-converged.
 template <class Visit>
 __device__ __forceinline__ void walk_intersections(int g_begin, int g_end, int tiles_x,
-                                                   const ushort4 *__restrict__ boxes, Visit visit) {
+                                                   const ushort4 *__restrict__ boxes, ushort4 first_box,
+                                                   Visit visit) {
     const int lane = threadIdx.x & 31;
     for (int base = g_begin; base < g_end; base += 32) {
         const int g = base + lane;
         ushort4 bx = make_ushort4(0, 0, 0, 0);
-        if (g < g_end) bx = __ldcg(boxes + g);
+        if (base == g_begin) bx = first_box;  // (prefetched by the caller: boxes[g_begin + lane] or zeros)
+        else if (g < g_end) bx = __ldcg(boxes + g);
         const int w = (int)bx.z - (int)bx.x;
         const int n = w * ((int)bx.w - (int)bx.y);
         const int incl = warp_scan_inclusive(n);
@@ -401,20 +439,25 @@ fit_place_kernel(gi2d_fit_params p, int with_backward, int gpb, int num_tiles,
     __shared__ int s_warp[kPlaceWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_launch_dependents();
+    const int gpw = gpb / kPlaceWarps;
+    const int g_begin = min(p.num_points, blockIdx.x * gpb + warp * gpw);
+    const int g_end = min(p.num_points, g_begin + gpw);
     pdl_wait();
+    // the first chunk of boxes is in flight while the tile starts are scanned
+    ushort4 first_box = make_ushort4(0, 0, 0, 0);
+    if (g_begin + lane < g_end) first_box = __ldcg(boxes + g_begin + lane);
     int total;
     if (kSmemScan) {
         total = scan_counts_to_smem<kPlaceThreads>(tile_count, num_tiles, s_base, s_warp);
     } else {
         total = num_tiles > 0 ? __ldcg(tile_incl + num_tiles - 1) : 0;
     }
-    // tile ranges: CTA 0 when they sit in its shared memory, else all CTAs share the tiles
+    // tile ranges: the CTAs share the tiles (every CTA has all the starts)
     if (kSmemScan) {
-        if (blockIdx.x == 0)
-            for (int t = threadIdx.x; t < num_tiles; t += kPlaceThreads) {
-                const int c = __ldcg(tile_count + t);
-                reinterpret_cast<int2 *>(tile_bins)[t] = c ? make_int2(s_base[t], s_base[t] + c) : make_int2(0, 0);
-            }
+        for (int t = blockIdx.x * kPlaceThreads + threadIdx.x; t < num_tiles; t += gridDim.x * kPlaceThreads) {
+            const int c = __ldcg(tile_count + t);
+            reinterpret_cast<int2 *>(tile_bins)[t] = c ? make_int2(s_base[t], s_base[t] + c) : make_int2(0, 0);
+        }
     } else {
         for (int t = blockIdx.x * kPlaceThreads + threadIdx.x; t < num_tiles; t += gridDim.x * kPlaceThreads) {
             const int e = __ldcg(tile_incl + t), c = __ldcg(tile_count + t);
@@ -429,17 +472,16 @@ fit_place_kernel(gi2d_fit_params p, int with_backward, int gpb, int num_tiles,
             *n_isect = total > p.isect_capacity ? p.isect_capacity : total;
         }
     }
-    const int gpw = gpb / kPlaceWarps;
-    const int g_begin = min(p.num_points, blockIdx.x * gpb + warp * gpw);
-    const int g_end = min(p.num_points, g_begin + gpw);
-    walk_intersections(g_begin, g_end, p.tiles_x, boxes, [&](bool valid, int tile, int g) {
+    walk_intersections(g_begin, g_end, p.tiles_x, boxes, first_box, [&](bool valid, int tile, int g) {
         if (valid) {
+            // (record loads and the cursor atomic are independent: all in flight together)
+            const float4 r0 = __ldcg(proj + 2 * g), r1 = __ldcg(proj + 2 * g + 1);
             const int start = kSmemScan ? s_base[tile] : (__ldcg(tile_incl + tile) - __ldcg(tile_count + tile));
             const int pos = start + atomicAdd(tile_fill + tile, 1);
             if (pos < p.isect_capacity) {
                 keys_out[pos] = ((uint64_t)(uint32_t)tile << 32) | (uint32_t)g;
-                records[2 * (size_t)pos] = __ldcg(proj + 2 * g);
-                records[2 * (size_t)pos + 1] = __ldcg(proj + 2 * g + 1);
+                records[2 * (size_t)pos] = r0;
+                records[2 * (size_t)pos + 1] = r1;
             }
         }
     });
@@ -645,8 +687,7 @@ fit_adam_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bou
         if (pending) {
             float2 x;
             float q[3];
-            adam_update_gaussian(p, a, g, __ldcg(proj + 2 * g), __ldcg(proj + 2 * g + 1), __ldcg(grads + 2 * g),
-                                 __ldcg(grads + 2 * g + 1), stats, veto, x, c, q);
+            adam_update_gaussian(p, a, g, proj, grads, stats, veto, x, c, q);
             if (s_best) {
                 best[2 * g] = make_float4(x.x, x.y, c[0], c[1]);
                 best[2 * g + 1] = make_float4(c[2], q[0], q[1], q[2]);
@@ -710,7 +751,14 @@ fit_exchange_adam_kernel(gi2d_fit_params p, AdamPtrs local, PeerPtrs peers, int 
     }
     float2 x;
     float c[3], col[3];
-    adam_update_gaussian(p, local, g, __ldcg(proj + 2 * g), __ldcg(proj + 2 * g + 1), s0, s1, stats, veto, x, c, col);
+    AdamRegs r;
+    adam_load(local, g, proj, peers.grads[rank], r);
+    r.g0 = s0;  // the reduced gradient replaces the local partial
+    r.g1 = s1;
+    if (!veto) adam_apply(p, local, g, r, stats);
+    x = r.x;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { c[k] = r.c[k]; col[k] = r.q[k]; }
     if (veto) return;
     for (int q = 0; q < world; ++q) {
         if (q == rank) continue;  // the local copy was written by adam_update_gaussian
@@ -782,7 +830,7 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     const int proj_threads = p->num_points <= (1 << 16) ? 64 : kProjThreads;
     launch_pdl(fit_project_kernel, dim3(max(1, cdiv(p->num_points, proj_threads))), dim3(proj_threads), 0, st,
         *p, ap, b->cov_bound, (float4 *)b->proj, (float4 *)b->grads, w.boxes, w.tile_count, b->stats, with_backward,
-        (float4 *)b->best);
+        (float4 *)b->best, (with_backward && !p->external_optimizer) ? 1 : 0);
     if (mk) mk->mark(st);
     if (!pl.smem_scan) {
         // more tiles than one CTA scans in shared memory: device-wide inclusive prefix sum of the counts
