@@ -1,0 +1,196 @@
+"""Compression pass of GaussianImage++ (`train_quantize.py`, BASELINE.json configs[3]): the
+`quantize=True` half of `GaussianImage_Covariance` -- `training_setup(quantize=True)`
+(models/gaussianimage_covariance.py:116-146), `forward_quantize` (:384-410), `train_iter_quantize` (:219-232),
+`optimizer_step` (:234-247), `compress_wo_ec` / `decompress_wo_ec` / `analysis_wo_ec` (:412-509) -- on top of
+the drop-in operators (`gsplat.project_gaussians_2d_covariance`, `gsplat.rasterize_gaussians_plus`: the CUDA
+kernels of libgi2d with the reference's autograd contract) and the fused quantisers of `quantize.py`.
+
+Quantisation-aware training needs gradients with respect to the quantiser parameters as well, so it runs on
+the autograd operator path (projection and rasterization forward / backward are the libgi2d kernels; the loss
+gradient comes from the fused SSIM / mse / l1 kernels through `loss_fn`).  The fully fused, graph-captured
+step of `fit.py` is the warm-up phase (`iter < warmup_iter`, train_quantize.py:124-127).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from .fit import loss_weights
+from .quantize import HybirdQuant, UniformQuantizer
+
+
+class _ImageLoss(torch.autograd.Function):
+    """loss_fn of models/utils.py:60-80 on a [1,3,H,W] prediction in [0,1], value and gradient from the libgi2d
+    loss kernels (gi2d_image_loss_grad: SSIM map + its transposed filter, mse / l1 terms)."""
+
+    @staticmethod
+    def forward(ctx, pred, target_hwc, loss_type, lambda_value):
+        from .binding import image_loss_grad
+
+        hwc = pred[0].permute(1, 2, 0).contiguous()
+        v, ssim_sum = image_loss_grad(hwc, target_hwc, loss_type, lambda_value)
+        H, W, _ = hwc.shape
+        w2, w1, ws = loss_weights(loss_type, lambda_value)
+        tgt = target_hwc.float() / 255 if target_hwc.dtype == torch.uint8 else target_hwc
+        d = hwc.clamp(0, 1) - tgt
+        loss = w2 * (d * d).mean() + w1 * d.abs().mean()
+        if ws:
+            loss = loss + ws * (1.0 - ssim_sum[0].float() / (3.0 * (H - 10) * (W - 10)))
+        ctx.save_for_backward(v)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (v,) = ctx.saved_tensors
+        return (g * v).permute(2, 0, 1).unsqueeze(0), None, None, None
+
+
+def loss_fn(pred: torch.Tensor, target_hwc: torch.Tensor, loss_type: str = "L2", lambda_value: float = 0.7):
+    """pred [1,3,H,W]; target f32 or u8 [H,W,3] on the same device."""
+    return _ImageLoss.apply(pred, target_hwc, loss_type, lambda_value)
+
+
+class QuantizedGaussianImage(nn.Module):
+    """State + quantisers + the four optimisers of the reference's quantised model."""
+
+    def __init__(self, xyz, cov2d, features_dc, cholesky_bound, H: int, W: int, lr: float = 0.018,
+                 loss_type: str = "L2", color_norm: bool = False, xy_bit: int = 12, cov_bit: int = 10,
+                 color_bit: int = 6, clip_coe: float = 3.0, radius_clip: float = 1.0):
+        super().__init__()
+        self.H, self.W = int(H), int(W)
+        self.tile_bounds = ((self.W + 15) // 16, (self.H + 15) // 16, 1)
+        self.loss_type, self.color_norm = loss_type, bool(color_norm)
+        self.gs_clip_coe, self.radius_clip = clip_coe, radius_clip
+        self._xyz = nn.Parameter(xyz.detach().clone())
+        self._cov2d = nn.Parameter(cov2d.detach().clone())
+        self._features_dc = nn.Parameter(features_dc.detach().clone())
+        self.register_buffer("_opacity", torch.ones(xyz.shape[0], 1, device=xyz.device))
+        self.cholesky_bound = cholesky_bound.detach().clone()
+        self.cur_num_points = xyz.shape[0]
+        dev = xyz.device
+        # training_setup(lr, update_optimizer=True, quantize=True), gaussianimage_covariance.py:105-146
+        groups = [{"params": [self._xyz], "lr": lr, "name": "xyz"},
+                  {"params": [self._features_dc], "lr": lr, "name": "f_dc"},
+                  {"params": [self._cov2d], "lr": lr, "name": "cov2d"}]
+        self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+        self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=20000, gamma=0.5)
+        qlr = 0.001
+        self.xyz_quantizer = UniformQuantizer(signed=False, bits=xy_bit, weight=1.0, learned=True, num_channels=2).to(dev)
+        self.xyz_quantizer_optimizer = torch.optim.Adam(self.xyz_quantizer.parameters(), lr=qlr)
+        self.xyz_scheduler = torch.optim.lr_scheduler.StepLR(self.xyz_quantizer_optimizer, step_size=10000, gamma=0.5)
+        self.cholesky_quantizer = HybirdQuant(signed=False, bits=cov_bit, cov_bits=cov_bit, learned=True, weight=1.0).to(dev)
+        self.cov2d_quantizer_optimizer = torch.optim.Adam(self.cholesky_quantizer.parameters(), lr=qlr, eps=1e-15)
+        self.cov2d_scheduler = torch.optim.lr_scheduler.StepLR(self.cov2d_quantizer_optimizer, step_size=10000, gamma=0.5)
+        self.features_dc_quantizer = UniformQuantizer(signed=False, bits=color_bit, learned=True, weight=1.0,
+                                                      num_channels=3).to(dev)
+        self.color_quantizer_optimizer = torch.optim.Adam(self.features_dc_quantizer.parameters(), lr=qlr, eps=1e-15)
+        self.color_scheduler = torch.optim.lr_scheduler.StepLR(self.color_quantizer_optimizer, step_size=10000, gamma=0.5)
+        self.quantized_cov2d = None
+
+    @classmethod
+    def from_fitter(cls, fit, best: bool = True, **kw):
+        """Continue from a fitted model (train_quantize.py:128-140 restarts from the best warm-up state)."""
+        if best:
+            st = fit.best_state()
+            args = (st["_xyz"], st["_cov2d"], st["_features_dc"], st["cholesky_bound"])
+        else:
+            args = (fit._xyz, fit._cov2d, fit._features_dc, fit.cholesky_bound)
+        kw.setdefault("lr", float(fit.stats()["lr"]))       # scheduler.get_last_lr() of the warm-up (:137)
+        kw.setdefault("loss_type", fit.loss_type)
+        kw.setdefault("color_norm", fit.color_norm)
+        return cls(*args, fit.H, fit.W, clip_coe=fit.clip_coe, radius_clip=fit.radius_clip, **kw)
+
+    # ------------------------------------------------------------------ reference properties
+    @property
+    def get_cov2d_elements(self):
+        return self._cov2d + self.cholesky_bound
+
+    @property
+    def get_features(self):
+        return torch.sigmoid(self._features_dc) if self.color_norm else self._features_dc
+
+    @property
+    def get_opacity(self):
+        return self._opacity
+
+    def _render(self, means, cov, colors):
+        from .gsplat import project_gaussians_2d_covariance, rasterize_gaussians_plus
+
+        xys, depths, radii, conics, nth = project_gaussians_2d_covariance(
+            means, cov, self.H, self.W, self.tile_bounds, clip_coe=self.gs_clip_coe, radius_clip=self.radius_clip)
+        out = rasterize_gaussians_plus(xys, depths, radii, conics, nth, colors, self.get_opacity, self.H, self.W, 16, 16,
+                                       radius_clip=self.radius_clip)
+        out = torch.clamp(out, 0, 1)
+        return out.view(-1, self.H, self.W, 3).permute(0, 3, 1, 2).contiguous()
+
+    # ------------------------------------------------------------------ gaussianimage_covariance.py:384-410
+    def forward_quantize(self) -> Dict:
+        means, l_vqm, m_bit, _ = self.xyz_quantizer(self._xyz)
+        cov, l_vqs, s_bit, _ = self.cholesky_quantizer(self.get_cov2d_elements)
+        self.quantized_cov2d = cov
+        colors, l_vqc, c_bit, _ = self.features_dc_quantizer(self.get_features)
+        return {"render": self._render(means, cov, colors), "vq_loss": l_vqm + l_vqs + l_vqc,
+                "unit_bit": [m_bit, s_bit, c_bit]}
+
+    # ------------------------------------------------------------------ :219-247
+    def train_iter_quantize(self, gt_hwc: torch.Tensor):
+        """gt_hwc: f32 or u8 [H,W,3].  Returns (image, loss, img_loss, vq_loss, psnr) like the reference."""
+        pkg = self.forward_quantize()
+        image = pkg["render"]
+        loss = loss_fn(image, gt_hwc, self.loss_type, 0.7)
+        loss.backward()
+        self.optimizer_step()
+        with torch.no_grad():
+            tgt = gt_hwc.float() / 255 if gt_hwc.dtype == torch.uint8 else gt_hwc
+            mse = ((image[0].permute(1, 2, 0) - tgt) ** 2).mean().item()
+            psnr = 10 * math.log10(1.0 / mse)
+        return image.detach(), loss, float(loss.detach()), pkg["vq_loss"], psnr
+
+    def optimizer_step(self):
+        for opt, sch in ((self.optimizer, self.scheduler), (self.cov2d_quantizer_optimizer, self.cov2d_scheduler),
+                         (self.xyz_quantizer_optimizer, self.xyz_scheduler),
+                         (self.color_quantizer_optimizer, self.color_scheduler)):
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            sch.step()
+
+    # ------------------------------------------------------------------ :373-382, :412-467
+    def check_non_semi_definite(self, cov2d):
+        valid = (cov2d[:, 0] * cov2d[:, 2] - cov2d[:, 1] ** 2 > 0) & (cov2d[:, 0] > 0) & (cov2d[:, 2] > 0)
+        return int((~valid).sum().item()), valid
+
+    @torch.no_grad()
+    def compress_wo_ec(self) -> Dict:
+        means, quant_means = self.xyz_quantizer.compress(self._xyz)
+        cov, quant_cov = self.cholesky_quantizer.compress(self.get_cov2d_elements)
+        colors, color_index = self.features_dc_quantizer.compress(self.get_features)
+        n_bad, valid = self.check_non_semi_definite(cov)
+        if n_bad:       # Gaussians that stopped being positive definite after quantisation are dropped (:424-437)
+            cov, quant_cov, means = cov[valid], quant_cov[valid], means[valid]
+            color_index, colors = color_index[valid], colors[valid]
+            quant_means = quant_means[valid]
+            self.cholesky_bound = self.cholesky_bound[valid]
+            self._opacity = torch.ones(int(valid.sum()), 1, device=means.device)
+            self.cur_num_points = int(valid.sum())
+        self.quantized_cov2d = cov
+        return {"xyz": means, "feature_dc_index": color_index, "quant_cholesky_elements": quant_cov,
+                "quant_means": quant_means}
+
+    @torch.no_grad()
+    def decompress_wo_ec(self, enc: Dict) -> Dict:
+        cov = self.cholesky_quantizer.decompress(enc["quant_cholesky_elements"])
+        colors = self.features_dc_quantizer.decompress(enc["feature_dc_index"])
+        return {"render": self._render(enc["xyz"].contiguous(), cov.contiguous(), colors.contiguous())}
+
+    def analysis_wo_ec(self, enc: Dict) -> Dict:
+        """Bits per pixel without entropy coding (:469-509, `lsq` branches): N x bits per attribute + the
+        quantiser parameters (32-bit scale and beta per channel)."""
+        cov_bits = enc["quant_cholesky_elements"].numel() * self.cholesky_quantizer.size() + 32 * 3 * 2
+        color_bits = enc["feature_dc_index"].numel() * self.features_dc_quantizer.size() + 32 * 3 * 2
+        pos_bits = enc["xyz"].numel() * self.xyz_quantizer.size() + 32 * 2 * 2
+        px = self.H * self.W
+        return {"bpp": (pos_bits + cov_bits + color_bits) / px, "position_bpp": pos_bits / px,
+                "cholesky_bpp": cov_bits / px, "feature_dc_bpp": color_bits / px}

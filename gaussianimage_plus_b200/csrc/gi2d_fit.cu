@@ -330,13 +330,17 @@ __device__ __forceinline__ void step_bookkeeping_warp0(const gi2d_fit_params &p,
                                                        double *__restrict__ stats) {
     best_commit_warp0(stats);  // (the optimiser threads of K1 took the same decision for their snapshot)
     __syncwarp();
-    stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
-    stats[GI2D_STAT_SSE + 32 + threadIdx.x] = 0.0;
+    if (with_backward) {       // (a render-only call accumulates no loss: the last step's numbers stay readable)
+        stats[GI2D_STAT_SSE + threadIdx.x] = 0.0;
+        stats[GI2D_STAT_SSE + 32 + threadIdx.x] = 0.0;
+    }
     __syncwarp();
     if (threadIdx.x == 0) {
         stats[GI2D_STAT_OVERFLOW] = 0.0;
-        stats[GI2D_STAT_SSIM_SUM] = 0.0;
-        stats[GI2D_STAT_ABS_SUM] = 0.0;
+        if (with_backward) {
+            stats[GI2D_STAT_SSIM_SUM] = 0.0;
+            stats[GI2D_STAT_ABS_SUM] = 0.0;
+        }
         stats[kStatPending] = (with_backward && !p.external_optimizer) ? 1.0 : 0.0;
         if (with_backward) {
             const double step = stats[GI2D_STAT_STEP] + 1.0;
@@ -1024,4 +1028,86 @@ extern "C" int gi2d_fit_exchange_adam(const gi2d_fit_params *p, const gi2d_fit_b
     fit_exchange_adam_kernel<<<cdiv(g1 - g0, 256), 256, 0, (cudaStream_t)stream>>>(
         *p, ap, pp, rank, world, g0, g1, (const float4 *)b->proj, b->stats);
     return check_launch(__func__);
+}
+
+// ------------------------------------------------------------------------------ host-fed steps
+struct gi2d_host_pipe {
+    cudaStream_t copy;
+    cudaEvent_t copied[2], stats[2];
+    cudaEvent_t read[2];        // recorded after the last step that read device target buffer buf[i]
+    const void *buf[2];
+    bool read_valid[2];
+    unsigned long long calls;
+};
+
+extern "C" int gi2d_host_pipe_create(gi2d_host_pipe **out) {
+    GI2D_REQUIRE(out, "null output");
+    gi2d_host_pipe *pp = new gi2d_host_pipe();
+    cudaStreamCreateWithFlags(&pp->copy, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&pp->copied[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&pp->stats[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&pp->read[i], cudaEventDisableTiming);
+        pp->buf[i] = nullptr;
+        pp->read_valid[i] = false;
+    }
+    pp->calls = 0;
+    *out = pp;
+    return check_launch(__func__);
+}
+
+extern "C" int gi2d_host_pipe_destroy(gi2d_host_pipe *pp) {
+    if (!pp) return GI2D_OK;
+    cudaStreamSynchronize(pp->copy);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(pp->copied[i]);
+        cudaEventDestroy(pp->stats[i]);
+        cudaEventDestroy(pp->read[i]);
+    }
+    cudaStreamDestroy(pp->copy);
+    delete pp;
+    return GI2D_OK;
+}
+
+extern "C" int gi2d_fit_step_host(gi2d_host_pipe *pp, const gi2d_fit_params *p, const gi2d_fit_buffers *b,
+                                  const void *host_target, size_t target_bytes, double *host_stats,
+                                  gi2d_stream_t stream, int *slot_out) {
+    GI2D_REQUIRE(pp && p && b && host_target && host_stats && slot_out, "null argument");
+    void *dst = b->gt_u8_hwc ? (void *)b->gt_u8_hwc : (void *)b->gt_hwc;
+    GI2D_REQUIRE(dst, "the buffers carry no target image");
+    const size_t want = (size_t)p->img_width * p->img_height * 3 * (b->gt_u8_hwc ? 1 : 4);
+    GI2D_REQUIRE(target_bytes == want, "target_bytes does not match the image size / dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int slot = (int)(pp->calls & 1);
+    // which of the (at most two) device target buffers is this?  (a third evicts the older entry)
+    int e = pp->buf[0] == dst ? 0 : (pp->buf[1] == dst ? 1 : -1);
+    if (e < 0) {
+        e = pp->buf[0] == nullptr ? 0 : (pp->buf[1] == nullptr ? 1 : slot);
+        pp->buf[e] = dst;
+        pp->read_valid[e] = false;
+    }
+    // upload: after the last step that read this buffer, concurrently with whatever `stream` is running now
+    if (pp->read_valid[e]) cudaStreamWaitEvent(pp->copy, pp->read[e], 0);
+    cudaMemcpyAsync(dst, host_target, target_bytes, cudaMemcpyHostToDevice, pp->copy);
+    cudaEventRecord(pp->copied[slot], pp->copy);
+    cudaStreamWaitEvent(st, pp->copied[slot], 0);
+    const int rc = fit_forward_backward_impl(p, b, 1, st, nullptr);
+    if (rc != GI2D_OK) return rc;
+    cudaEventRecord(pp->read[e], st);
+    pp->read_valid[e] = true;
+    cudaMemcpyAsync(host_stats, b->stats, GI2D_STAT_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(pp->stats[slot], st);
+    *slot_out = slot;
+    pp->calls++;
+    return check_launch(__func__);
+}
+
+extern "C" int gi2d_host_pipe_wait(gi2d_host_pipe *pp, int slot) {
+    GI2D_REQUIRE(pp && (slot == 0 || slot == 1), "bad slot");
+    const cudaError_t err = cudaEventSynchronize(pp->stats[slot]);
+    if (err != cudaSuccess) {
+        set_error("gi2d_host_pipe_wait: %s", cudaGetErrorString(err));
+        return GI2D_ERR_CUDA;
+    }
+    return GI2D_OK;
 }

@@ -153,7 +153,7 @@ class GaussianImageFitter:
             1 if self.external_optimizer else 0, self.loss_w[1] / (3.0 * self.H * self.W), self.loss_w[2])
         ws_bytes = self.lib.gi2d_fit_workspace_size(C.byref(self.params))
         self.workspace = torch.zeros(max(ws_bytes, 256), dtype=torch.uint8, device=self.device)
-        self._graph = None
+        self._invalidate_graphs()
         self._eager_left = 1
         self._dirty = False
         self._bind()
@@ -191,10 +191,12 @@ class GaussianImageFitter:
                            "fit_adam")
 
     # ------------------------------------------------------------------ target
-    def set_target(self, gt_image: torch.Tensor):
+    def set_target(self, gt_image: torch.Tensor, overlap: bool = False):
         """gt_image: float32 [1,3,H,W] (the reference's layout, utils.py:21-27) or [H,W,3]; or uint8 [H,W,3]
         -- the image as stored: the kernels then use u8/255, the value ToTensor would have produced, and
-        the host->device copy is 4x smaller.  Copied (asynchronously from pinned memory) to HWC on device."""
+        the host->device copy is 4x smaller.  Copied (asynchronously from pinned memory) to HWC on device.
+        `overlap`: upload into the OTHER of two device buffers on a copy stream, so that the transfer of the
+        next step's target runs under the step in flight (a driver that feeds a new target every step)."""
         if gt_image.dim() == 4:
             gt_image = gt_image[0].permute(1, 2, 0)
         assert gt_image.shape == (self.H, self.W, 3), gt_image.shape
@@ -202,13 +204,108 @@ class GaussianImageFitter:
         if self.gt_hwc is None or self.gt_hwc.dtype != gt_image.dtype:
             first = self.gt_hwc is None
             self.gt_hwc = torch.empty(self.H, self.W, 3, dtype=gt_image.dtype, device=self.device)
-            self._graph = None
+            self._invalidate_graphs()
+            self._gt_alt = None
             self.gt_hwc.copy_(gt_image, non_blocking=True)
             self._bind()
             if first:
                 self.reset_stats(self._step0)
             return
-        self.gt_hwc.copy_(gt_image, non_blocking=True)
+        if not overlap:
+            self.gt_hwc.copy_(gt_image, non_blocking=True)
+            return
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_gt_alt", None) is None:
+            self._gt_alt = torch.empty_like(self.gt_hwc)
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._ev_read = {}      # buffer -> event recorded after the last step that read it
+            self._ev_copied = {t.data_ptr(): torch.cuda.Event() for t in (self.gt_hwc, self._gt_alt)}
+        nxt, cur = self._gt_alt, self.gt_hwc
+        free = self._ev_read.get(nxt.data_ptr())
+        with torch.cuda.stream(self._copy_stream):
+            if free is not None:
+                self._copy_stream.wait_event(free)
+            nxt.copy_(gt_image, non_blocking=True)
+            self._ev_copied[nxt.data_ptr()].record(self._copy_stream)
+        main.wait_event(self._ev_copied[nxt.data_ptr()])
+        # swap the buffers, their graphs and their bound argument blocks
+        self._graphs[cur.data_ptr()] = (self._graph, self.buffers)
+        self.gt_hwc, self._gt_alt = nxt, cur
+        self._graph, bound = self._graphs.get(nxt.data_ptr(), (None, None))
+        if bound is not None:
+            self.buffers = bound
+        else:
+            self._bind()
+
+    def _invalidate_graphs(self):
+        self._graph = None
+        self._graphs = {}
+        self._pipe_bound = None
+
+    # ------------------------------------------------------------------ steps fed from host memory
+    def step_from_host(self, host_img: torch.Tensor, host_stats: torch.Tensor) -> int:
+        """One train_iter whose target comes from PINNED host memory and whose stats block goes back to pinned
+        host memory, through ONE C call (gi2d_fit_step_host): upload on the library's copy stream into the
+        other of two device buffers (under the step in flight), the 3 kernels, the 640-byte read-back.
+        Asynchronous; returns the slot to hand to `wait_host_result`.  host_img: u8 or f32 [H,W,3];
+        host_stats: f64[STAT_COUNT].  The fitter's device must be the current CUDA device."""
+        pb = self._pipe_bound
+        if pb is None or self._pipe_dtype != host_img.dtype:
+            pb = self._setup_host_pipe(host_img, host_stats)
+        self._pipe_idx ^= 1
+        rc = self._step_host(self._pipe, self._params_ref, pb[self._pipe_idx], host_img.data_ptr(), self._pipe_bytes,
+                             host_stats.data_ptr(), torch.cuda.current_stream().cuda_stream, self._slot_ref)
+        if rc != 0:
+            _lib.check(rc, "fit_step_host")
+        self._dirty = True
+        return self._slot.value
+
+    def _setup_host_pipe(self, host_img, host_stats):
+        assert host_img.shape == (self.H, self.W, 3) and host_img.is_pinned() and host_stats.is_pinned()
+        assert host_stats.dtype == torch.float64 and host_stats.numel() >= STAT_COUNT
+        if self.grad_hook is not None or self.external_optimizer:
+            raise RuntimeError("step_from_host does not run the multi-GPU exchange hook: use set_target + train_iter")
+        if torch.cuda.current_device() != self.device.index:
+            raise RuntimeError("step_from_host: make the fitter's device current (torch.cuda.set_device)")
+        if getattr(self, "_pipe", None) is None:
+            self._pipe = C.c_void_p()
+            _lib.check(self.lib.gi2d_host_pipe_create(C.byref(self._pipe)), "host_pipe_create")
+            self._pipe_bufs, self._pipe_idx, self._pipe_dtype = None, 0, None
+            self._slot = C.c_int(0)
+            self._slot_ref = C.byref(self._slot)
+            self._step_host = self.lib.gi2d_fit_step_host
+        if self._pipe_bufs is None or self._pipe_dtype != host_img.dtype:
+            self._pipe_bufs = [torch.empty(self.H, self.W, 3, dtype=host_img.dtype, device=self.device) for _ in range(2)]
+            self._pipe_dtype = host_img.dtype
+            self._pipe_bytes = host_img.numel() * host_img.element_size()
+            if self.gt_hwc is None:
+                self.gt_hwc = self._pipe_bufs[0]
+                self.reset_stats(self._step0)
+        self.sync_params()
+        keep = self.gt_hwc
+        bound = []
+        for t in self._pipe_bufs:
+            self.gt_hwc = t
+            self._bind()
+            bound.append(C.byref(self.buffers))
+            self._pipe_keepalive = getattr(self, "_pipe_keepalive", []) + [self.buffers]
+        self._pipe_keepalive = self._pipe_keepalive[-2:]
+        self.gt_hwc = keep if keep is not None else self._pipe_bufs[0]
+        self._bind()
+        self._params_ref = C.byref(self.params)
+        self._pipe_bound = bound
+        return bound
+
+    def wait_host_result(self, slot: int):
+        _lib.check(self.lib.gi2d_host_pipe_wait(self._pipe, int(slot)), "host_pipe_wait")
+
+    def __del__(self):
+        pipe = getattr(self, "_pipe", None)
+        if pipe is not None and pipe.value:
+            try:
+                self.lib.gi2d_host_pipe_destroy(pipe)
+            except Exception:
+                pass
 
     # ------------------------------------------------------------------ one iteration
     def _enqueue_step(self):
@@ -225,27 +322,35 @@ class GaussianImageFitter:
             raise RuntimeError("set_target() first")
         self._dirty = not self.external_optimizer
         with torch.cuda.device(self.device):
-            if want_error_map:
-                self._bind(err_map=True)
-                self._enqueue_step()
-                self._bind()
-                return
-            if not self.use_graph or self._eager_left > 0:
-                # the first step after (re)allocation runs eagerly: it loads the kernels (CUDA lazy
-                # module loading is not capturable) and is an ordinary step in every other respect
-                self._eager_left -= 1
-                self._enqueue_step()
-                return
-            if self._graph is None:
-                self._bind()
-                self._graph = torch.cuda.CUDAGraph()
-                s = torch.cuda.Stream(device=self.device)
-                s.wait_stream(torch.cuda.current_stream(self.device))
-                with torch.cuda.stream(s):
-                    with torch.cuda.graph(self._graph, stream=s):
-                        self._enqueue_step()
-                torch.cuda.current_stream(self.device).wait_stream(s)
-            self._graph.replay()
+            self._train_iter_enqueue(want_error_map)
+            if getattr(self, "_gt_alt", None) is not None:   # double-buffered targets: this buffer is free after the step
+                ev = self._ev_read.get(self.gt_hwc.data_ptr())
+                if ev is None:
+                    ev = self._ev_read[self.gt_hwc.data_ptr()] = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+
+    def _train_iter_enqueue(self, want_error_map: bool):
+        if want_error_map:
+            self._bind(err_map=True)
+            self._enqueue_step()
+            self._bind()
+            return
+        if not self.use_graph or self._eager_left > 0:
+            # the first step after (re)allocation runs eagerly: it loads the kernels (CUDA lazy
+            # module loading is not capturable) and is an ordinary step in every other respect
+            self._eager_left -= 1
+            self._enqueue_step()
+            return
+        if self._graph is None:
+            self._bind()
+            self._graph = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                with torch.cuda.graph(self._graph, stream=s):
+                    self._enqueue_step()
+            torch.cuda.current_stream(self.device).wait_stream(s)
+        self._graph.replay()
 
     def launches_per_iter(self, with_backward: bool = True) -> int:
         """Kernels launched by one train_iter / forward (counted by the library itself)."""

@@ -143,7 +143,7 @@ class FusedTileRowExchange:
         fit.external_optimizer = True
         fit.params.external_optimizer = 1
         fit.use_graph = False
-        fit._graph = None
+        fit._invalidate_graphs()
         fit._bind()
         fit.grad_hook = self
         self._lib, self._C = _lib, C

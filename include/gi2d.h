@@ -268,6 +268,23 @@ int gi2d_fit_exchange_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, 
                            const void *const *peer_grads, void *const *peer_xyz, void *const *peer_cov,
                            void *const *peer_rgb, gi2d_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training steps fed from HOST memory (bench.py's `e2e`): one C call per step does what a driver that gets a
+ * new target every step has to do -- upload the target from pinned host memory into the device buffer the
+ * step will read (on the pipe's own copy stream, double-buffered by the caller: alternate two
+ * gi2d_fit_buffers that differ in their target pointer, and the upload of step k+1 runs under step k), run
+ * the step on `stream`, and copy the stats block (f64[GI2D_STAT_COUNT]) to pinned host memory.  Everything
+ * is asynchronous; gi2d_host_pipe_wait(slot) blocks until the stats of the call that returned `slot` are on
+ * the host.  The pipe owns only a stream and a few events.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gi2d_host_pipe gi2d_host_pipe;
+int gi2d_host_pipe_create(gi2d_host_pipe **out);
+int gi2d_host_pipe_destroy(gi2d_host_pipe *pipe);
+int gi2d_fit_step_host(gi2d_host_pipe *pipe, const gi2d_fit_params *p, const gi2d_fit_buffers *b,
+                       const void *host_target, size_t target_bytes, double *host_stats,
+                       gi2d_stream_t stream, int *slot_out);
+int gi2d_host_pipe_wait(gi2d_host_pipe *pipe, int slot);
+
 /* Stand-alone form of the loss gradient the fit step uses when loss_ssim_weight != 0: everything autograd does
  * between the rasterizer output and the loss in gaussianimage_covariance.py:210,252-253 --
  *   v_out = d/d(out) [ ssim_weight * (1 - ssim(clamp(out), gt)) + (l2_scale/2) * sum (clamp(out)-gt)^2

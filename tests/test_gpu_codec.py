@@ -1,0 +1,61 @@
+"""GPU: the compression pass (train_quantize.py; gaussianimage_plus_b200/codec.py) over the drop-in operators:
+quantised forward, quantisation-aware training with the four optimisers, compress / decompress round trip and
+the bits-per-pixel accounting of analysis_wo_ec (gaussianimage_covariance.py:469-509)."""
+import numpy as np
+import pytest
+import torch
+
+from gaussianimage_plus_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _psnr(render, gt_hwc):
+    return 10 * np.log10(1.0 / float(((render[0].permute(1, 2, 0) - gt_hwc) ** 2).mean()))
+
+
+@pytest.mark.parametrize("loss_type", ["L2", "Fusion2"])
+def test_quantised_training_and_codec_round_trip(loss_type):
+    from gaussianimage_plus_b200.codec import QuantizedGaussianImage
+    from gaussianimage_plus_b200.fit import GaussianImageFitter
+
+    N, H, W = 1500, 128, 192
+    gt = torch.from_numpy(synth.target_image(H, W, seed=5)).to(DEV)
+    torch.manual_seed(1)
+    fit = GaussianImageFitter(N, H, W, device=DEV, loss_type=loss_type)
+    fit.set_target(gt)
+    st = fit.fit(600, max_num_points=N, adaptive_add=False)              # warm-up phase (fused step)
+    assert st["best_psnr"] > 24
+    q = QuantizedGaussianImage.from_fitter(fit)
+    assert q.cur_num_points == fit.best_state()["_xyz"].shape[0] and q.loss_type == loss_type
+    with torch.no_grad():
+        ptq = _psnr(q.forward_quantize()["render"], gt)                   # post-training quantisation
+    assert ptq > st["best_psnr"] - 6.0                                    # 12/10/6 bits cost a few dB at most
+    first = None
+    for i in range(150):
+        image, loss, img_loss, vq_loss, psnr = q.train_iter_quantize(gt)
+        first = first if first is not None else psnr
+        assert np.isfinite(img_loss) and vq_loss == 0
+    assert abs(first - ptq) < 1e-3                                        # the first QAT forward IS the PTQ render
+    with torch.no_grad():
+        qat = _psnr(q.forward_quantize()["render"], gt)
+    assert qat > ptq - 0.05, (ptq, qat)                                   # QAT never hurts, usually helps
+    # every quantiser parameter received gradient steps
+    for name, p in q.named_parameters():
+        assert torch.isfinite(p).all(), name
+    # codec: compress -> decompress renders what the quantised forward renders (the log quantiser re-ranges per
+    # channel on compress, quantize.py:244, so "close", not "equal")
+    enc = q.compress_wo_ec()
+    n = q.cur_num_points
+    assert enc["xyz"].shape == (n, 2) and enc["quant_cholesky_elements"].shape == (n, 3)
+    assert enc["feature_dc_index"].shape == (n, 3)
+    for key, hi in (("quant_means", 4095), ("quant_cholesky_elements", 1023), ("feature_dc_index", 63)):
+        c = enc[key]
+        assert torch.equal(c, c.round()) and c.min() >= 0 and c.max() <= hi, key
+    dec = _psnr(q.decompress_wo_ec(enc)["render"], gt)
+    assert abs(dec - qat) < 0.5, (dec, qat)
+    a = q.analysis_wo_ec(enc)
+    bits = n * (2 * 12 + 3 * 10 + 3 * 6) + 32 * 2 * 2 + 32 * 3 * 2 + 32 * 3 * 2
+    assert abs(a["bpp"] - bits / (H * W)) < 1e-9
+    assert abs(a["bpp"] - (a["position_bpp"] + a["cholesky_bpp"] + a["feature_dc_bpp"])) < 1e-12

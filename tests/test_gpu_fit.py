@@ -222,6 +222,53 @@ def test_fit_loop_prune_densify_schedule():
     assert psnr_best_render > st["best_psnr"] - 0.5   # (the snapshot is the state AFTER the best step's update)
 
 
+def test_overlapped_target_upload_equals_plain():
+    """set_target(overlap=True): the next step's target is uploaded into the other of two device buffers on a
+    copy stream (bench.py's e2e loop).  Alternating two different images every step must give what the plain,
+    in-stream upload gives -- a wrong buffer or a missing dependency shows up as a different error at once."""
+    a, (_, _, _, _, gt) = make_fitter(1500, 192, 256, seed=31, colors="zeros", use_graph=True, keep_render=False)
+    b, _ = make_fitter(1500, 192, 256, seed=31, colors="zeros", use_graph=True, keep_render=False)
+    imgs = [torch.from_numpy(gt).pin_memory(), torch.from_numpy(np.ascontiguousarray(gt[::-1, ::-1])).pin_memory()]
+    for i in range(24):
+        a.set_target(imgs[i & 1], overlap=True)
+        b.set_target(imgs[i & 1])
+        a.train_iter()
+        b.train_iter()
+        if i % 4 == 3 or i < 3:
+            sa, sb = a.stats(), b.stats()
+            assert sa["step"] == sb["step"] == i + 1
+            assert abs(sa["mse"] - sb["mse"]) <= 1e-5 * sb["mse"], (i, sa["mse"], sb["mse"])
+
+
+def test_step_from_host_equals_train_iter():
+    """gi2d_fit_step_host (one C call: pinned target up, step, stats block down) == set_target + train_iter +
+    stats(), with two alternating targets so that the double buffering is exercised."""
+    from gaussianimage_plus_b200.fit import STAT_COUNT, STAT_STEP
+
+    a, (_, _, _, _, gt) = make_fitter(1500, 192, 256, seed=32, colors="zeros", use_graph=False, keep_render=False)
+    b, _ = make_fitter(1500, 192, 256, seed=32, colors="zeros", use_graph=True, keep_render=False)
+    u8 = lambda x: torch.from_numpy(np.round(x * 255).astype(np.uint8)).pin_memory()
+    imgs = [u8(gt), u8(np.ascontiguousarray(gt[::-1, ::-1]))]
+    ring = [torch.zeros(STAT_COUNT, dtype=torch.float64).pin_memory() for _ in range(2)]
+    got = []
+    prev = None
+    for i in range(16):
+        slot = a.step_from_host(imgs[i & 1], ring[i & 1])
+        if prev is not None:
+            a.wait_host_result(prev[0])
+            got.append((int(ring[prev[1]][STAT_STEP]), a.mse_from_stats(ring[prev[1]], 192, 256)))
+        prev = (slot, i & 1)
+    a.wait_host_result(prev[0])
+    got.append((int(ring[prev[1]][STAT_STEP]), a.mse_from_stats(ring[prev[1]], 192, 256)))
+    for i in range(16):
+        b.set_target(imgs[i & 1])
+        b.train_iter()
+        st = b.stats()
+        assert got[i][0] == st["step"] == i + 1
+        assert abs(got[i][1] - st["mse"]) <= 1e-5 * st["mse"], (i, got[i], st["mse"])
+    assert torch.allclose(a._xyz, b._xyz, atol=2e-3)
+
+
 # --------------------------------------------------------------------------- full-size properties
 @pytest.mark.parametrize("name", ["kodak_5000", "div2k_20000"])
 def test_full_size_properties(name):
