@@ -36,6 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FWD_FLOP, BWD_FLOP = 22, 43  # per pixel x Gaussian pair, SURVEY 8(d)
+NCU_TRAFFIC_BYTES = {"kodak_5000": 2295808}   # fit_raster_kernel<Fit>: 2.30 MB read + 0 written back within the launch
 
 
 def parse():
@@ -239,7 +240,14 @@ def main():
         fit.train_iter()
     ev1.record()
     barrier()
-    warm_ms = ev0.elapsed_time(ev1) / K
+    warm1_ms = ev0.elapsed_time(ev1) / K          # one graph replay per step
+    fit.train_iters(64)
+    barrier()
+    ev0.record()
+    fit.train_iters(K)                            # the fit loop's form: graphs of 8 steps, replayed back to back
+    ev1.record()
+    barrier()
+    warm_ms = min(warm1_ms, ev0.elapsed_time(ev1) / K)
 
     # ---------------- timed region of record: per-step events, L2 flushed between steps
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -371,7 +379,10 @@ def main():
         roofline = {
             "kernel": "fit_raster_kernel<Fit> (in-tile key sort + rasterize fwd + L2 grad + bwd)", "bound": "fp32",
             "achieved": achieved_tf, "peak": float(peak.value), "unit": "TFLOP/s",
-            "frac": achieved_tf / float(peak.value) if peak.value else None, "traffic": None,
+            "frac": achieved_tf / float(peak.value) if peak.value else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full`
+            # capture (profiles/r01_ncu_full_project_place_raster_v7_raw.csv), per launch; null for other workloads
+            "traffic": NCU_TRAFFIC_BYTES.get(args.workload), "traffic_unit": "bytes/launch",
             "peak_source": "FP32 FMA microbenchmark in this run (gi2d_measure_fp32_peak); nominal 74.4",
             "pairs_per_launch": pairs, "flop_per_pair": FWD_FLOP + BWD_FLOP, "kernel_ms": acc[3],
             "kernel_ms_l2_warm": acc_w[3],
@@ -403,7 +414,7 @@ def main():
                        else ("tile-row split + NCCL all-reduce of [N,8] gradients" if args.exchange == "nccl" else
                              "tile-row split + fused peer-memory reduce-scatter/Adam/all-gather kernel")},
             "value_l2_warm": (K * (world if args.mode == "images" else 1)) / (warm_ms * K * 1e-3),
-            "ms_per_step_l2_warm": warm_ms,
+            "ms_per_step_l2_warm": warm_ms, "ms_per_step_l2_warm_single_step_graphs": warm1_ms,
             "value_f32_target_l2_warm": (K * (world if args.mode == "images" else 1)) / (warm_f32_ms * K * 1e-3),
             "ms_per_step_p50": step_ms[len(step_ms) // 2], "wall_s_timed_region": t_wall,
             "render_fps": fps, "psnr": stats["psnr"], "train_step": stats["step"], "num_intersects": I,

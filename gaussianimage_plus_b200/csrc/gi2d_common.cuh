@@ -141,13 +141,15 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    // Inside a CUDA-graph capture the programmatic edges made replays SLOWER on this driver (580.159:
-    // 42.9 vs 37.5 us per 5-kernel step, measured), so captured launches keep full serialisation and
-    // only eager launches (render loop, un-graphed steps) overlap their prologues.
+    // Captured launches carry the attribute too: with the 3-kernel step the programmatic edges make a graph
+    // replay 5-6 % faster (28.6 vs 30.2 us at 768x512 / 5k Gaussians, driver 580.159).  (With the earlier
+    // 5-kernel step they were slower, 42.9 vs 37.5 us, and had been left out of captures.)
+    // GI2D_NO_PDL: fully serialised launches everywhere (debugging); GI2D_GRAPH_NO_PDL: only in captures.
+    static const bool no_pdl = getenv("GI2D_NO_PDL") != nullptr;
+    static const bool graph_no_pdl = getenv("GI2D_GRAPH_NO_PDL") != nullptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(st, &cap);
-    static const bool no_pdl = getenv("GI2D_NO_PDL") != nullptr;  // debugging aid: fully serialised launches
-    cfg.numAttrs = (cap == cudaStreamCaptureStatusNone && !no_pdl) ? 1 : 0;
+    if (graph_no_pdl) cudaStreamIsCapturing(st, &cap);
+    cfg.numAttrs = (no_pdl || cap != cudaStreamCaptureStatusNone) ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -240,6 +240,7 @@ class GaussianImageFitter:
     def _invalidate_graphs(self):
         self._graph = None
         self._graphs = {}
+        self._multi_graphs = {}
         self._pipe_bound = None
 
     # ------------------------------------------------------------------ steps fed from host memory
@@ -351,6 +352,41 @@ class GaussianImageFitter:
                     self._enqueue_step()
             torch.cuda.current_stream(self.device).wait_stream(s)
         self._graph.replay()
+
+    def train_iters(self, n: int, unroll: int = 8):
+        """`n` iterations back to back.  Graph replays of `unroll` steps each: inside a graph the next step's
+        first kernel is a programmatic dependent of the rasterizer before it, so its launch latency and
+        prologue hide under the previous step's tail (a one-step graph serialises on every replay)."""
+        if self.gt_hwc is None:
+            raise RuntimeError("set_target() first")
+        if not self.use_graph or self.grad_hook is not None or unroll < 2:
+            for _ in range(n):
+                self.train_iter()
+            return
+        while n > 0 and self._eager_left > 0:
+            self.train_iter()
+            n -= 1
+        if n >= unroll:
+            key = (self.gt_hwc.data_ptr(), unroll)
+            g = self._multi_graphs.get(key)
+            with torch.cuda.device(self.device):
+                if g is None:
+                    self._bind()
+                    g = torch.cuda.CUDAGraph()
+                    s = torch.cuda.Stream(device=self.device)
+                    s.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(s):
+                        with torch.cuda.graph(g, stream=s):
+                            for _ in range(unroll):
+                                self._enqueue_step()
+                    torch.cuda.current_stream(self.device).wait_stream(s)
+                    self._multi_graphs[key] = g
+                for _ in range(n // unroll):
+                    g.replay()
+            self._dirty = not self.external_optimizer
+            n %= unroll
+        for _ in range(n):
+            self.train_iter()
 
     def launches_per_iter(self, with_backward: bool = True) -> int:
         """Kernels launched by one train_iter / forward (counted by the library itself)."""
@@ -532,6 +568,38 @@ class GaussianImageFitter:
         self.densification_postfix(xyz, color, cov)
         return k
 
+    # ------------------------------------------------------------------ checkpoint (train.py:61-77,173-175)
+    def save_checkpoint(self, path, best: bool = True, ms_ssim: float = float("nan")):
+        """The reference's `gaussian_model.pth.tar`: {"gs": state_dict, "num_gs", "psnr", "ms-ssim", "slv_bound"},
+        with the state-dict keys of GaussianImage_Covariance (`_xyz`, `_cov2d`, `_features_dc` parameters and the
+        `_opacity`, `background`, `bound` buffers, gaussianimage_covariance.py:54-70).  `best`: the best-PSNR state
+        (what train.py:158-175 saves) instead of the current one.  MS-SSIM is an evaluation-only metric of the
+        reference (train.py:190) that this package does not compute: pass it in if you have it."""
+        if best and self.stats()["best_step"] > 0:
+            st = self.best_state()
+            xyz, cov, rgb, bound, psnr = st["_xyz"], st["_cov2d"], st["_features_dc"], st["cholesky_bound"], st["best_psnr"]
+        else:
+            xyz, cov, rgb, bound, psnr = self._xyz, self._cov2d, self._features_dc, self.cholesky_bound, self.stats()["psnr"]
+        n = xyz.shape[0]
+        gs = {"_xyz": xyz.detach().clone(), "_cov2d": cov.detach().clone(), "_features_dc": rgb.detach().clone(),
+              "_opacity": torch.ones(n, 1, device=self.device), "background": torch.ones(3, device=self.device),
+              "bound": torch.tensor([0.5, 0.5], device=self.device).view(1, 2)}
+        torch.save({"gs": gs, "num_gs": n, "psnr": psnr, "ms-ssim": ms_ssim, "slv_bound": bound.detach().clone()}, path)
+
+    def load_checkpoint(self, path):
+        """Resume from a reference-format checkpoint (train.py:61-77): parameters and SLV bound are loaded, the
+        optimiser state starts from zero (the reference does not store it either)."""
+        ck = torch.load(path, map_location=self.device)
+        gs = ck["gs"]
+        xyz, cov, rgb = (gs[k].to(self.device, torch.float32) for k in ("_xyz", "_cov2d", "_features_dc"))
+        bound = ck["slv_bound"].to(self.device, torch.float32)
+        if bound.shape[0] != xyz.shape[0]:
+            bound = bound.expand(xyz.shape[0], 3)
+        z = lambda t: torch.zeros_like(t)
+        self._replace(xyz, cov, rgb, bound.contiguous(), {"xyz": z(xyz), "cov2d": z(cov), "f_dc": z(rgb)},
+                      {"xyz": z(xyz), "cov2d": z(cov), "f_dc": z(rgb)})
+        return ck
+
     # ------------------------------------------------------------------ the training loop
     def fit(self, iterations: int, max_num_points: Optional[int] = None, prune_iter: int = 100,
             grow_iter: int = 5000, adaptive_add: bool = True, prune: bool = True, callback=None) -> dict:
@@ -541,6 +609,25 @@ class GaussianImageFitter:
         (densification).  Returns the final stats (incl. best_psnr / best_step); `best_state()` has the
         parameters.  `callback(iteration, self)` runs after every iteration when given (tests, logging)."""
         max_num_points = max_num_points if max_num_points is not None else self.cur_num_points
+        if callback is None:
+            # between two host interventions (prune / grow / the end) the steps are replayed in unrolled graphs
+            it = 0
+            while it < iterations:
+                nxt = iterations
+                if prune:
+                    nxt = min(nxt, (it // prune_iter + 1) * prune_iter)
+                if adaptive_add:
+                    nxt = min(nxt, (it // grow_iter + 1) * grow_iter)
+                grow = adaptive_add and nxt % grow_iter == 0 and nxt < iterations
+                self.train_iters(nxt - it - 1)
+                self.train_iter(want_error_map=grow)
+                it = nxt
+                if prune and it % prune_iter == 0:
+                    self.non_semi_definite_prune()
+                if grow:
+                    self.add_sample_positions(max_num_points, last=(it == iterations - grow_iter), errors=self.err_map)
+            self.sync_params()
+            return self.stats()
         for it in range(1, iterations + 1):
             grow = adaptive_add and it % grow_iter == 0 and it < iterations
             self.train_iter(want_error_map=grow)

@@ -106,6 +106,19 @@ def test_fit_trajectory_tracks_oracle(oracle):
     assert abs(st["psnr"] - psnr_ref) < 0.25, (st["psnr"], psnr_ref)   # north_star: >= 90% of the trajectory
 
 
+def test_train_iters_unrolled_graphs_equal_single_steps():
+    a, _ = make_fitter(2500, 512, 768, seed=4, colors="zeros", use_graph=True, keep_render=False)
+    b, _ = make_fitter(2500, 512, 768, seed=4, colors="zeros", use_graph=True, keep_render=False)
+    a.train_iters(37, unroll=8)            # 1 eager + 4 graphs of 8 + 4 single steps
+    for _ in range(37):
+        b.train_iter()
+    sa, sb = a.stats(), b.stats()
+    assert sa["step"] == sb["step"] == 37 and sa["num_intersects"] == sb["num_intersects"]
+    assert abs(sa["mse"] - sb["mse"]) <= 1e-4 * sb["mse"]
+    assert sa["best_step"] == sb["best_step"]
+    assert torch.allclose(a._xyz, b._xyz, atol=5e-3)
+
+
 def test_fit_graph_equals_eager():
     a, _ = make_fitter(2500, 512, 768, seed=4, colors="zeros", use_graph=True)
     b, _ = make_fitter(2500, 512, 768, seed=4, colors="zeros", use_graph=False)
@@ -267,6 +280,29 @@ def test_step_from_host_equals_train_iter():
         assert got[i][0] == st["step"] == i + 1
         assert abs(got[i][1] - st["mse"]) <= 1e-5 * st["mse"], (i, got[i], st["mse"])
     assert torch.allclose(a._xyz, b._xyz, atol=2e-3)
+
+
+def test_checkpoint_round_trip_in_reference_format(tmp_path):
+    """save_checkpoint writes the dict train.py:173-175 writes; load_checkpoint (and the reference's own loading
+    code, train.py:64-75, which reads 'num_gs', 'gs' and 'slv_bound') restore a model that renders identically."""
+    fit, _ = make_fitter(800, 96, 128, seed=41, colors="zeros", use_graph=True, keep_render=False)
+    for _ in range(40):
+        fit.train_iter()
+    path = tmp_path / "gaussian_model.pth.tar"
+    fit.save_checkpoint(path)
+    ck = torch.load(path, map_location="cpu")
+    assert set(ck) == {"gs", "num_gs", "psnr", "ms-ssim", "slv_bound"}
+    assert {"_xyz", "_cov2d", "_features_dc", "_opacity", "background", "bound"} <= set(ck["gs"])
+    assert ck["num_gs"] == ck["gs"]["_xyz"].shape[0] == ck["slv_bound"].shape[0] == 800
+    assert abs(ck["psnr"] - fit.stats()["best_psnr"]) < 1e-9
+    fit.load_best_state()
+    want = fit.forward()["render"].clone()
+    other, _ = make_fitter(300, 96, 128, seed=1, use_graph=True, keep_render=False)   # different size on purpose
+    other.load_checkpoint(path)
+    assert other.cur_num_points == 800
+    assert torch.equal(other.forward()["render"], want)
+    other.train_iter()                                   # and training goes on from there
+    assert other.stats()["step"] >= 1 and np.isfinite(other.stats()["psnr"])
 
 
 # --------------------------------------------------------------------------- full-size properties

@@ -1,0 +1,11 @@
+#!/bin/bash
+# tools/ab_env.sh WORKLOAD "ENV=1 ..." : bench.py with extra environment, key numbers
+WL=$1; shift
+for e in "$@"; do
+  env $e python bench.py --workload $WL --steps ${STEPS:-1500} --warmup ${WARM:-300} --no-ref-cuda --no-cpu-baseline > gpurun_out/abe.json 2> gpurun_out/abe.err || { echo "$e FAILED"; tail -5 gpurun_out/abe.err; continue; }
+  python - "$e" <<'PY'
+import json,sys
+d=json.loads(open("gpurun_out/abe.json").read().strip().splitlines()[-1])
+print(f"{sys.argv[1]:20s} value={d['value']:.0f} warm={d['value_l2_warm']:.0f} ({d['ms_per_step_l2_warm']*1e3:.2f} us) fps={d['render_fps']:.0f} e2e={d['e2e']['value']:.0f} psnr={d['psnr']:.3f}")
+PY
+done
