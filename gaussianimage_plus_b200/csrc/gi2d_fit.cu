@@ -268,6 +268,11 @@ fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_
     const bool early = expect_pending && a.m_xyz != nullptr && mine;
     AdamRegs r;
     if (early) adam_load(a, g, proj, grads, r);
+    float bnd[3] = {0.f, 0.f, 0.f};
+    if (mine) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bnd[k] = __ldg(cov_bound + 3 * g + k);
+    }
     const bool pending = a.m_xyz != nullptr && __ldcg(stats + kStatPending) != 0.0;
     const bool veto = __ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0;  // that step overflowed: the host re-runs it
     best_flag_warp0(stats, best != nullptr && pending && !veto, &s_best);
@@ -296,9 +301,9 @@ fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_
         for (int k = 0; k < 3; ++k) { c[k] = a.cov[3 * g + k]; q[k] = a.rgb[3 * g + k]; }
     }
     // get_cov2d_elements = _cov2d + cholesky_bound (gaussianimage_covariance.py:169)
-    const float sx = __fadd_rn(c[0], __ldg(cov_bound + 3 * g));
-    const float sxy = __fadd_rn(c[1], __ldg(cov_bound + 3 * g + 1));
-    const float sy = __fadd_rn(c[2], __ldg(cov_bound + 3 * g + 2));
+    const float sx = __fadd_rn(c[0], bnd[0]);
+    const float sxy = __fadd_rn(c[1], bnd[1]);
+    const float sy = __fadd_rn(c[2], bnd[2]);
     float cr = q[0], cg = q[1], cb = q[2];
     if (p.color_sigmoid) { cr = sigmoidf(cr); cg = sigmoidf(cg); cb = sigmoidf(cb); }
     const Projected pr = project_cov(m.x, m.y, sx, sxy, sy, p.clip_coe, p.radius_clip, p.tiles_x, p.tiles_y);
