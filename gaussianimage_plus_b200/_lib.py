@@ -71,6 +71,7 @@ SIGNATURES = {
     "gi2d_fit_adam": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _P]),
     "gi2d_fit_launch_count": (_I, [C.POINTER(FitParams), _I]),
     "gi2d_fit_profile": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), C.POINTER(C.c_float), _P]),
+    "gi2d_fit_profile_raster": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, C.POINTER(C.c_float), _P]),
     "gi2d_measure_fp32_peak": (_I, [C.POINTER(C.c_float), _P]),
     "gi2d_fit_exchange_adam": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _I, C.POINTER(_P),
                                    C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P]),

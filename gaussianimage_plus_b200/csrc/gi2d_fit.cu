@@ -972,6 +972,41 @@ extern "C" int gi2d_fit_profile(const gi2d_fit_params *p, const gi2d_fit_buffers
     return rc;
 }
 
+extern "C" int gi2d_fit_profile_raster(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int reps, float *ms_host,
+                                       gi2d_stream_t stream) {
+    GI2D_REQUIRE(ms_host && reps > 0, "bad arguments");
+    GI2D_REQUIRE(p && p->loss_ssim_weight == 0.f, "profiles the single-launch rasterizer (no SSIM term)");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = fit_forward_backward_impl(p, b, 1, st, nullptr);
+    if (rc != GI2D_OK) return rc;
+    const Plan pl = make_plan(*p);
+    const Workspace w = carve(*p, pl, b->workspace);
+    const int band = p->tile_row_end - p->tile_row_begin;
+    GI2D_REQUIRE(band > 0, "empty band");
+    const dim3 grid(p->tiles_x, band);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < reps; ++i)
+        launch_pdl(fit_raster_kernel<RasterMode::Fit>, grid, dim3(kRasterThreads), 0, st,
+            *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count, w.tile_fill, (const float4 *)w.records,
+            b->gt_hwc, b->gt_u8_hwc, (float *)nullptr, b->grads, b->stats, (float *)nullptr, (const float *)nullptr);
+    cudaEventRecord(e1, st);
+    // nothing pending (the accumulated gradient is garbage), loss accumulators back to zero
+    cudaMemsetAsync(b->stats + kStatPending, 0, sizeof(double), st);
+    cudaMemsetAsync(b->stats + GI2D_STAT_SSE, 0, GI2D_STAT_SSE_SLOTS * sizeof(double), st);
+    cudaMemsetAsync(b->stats + GI2D_STAT_ABS_SUM, 0, sizeof(double), st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_host = ms / (float)reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamSynchronize(st);
+    return check_launch(__func__);
+}
+
 // Measurement utility: FP32 FMA issue peak of this GPU (the roofline denominator of the raster
 // kernels; MEASURED_PEAKS.json only carries HBM and bf16 tensor figures).  Returns TFLOP/s.
 extern "C" int gi2d_measure_fp32_peak(float *tflops_host, gi2d_stream_t stream) {

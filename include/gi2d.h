@@ -307,6 +307,13 @@ int gi2d_image_loss_grad(int img_height, int img_width, const float *render_hwc,
 int gi2d_fit_profile(const gi2d_fit_params *p, const gi2d_fit_buffers *b, float *ms_host,
                      gi2d_stream_t stream);
 
+/* Duration of the rasterize kernel alone: one full step, then `reps` back-to-back launches of
+ * fit_raster_kernel<Fit> on the state that step left, between two events; *ms_host = average per launch.
+ * (CUDA events around ONE ~20 us kernel add several us of launch / drain latency; back-to-back replays do
+ * not.)  Leaves no gradient pending and the loss accumulators zeroed; b->grads holds garbage afterwards. */
+int gi2d_fit_profile_raster(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int reps, float *ms_host,
+                            gi2d_stream_t stream);
+
 /* FP32 FMA throughput of the current device in TFLOP/s (HOST pointer): the roofline denominator
  * of the rasterize kernels. */
 int gi2d_measure_fp32_peak(float *tflops_host, gi2d_stream_t stream);
