@@ -307,6 +307,10 @@ def main():
         return Ke * (world if args.mode == "images" else 1) / float(tt.item())
 
     Ke = min(K, 2000)
+    if fit.grad_hook is None:      # untimed: creates the host pipe, its two device buffers and the bound argument blocks
+        _ring = [torch.zeros(fit.stats_buf.numel(), dtype=torch.float64).pin_memory() for _ in range(2)]
+        for i in range(4):
+            fit.wait_host_result(fit.step_from_host(gt_u8_pinned, _ring[i & 1]))
     # image bytes in, per-step result read one step behind: best of 3 trials (all reported)
     e2e_trials = [e2e_loop(gt_u8_pinned, pipelined=True) for _ in range(3)]
     e2e_value = max(e2e_trials)
