@@ -60,7 +60,16 @@ constexpr int kStatBc2Sqrt = 7;   // sqrt(1 - beta2^step)
 constexpr int kStatPending = 8;   // != 0: grads of the last step have not been applied yet (Adam is folded
                                   // into the NEXT step's projection kernel, or flushed by gi2d_fit_adam)
 
+[[maybe_unused]] constexpr int kStatDebug = 15;      // GI2D_DEBUG_CHECKS builds: number of violated device-side invariants (stays 0)
 constexpr int kStatNonPsdAcc = 12;  // accumulator behind GI2D_STAT_NON_PSD (moved + zeroed by the clear kernel)
+
+// compute-sanitizer is closed on the development pool: a -DGI2D_DEBUG_CHECKS build counts violated index /
+// range invariants of the binning and staging code into stats[kStatDebug] instead (tools/debug_checks.py).
+#ifdef GI2D_DEBUG_CHECKS
+#define GI2D_CHECK(stats, cond) do { if (!(cond)) atomicAdd((stats) + kStatDebug, 1.0); } while (0)
+#else
+#define GI2D_CHECK(stats, cond) do { } while (0)
+#endif
 
 // Squared error of the last training step: the 64 partials summed by ONE warp in a fixed order, so that
 // every CTA of the optimiser kernel and the bookkeeping thread take the same best-so-far decision.
@@ -323,7 +332,10 @@ fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_
     }
     boxes[g] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
     for (int ty = y0; ty < y1; ++ty)
-        for (int tx = x0; tx < x1; ++tx) atomicAdd(tile_count + ty * p.tiles_x + tx, 1);
+        for (int tx = x0; tx < x1; ++tx) {
+            GI2D_CHECK(const_cast<double *>(stats), ty >= p.tile_row_begin && ty < p.tile_row_end && tx >= 0 && tx < p.tiles_x);
+            atomicAdd(tile_count + ty * p.tiles_x + tx, 1);
+        }
 }
 
 // Bookkeeping of the step in flight, by warp 0 of ONE CTA of K2 (K1 has already consumed the previous
@@ -486,7 +498,10 @@ fit_place_kernel(gi2d_fit_params p, int with_backward, int gpb, int num_tiles,
             // (record loads and the cursor atomic are independent: all in flight together)
             const float4 r0 = __ldcg(proj + 2 * g), r1 = __ldcg(proj + 2 * g + 1);
             const int start = kSmemScan ? s_base[tile] : (__ldcg(tile_incl + tile) - __ldcg(tile_count + tile));
-            const int pos = start + atomicAdd(tile_fill + tile, 1);
+            const int slot = atomicAdd(tile_fill + tile, 1);
+            const int pos = start + slot;
+            GI2D_CHECK(stats, tile >= 0 && tile < num_tiles && g >= 0 && g < p.num_points && start >= 0 &&
+                                  slot >= 0 && slot < __ldcg(tile_count + tile));
             if (pos < p.isect_capacity) {
                 keys_out[pos] = ((uint64_t)(uint32_t)tile << 32) | (uint32_t)g;
                 records[2 * (size_t)pos] = r0;
@@ -554,7 +569,12 @@ fit_raster_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_
     const int total_cnt = max(0, min(range.y, p.isect_capacity) - range.x);
     const int cnt = min(kMaxPerTile, total_cnt);
     // the counters of this tile go back to K1 / K2 of the next step zeroed
-    if (kHasFwd && tid == 0) { tile_count[tile_id] = 0; tile_fill[tile_id] = 0; }
+    if (kHasFwd && tid == 0) {
+        GI2D_CHECK(stats, range.x >= 0 && range.y >= range.x && tile_fill[tile_id] == tile_count[tile_id] &&
+                              (range.y - range.x == tile_count[tile_id] || n_isect > (double)p.isect_capacity));
+        tile_count[tile_id] = 0;
+        tile_fill[tile_id] = 0;
+    }
     // Finish the key sort: K2 placed this tile's entries in arbitrary order.  Rank every entry by its
     // gaussian id (ids are unique within a tile, so ranks are a permutation) and stage it at its rank:
     // shared memory then holds the reference's order (ascending id == the stable sort of Gaussian-major
@@ -578,6 +598,7 @@ fit_raster_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_
             const int id = (int)(uint32_t)key;
             int rank = 0;
             for (int jj = 0; jj < cnt; ++jj) rank += (s_sort[jj] < id) ? 1 : 0;
+            GI2D_CHECK(stats, rank >= 0 && rank < cnt && (int)(key >> 32) == tile_id && id >= 0 && id < p.num_points);
             stage_record(sg, rank, r0, r1, tx0, ty0);
             if (kHasBwd) s_ids[rank] = id;
             if (kWriteBack && rank != tid) sorted_keys[range.x + rank] = key;
@@ -589,6 +610,7 @@ fit_raster_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_
             const int id = (int)(uint32_t)key;
             int rank = 0;
             for (int jj = 0; jj < total_cnt; ++jj) rank += ((int)(uint32_t)__ldcg(sorted_keys + range.x + jj) < id) ? 1 : 0;
+            GI2D_CHECK(stats, rank >= 0 && rank < total_cnt && (int)(key >> 32) == tile_id);
             keys_tmp[range.x + rank] = key;
             if (rank < kMaxPerTile) {
                 stage_record(sg, rank, __ldcg(records + 2 * (size_t)(range.x + e)),
