@@ -77,6 +77,8 @@ SIGNATURES = {
                                    C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P]),
     "gi2d_ssim_workspace_size": (_SZ, [_I, _I]),
     "gi2d_image_loss_grad": (_I, [_I, _I, _P, _P, _P, _F, _F, _F, _P, _P, _P, _SZ, _P]),
+    "gi2d_ms_ssim_workspace_size": (_SZ, [_I, _I]),
+    "gi2d_ms_ssim": (_I, [_I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "gi2d_host_pipe_create": (_I, [C.POINTER(_P)]),
     "gi2d_host_pipe_destroy": (_I, [_P]),
     "gi2d_fit_step_host": (_I, [_P, C.POINTER(FitParams), C.POINTER(FitBuffers), _P, _SZ, _P, _P, C.POINTER(_I)]),

@@ -322,3 +322,31 @@ def image_loss_grad(render_hwc: torch.Tensor, gt_hwc: torch.Tensor, loss_type: s
                                             w1 / (3.0 * H * W), _p(v_out), _p(ssim_sum), _p(ws_buf), ws_buf.numel(),
                                             _stream(dev)), "image_loss_grad")
     return v_out, ssim_sum
+
+
+MS_SSIM_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)   # pytorch_msssim.ms_ssim defaults
+
+
+def ms_ssim(render_hwc: torch.Tensor, gt_hwc: torch.Tensor) -> float:
+    """MS-SSIM of clamp(render) against the target (train.py:190: `ms_ssim(render, gt, data_range=1,
+    size_average=True)`), evaluated by gi2d_ms_ssim.  render f32[H,W,3], gt f32 or u8 [H,W,3].  Synchronises."""
+    lib = _lib.load()
+    _check_input(render_hwc, "render", f32)
+    _check_input(gt_hwc, "gt")
+    H, W, _ = render_hwc.shape
+    dev = render_hwc.device
+    sums = torch.zeros(5, 3, 2, dtype=torch.float64, device=dev)
+    ws = _workspace(lib.gi2d_ms_ssim_workspace_size(H, W), dev)
+    is_u8 = gt_hwc.dtype == torch.uint8
+    with torch.cuda.device(dev):
+        _lib.check(lib.gi2d_ms_ssim(H, W, _p(render_hwc), None if is_u8 else _p(gt_hwc), _p(gt_hwc) if is_u8 else None,
+                                    _p(sums), _p(ws), ws.numel(), _stream(dev)), "ms_ssim")
+    s = sums.cpu()
+    val = torch.ones(3, dtype=torch.float64)
+    h, w = H, W
+    for lvl in range(5):
+        n = (h - 10) * (w - 10)
+        mean = s[lvl, :, 1 if lvl < 4 else 0] / n          # cs for levels 0..3, ssim for the last
+        val = val * torch.relu(mean) ** MS_SSIM_WEIGHTS[lvl]
+        h, w = (h + 2 * (h & 1) - 2) // 2 + 1, (w + 2 * (w & 1) - 2) // 2 + 1
+    return float(val.mean())

@@ -48,6 +48,9 @@ __device__ __forceinline__ float target_at(const float *gt, const uint8_t *gt_u8
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
 
 // S1.  dm: 9 planes f32[H*W], plane 3*c+q for channel c and q in {M,S,T}.
+// kEval: no derivative planes; instead the per-channel sums of the SSIM map and of the contrast-structure map
+// (`cs` of pytorch_msssim `_ssim`) go to ssim_sum[2*c], ssim_sum[2*c+1] -- one level of MS-SSIM.
+template <bool kEval>
 __global__ void __launch_bounds__(256)
 ssim_stats_kernel(int H, int W, const float *__restrict__ render, const float *__restrict__ gt,
                   const uint8_t *__restrict__ gt_u8, float *__restrict__ dm, double *__restrict__ ssim_sum) {
@@ -102,6 +105,7 @@ ssim_stats_kernel(int H, int W, const float *__restrict__ render, const float *_
             xy = fmaf(w, sh[4][ly + k][lx], xy);
         }
         float M = 0.f, S = 0.f, T = 0.f;
+        float ev_ssim = 0.f, ev_cs = 0.f;
         if (valid) {
             const float s1 = xx - m1 * m1, s2 = yy - m2 * m2, s12 = xy - m1 * m2;
             const float A1 = fmaf(2.f * m1, m2, kC1), A2 = fmaf(2.f, s12, kC2);
@@ -109,30 +113,76 @@ ssim_stats_kernel(int H, int W, const float *__restrict__ render, const float *_
             const float iB1 = 1.f / B1, iB2 = 1.f / B2;
             const float lum = A1 * iB1, cs = A2 * iB2;
             acc += lum * cs;
+            ev_ssim = lum * cs;
+            ev_cs = cs;
             // partials at fixed (s1, s12), then the chain through s1 = E[x^2] - mu1^2, s12 = E[xy] - mu1 mu2
             S = -lum * cs * iB2;
             T = 2.f * lum * iB2;
             const float dmu = 2.f * (m2 - m1 * lum) * iB1 * cs;
             M = dmu - 2.f * m1 * S - m2 * T;
         }
-        if (px < W && py < H) {
+        if (!kEval && px < W && py < H) {
             const size_t pix = (size_t)py * W + px;
             dm[(3 * c + 0) * plane + pix] = M;
             dm[(3 * c + 1) * plane + pix] = S;
             dm[(3 * c + 2) * plane + pix] = T;
         }
         __syncthreads();  // sx/sy/sh are rewritten by the next channel
-    }
+        if constexpr (kEval) {
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    if ((tid & 31) == 0) s_red[tid >> 5] = acc;
-    __syncthreads();
-    if (tid == 0) {
-        float t = 0.f;
+            for (int q = 0; q < 2; ++q) {   // this channel's sums of the SSIM map and of the cs map
+                float v = q ? ev_cs : ev_ssim;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += s_red[w];
-        if (ssim_sum) atomicAdd(ssim_sum, (double)t);
+                for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                if ((tid & 31) == 0) s_red[tid >> 5] = v;
+                __syncthreads();
+                if (tid == 0) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) t += s_red[w];
+                    atomicAdd(ssim_sum + 2 * c + q, (double)t);
+                }
+                __syncthreads();
+            }
+        }
     }
+    if constexpr (!kEval) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if ((tid & 31) == 0) s_red[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += s_red[w];
+            if (ssim_sum) atomicAdd(ssim_sum, (double)t);
+        }
+    }
+}
+
+// F.avg_pool2d(x, kernel_size=2, padding=(H%2, W%2)) of pytorch_msssim.ms_ssim on an HWC image: stride 2, the
+// zero padding counts in the average.  `clamp`/`u8`: level 0 reads the unclamped render / the 8-bit target.
+__global__ void __launch_bounds__(256)
+avgpool2_kernel(int H, int W, const float *__restrict__ in, const uint8_t *__restrict__ in_u8, int clamp, int H2,
+                int W2, float *__restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= H2 * W2 * 3) return;
+    const int c = i % 3, x = (i / 3) % W2, y = i / (3 * W2);
+    const int y0 = 2 * y - (H & 1), x0 = 2 * x - (W & 1);
+    float s = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int yy = y0 + dy, xx = x0 + dx;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const size_t idx = 3 * ((size_t)yy * W + xx) + c;
+                float v = in ? __ldg(in + idx) : u8_to_unit(__ldg(in_u8 + idx));
+                if (clamp) v = clamp01(v);
+                s += v;
+            }
+        }
+    out[i] = 0.25f * s;
 }
 
 // S2.  v_out f32[H,W,3] = mask * (ssim_coef * filter^T(M,S,T) + l2_scale * d + l1_scale * sign(d)),
@@ -200,7 +250,7 @@ int ssim_grad_launch(int H, int W, const float *render, const float *gt, const u
                      float ssim_weight, float l2_scale, float l1_scale, float *v_out, double *ssim_sum,
                      cudaStream_t st) {
     const dim3 grid(cdiv(W, kLT), cdiv(H, kLT));
-    ssim_stats_kernel<<<grid, 256, 0, st>>>(H, W, render, gt, gt_u8, dm_ws, ssim_sum);
+    ssim_stats_kernel<false><<<grid, 256, 0, st>>>(H, W, render, gt, gt_u8, dm_ws, ssim_sum);
     // loss term = ssim_weight * (1 - mean(map)), mean over 3 channels x (H-10)(W-10) windows
     const float coef = -ssim_weight / (3.f * (float)(H - 2 * kHalo) * (float)(W - 2 * kHalo));
     ssim_grad_kernel<<<grid, 256, 0, st>>>(H, W, render, gt, gt_u8, dm_ws, coef, l2_scale, l1_scale, v_out);
@@ -229,5 +279,50 @@ extern "C" int gi2d_image_loss_grad(int img_height, int img_width, const float *
     if (ssim_sum) cudaMemsetAsync(ssim_sum, 0, sizeof(double), st);
     ssim_grad_launch(img_height, img_width, render_hwc, gt_hwc, gt_u8_hwc, (float *)workspace, ssim_weight, l2_scale,
                      l1_scale, v_out_hwc, ssim_sum, st);
+    return check_launch(__func__);
+}
+
+// ---- MS-SSIM (evaluation metric of train.py:190 / train_quantize.py:214; pytorch_msssim.ms_ssim, 5 levels)
+static inline int pooled(int s) { return (s + 2 * (s & 1) - 2) / 2 + 1; }
+
+extern "C" size_t gi2d_ms_ssim_workspace_size(int img_height, int img_width) {
+    size_t px = 0;
+    int h = img_height, w = img_width;
+    for (int l = 1; l < 5; ++l) {
+        h = pooled(h);
+        w = pooled(w);
+        px += (size_t)h * w;
+    }
+    return px * 3 * sizeof(float) * 2;   // both images, levels 1..4
+}
+
+extern "C" int gi2d_ms_ssim(int img_height, int img_width, const float *render_hwc, const float *gt_hwc,
+                            const uint8_t *gt_u8_hwc, double *level_sums, void *workspace, size_t workspace_bytes,
+                            gi2d_stream_t stream) {
+    GI2D_REQUIRE(render_hwc && (gt_hwc || gt_u8_hwc) && level_sums && workspace, "null buffer");
+    GI2D_REQUIRE((img_height < img_width ? img_height : img_width) > (kWin - 1) * 16,
+                 "MS-SSIM needs the smaller image side to exceed 160 pixels (pytorch_msssim's own assertion)");
+    if (workspace_bytes < gi2d_ms_ssim_workspace_size(img_height, img_width)) {
+        set_error("gi2d_ms_ssim: workspace too small");
+        return GI2D_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(level_sums, 0, 5 * 6 * sizeof(double), st);
+    float *ws = (float *)workspace;
+    const float *x = render_hwc, *y = gt_hwc;
+    const uint8_t *y8 = gt_hwc ? nullptr : gt_u8_hwc;
+    int h = img_height, w = img_width;
+    for (int l = 0; l < 5; ++l) {
+        ssim_stats_kernel<true><<<dim3(cdiv(w, kLT), cdiv(h, kLT)), 256, 0, st>>>(h, w, x, y, y8, nullptr,
+                                                                                 level_sums + 6 * l);
+        if (l == 4) break;
+        const int h2 = pooled(h), w2 = pooled(w);
+        float *x2 = ws, *y2 = ws + (size_t)h2 * w2 * 3;
+        ws += (size_t)h2 * w2 * 6;
+        const int n = h2 * w2 * 3;
+        avgpool2_kernel<<<cdiv(n, 256), 256, 0, st>>>(h, w, x, nullptr, l == 0, h2, w2, x2);
+        avgpool2_kernel<<<cdiv(n, 256), 256, 0, st>>>(h, w, y, y8, 0, h2, w2, y2);
+        x = x2; y = y2; y8 = nullptr; h = h2; w = w2;
+    }
     return check_launch(__func__);
 }

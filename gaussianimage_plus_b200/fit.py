@@ -430,6 +430,14 @@ class GaussianImageFitter:
     def psnr(self) -> float:
         return self.stats()["psnr"]
 
+    def ms_ssim(self) -> float:
+        """MS-SSIM of the current render against the target: the second quality metric the reference reports
+        (train.py:190), evaluated by the libgi2d kernels.  Synchronises."""
+        from .binding import ms_ssim
+
+        render = self.forward()["render"][0].permute(1, 2, 0).contiguous()
+        return ms_ssim(render, self.gt_hwc)
+
     def stats_async(self, host_slot: torch.Tensor, event: "torch.cuda.Event"):
         """Enqueue a device->host copy of the stats block of the step just issued into pinned `host_slot`
         (f64[STAT_COUNT]) and record `event` after it; the caller waits on the event when it wants the
@@ -569,12 +577,15 @@ class GaussianImageFitter:
         return k
 
     # ------------------------------------------------------------------ checkpoint (train.py:61-77,173-175)
-    def save_checkpoint(self, path, best: bool = True, ms_ssim: float = float("nan")):
+    def save_checkpoint(self, path, best: bool = True, ms_ssim: Optional[float] = None):
         """The reference's `gaussian_model.pth.tar`: {"gs": state_dict, "num_gs", "psnr", "ms-ssim", "slv_bound"},
         with the state-dict keys of GaussianImage_Covariance (`_xyz`, `_cov2d`, `_features_dc` parameters and the
         `_opacity`, `background`, `bound` buffers, gaussianimage_covariance.py:54-70).  `best`: the best-PSNR state
-        (what train.py:158-175 saves) instead of the current one.  MS-SSIM is an evaluation-only metric of the
-        reference (train.py:190) that this package does not compute: pass it in if you have it."""
+        (what train.py:158-175 saves) instead of the current one.  `ms_ssim`: the value to store; by default the
+        MS-SSIM of the CURRENT render (train.py:167,190 evaluate after loading the best state), nan for images
+        whose smaller side is <= 160 pixels (pytorch_msssim's own limit)."""
+        if ms_ssim is None:
+            ms_ssim = self.ms_ssim() if min(self.H, self.W) > 160 and self.gt_hwc is not None else float("nan")
         if best and self.stats()["best_step"] > 0:
             st = self.best_state()
             xyz, cov, rgb, bound, psnr = st["_xyz"], st["_cov2d"], st["_features_dc"], st["cholesky_bound"], st["best_psnr"]

@@ -298,6 +298,15 @@ int gi2d_image_loss_grad(int img_height, int img_width, const float *render_hwc,
                          float *v_out_hwc, double *ssim_sum, void *workspace, size_t workspace_bytes,
                          gi2d_stream_t stream);
 
+/* MS-SSIM, the evaluation metric of train.py:190 (pytorch_msssim.ms_ssim(data_range=1): 5 levels, 2x2 average
+ * pooling with padding size%2 between them).  level_sums (device, f64[5][3][2]) receives per level and channel the
+ * sums of the SSIM map and of the contrast-structure map over the level's valid windows; the caller forms
+ * prod_l relu(mean)^w_l (cs for levels 0..3, ssim for level 4; weights 0.0448 0.2856 0.3001 0.2363 0.1333). */
+size_t gi2d_ms_ssim_workspace_size(int img_height, int img_width);
+int gi2d_ms_ssim(int img_height, int img_width, const float *render_hwc, const float *gt_hwc,
+                 const uint8_t *gt_u8_hwc, double *level_sums, void *workspace, size_t workspace_bytes,
+                 gi2d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Measurement utilities for bench.py (these two SYNCHRONISE; never call them while capturing).
  * ------------------------------------------------------------------------------------------ */

@@ -48,6 +48,39 @@ def ssim(X: torch.Tensor, Y: torch.Tensor, data_range: float = 1.0, K=(0.01, 0.0
     return torch.flatten(ssim_map, 2).mean(-1).mean()
 
 
+def _ssim_and_cs(X, Y, data_range=1.0, K=(0.01, 0.03)):
+    """pytorch_msssim `_ssim(..., size_average=False)`: per-channel means of the SSIM map and of the cs map."""
+    win = fspecial_gauss_1d()
+    C1, C2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
+    mu1, mu2 = gaussian_filter(X, win), gaussian_filter(Y, win)
+    sigma1_sq = gaussian_filter(X * X, win) - mu1 * mu1
+    sigma2_sq = gaussian_filter(Y * Y, win) - mu2 * mu2
+    sigma12 = gaussian_filter(X * Y, win) - mu1 * mu2
+    cs_map = (2 * sigma12 + C2) / (sigma1_sq + sigma2_sq + C2)
+    ssim_map = ((2 * mu1 * mu2 + C1) / (mu1 * mu1 + mu2 * mu2 + C1)) * cs_map
+    return torch.flatten(ssim_map, 2).mean(-1), torch.flatten(cs_map, 2).mean(-1)
+
+
+MS_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+
+
+def ms_ssim(X: torch.Tensor, Y: torch.Tensor, data_range: float = 1.0) -> torch.Tensor:
+    """pytorch_msssim `ms_ssim(X, Y, data_range, size_average=True)` (the evaluation metric of train.py:190):
+    5 levels, avg_pool2d(kernel 2, padding = size % 2) between them, relu on cs / ssim, weighted product."""
+    assert min(X.shape[-2:]) > (11 - 1) * 2 ** 4
+    w = X.new_tensor(MS_WEIGHTS)
+    mcs = []
+    for i in range(5):
+        ssim_c, cs = _ssim_and_cs(X, Y, data_range)
+        if i < 4:
+            mcs.append(torch.relu(cs))
+            pad = [s % 2 for s in X.shape[2:]]
+            X = F.avg_pool2d(X, kernel_size=2, padding=pad)
+            Y = F.avg_pool2d(Y, kernel_size=2, padding=pad)
+    stack = torch.stack(mcs + [torch.relu(ssim_c)], dim=0)
+    return torch.prod(stack ** w.view(-1, 1, 1), dim=0).mean()
+
+
 def loss_fn(pred: torch.Tensor, target: torch.Tensor, loss_type: str = "L2", lambda_value: float = 0.7):
     """models/utils.py:60-80 (without the MS-SSIM variants)."""
     if loss_type == "L2":

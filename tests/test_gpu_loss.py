@@ -125,3 +125,25 @@ def test_ssim_fit_improves_ssim():
         assert st["loss"] < 0.5 * first, (lt, first, st["loss"])
         out[lt] = st
     assert out["Fusion2"]["psnr"] > 17 and out["L2"]["psnr"] > 17
+
+
+@pytest.mark.parametrize("H,W,u8", [(512, 768, True), (173, 201, False), (1356, 2040, False)])
+def test_ms_ssim_vs_oracle(H, W, u8):
+    """gi2d_ms_ssim == pytorch_msssim.ms_ssim restated in float64 (5 levels; odd sizes exercise the padded
+    average pooling)."""
+    from gaussianimage_plus_b200.binding import ms_ssim
+    from oracle import ssim_oracle as S
+
+    render, gt = _images(H, W, seed=H)
+    if u8:
+        gt_u8 = np.round(gt * 255).astype(np.uint8)
+        gt = gt_u8.astype(np.float32) / np.float32(255.0)
+        gt_dev = torch.from_numpy(gt_u8).to(DEV)
+    else:
+        gt_dev = torch.from_numpy(gt).to(DEV)
+    got = ms_ssim(torch.from_numpy(render).to(DEV), gt_dev)
+    X = torch.from_numpy(render).double().clamp(0, 1).permute(2, 0, 1).unsqueeze(0)
+    Y = torch.from_numpy(gt).double().permute(2, 0, 1).unsqueeze(0)
+    want = float(S.ms_ssim(X, Y))
+    assert abs(got - want) < 2e-5, (got, want)
+    assert abs(ms_ssim(gt_dev.float() / 255 if u8 else gt_dev, gt_dev) - 1.0) < 1e-5

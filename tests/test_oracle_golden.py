@@ -115,3 +115,17 @@ def test_ssim_oracle_anchors():
     assert abs(float(S.loss_fn(x, y, "Fusion1")) - (0.7 * l2 + 0.3 * ss)) < 1e-12
     assert abs(float(S.loss_fn(x, y, "Fusion2")) - (0.7 * l1 + 0.3 * ss)) < 1e-12
     assert abs(float(S.loss_fn(x, y, "Fusion3")) - (0.7 * l2 + 0.3 * l1)) < 1e-12
+
+
+def test_ms_ssim_oracle_anchors():
+    import torch
+
+    from oracle import ssim_oracle as S
+
+    torch.manual_seed(0)
+    x = torch.rand(1, 3, 176, 200, dtype=torch.float64)
+    y = (x + 0.1 * torch.rand_like(x)).clamp(0, 1)
+    assert abs(float(S.ms_ssim(x, x)) - 1.0) < 1e-12
+    v = float(S.ms_ssim(x, y))
+    assert 0.5 < v < 1.0 and abs(v - float(S.ms_ssim(y, x))) < 1e-12
+    assert abs(sum(S.MS_WEIGHTS) - 1.0) < 1e-3
