@@ -227,48 +227,12 @@ size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace
 
-// ---- internal entry points for the fused fit step (gi2d_fit.cu): the element count lives on
-// the device (`n_dev`, clamped to n_capacity), grids are sized for the capacity.
-size_t radix_pass_workspace_size(int n_capacity) {
-    const size_t nb = (size_t)cdiv(n_capacity > 0 ? n_capacity : 1, kTileItems);
-    const size_t mat = align_up(nb * kRadix * sizeof(int32_t));
-    return 2 * mat + gi2d_scan_workspace_size((int)(nb * kRadix));
-}
-
-int radix_pass_keys_u64(int n_capacity, const int32_t *n_dev, const uint64_t *keys_in, uint64_t *keys_out,
-                        int shift, int bits, void *workspace, size_t workspace_bytes, cudaStream_t st) {
-    if (workspace_bytes < radix_pass_workspace_size(n_capacity)) {
-        set_error("radix_pass_keys_u64: workspace too small");
-        return GI2D_ERR_WORKSPACE;
-    }
-    const int nb = cdiv(n_capacity, kTileItems);
-    const size_t mat = align_up((size_t)nb * kRadix * sizeof(int32_t));
-    char *w = (char *)workspace;
-    int32_t *counts = (int32_t *)w;
-    int32_t *incl = (int32_t *)(w + mat);
-    int32_t *scan_ws = (int32_t *)(w + 2 * mat);
-    radix_hist_kernel<<<nb, kThreads, 0, st>>>(n_capacity, n_dev, (const int64_t *)keys_in, shift, bits, nb, counts);
-    const int rc = launch_cumsum(nb * kRadix, counts, incl, nullptr, scan_ws, st);
-    if (rc != GI2D_OK) return rc;
-    radix_scatter_kernel<<<nb, kThreads, 0, st>>>(n_capacity, n_dev, (const int64_t *)keys_in, nullptr,
-                                                 (int64_t *)keys_out, nullptr, shift, bits, nb, counts, incl);
-    return check_launch("radix_pass_keys_u64");
-}
-
 // inclusive prefix sum for the fit step's per-tile overlap counts (gi2d_fit.cu)
 int cumsum_i32_launch(int n, const int32_t *in, int32_t *out, int32_t *total, int32_t *block_sums,
                       cudaStream_t st) {
     return launch_cumsum(n, in, out, total, block_sums, st);
 }
 size_t cumsum_i32_workspace(int n) { return gi2d_scan_workspace_size(n); }
-
-int tile_edges_from_keys_u64(int n_capacity, const int32_t *n_dev, const uint64_t *keys, int32_t *tile_bins,
-                             int rows, cudaStream_t st) {
-    cudaMemsetAsync(tile_bins, 0, (size_t)rows * 2 * sizeof(int32_t), st);
-    tile_edges_kernel<<<cdiv(n_capacity, kThreads), kThreads, 0, st>>>(n_capacity, n_dev, (const int64_t *)keys,
-                                                                      tile_bins, rows);
-    return check_launch("tile_edges_from_keys_u64");
-}
 
 }  // namespace gi2d
 
