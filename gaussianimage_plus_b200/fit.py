@@ -102,6 +102,7 @@ class GaussianImageFitter:
         self._dirty = False         # a gradient is pending on the device
         self.external_optimizer = False  # True: grad_hook applies the gradients itself (parallel.FusedTileRowExchange)
         self.keep_render = False    # tests: also store the unclamped [H,W,3] render of every train_iter
+        self.eager_steps_after_resize = 150
         self.track_best = True      # keep the parameters of the best-PSNR step on the device (train.py:132-137)
         self._best_frozen = None    # best state of an EARLIER Gaussian count (prune/densify happened since)
         f = dict(dtype=torch.float32, device=self.device)
@@ -125,7 +126,7 @@ class GaussianImageFitter:
     def _raw_params(self):
         return {"xyz": self._t_xyz, "cov2d": self._t_cov2d, "f_dc": self._t_f_dc}
 
-    def _alloc_state(self, zero_moments: bool):
+    def _alloc_state(self, zero_moments: bool, eager_steps: int = 1):
         n = self.cur_num_points
         f = dict(dtype=torch.float32, device=self.device)
         if zero_moments:
@@ -154,7 +155,11 @@ class GaussianImageFitter:
         ws_bytes = self.lib.gi2d_fit_workspace_size(C.byref(self.params))
         self.workspace = torch.zeros(max(ws_bytes, 256), dtype=torch.uint8, device=self.device)
         self._invalidate_graphs()
-        self._eager_left = 1
+        # steps to run un-graphed before the next capture: 1 loads the kernels (lazy module loading cannot be
+        # captured); after a change of the Gaussian count more, because torch's graph capture costs ~3 ms (two
+        # graphs per count) while pruning can change the count every 100 iterations -- an eager step (3
+        # launches with programmatic edges) costs only ~2 us more than a replay
+        self._eager_left = eager_steps
         self._dirty = False
         self._bind()
 
@@ -517,7 +522,7 @@ class GaussianImageFitter:
             t.contiguous() for t in (xyz, cov, rgb, bound))
         self._t_m, self._t_v = m, v
         self._step0 = step
-        self._alloc_state(zero_moments=False)
+        self._alloc_state(zero_moments=False, eager_steps=self.eager_steps_after_resize)
         self._reset_keep_best(step, st)
 
     def non_semi_definite_prune(self):
