@@ -23,27 +23,66 @@ TILE = 16
 
 
 def _check_input(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
-    if not isinstance(t, torch.Tensor):
-        raise TypeError(f"{name} must be a torch.Tensor")
+    try:   # (the happy path first: these checks run ~30 times per iteration of a host-bound loop)
+        if t.is_cuda and t.is_contiguous() and (dtype is None or t.dtype == dtype):
+            return t
+    except AttributeError:
+        raise TypeError(f"{name} must be a torch.Tensor") from None
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")
     if not t.is_contiguous():
         raise RuntimeError(f"{name} must be contiguous")
-    if dtype is not None and t.dtype != dtype:
-        raise RuntimeError(f"{name} must have dtype {dtype}, got {t.dtype}")
-    return t
+    raise RuntimeError(f"{name} must have dtype {dtype}, got {t.dtype}")
 
 
 def _p(t: Optional[torch.Tensor]):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    # (a plain int converts to a c_void_p argument as well, without building a ctypes object)
+    return None if t is None else t.data_ptr()
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def _stream(dev) -> C.c_void_p:
+    if _raw_stream is not None:
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        return C.c_void_p(_raw_stream(idx))
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+_WS_CACHE = {}
+
+
 def _workspace(nbytes: int, dev) -> torch.Tensor:
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+    """Scratch for one C-ABI call.  Cached per (device, stream): calls on one stream execute in order, so the
+    next call may reuse the bytes; a fresh torch.empty per call costs ~3 us of host time, and the operator path
+    is host bound (several calls per iteration)."""
+    nbytes = max(int(nbytes), 256)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _WS_CACHE[key] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+    return ws
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _NullCtx()
+
+
+def _on(dev):
+    """`with _on(dev):` == `with _on(dev):` without the ~5 us of the context manager when `dev`
+    already is the current device (the common case)."""
+    idx = dev.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(dev)
 
 
 f32, i32, i64 = torch.float32, torch.int32, torch.int64
@@ -68,7 +107,7 @@ def _project_fwd(fn_name, num_points, clip_coe, means2d, p3, rot, img_height, im
         args.append(_p(rot))
     args += [int(img_width), int(img_height), int(tile_bounds[0]), int(tile_bounds[1]), float(clip_coe),
              float(radius_clip), _p(xys), _p(depths), _p(radii), _p(conics), _p(nth), _stream(dev)]
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(getattr(lib, fn_name)(*args), fn_name)
     return xys, depths, radii, conics, nth
 
@@ -102,7 +141,7 @@ def compute_cov2d_bounds(num_pts, clip_coe, cov2d):
     n = int(num_pts)
     conics = torch.empty((n, 3), dtype=f32, device=dev)
     radii = torch.empty((n, 1), dtype=f32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_compute_cov2d_bounds(n, float(clip_coe), _p(cov2d), _p(conics), _p(radii), _stream(dev)),
                    "compute_cov2d_bounds")
     return conics, radii
@@ -125,7 +164,7 @@ def project_gaussians_2d_covariance_backward(num_points, means2d, L_elements, im
     v_cov2d = torch.empty((n, 3), dtype=f32, device=dev)
     v_mean2d = torch.empty((n, 2), dtype=f32, device=dev)
     v_L = torch.empty((n, 3), dtype=f32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_project_cov_bwd(n, _p(radii), _p(conics), _p(v_xy), _p(v_conic), _p(v_cov2d),
                                             _p(v_mean2d), _p(v_L), _stream(dev)), "project_cov_bwd")
     return v_cov2d, v_mean2d, v_L
@@ -141,7 +180,7 @@ def project_gaussians_2d_backward(num_points, means2d, L_elements, img_height, i
     v_cov2d = torch.empty((n, 3), dtype=f32, device=dev)
     v_mean2d = torch.empty((n, 2), dtype=f32, device=dev)
     v_L = torch.empty((n, 3), dtype=f32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_project_chol_bwd(n, _p(L_elements), int(img_width), int(img_height), _p(radii),
                                              _p(conics), _p(v_xy), _p(v_conic), _p(v_cov2d), _p(v_mean2d),
                                              _p(v_L), _stream(dev)), "project_chol_bwd")
@@ -160,7 +199,7 @@ def project_gaussians_2d_scale_rot_backward(num_points, means2d, scales2d, rotat
     v_mean2d = torch.empty((n, 2), dtype=f32, device=dev)
     v_scale = torch.empty((n, 2), dtype=f32, device=dev)
     v_rot = torch.empty((n, 1), dtype=f32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_project_rs_bwd(n, _p(scales2d), _p(rotation), _p(radii), _p(conics), _p(v_xy),
                                            _p(v_conic), _p(v_cov2d), _p(v_mean2d), _p(v_scale), _p(v_rot),
                                            _stream(dev)), "project_rs_bwd")
@@ -176,7 +215,7 @@ def cumsum_i32(num_tiles_hit: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]
     cum = torch.empty((n,), dtype=i32, device=dev)
     total = torch.empty((1,), dtype=i32, device=dev)
     ws = _workspace(lib.gi2d_scan_workspace_size(n), dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_cumsum_i32(n, _p(num_tiles_hit), _p(cum), _p(total), _p(ws), ws.numel(), _stream(dev)),
                    "cumsum_i32")
     return cum, total
@@ -193,7 +232,7 @@ def map_gaussian_to_intersects(num_points, num_intersects, xys, depths, radii, c
     dev = xys.device
     isect_ids = torch.zeros((int(num_intersects),), dtype=i64, device=dev)
     gaussian_ids = torch.zeros((int(num_intersects),), dtype=i32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_map_gaussian_to_intersects(int(num_points), _p(xys), _p(depths), _p(radii),
                                                        _p(cum_tiles_hit), int(tile_bounds[0]), int(tile_bounds[1]),
                                                        float(radius_clip), _p(isect_ids), _p(gaussian_ids),
@@ -209,7 +248,7 @@ def sort_pairs_i64(keys: torch.Tensor, vals: torch.Tensor, begin_bit: int = 0, e
     dev, n = keys.device, keys.numel()
     keys_out, vals_out = torch.empty_like(keys), torch.empty_like(vals)
     ws = _workspace(lib.gi2d_sort_workspace_size(n), dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_sort_pairs_i64(n, _p(keys), _p(vals), _p(keys_out), _p(vals_out), int(begin_bit),
                                            int(end_bit), _p(ws), ws.numel(), _stream(dev)), "sort_pairs_i64")
     return keys_out, vals_out
@@ -223,7 +262,7 @@ def get_tile_bin_edges(num_intersects, isect_ids_sorted, num_rows: Optional[int]
     dev = isect_ids_sorted.device
     rows = int(num_intersects) if num_rows is None else int(num_rows)
     tile_bins = torch.empty((rows, 2), dtype=i32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_get_tile_bin_edges(int(num_intersects), _p(isect_ids_sorted), _p(tile_bins), rows,
                                                _stream(dev)), "get_tile_bin_edges")
     return tile_bins
@@ -253,7 +292,7 @@ def rasterize_sum_plus_forward(tile_bounds, block, img_size, gaussian_ids_sorted
     out_img = torch.empty((H, W, 3), dtype=f32, device=dev)
     final_Ts = torch.empty((H, W), dtype=f32, device=dev)
     final_idx = torch.empty((H, W), dtype=i32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_rasterize_sum_fwd(int(tile_bounds[0]), int(tile_bounds[1]), W, H,
                                               _p(gaussian_ids_sorted), _p(tile_bins), int(tile_bins.shape[0]),
                                               _p(xys), _p(conics), _p(colors), _p(opacities), _p(out_img),
@@ -286,7 +325,7 @@ def rasterize_sum_plus_backward(img_height, img_width, BLOCK_H, BLOCK_W, gaussia
     v_conic = torch.empty((n, 3), dtype=f32, device=dev)
     v_colors = torch.empty((n, 3), dtype=f32, device=dev)
     v_opacity = torch.empty((n, 1), dtype=f32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_rasterize_sum_bwd(n, tb[0], tb[1], W, H, _p(gaussian_ids_sorted), _p(tile_bins),
                                               int(tile_bins.shape[0]), _p(xys), _p(conics), _p(colors),
                                               _p(opacities), _p(final_idx), _p(v_output), _p(v_xy), _p(v_conic),
@@ -316,7 +355,7 @@ def image_loss_grad(render_hwc: torch.Tensor, gt_hwc: torch.Tensor, loss_type: s
     ssim_sum = torch.zeros(1, dtype=torch.float64, device=dev)
     ws_buf = _workspace(lib.gi2d_ssim_workspace_size(H, W), dev)
     is_u8 = gt_hwc.dtype == torch.uint8
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_image_loss_grad(H, W, _p(render_hwc), None if is_u8 else _p(gt_hwc),
                                             _p(gt_hwc) if is_u8 else None, ws, 2.0 * w2 / (3.0 * H * W),
                                             w1 / (3.0 * H * W), _p(v_out), _p(ssim_sum), _p(ws_buf), ws_buf.numel(),
@@ -338,7 +377,7 @@ def ms_ssim(render_hwc: torch.Tensor, gt_hwc: torch.Tensor) -> float:
     sums = torch.zeros(5, 3, 2, dtype=torch.float64, device=dev)
     ws = _workspace(lib.gi2d_ms_ssim_workspace_size(H, W), dev)
     is_u8 = gt_hwc.dtype == torch.uint8
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.gi2d_ms_ssim(H, W, _p(render_hwc), None if is_u8 else _p(gt_hwc), _p(gt_hwc) if is_u8 else None,
                                     _p(sums), _p(ws), ws.numel(), _stream(dev)), "ms_ssim")
     s = sums.cpu()

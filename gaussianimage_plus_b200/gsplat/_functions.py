@@ -12,7 +12,7 @@ import torch
 from torch.autograd import Function
 
 from . import cuda as _C
-from .utils import bin_and_sort_gaussians, compute_cumulative_intersects
+from .utils import bin_and_sort_gaussians, compute_cumulative_intersects, cumulative_intersects_and_depth_flag
 
 
 class ProjectCovariance(Function):
@@ -103,10 +103,14 @@ class RasterizeSum(Function):
 
     @staticmethod
     def forward(ctx, xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height, img_width, BLOCK_H,
-                BLOCK_W, background, radius_clip, isprint):
+                BLOCK_W, background, radius_clip, isprint, depths_zero=None):
         n = xys.size(0)
         tile_bounds = ((img_width + BLOCK_W - 1) // BLOCK_W, (img_height + BLOCK_H - 1) // BLOCK_H, 1)
-        num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
+        if depths_zero:    # depths straight from one of this package's 2-D projections: known to be all 0.0
+            num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
+            uniform = True
+        else:
+            num_intersects, cum_tiles_hit, uniform = cumulative_intersects_and_depth_flag(num_tiles_hit, depths)
         if num_intersects < 1:
             # rasterize_sum_plus.py:110-118 -- a constant background image, no gradients
             out_img = torch.ones(img_height, img_width, colors.shape[-1], device=xys.device) * background
@@ -115,7 +119,7 @@ class RasterizeSum(Function):
             final_Ts = torch.zeros(img_height, img_width, device=xys.device)
         else:
             _, _, _, ids, bins = bin_and_sort_gaussians(n, num_intersects, xys, depths, radii, cum_tiles_hit,
-                                                        tile_bounds, radius_clip)
+                                                        tile_bounds, radius_clip, _depths_uniform=uniform)
             out_img, final_Ts, _ = _C.rasterize_sum_plus_forward(
                 tile_bounds, (BLOCK_W, BLOCK_H, 1), (img_width, img_height, 1), ids, bins, xys, conics, colors,
                 opacity, background, isprint)
@@ -134,4 +138,4 @@ class RasterizeSum(Function):
             grads = _C.rasterize_sum_plus_backward(H, W, BH, BW, ids, bins, xys, conics, colors, opacity, None,
                                                    None, None, v_out_img.contiguous(), None)
         v_xy, v_conic, v_colors, v_opacity = grads
-        return (v_xy, None, None, v_conic, None, v_colors, v_opacity.view_as(opacity)) + (None,) * 7
+        return (v_xy, None, None, v_conic, None, v_colors, v_opacity.view_as(opacity)) + (None,) * 8

@@ -14,5 +14,7 @@ def project_gaussians_2d_covariance(means2d: Tensor, L_elements: Tensor, img_hei
 
     Differentiable w.r.t. means2d and L_elements.  `coords_norm`, `clip_thresh` are accepted and unused
     and `isprint` only enabled debug printing in the reference."""
-    return _ProjectGaussians2d_covariance.apply(means2d.contiguous(), L_elements.contiguous(), img_height,
+    out = _ProjectGaussians2d_covariance.apply(means2d.contiguous(), L_elements.contiguous(), img_height,
                                                 img_width, tile_bounds, clip_thresh, clip_coe, radius_clip, isprint)
+    out[1]._gi2d_depths_zero = True   # the 2-D projections emit depth 0.0: rasterize_* need not check
+    return out

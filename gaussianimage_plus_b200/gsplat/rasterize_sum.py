@@ -43,7 +43,8 @@ def _sum(xys, depths, radii, conics, num_tiles_hit, colors, opacity, img_height,
     out_img = _RasterizeGaussiansSum.apply(xys.contiguous(), depths.contiguous(), radii.contiguous(),
                                            conics.contiguous(), num_tiles_hit.contiguous(), colors.contiguous(),
                                            opacity.contiguous(), img_height, img_width, BLOCK_H, BLOCK_W,
-                                           background.contiguous(), 1.0, isprint)
+                                           background.contiguous(), 1.0, isprint,
+                                           getattr(depths, "_gi2d_depths_zero", None))
     if return_alpha:
         # out_alpha = 1 - final_Ts and the kernel leaves T == 1 (forward.cu:617,682)
         return out_img, torch.zeros(img_height, img_width, device=out_img.device)

@@ -33,4 +33,4 @@ def rasterize_gaussians_plus(xys: Tensor, depths: Tensor, radii: Tensor, conics:
     return _RasterizeGaussiansSum.apply(xys.contiguous(), depths.contiguous(), radii.contiguous(),
                                         conics.contiguous(), num_tiles_hit.contiguous(), colors.contiguous(),
                                         opacity.contiguous(), img_height, img_width, BLOCK_H, BLOCK_W,
-                                        background.contiguous(), radius_clip, isprint)
+                                        background.contiguous(), radius_clip, isprint, getattr(depths, "_gi2d_depths_zero", None))

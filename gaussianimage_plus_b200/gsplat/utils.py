@@ -12,6 +12,18 @@ from . import cuda as _C
 from .. import binding as _b
 
 
+def cumulative_intersects_and_depth_flag(num_tiles_hit: Tensor, depths: Tensor):
+    """(num_intersects, cum_tiles_hit, depths_uniform) with ONE host read-back: the total of the prefix sum and
+    "all depths share one bit pattern" travel together (the reference's .item() at utils.py:249 is the one
+    synchronisation this path keeps)."""
+    cum, total = _b.cumsum_i32(num_tiles_hit.contiguous().view(-1).to(torch.int32))
+    if depths.numel() == 0:
+        return int(total.item()), cum, True
+    lo, hi = torch.aminmax(depths.contiguous().view(-1).view(torch.int32))
+    both = torch.stack((total[0], (lo == hi).to(torch.int32))).tolist()
+    return int(both[0]), cum, bool(both[1])
+
+
 def compute_cumulative_intersects(num_tiles_hit: Tensor) -> Tuple[int, Tensor]:
     """utils.py:231-250: (int num_intersects, cum_tiles_hit int32[N]); reads one int back like the reference."""
     cum, total = _b.cumsum_i32(num_tiles_hit.contiguous().view(-1).to(torch.int32))
@@ -41,7 +53,7 @@ def compute_cov2d_bounds(cov2d: Tensor, clip_coe: float = 3.0) -> Tuple[Tensor, 
 
 
 def bin_and_sort_gaussians(num_points, num_intersects, xys, depths, radii, cum_tiles_hit, tile_bounds,
-                           radius_clip=1.0, isprint=False):
+                           radius_clip=1.0, isprint=False, _depths_uniform=None):
     """utils.py:253-311 -> (isect_ids, gaussian_ids, isect_ids_sorted, gaussian_ids_sorted, tile_bins).
 
     tile_bins gets max(num_intersects, #tiles) rows so that every tile has a row (the
@@ -52,8 +64,12 @@ def bin_and_sort_gaussians(num_points, num_intersects, xys, depths, radii, cum_t
     begin_bit, end_bit = 0, 64
     if depths.numel() > 0:
         # when every depth has the same bit pattern (the 2-D projections emit 0.0) only the tile bits order keys
-        lo, hi = torch.aminmax(depths.view(torch.int32))
-        if bool(lo == hi):
+        # (`_depths_uniform`: the caller already knows -- rasterize_gaussians_* read the answer back together
+        #  with num_intersects, one synchronisation instead of two)
+        if _depths_uniform is None:
+            lo, hi = torch.aminmax(depths.view(torch.int32))
+            _depths_uniform = bool(lo == hi)
+        if _depths_uniform:
             tiles = max(int(tile_bounds[0]) * int(tile_bounds[1]), 2)
             begin_bit, end_bit = 32, min(64, 32 + (tiles - 1).bit_length())
     isect_ids_sorted, gaussian_ids_sorted = _b.sort_pairs_i64(isect_ids, gaussian_ids, begin_bit, end_bit)
