@@ -73,6 +73,7 @@ SIGNATURES = {
     "gi2d_fit_profile": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), C.POINTER(C.c_float), _P]),
     "gi2d_fit_profile_raster": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, C.POINTER(C.c_float), _P]),
     "gi2d_measure_fp32_peak": (_I, [C.POINTER(C.c_float), _P]),
+    "gi2d_fit_input_grads": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _P, _P]),
     "gi2d_fit_exchange_adam": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _I, C.POINTER(_P),
                                    C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P]),
     "gi2d_ssim_workspace_size": (_SZ, [_I, _I]),

@@ -5,10 +5,18 @@
 the drop-in operators (`gsplat.project_gaussians_2d_covariance`, `gsplat.rasterize_gaussians_plus`: the CUDA
 kernels of libgi2d with the reference's autograd contract) and the fused quantisers of `quantize.py`.
 
-Quantisation-aware training needs gradients with respect to the quantiser parameters as well, so it runs on
-the autograd operator path (projection and rasterization forward / backward are the libgi2d kernels; the loss
-gradient comes from the fused SSIM / mse / l1 kernels through `loss_fn`).  The fully fused, graph-captured
-step of `fit.py` is the warm-up phase (`iter < warmup_iter`, train_quantize.py:124-127).
+Two forms of the quantisation-aware iteration:
+
+* `QuantizedGaussianImage` -- the reference's structure, operator by operator: quantisers -> projection ->
+  rasterization (the libgi2d operators with the reference's autograd contract) -> `loss_fn` (the fused SSIM /
+  mse / l1 kernels) -> four optimisers; one host read-back per iteration like the reference; ~3 ms/iteration.
+* `FusedQuantizedTrainer` -- same quantisers, same optimisers, but everything between the de-quantised
+  attributes and their gradients is the fused fit step (3 kernels, `external_optimizer` mode +
+  gi2d_fit_input_grads), nothing synchronises, and the whole iteration is replayed from ONE CUDA graph:
+  ~0.5 ms/iteration.
+
+The fully fused, graph-captured step of `fit.py` is the warm-up phase (`iter < warmup_iter`,
+train_quantize.py:124-127).
 """
 from __future__ import annotations
 
@@ -194,3 +202,144 @@ class QuantizedGaussianImage(nn.Module):
         px = self.H * self.W
         return {"bpp": (pos_bits + cov_bits + color_bits) / px, "position_bpp": pos_bits / px,
                 "cholesky_bpp": cov_bits / px, "feature_dc_bpp": color_bits / px}
+
+
+# ----------------------------------------------------------------------------------- fused QAT
+class _FusedRenderLoss(torch.autograd.Function):
+    """loss(means, cov, colors): projection + binning + rasterize forward + loss + rasterize backward +
+    projection backward are the 3 kernels of the fused fit step (gi2d_fit.cu, `external_optimizer` mode: the
+    step leaves parameters and optimiser to the caller) + gi2d_fit_input_grads; no host synchronisation, so the
+    whole quantisation-aware iteration can live in one CUDA graph."""
+
+    @staticmethod
+    def forward(ctx, means, cov, colors, owner):
+        import ctypes as C
+
+        from . import _lib
+        from .binding import _stream
+
+        fit = owner._fit
+        fit._t_xyz.copy_(means)
+        fit._t_cov2d.copy_(cov)
+        fit._t_f_dc.copy_(colors)
+        fit._enqueue_step()
+        _lib.check(fit.lib.gi2d_fit_input_grads(C.byref(fit.params), C.byref(fit.buffers), owner._gbuf.data_ptr(),
+                                                _stream(fit.device)), "fit_input_grads")
+        ctx.owner = owner
+        return owner._loss_from_stats()
+
+    @staticmethod
+    def backward(ctx, g):
+        gb = ctx.owner._gbuf
+        return g * gb[:, 0:2], g * gb[:, 2:5], g * gb[:, 5:8], None
+
+
+class FusedQuantizedTrainer(QuantizedGaussianImage):
+    """`QuantizedGaussianImage` whose iteration runs sync-free: the quantisers and the four optimisers stay the
+    torch modules / torch.optim.Adam of the parent class (capturable), everything between the de-quantised
+    attributes and their gradients is the fused fit step, and forward + backward + optimiser steps are replayed
+    from ONE CUDA graph (re-captured when a StepLR changes a learning rate).  PSNR is read on demand
+    (`psnr()`), not every iteration."""
+
+    def __init__(self, *a, use_graph: bool = True, **kw):
+        super().__init__(*a, **kw)
+        from .fit import GaussianImageFitter
+
+        dev = self._xyz.device
+        n = self._xyz.shape[0]
+        fit = GaussianImageFitter(n, self.H, self.W, device=dev, lr=0.0, clip_coe=self.gs_clip_coe,
+                                  radius_clip=self.radius_clip, color_norm=False, use_graph=False,
+                                  loss_type=self.loss_type)
+        fit.external_optimizer = True          # the step never touches parameters / moments
+        fit.track_best = False
+        fit.params.external_optimizer = 1
+        fit.cholesky_bound.zero_()             # the inputs are complete covariances (bound already added)
+        fit._bind()
+        self._fit = fit
+        self._gbuf = torch.zeros(n, 8, device=dev)
+        self.use_graph = use_graph
+        self._graph = None
+        self._graph_lrs = None
+        self._side = None
+        self._warm = 0
+        for opt in (self.optimizer, self.cov2d_quantizer_optimizer, self.xyz_quantizer_optimizer,
+                    self.color_quantizer_optimizer):
+            for gr in opt.param_groups:
+                gr["capturable"] = True
+
+    def set_target(self, gt_hwc: torch.Tensor):
+        self._fit.set_target(gt_hwc)
+
+    def _loss_from_stats(self) -> torch.Tensor:
+        from .fit import STAT_ABS_SUM, STAT_SSE, STAT_SSE_SLOTS, STAT_SSIM_SUM
+
+        s, f = self._fit.stats_buf, self._fit
+        w2, w1, ws = f.loss_w
+        px3 = 3.0 * self.H * self.W
+        loss = w2 * s[STAT_SSE:STAT_SSE + STAT_SSE_SLOTS].sum() / px3
+        if w1:
+            loss = loss + w1 * s[STAT_ABS_SUM] / px3
+        if ws:
+            loss = loss + ws * (1.0 - s[STAT_SSIM_SUM] / (3.0 * (self.H - 10) * (self.W - 10)))
+        return loss.float()
+
+    def _iteration(self):
+        means, _, _, _ = self.xyz_quantizer(self._xyz)
+        cov, _, _, _ = self.cholesky_quantizer(self.get_cov2d_elements)
+        colors, _, _, _ = self.features_dc_quantizer(self.get_features)
+        loss = _FusedRenderLoss.apply(means, cov, colors, self)
+        loss.backward()
+        for opt in (self.optimizer, self.cov2d_quantizer_optimizer, self.xyz_quantizer_optimizer,
+                    self.color_quantizer_optimizer):
+            opt.step()
+        return loss
+
+    def _lrs(self):
+        return tuple(g["lr"] for o in (self.optimizer, self.cov2d_quantizer_optimizer, self.xyz_quantizer_optimizer,
+                                       self.color_quantizer_optimizer) for g in o.param_groups)
+
+    def train_iter_quantize(self, gt_hwc: Optional[torch.Tensor] = None):
+        """One quantisation-aware iteration (gaussianimage_covariance.py:219-247), asynchronous; returns the
+        loss as a device scalar.  `gt_hwc` (optional) replaces the target first."""
+        if gt_hwc is not None:
+            self._fit.set_target(gt_hwc)
+        opts = (self.optimizer, self.cov2d_quantizer_optimizer, self.xyz_quantizer_optimizer,
+                self.color_quantizer_optimizer)
+        scheds = (self.scheduler, self.cov2d_scheduler, self.xyz_scheduler, self.color_scheduler)
+        dev = self._xyz.device
+        cur = torch.cuda.current_stream(dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side
+        if not self.use_graph or self._warm < 3:
+            # eager: the first call initialises the quantisers from the data (quantize.py:72-80), the optimisers
+            # create their state, the kernels get loaded -- none of which can be captured.  It runs on the SAME
+            # side stream the capture will use: autograd ties the parameters' gradient accumulation to the stream
+            # of the first backward, and a capture may not depend on the legacy default stream.
+            self._warm += 1
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for o in opts:
+                    o.zero_grad(set_to_none=True)
+                loss = self._iteration().detach()
+            cur.wait_stream(side)
+        else:
+            if self._graph is None or self._graph_lrs != self._lrs():
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    for o in opts:
+                        o.zero_grad(set_to_none=True)
+                    self._graph = torch.cuda.CUDAGraph()
+                    self._graph_lrs = self._lrs()
+                    with torch.cuda.graph(self._graph, stream=side):
+                        self._static_loss = self._iteration().detach()
+                cur.wait_stream(side)
+            self._graph.replay()
+            loss = self._static_loss
+        for sc in scheds:
+            sc.step()
+        return loss
+
+    def psnr(self) -> float:
+        """PSNR of the render of the LAST iteration (before its update); synchronises."""
+        return self._fit.stats()["psnr"]

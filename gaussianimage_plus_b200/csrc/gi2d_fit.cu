@@ -802,6 +802,22 @@ fit_exchange_adam_kernel(gi2d_fit_params p, AdamPtrs local, PeerPtrs peers, int 
     }
 }
 
+// d loss / d (the step's inputs) for callers with their own optimiser: projection backward only
+__global__ void __launch_bounds__(256)
+fit_input_grads_kernel(int n, const float4 *__restrict__ proj, const float4 *__restrict__ grads,
+                       float4 *__restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= n) return;
+    const float4 p0 = __ldcg(proj + 2 * g), p1 = __ldcg(proj + 2 * g + 1);
+    const float4 g0 = __ldcg(grads + 2 * g), g1 = __ldcg(grads + 2 * g + 1);
+    float gc[3];
+    conic_vjp(p0.z, p0.w, p1.x, g0.z, g0.w, g1.x, gc[0], gc[1], gc[2]);
+    out[2 * g] = make_float4(g0.x, g0.y, gc[0], gc[1]);
+    out[2 * g + 1] = make_float4(gc[2], g1.y, g1.z, g1.w);
+}
+
 __global__ void fit_reset_kernel(gi2d_fit_params p, double *stats, int step) {
     const int i = threadIdx.x;
     if (i >= GI2D_STAT_COUNT) return;
@@ -1058,6 +1074,17 @@ extern "C" int gi2d_measure_fp32_peak(float *tflops_host, gi2d_stream_t stream) 
     cudaEventDestroy(e1);
     cudaFree(d);
     *tflops_host = best;
+    return check_launch(__func__);
+}
+
+extern "C" int gi2d_fit_input_grads(const gi2d_fit_params *p, const gi2d_fit_buffers *b, float *out,
+                                    gi2d_stream_t stream) {
+    const int rc = validate(p, b);
+    if (rc != GI2D_OK) return rc;
+    GI2D_REQUIRE(b->grads && out, "null buffer");
+    if (p->num_points == 0) return GI2D_OK;
+    launch_pdl(fit_input_grads_kernel, dim3(cdiv(p->num_points, 256)), dim3(256), 0, (cudaStream_t)stream,
+               p->num_points, (const float4 *)b->proj, (const float4 *)b->grads, (float4 *)out);
     return check_launch(__func__);
 }
 

@@ -259,6 +259,12 @@ int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fit_buffers *
  * gaussianimage_covariance.py:373-382), so the prune decision costs no extra launch. */
 int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, gi2d_stream_t stream);
 
+/* Gradients of the last training step with respect to the step's INPUTS, for a caller that keeps its own
+ * parameters and optimiser (p->external_optimizer: the quantisation-aware pass feeds de-quantised means /
+ * covariances / colours and back-propagates into its quantisers): out f32[N,8] = d loss / d (x, y, sxx, sxy,
+ * syy, r, g, b) -- b->grads pushed through the projection backward (-X G X, backward2d.cu:157-214). */
+int gi2d_fit_input_grads(const gi2d_fit_params *p, const gi2d_fit_buffers *b, float *out, gi2d_stream_t stream);
+
 /* Multi-GPU tile-row split: fused reduce-scatter of the partial gradients + projection
  * backward + Adam on the owned slice (sharded optimiser state) + all-gather of the updated parameters,
  * ONE kernel over NVLink peer memory.  peer_* are HOST arrays of `world` device pointers to every

@@ -59,3 +59,54 @@ def test_quantised_training_and_codec_round_trip(loss_type):
     bits = n * (2 * 12 + 3 * 10 + 3 * 6) + 32 * 2 * 2 + 32 * 3 * 2 + 32 * 3 * 2
     assert abs(a["bpp"] - bits / (H * W)) < 1e-9
     assert abs(a["bpp"] - (a["position_bpp"] + a["cholesky_bpp"] + a["feature_dc_bpp"])) < 1e-12
+
+
+@pytest.mark.parametrize("loss_type", ["L2", "Fusion2"])
+def test_fused_qat_matches_operator_path(loss_type):
+    """FusedQuantizedTrainer (quantisers in torch, everything between the de-quantised attributes and their
+    gradients in the fused fit step, the iteration replayed from one CUDA graph) against the operator-path
+    QuantizedGaussianImage: same loss and gradients for one iteration, same PSNR trajectory over 150."""
+    from gaussianimage_plus_b200.codec import (FusedQuantizedTrainer, QuantizedGaussianImage, _FusedRenderLoss,
+                                               loss_fn)
+    from gaussianimage_plus_b200.fit import GaussianImageFitter
+
+    N, H, W = 1500, 128, 192
+    gt = torch.from_numpy(synth.target_image(H, W, seed=5)).to(DEV)
+    torch.manual_seed(1)
+    fit = GaussianImageFitter(N, H, W, device=DEV, loss_type=loss_type)
+    fit.set_target(gt)
+    fit.fit(400, max_num_points=N, adaptive_add=False)
+    st = fit.best_state()
+    args = (st["_xyz"], st["_cov2d"], st["_features_dc"], st["cholesky_bound"], H, W)
+    q_op = QuantizedGaussianImage(*args, lr=0.018, loss_type=loss_type)
+    q_fu = FusedQuantizedTrainer(*args, lr=0.018, loss_type=loss_type)
+    q_fu.set_target(gt)
+    # ---- one iteration, gradients only
+    loss_op = loss_fn(q_op.forward_quantize()["render"], gt, loss_type, 0.7)
+    loss_op.backward()
+    means, _, _, _ = q_fu.xyz_quantizer(q_fu._xyz)
+    cov, _, _, _ = q_fu.cholesky_quantizer(q_fu.get_cov2d_elements)
+    colors, _, _, _ = q_fu.features_dc_quantizer(q_fu.get_features)
+    loss_fu = _FusedRenderLoss.apply(means, cov, colors, q_fu)
+    loss_fu.backward()
+    assert abs(float(loss_op.detach()) - float(loss_fu.detach())) <= 2e-5 * abs(float(loss_op.detach())) + 1e-7
+    del loss_op, loss_fu, means, cov, colors          # (nothing may keep this autograd graph alive)
+    po, pf = dict(q_op.named_parameters()), dict(q_fu.named_parameters())
+    assert set(po) == set(pf)
+    for name in po:
+        a, b = pf[name].grad.double(), po[name].grad.double()
+        rel = float(torch.linalg.norm(a - b) / (torch.linalg.norm(b) + 1e-30))
+        assert rel < 5e-4, (name, rel)
+    for q in (q_op, q_fu):
+        for o in (q.optimizer, q.cov2d_quantizer_optimizer, q.xyz_quantizer_optimizer, q.color_quantizer_optimizer):
+            o.zero_grad(set_to_none=True)
+    # ---- 150 iterations: eager warm-up + graph replays vs the operator path
+    for _ in range(150):
+        q_fu.train_iter_quantize()
+        _, _, _, _, psnr_op = q_op.train_iter_quantize(gt)
+    assert q_fu._graph is not None
+    psnr_fu = q_fu.psnr()
+    assert abs(psnr_fu - psnr_op) < 0.6, (psnr_fu, psnr_op)
+    # the codec half of the parent class works on the fused trainer's parameters
+    enc = q_fu.compress_wo_ec()
+    assert q_fu.decompress_wo_ec(enc)["render"].shape == (1, 3, H, W)

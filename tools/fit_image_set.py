@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 from gaussianimage_plus_b200 import synth
-from gaussianimage_plus_b200.codec import QuantizedGaussianImage
+from gaussianimage_plus_b200.codec import FusedQuantizedTrainer, QuantizedGaussianImage
 from gaussianimage_plus_b200.fit import GaussianImageFitter
 from gaussianimage_plus_b200.parallel import gather_metrics, shard_images
 
@@ -33,6 +33,8 @@ ap.add_argument("--max-points", type=int, default=5000)
 ap.add_argument("--grow-iter", type=int, default=1000)
 ap.add_argument("--qat", type=int, default=200)
 ap.add_argument("--color-norm", action="store_true")
+ap.add_argument("--qat-operator-path", action="store_true", help="quantisation-aware steps on the autograd operator "
+                "path instead of the fused, graph-captured FusedQuantizedTrainer")
 args = ap.parse_args()
 
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -59,12 +61,22 @@ for i in shard_images(args.images, world, rank):
     rec = {"image": i, "HxW": f"{H}x{W}", "gaussians": fit.cur_num_points, "best_psnr": st["best_psnr"],
            "ms_ssim": ms, "fit_seconds": t_fit, "it_per_s": args.iterations / t_fit}
     if args.qat:
-        q = QuantizedGaussianImage.from_fitter(fit, best=False)
-        t0 = time.perf_counter()
-        q_first = None
-        for _ in range(args.qat):
-            _, _, _, _, qpsnr = q.train_iter_quantize(gt_u8)
-            q_first = qpsnr if q_first is None else q_first
+        if args.qat_operator_path:
+            q = QuantizedGaussianImage.from_fitter(fit, best=False)
+            t0 = time.perf_counter()
+            q_first = None
+            for _ in range(args.qat):
+                _, _, _, _, qpsnr = q.train_iter_quantize(gt_u8)
+                q_first = qpsnr if q_first is None else q_first
+        else:
+            q = FusedQuantizedTrainer.from_fitter(fit, best=False)
+            q.set_target(gt_u8)
+            t0 = time.perf_counter()
+            q.train_iter_quantize()
+            q_first = q.psnr()                      # the first quantised forward == post-training quantisation
+            for _ in range(args.qat - 1):
+                q.train_iter_quantize()
+            qpsnr = q.psnr()
         torch.cuda.synchronize(dev)
         enc = q.compress_wo_ec()
         dec = q.decompress_wo_ec(enc)["render"]
