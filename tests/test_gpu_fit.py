@@ -369,3 +369,28 @@ def test_u8_target_equals_float_target():
     fa.train_iter()
     fb.train_iter()
     assert abs(fa.stats()["mse"] - fb.stats()["mse"]) <= 1e-5 * fa.stats()["mse"]
+
+
+def test_fit_step_with_nothing_on_screen_and_tiny_images():
+    """Edge cases of the fit step: no Gaussian intersects the image (the reference returns ones * background and
+    no gradient, rasterize_sum_plus.py:110-118), an image smaller than one tile, zero-size tails."""
+    from gaussianimage_plus_b200.fit import GaussianImageFitter
+
+    for H, W, N in ((40, 56, 50), (7, 9, 12), (16, 16, 1)):
+        fit = GaussianImageFitter(N, H, W, device=DEV, use_graph=False)
+        fit.set_target(torch.full((H, W, 3), 0.25, device=DEV))
+        fit._xyz[:] = torch.tensor([-500.0, -500.0], device=DEV)        # everything far off screen
+        x0, c0 = fit._xyz.clone(), fit._features_dc.clone()
+        for _ in range(3):
+            fit.train_iter()
+        st = fit.stats()
+        assert st["num_intersects"] == 0 and st["step"] == 3 and not st["overflow"]
+        assert abs(st["mse"] - 0.75 ** 2) < 1e-6                        # render == 1 everywhere
+        assert torch.equal(fit._xyz, x0) and torch.equal(fit._features_dc, c0)   # zero gradient: Adam does not move
+        assert float((fit.forward()["render"] - 1.0).abs().max()) == 0.0
+        # and back on screen it fits
+        fit._xyz[:] = torch.rand(N, 2, device=DEV) * torch.tensor([W, H], device=DEV)
+        for _ in range(30):
+            fit.train_iter()
+        st2 = fit.stats()
+        assert st2["num_intersects"] > 0 and np.isfinite(st2["psnr"]) and st2["mse"] < 0.75 ** 2
