@@ -3,7 +3,7 @@
 `GaussianImageFitter` keeps the reference model's vocabulary (models/gaussianimage_covariance.py):
 `_xyz`, `_cov2d`, `_features_dc`, `cholesky_bound`, `forward()`, `train_iter()`,
 `densification_postfix()`, `non_semi_definite_prune()` -- but one `train_iter` is a single CUDA
-graph replay of 4 kernels (gi2d_fit.cu) instead of ~70 launches and two host syncs
+graph replay of 3 kernels (gi2d_fit.cu) instead of ~70 launches and two host syncs
 (SURVEY 3.1).  Nothing here computes on the CPU; without libgi2d.so it raises.
 
 Two things differ from a literal transcription, both invisible in the results:

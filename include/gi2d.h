@@ -164,9 +164,11 @@ int gi2d_rasterize_sum_bwd(int num_points, int tiles_x, int tiles_y, int img_wid
 
 /* ------------------------------------------------------------------------------------------
  * Fused fit step: the whole `train_iter` of
- * models/gaussianimage_covariance.py:249-259 for the covariance model with L2 loss, with no
- * host synchronisation: project+count -> tile scan -> stable scatter (64-bit tile|gaussian
- * keys) -> rasterize fwd + L2 loss gradient + backward -> project backward + Adam.
+ * models/gaussianimage_covariance.py:249-259 for the covariance model, with no host synchronisation, in
+ * 3 launches: [project backward + Adam of the previous step] + project + per-tile overlap counts ->
+ * prefix sum of the counts + placement of the 64-bit (tile|gaussian) keys and 32-B records -> in-tile
+ * key sort + rasterize forward + loss gradient (mse / l1 inline; SSIM through two more kernels) +
+ * rasterize backward.
  * ------------------------------------------------------------------------------------------ */
 
 typedef struct gi2d_fit_params {
@@ -318,7 +320,8 @@ int gi2d_ms_ssim(int img_height, int img_width, const float *render_hwc, const f
  * ------------------------------------------------------------------------------------------ */
 
 /* One full fit step with a CUDA event between kernels.  ms_host[0..4] (HOST pointer) =
- * project, scan, scatter (+ extra radix passes + tile edges), raster fwd+bwd, adam. */
+ * [adam +] project + count, device-wide scan of the tile counts (0 up to 2048 tiles), place,
+ * sort + raster fwd+bwd, 0.  (Event brackets add a few us per kernel: see gi2d_fit_profile_raster.) */
 int gi2d_fit_profile(const gi2d_fit_params *p, const gi2d_fit_buffers *b, float *ms_host,
                      gi2d_stream_t stream);
 
