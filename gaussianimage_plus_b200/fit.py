@@ -247,6 +247,7 @@ class GaussianImageFitter:
         self._graphs = {}
         self._multi_graphs = {}
         self._pipe_bound = None
+        self._render_bound = None
 
     # ------------------------------------------------------------------ steps fed from host memory
     def step_from_host(self, host_img: torch.Tensor, host_stats: torch.Tensor) -> int:
@@ -401,13 +402,22 @@ class GaussianImageFitter:
     def forward(self) -> dict:
         """The model's forward (gaussianimage_covariance.py:187-218): {'render': [1,3,H,W] clamped}.
         A pending optimiser step is applied by the same launch before projecting."""
-        with torch.cuda.device(self.device):
+        rb = self._render_bound
+        if rb is None:      # the argument block of a render call (cached: building it costs ~10 us of host time)
+            keep = self.buffers
             self._bind(out_img=self.render_chw.data_ptr())
-            _lib.check(self.lib.gi2d_fit_forward_backward(C.byref(self.params), C.byref(self.buffers), 0,
-                                                          _stream(self.device)), "fit_forward (render)")
-            self._bind(out_img=None)
+            rb = self._render_bound = (self.buffers, C.byref(self.buffers), C.byref(self.params),
+                                       self.render_chw.view(1, 3, self.H, self.W))
+            self.buffers = keep
+        if torch.cuda.current_device() == self.device.index:
+            _lib.check(self.lib.gi2d_fit_forward_backward(rb[2], rb[1], 0, _stream(self.device)),
+                       "fit_forward (render)")
+        else:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.gi2d_fit_forward_backward(rb[2], rb[1], 0, _stream(self.device)),
+                           "fit_forward (render)")
         self._dirty = False
-        return {"render": self.render_chw.view(1, 3, self.H, self.W)}
+        return {"render": rb[3]}
 
     __call__ = forward
 
