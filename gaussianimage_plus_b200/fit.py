@@ -464,10 +464,11 @@ class GaussianImageFitter:
     def mse_from_stats(host_slot: torch.Tensor, H: int, W: int) -> float:
         return _sse_total(host_slot) / (3.0 * H * W)
 
-    def ensure_capacity(self) -> bool:
+    def ensure_capacity(self, st: Optional[dict] = None) -> bool:
         """Host check of the overflow flag; grows the intersection buffers when it tripped.
-        Returns True when a regrow happened (the overflowing step's gradient is dropped, not applied)."""
-        st = self.stats()
+        Returns True when a regrow happened (the overflowing step's gradient is dropped, not applied).
+        `st`: a stats() result the caller already has (saves the read-back)."""
+        st = st if st is not None else self.stats()
         if not st["overflow"]:
             return False
         self._capacity_hint = int(st["num_intersects"] * 2)
@@ -541,7 +542,11 @@ class GaussianImageFitter:
         # the flush kernel counts the non-PSD Gaussians while it applies the pending step: the common
         # "nothing to prune" outcome costs that launch + one small read-back, no torch ops
         self.sync_params(force=True)
-        if self.stats()["non_psd"] == 0:
+        st = self.stats()
+        # the same read-back tells whether the intersection buffers overflowed since the last look (the steps since
+        # then were vetoed on the device): grow them here, so that a long fit() never stalls silently
+        self.ensure_capacity(st)
+        if st["non_psd"] == 0:
             return 0, self.cur_num_points
         n_bad, valid = self.check_non_semi_definite()
         if n_bad and self.cur_num_points - n_bad > 0:

@@ -144,6 +144,15 @@ def test_capacity_overflow_is_detected_and_recovered():
     assert not st["overflow"] and st["step"] == 1
 
 
+def test_fit_loop_grows_the_intersection_buffers_by_itself():
+    fit, _ = make_fitter(3000, 256, 384, seed=3, colors="zeros", use_graph=True, keep_render=False, isect_capacity=6000)
+    fit.train_iter()
+    assert fit.stats()["overflow"]                       # 3000 Gaussians x ~4 tiles do not fit 6000 slots
+    st = fit.fit(250, prune_iter=100, adaptive_add=False)
+    assert not st["overflow"] and fit.isect_capacity > 6000
+    assert st["psnr"] > 15 and st["num_intersects"] > 6000
+
+
 def test_prune_and_densify_keep_state_consistent():
     fit, _ = make_fitter(2000, 256, 384, seed=6, colors="zeros", use_graph=True)
     for _ in range(20):
