@@ -445,6 +445,15 @@ class GaussianImageFitter:
     def psnr(self) -> float:
         return self.stats()["psnr"]
 
+    def tile_row_load(self) -> torch.Tensor:
+        """Intersections per tile ROW of the last step, f64[tiles_y] on the host: the weights
+        `parallel.TileRowPartition(tiles_y, world, row_load=...)` balances the bands with when adaptive
+        densification has concentrated the Gaussians (load-balance caveat).  In a band-split run
+        every rank sees its own band only: all-reduce (SUM) the result before partitioning.  Synchronises."""
+        tx, ty = self.tile_bounds[0], self.tile_bounds[1]
+        cnt = (self.tile_bins[:, 1] - self.tile_bins[:, 0]).clamp(min=0).view(ty, tx)
+        return cnt.sum(dim=1).double().cpu()
+
     def ms_ssim(self) -> float:
         """MS-SSIM of the current render against the target: the second quality metric the reference reports
         (train.py:190), evaluated by the libgi2d kernels.  Synchronises."""

@@ -99,6 +99,39 @@ def allreduce_packed_gradients(v_xy, v_conic, v_colors, group=None):
     return packed[:, 0:2], packed[:, 2:5], packed[:, 5:8]
 
 
+def global_topk(values, k: int, group=None):
+    """Top-k over a tensor whose entries are spread over the ranks (densification of a band-split
+    image needs the k pixels of largest error of the WHOLE image): every rank contributes its local top-k
+    candidates (value, global index), one all-gather of 2k numbers per rank, re-selection everywhere.
+    `values`: (local_values f32[n], global_index i64[n]).  Returns (values[k'], global_index[k']) sorted by
+    descending value, identical on every rank (ties broken by the smaller global index); k' = min(k, total)."""
+    import torch
+    import torch.distributed as dist
+
+    vals, idx = values
+    kk = min(int(k), vals.numel())
+    top_v, pos = torch.topk(vals, kk) if kk else (vals[:0], idx[:0])
+    top_i = idx[pos] if kk else idx[:0]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        pad_v = torch.full((int(k),), float("-inf"), dtype=vals.dtype, device=vals.device)
+        pad_i = torch.full((int(k),), -1, dtype=torch.int64, device=vals.device)
+        pad_v[:kk], pad_i[:kk] = top_v, top_i
+        all_v = [torch.empty_like(pad_v) for _ in range(world)]
+        all_i = [torch.empty_like(pad_i) for _ in range(world)]
+        dist.all_gather(all_v, pad_v, group=group)
+        dist.all_gather(all_i, pad_i, group=group)
+        top_v, top_i = torch.cat(all_v), torch.cat(all_i)
+        keep = top_i >= 0
+        top_v, top_i = top_v[keep], top_i[keep]
+    # deterministic order: value descending, then index ascending
+    order = torch.argsort(top_i)
+    top_v, top_i = top_v[order], top_i[order]
+    order = torch.argsort(top_v, descending=True, stable=True)
+    kk = min(int(k), top_v.numel())
+    return top_v[order][:kk], top_i[order][:kk]
+
+
 class FusedTileRowExchange:
     """Tile-row split with the exchange step fused into ONE kernel over NVLink peer memory.
 

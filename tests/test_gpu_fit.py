@@ -403,3 +403,19 @@ def test_fit_step_with_nothing_on_screen_and_tiny_images():
             fit.train_iter()
         st2 = fit.stats()
         assert st2["num_intersects"] > 0 and np.isfinite(st2["psnr"]) and st2["mse"] < 0.75 ** 2
+
+
+def test_tile_row_load_drives_the_band_partition():
+    from gaussianimage_plus_b200.parallel import TileRowPartition
+
+    fit, _ = make_fitter(3000, 256, 384, seed=9, colors="zeros", use_graph=False, keep_render=False)
+    fit._xyz[:, 1] = fit._xyz[:, 1] * 0.5           # every Gaussian in the upper half of the image
+    fit.train_iter()
+    load = fit.tile_row_load()
+    assert load.shape == (16,) and float(load.sum()) == fit.stats()["num_intersects"]
+    assert float(load[:8].sum()) > 0.95 * float(load.sum())
+    even = TileRowPartition(16, 2)
+    part = TileRowPartition(16, 2, row_load=load.tolist())
+    assert even.band(0) == (0, 8) and part.band(0)[1] < 8      # the loaded half is split between the ranks
+    halves = [float(load[a:b].sum()) for a, b in (part.band(0), part.band(1))]
+    assert max(halves) / sum(halves) < 0.75

@@ -80,6 +80,15 @@ def _worker(rank, world, port, out_dir):
     other = [torch.zeros_like(mine_bytes) for _ in range(world)]
     dist.all_gather(other, mine_bytes)
     assert all(torch.equal(other[0], o) for o in other)
+    # --- global top-k of a per-pixel error map whose rows are spread over the ranks (band-split densification)
+    from gaussianimage_plus_b200.parallel import global_topk
+
+    full = torch.from_numpy(np.random.default_rng(5).random(H * W).astype(np.float32))
+    rows_lo, rows_hi = r0 * 16 * W, min(H, r1 * 16) * W
+    mine_idx = torch.arange(rows_lo, rows_hi, dtype=torch.int64)
+    v, i = global_topk((full[rows_lo:rows_hi], mine_idx), 37)
+    ref_v, ref_i = torch.topk(full, 37)
+    assert torch.equal(v, ref_v) and torch.equal(i, ref_i)
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 
