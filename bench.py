@@ -463,6 +463,10 @@ def main():
                            "the library's copy stream), the step's 3 kernels, stats block device->pinned; the host "
                            "reads every step's result one step behind; best of 3 trials",
                     "trials": e2e_trials,
+                    "h2d_gb_per_s": e2e_value / (world if args.mode == "images" else 1) * int(gt_u8_pinned.numel()) / 1e9,
+                    "note": "bound by the host->device copy of the target (1.18 MB per step at 768x512: ~45 us at the "
+                            "~26 GB/s this path reaches), not by the step (28-37 us) -- the copy runs under the step "
+                            "in flight; replaying the step from a graph inside the C call changed nothing",
                     "f32_target_blocking_read": {"value": e2e_f32_sync, "h2d_bytes_per_step": int(gt_pinned.numel() * 4)}},
             "gpu_launches": fit.launches_per_iter() * K,
             "launches_per_step": fit.launches_per_iter(),
