@@ -127,6 +127,9 @@ def run_reference(args):
     host thread OpenMP gives it.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is the CPU implementation "with all the host
+    # threads it can use": undo that before the OpenMP runtime of the oracle library initialises
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     from gaussianimage_plus_b200 import synth
 
     H, W, N = synth.CONFIGS[args.workload]
