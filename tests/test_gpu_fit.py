@@ -419,3 +419,23 @@ def test_tile_row_load_drives_the_band_partition():
     assert even.band(0) == (0, 8) and part.band(0)[1] < 8      # the loaded half is split between the ranks
     halves = [float(load[a:b].sum()) for a, b in (part.band(0), part.band(1))]
     assert max(halves) / sum(halves) < 0.75
+
+
+def test_fit_with_color_norm_matches_oracle(oracle):
+    """color_norm (colours = sigmoid(features), gaussianimage_covariance.py:74,160-162; the setting of the
+    compression pass): several fused steps against the oracle's train_iter with the same activation."""
+    N, H, W = 1200, 96, 144
+    fit, (xyz, cov, bound, rgb, gt) = make_fitter(N, H, W, seed=13, colors="rand", cov_scale=1.5, use_graph=True,
+                                                  color_norm=True)
+    ref = oracle.FitState(xyz, cov, bound, rgb, gt, color_sigmoid=True)
+    for it in range(6):
+        mse_ref, img_ref = ref.train_iter(want_image=True)
+        fit.train_iter()
+        st = fit.stats()
+        assert st["step"] == it + 1 and st["num_intersects"] == ref.num_intersects
+        assert abs(st["mse"] - mse_ref) <= 2e-4 * mse_ref, (it, st["mse"], mse_ref)
+    for a, b in ((fit._xyz, ref.xyz), (fit._cov2d, ref.cov), (fit._features_dc, ref.rgb)):
+        d = np.abs(N_(a) - b)
+        assert np.quantile(d, 0.99) < 2e-3, np.quantile(d, 0.99)
+    r = N_(fit.forward()["render"])
+    assert r.min() >= 0 and r.max() <= 1
