@@ -511,6 +511,35 @@ fit_place_kernel(gi2d_fit_params p, int with_backward, int gpb, int num_tiles,
     });
 }
 
+// ---- optional TMA staging of a tile's records (-DGI2D_TMA_STAGE; measured, not the default: DESIGN.md 2).
+// One elected thread arms an mbarrier with the byte count and issues ONE cp.async.bulk (SASS: UBLKCP) for the
+// tile's contiguous cnt x 32-B block; everybody waits on the barrier phase.
+#ifdef GI2D_TMA_STAGE
+__device__ __forceinline__ uint32_t smem_addr(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_addr(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+#endif
+
 // ------------------------------------------------------------------------------------ K4
 // Render      : forward, clamped CHW `render` tensor out
 // Fit         : forward + pointwise loss gradient (mse / l1) + backward, one launch
@@ -539,6 +568,12 @@ fit_raster_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_
     __shared__ int s_ids[kMaxPerTile];
     __shared__ int s_sort[kMaxPerTile];
     __shared__ float s_red[2][kRasterWarps];
+#ifdef GI2D_TMA_STAGE
+    __shared__ __align__(128) float4 s_raw[2 * kMaxPerTile];
+    __shared__ __align__(8) uint64_t s_mbar;
+    if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
+    __syncthreads();
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_y = p.tile_row_begin + blockIdx.y;
     const int tile_id = tile_y * p.tiles_x + blockIdx.x;
@@ -586,6 +621,22 @@ fit_raster_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_
     if (total_cnt <= kMaxPerTile) {
         uint64_t key = 0;
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+#ifdef GI2D_TMA_STAGE
+        if (tid == 0 && cnt > 0) {
+            mbar_expect_tx(&s_mbar, (uint32_t)cnt * 32u);
+            bulk_copy_g2s(s_raw, records + 2 * (size_t)range.x, (uint32_t)cnt * 32u, &s_mbar);
+        }
+        if (tid < cnt) {
+            key = __ldcg(sorted_keys + range.x + tid);
+            s_sort[tid] = (int)(uint32_t)key;
+        }
+        if (cnt > 0) mbar_wait(&s_mbar, 0);
+        __syncthreads();
+        if (tid < cnt) {
+            r0 = s_raw[2 * tid];
+            r1 = s_raw[2 * tid + 1];
+        }
+#else
         if (tid < cnt) {
             // one contiguous block of cnt x (8 + 32) B
             key = __ldcg(sorted_keys + range.x + tid);
@@ -594,6 +645,7 @@ fit_raster_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_
             s_sort[tid] = (int)(uint32_t)key;
         }
         __syncthreads();
+#endif
         if (tid < cnt) {
             const int id = (int)(uint32_t)key;
             int rank = 0;
