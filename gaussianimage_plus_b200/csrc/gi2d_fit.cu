@@ -28,6 +28,7 @@
 // The LSD radix sort of arbitrary 64-bit keys lives in gi2d_binning.cu (gi2d_sort_pairs_i64).
 #include "gi2d_project_core.cuh"
 #include "gi2d_raster_core.cuh"
+#include "gi2d_raster_quad.cuh"
 #include "gi2d_scan.cuh"
 
 namespace gi2d {
@@ -344,7 +345,7 @@ fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_
 // and the StepLR schedule.  torch evaluates beta^t and gamma^floor((t-1)/size) in double precision as
 // well.  The Adam that uses them runs inside the NEXT K1 (or gi2d_fit_adam).
 __device__ __forceinline__ void step_bookkeeping_warp0(const gi2d_fit_params &p, int with_backward,
-                                                       double *__restrict__ stats) {
+                                                       double *__restrict__ stats, bool overflow) {
     best_commit_warp0(stats);  // (the optimiser threads of K1 took the same decision for their snapshot)
     __syncwarp();
     if (with_backward) {       // (a render-only call accumulates no loss: the last step's numbers stay readable)
@@ -353,13 +354,17 @@ __device__ __forceinline__ void step_bookkeeping_warp0(const gi2d_fit_params &p,
     }
     __syncwarp();
     if (threadIdx.x == 0) {
-        stats[GI2D_STAT_OVERFLOW] = 0.0;
+        // A step whose intersection list does not fit the buffers is a NO-OP for the optimiser: its (truncated)
+        // gradient is never applied and neither the step counter, the bias-correction powers nor the StepLR
+        // schedule move, so the host can re-run exactly the iterations that did not happen (device step vs the
+        // number it asked for) after it has grown the buffers.  The flag is recomputed by every step.
+        stats[GI2D_STAT_OVERFLOW] = overflow ? 1.0 : 0.0;
         if (with_backward) {
             stats[GI2D_STAT_SSIM_SUM] = 0.0;
             stats[GI2D_STAT_ABS_SUM] = 0.0;
         }
-        stats[kStatPending] = (with_backward && !p.external_optimizer) ? 1.0 : 0.0;
-        if (with_backward) {
+        stats[kStatPending] = (with_backward && !p.external_optimizer && !overflow) ? 1.0 : 0.0;
+        if (with_backward && !overflow) {
             const double step = stats[GI2D_STAT_STEP] + 1.0;
             stats[GI2D_STAT_STEP] = step;
             stats[kStatB1Pow] *= (double)p.beta1;
@@ -486,10 +491,9 @@ fit_place_kernel(gi2d_fit_params p, int with_backward, int gpb, int num_tiles,
         }
     }
     if (blockIdx.x == 0 && warp == 0) {
-        step_bookkeeping_warp0(p, with_backward, stats);
+        step_bookkeeping_warp0(p, with_backward, stats, total > p.isect_capacity);
         if (lane == 0) {
             stats[GI2D_STAT_ISECTS] = (double)total;
-            if (total > p.isect_capacity) stats[GI2D_STAT_OVERFLOW] = 1.0;
             *n_isect = total > p.isect_capacity ? p.isect_capacity : total;
         }
     }
@@ -749,6 +753,254 @@ fit_raster_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_
         backward_tile<false, kRasterWarps, false>(sg, s_ids, cnt, lp, tg, grad_of, nullptr);
 }
 
+// ------------------------------------------------------------------------------------ K3, round 2
+// The same work as fit_raster_kernel, reorganised around what the hardware issues fastest (gi2d_raster_quad.cuh):
+// one CTA per tile of kWarps warps (1 or 2), every warp owning 4 / kWarps quadrants of 8x8 pixels with its lanes
+// holding pixel PAIRS as f32x2, so that the sweeps are packed FFMA2 / FMUL2 / FADD2; the loss gradient of a
+// lane's pixels stays in its registers between the forward and the backward sweep; one block barrier (after
+// the rank sort), none between the passes.  Results: tile ranges, sorted keys and the image are bit-identical
+// to fit_raster_kernel (same operations per pixel, same order); gradients agree to fp32 summation order.
+template <RasterMode kMode, int kWarps>
+__global__ void __launch_bounds__(32 * kWarps, kWarps == 1 ? 16 : 10)
+fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_t *__restrict__ keys_tmp,
+                   const int32_t *__restrict__ tile_bins, int32_t *__restrict__ tile_count,
+                   int32_t *__restrict__ tile_fill, const float4 *__restrict__ records,
+                   const float *__restrict__ gt, const uint8_t *__restrict__ gt_u8,
+                   float *__restrict__ out_img, float *__restrict__ grads, double *__restrict__ stats,
+                   float *__restrict__ err_map, const float *__restrict__ v_out) {
+    constexpr bool kHasFwd = kMode != RasterMode::FitBackward;
+    constexpr bool kHasLoss = kMode == RasterMode::Fit || kMode == RasterMode::FitForward;
+    constexpr bool kHasBwd = kMode == RasterMode::Fit || kMode == RasterMode::FitBackward;
+    constexpr int kNQ = kQuads / kWarps;   // quadrants per warp
+    constexpr int kThreads = 32 * kWarps;
+    __shared__ QuadRecords sg;
+    __shared__ int s_ids[kMaxPerTile];
+    __shared__ __align__(16) int s_sort[kMaxPerTile + 4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_y = p.tile_row_begin + blockIdx.y;
+    const int tile_id = tile_y * p.tiles_x + blockIdx.x;
+    pdl_launch_dependents();
+    const int qrow0 = kWarps == 2 ? warp : 0;   // first quadrant row of this warp
+    const int qshift = 2 * qrow0;
+    const int px0 = blockIdx.x * kTile + (lane & 7);
+    const int py0 = tile_y * kTile + 8 * qrow0 + (lane >> 3);
+    const QuadLane<kNQ> ln = quad_lane<kNQ>(blockIdx.x * kTile, tile_y * kTile, qrow0);
+    // pixel (quadrant qi, pair element e) of this lane: (px0 + 8*(qi&1), py0 + 8*(qi>>1) + 4*e)
+    const bool full_tile = (blockIdx.x + 1) * kTile <= p.img_width && (tile_y + 1) * kTile <= p.img_height;
+    unsigned outside = 0;
+    if (!full_tile) {
+#pragma unroll
+        for (int qi = 0; qi < kNQ; ++qi)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (px0 + 8 * (qi & 1) >= p.img_width || py0 + 8 * (qi >> 1) + 4 * e >= p.img_height)
+                    outside |= 1u << (2 * qi + e);
+    }
+    // the target pixels are written by no kernel of the step: pull their lines towards L2 while the predecessor
+    // drains and the list is staged (they are loaded after the forward sweep, so they cost no registers here)
+    if (kHasLoss) {
+        const int bpp = gt ? 12 : 3;
+        const char *base = gt ? (const char *)gt : (const char *)gt_u8;
+#pragma unroll
+        for (int qi = 0; qi < kNQ; ++qi)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (!((outside >> (2 * qi + e)) & 1u) && (lane & 7) == 0) {
+                    const size_t pix = (size_t)(py0 + 8 * (qi >> 1) + 4 * e) * p.img_width + px0 + 8 * (qi & 1);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + pix * bpp));
+                }
+    }
+    pdl_wait();
+    const double n_isect = __ldcg(stats + GI2D_STAT_ISECTS);
+    const int2 range = __ldcg(reinterpret_cast<const int2 *>(tile_bins) + tile_id);
+    const int total_cnt = max(0, min(range.y, p.isect_capacity) - range.x);
+    const int cnt = min(kMaxPerTile, total_cnt);
+    if (kHasFwd && tid == 0) {   // the counters of this tile go back to K1 / K2 of the next step zeroed
+        GI2D_CHECK(stats, range.x >= 0 && range.y >= range.x && tile_fill[tile_id] == tile_count[tile_id] &&
+                              (range.y - range.x == tile_count[tile_id] || n_isect > (double)p.isect_capacity));
+        tile_count[tile_id] = 0;
+        tile_fill[tile_id] = 0;
+    }
+    // ---- finish the key sort (see fit_raster_kernel): rank by gaussian id, stage at the rank
+    constexpr bool kWriteBack = kMode != RasterMode::FitForward;
+    const float tx0 = (float)(blockIdx.x * kTile), ty0 = (float)(tile_y * kTile);
+    if (total_cnt <= kMaxPerTile) {
+        uint64_t key0 = 0;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), b0 = a0;
+        if (tid < cnt) {   // first trip: key and record stay in registers (one round trip)
+            key0 = __ldcg(sorted_keys + range.x + tid);
+            a0 = __ldcg(records + 2 * (size_t)(range.x + tid));
+            b0 = __ldcg(records + 2 * (size_t)(range.x + tid) + 1);
+            s_sort[tid] = (int)(uint32_t)key0;
+        }
+        for (int e = tid + kThreads; e < cnt; e += kThreads) s_sort[e] = (int)(uint32_t)__ldcg(sorted_keys + range.x + e);
+        if (tid < 4) s_sort[cnt + tid] = 0x7fffffff;   // pads the vectorised rank loop
+        __syncthreads();
+        for (int e = tid; e < cnt; e += kThreads) {
+            float4 r0 = a0, r1 = b0;
+            if (e != tid) {
+                r0 = __ldcg(records + 2 * (size_t)(range.x + e));
+                r1 = __ldcg(records + 2 * (size_t)(range.x + e) + 1);
+            }
+            const int id = s_sort[e];
+            int rank = 0;
+            for (int jj = 0; jj < cnt; jj += 4) {
+                const int4 o = *reinterpret_cast<const int4 *>(s_sort + jj);
+                rank += (o.x < id) + (o.y < id) + (o.z < id) + (o.w < id);
+            }
+            GI2D_CHECK(stats, rank >= 0 && rank < cnt && id >= 0 && id < p.num_points);
+            stage_quad(sg, rank, r0, r1, tx0, ty0);
+            if (kHasBwd) s_ids[rank] = id;
+            // (keys are rebuilt from the tile id: nobody re-reads sorted_keys of this tile after the barrier)
+            if (kWriteBack && rank != e) sorted_keys[range.x + rank] = ((uint64_t)(uint32_t)tile_id << 32) | (uint32_t)id;
+        }
+    } else {
+        // more than 256 entries (a degenerate scene): full rank sort straight from global memory
+        for (int e = tid; e < total_cnt; e += kThreads) {
+            const uint64_t key = __ldcg(sorted_keys + range.x + e);
+            const int id = (int)(uint32_t)key;
+            int rank = 0;
+            for (int jj = 0; jj < total_cnt; ++jj) rank += ((int)(uint32_t)__ldcg(sorted_keys + range.x + jj) < id) ? 1 : 0;
+            GI2D_CHECK(stats, rank >= 0 && rank < total_cnt && (int)(key >> 32) == tile_id);
+            keys_tmp[range.x + rank] = key;
+            if (rank < kMaxPerTile) {
+                stage_quad(sg, rank, __ldcg(records + 2 * (size_t)(range.x + e)),
+                           __ldcg(records + 2 * (size_t)(range.x + e) + 1), tx0, ty0);
+                if (kHasBwd) s_ids[rank] = id;
+            }
+        }
+        if (kWriteBack) {
+            __syncthreads();
+            for (int e = tid; e < total_cnt; e += kThreads) sorted_keys[range.x + e] = __ldcg(keys_tmp + range.x + e);
+        }
+    }
+    __syncthreads();
+    // ---- forward: lane = pixel pairs of the warp's quadrants
+    f32x2 accR[kNQ], accG[kNQ], accB[kNQ];
+#pragma unroll
+    for (int qi = 0; qi < kNQ; ++qi) accR[qi] = accG[qi] = accB[qi] = 0ull;
+    if (kHasFwd) quad_forward<kNQ, false>(sg, cnt, ln, qshift, 0u, accR, accG, accB);
+    // no intersection in the whole image: the reference returns ones * background (== 1) and no gradient
+    // (rasterize_sum_plus.py:110-118); a band of a tile-row split cannot know, and renders its (empty) sum
+    const bool ones = n_isect == 0.0 && p.tile_row_begin == 0 && p.tile_row_end == p.tiles_y;
+    f32x2 vR[kNQ], vG[kNQ], vB[kNQ];
+    float se = 0.f, ae = 0.f;
+#pragma unroll
+    for (int qi = 0; qi < kNQ; ++qi) {
+        float cr[2], cg[2], cb[2], wr[2], wg[2], wb[2];
+        unpk2(accR[qi], cr[0], cr[1]);
+        unpk2(accG[qi], cg[0], cg[1]);
+        unpk2(accB[qi], cb[0], cb[1]);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const bool inside = !((outside >> (2 * qi + e)) & 1u);
+            const size_t pix = (size_t)(py0 + 8 * (qi >> 1) + 4 * e) * p.img_width + px0 + 8 * (qi & 1);
+            float r = cr[e], g = cg[e], b = cb[e];
+            if (ones) r = g = b = 1.f;
+            wr[e] = wg[e] = wb[e] = 0.f;
+            if (kMode == RasterMode::Render) {
+                // the model's `render`: clamp to [0,1], CHW planar (gaussianimage_covariance.py:210-211)
+                if (inside && out_img) {
+                    const size_t plane = (size_t)p.img_width * p.img_height;
+                    out_img[pix] = fminf(fmaxf(r, 0.f), 1.f);
+                    out_img[plane + pix] = fminf(fmaxf(g, 0.f), 1.f);
+                    out_img[2 * plane + pix] = fminf(fmaxf(b, 0.f), 1.f);
+                }
+            } else if (kHasLoss) {
+                // pointwise loss (mse and/or l1, models/utils.py:64-67,74-75): d/d out = loss_scale * d +
+                // loss_l1_scale * sign(d), d = clamp(out) - gt, where 0 <= out <= 1 (torch.clamp backward mask)
+                if (inside) {
+                    float tr, tg, tb;
+                    if (gt) {
+                        tr = __ldg(gt + 3 * pix); tg = __ldg(gt + 3 * pix + 1); tb = __ldg(gt + 3 * pix + 2);
+                    } else {   // 8-bit target: the value torchvision's ToTensor produces, u8 / 255
+                        tr = u8_to_unit(__ldg(gt_u8 + 3 * pix));
+                        tg = u8_to_unit(__ldg(gt_u8 + 3 * pix + 1));
+                        tb = u8_to_unit(__ldg(gt_u8 + 3 * pix + 2));
+                    }
+                    const float dr = fminf(fmaxf(r, 0.f), 1.f) - tr;
+                    const float dg = fminf(fmaxf(g, 0.f), 1.f) - tg;
+                    const float db = fminf(fmaxf(b, 0.f), 1.f) - tb;
+                    se += dr * dr + dg * dg + db * db;
+                    const float l1 = p.loss_l1_scale;
+                    if (l1 != 0.f) {
+                        ae += fabsf(dr) + fabsf(dg) + fabsf(db);
+                        wr[e] = (r >= 0.f && r <= 1.f) ? fmaf(l1, (float)((dr > 0.f) - (dr < 0.f)), p.loss_scale * dr) : 0.f;
+                        wg[e] = (g >= 0.f && g <= 1.f) ? fmaf(l1, (float)((dg > 0.f) - (dg < 0.f)), p.loss_scale * dg) : 0.f;
+                        wb[e] = (b >= 0.f && b <= 1.f) ? fmaf(l1, (float)((db > 0.f) - (db < 0.f)), p.loss_scale * db) : 0.f;
+                    } else {
+                        wr[e] = (r >= 0.f && r <= 1.f) ? p.loss_scale * dr : 0.f;
+                        wg[e] = (g >= 0.f && g <= 1.f) ? p.loss_scale * dg : 0.f;
+                        wb[e] = (b >= 0.f && b <= 1.f) ? p.loss_scale * db : 0.f;
+                    }
+                    if (out_img) {
+                        out_img[3 * pix] = r;
+                        out_img[3 * pix + 1] = g;
+                        out_img[3 * pix + 2] = b;
+                    }
+                    // torch.abs(render - gt).sum(dim=1) of train.py:87, channel order r,g,b
+                    if (err_map) err_map[pix] = __fadd_rn(__fadd_rn(fabsf(dr), fabsf(dg)), fabsf(db));
+                }
+            } else {   // FitBackward: dL/d(out) computed by the loss kernels between the two halves
+                if (inside && n_isect != 0.0) {
+                    wr[e] = __ldcg(v_out + 3 * pix);
+                    wg[e] = __ldcg(v_out + 3 * pix + 1);
+                    wb[e] = __ldcg(v_out + 3 * pix + 2);
+                }
+            }
+        }
+        vR[qi] = pk2(wr[0], wr[1]);
+        vG[qi] = pk2(wg[0], wg[1]);
+        vB[qi] = pk2(wb[0], wb[1]);
+    }
+    if (kMode == RasterMode::Render) return;
+    if (kHasLoss) {
+        se = warp_sum(se);
+        if (p.loss_l1_scale != 0.f) ae = warp_sum(ae);
+        if (lane == 0) {
+            atomicAdd(stats + GI2D_STAT_SSE + ((tile_id * kWarps + warp) & (GI2D_STAT_SSE_SLOTS - 1)), (double)se);
+            if (p.loss_l1_scale != 0.f) atomicAdd(stats + GI2D_STAT_ABS_SUM, (double)ae);
+        }
+    }
+    if (!kHasBwd || cnt == 0) return;
+    // ---- backward: the same walk, dL/d(out) in registers
+    if (full_tile)
+        quad_backward<kNQ, false>(sg, s_ids, cnt, ln, qshift, 0u, vR, vG, vB, grads);
+    else
+        quad_backward<kNQ, true>(sg, s_ids, cnt, ln, qshift, outside, vR, vG, vB, grads);
+}
+
+// which rasterizer a step launches: GI2D_RASTER=0 the round-1 kernel (8 warps per tile), 1 / 2 the quadrant
+// kernel with one / two warps per tile (default 2)
+int raster_variant() {
+    static const int v = [] {
+        const char *e = getenv("GI2D_RASTER");
+        return e ? atoi(e) : 2;
+    }();
+    return v;
+}
+
+template <RasterMode kMode>
+cudaError_t launch_raster(bool pdl, dim3 grid, cudaStream_t st, const gi2d_fit_params &p, uint64_t *sorted_keys,
+                          uint64_t *keys_tmp, const int32_t *tile_bins, int32_t *tile_count, int32_t *tile_fill,
+                          const float4 *records, const float *gt, const uint8_t *gt_u8, float *out_img, float *grads,
+                          double *stats, float *err_map, const float *v_out) {
+    const int v = raster_variant();
+#define GI2D_RASTER_ARGS p, sorted_keys, keys_tmp, tile_bins, tile_count, tile_fill, records, gt, gt_u8, out_img, grads, stats, err_map, v_out
+    if (v == 1) {
+        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 1>, grid, dim3(32), 0, st, GI2D_RASTER_ARGS);
+        fit_rasterq_kernel<kMode, 1><<<grid, 32, 0, st>>>(GI2D_RASTER_ARGS);
+    } else if (v == 2) {
+        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 2>, grid, dim3(64), 0, st, GI2D_RASTER_ARGS);
+        fit_rasterq_kernel<kMode, 2><<<grid, 64, 0, st>>>(GI2D_RASTER_ARGS);
+    } else {
+        if (pdl) return launch_pdl(fit_raster_kernel<kMode>, grid, dim3(kRasterThreads), 0, st, GI2D_RASTER_ARGS);
+        fit_raster_kernel<kMode><<<grid, kRasterThreads, 0, st>>>(GI2D_RASTER_ARGS);
+    }
+#undef GI2D_RASTER_ARGS
+    return cudaSuccess;
+}
+
 // ------------------------------------------------------------------------------------ K5
 // Stand-alone optimiser launch: applies a pending gradient NOW (before the host reads or edits the
 // parameters, renders, or all the steps are done).  In the steady state it is never launched: the
@@ -857,11 +1109,15 @@ fit_exchange_adam_kernel(gi2d_fit_params p, AdamPtrs local, PeerPtrs peers, int 
 // d loss / d (the step's inputs) for callers with their own optimiser: projection backward only
 __global__ void __launch_bounds__(256)
 fit_input_grads_kernel(int n, const float4 *__restrict__ proj, const float4 *__restrict__ grads,
-                       float4 *__restrict__ out) {
+                       float4 *__restrict__ out, const double *__restrict__ stats) {
     pdl_launch_dependents();
     pdl_wait();
     const int g = blockIdx.x * 256 + threadIdx.x;
     if (g >= n) return;
+    if (__ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0) {   // truncated list: the caller's optimiser step becomes a no-op
+        out[2 * g] = out[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     const float4 p0 = __ldcg(proj + 2 * g), p1 = __ldcg(proj + 2 * g + 1);
     const float4 g0 = __ldcg(grads + 2 * g), g1 = __ldcg(grads + 2 * g + 1);
     float gc[3];
@@ -952,40 +1208,55 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
         if (with_backward && p->loss_ssim_weight != 0.f) {
             // SSIM couples pixels across tile borders: forward everywhere, then the loss gradient image, then
             // the backward half.  (Band-split multi-GPU runs would need a halo exchange of the render.)
-            fit_raster_kernel<RasterMode::FitForward><<<grid, kRasterThreads, 0, st>>>(
-                *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count, w.tile_fill, w.records, b->gt_hwc,
-                b->gt_u8_hwc, w.loss_render, nullptr, b->stats, b->err_map, nullptr);
+            launch_raster<RasterMode::FitForward>(false, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins,
+                w.tile_count, w.tile_fill, (const float4 *)w.records, b->gt_hwc, b->gt_u8_hwc, w.loss_render, nullptr,
+                b->stats, b->err_map, nullptr);
             if (b->out_img)
                 cudaMemcpyAsync(b->out_img, w.loss_render, (size_t)p->img_width * p->img_height * 12,
                                 cudaMemcpyDeviceToDevice, st);
             ssim_grad_launch(p->img_height, p->img_width, w.loss_render, b->gt_hwc, b->gt_u8_hwc, w.loss_dm,
                              p->loss_ssim_weight, p->loss_scale, p->loss_l1_scale, w.loss_vout,
                              b->stats + GI2D_STAT_SSIM_SUM, st);
-            fit_raster_kernel<RasterMode::FitBackward><<<grid, kRasterThreads, 0, st>>>(
-                *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count, w.tile_fill, w.records, nullptr, nullptr,
-                nullptr, b->grads, b->stats, nullptr, w.loss_vout);
+            launch_raster<RasterMode::FitBackward>(false, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins,
+                w.tile_count, w.tile_fill, (const float4 *)w.records, nullptr, nullptr, nullptr, b->grads, b->stats,
+                nullptr, w.loss_vout);
         } else if (with_backward)
-            launch_pdl(fit_raster_kernel<RasterMode::Fit>, grid, dim3(kRasterThreads), 0, st,
-                *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count, w.tile_fill, (const float4 *)w.records,
-                b->gt_hwc, b->gt_u8_hwc, b->out_img, b->grads, b->stats, b->err_map, (const float *)nullptr);
+            launch_raster<RasterMode::Fit>(true, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count,
+                w.tile_fill, (const float4 *)w.records, b->gt_hwc, b->gt_u8_hwc, b->out_img, b->grads, b->stats,
+                b->err_map, nullptr);
         else
-            launch_pdl(fit_raster_kernel<RasterMode::Render>, grid, dim3(kRasterThreads), 0, st,
-                *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count, w.tile_fill, (const float4 *)w.records,
-                (const float *)nullptr, (const uint8_t *)nullptr, b->out_img, (float *)nullptr, b->stats,
-                (float *)nullptr, (const float *)nullptr);
+            launch_raster<RasterMode::Render>(true, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins,
+                w.tile_count, w.tile_fill, (const float4 *)w.records, nullptr, nullptr, b->out_img, nullptr, b->stats,
+                nullptr, nullptr);
     }
     if (mk) mk->mark(st);
     return check_launch("gi2d_fit_forward_backward");
 }
 
-__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters) {
-    float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    const float m = 1.0000001f, c = 1e-7f;
-    for (int i = 0; i < iters; ++i) {
-        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
-        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+// FP32 peak microbenchmark: 16 independent chains of packed FMAs (fma.rn.f32x2 -> SASS FFMA2), 512 per loop trip,
+// so that loop overhead is < 1 % of the issue slots.  tools/ubench/fp32_issue.cu measured on the B200: FFMA2 74.1
+// TFLOP/s = 0.995 of nominal (148 SMs x 128 lanes x 2 x 1.965 GHz = 74.45); scalar FFMA 71.3 (0.958, register-bank
+// limited).  (The round-1 kernel -- 8 scalar chains, 8 FFMAs per trip -- read 64.1 and inflated every fraction.)
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, float m, float c) {
+    constexpr int kChains = 16;
+    f32x2 a[kChains];
+    const f32x2 mm = pk2(m, m), cc = pk2(c, c);
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) a[i] = pk2((float)(threadIdx.x + i), (float)(threadIdx.x - i));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u)
+#pragma unroll
+            for (int i = 0; i < kChains; ++i) a[i] = fma2(a[i], mm, cc);
     }
-    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678f) out[0] = a0;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) {
+        float x, y;
+        unpk2(a[i], x, y);
+        s += x + y;
+    }
+    if (s == 12345.678f) out[0] = s;
 }
 
 }  // namespace
@@ -1079,9 +1350,9 @@ extern "C" int gi2d_fit_profile_raster(const gi2d_fit_params *p, const gi2d_fit_
     cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
     for (int i = 0; i < reps; ++i)
-        launch_pdl(fit_raster_kernel<RasterMode::Fit>, grid, dim3(kRasterThreads), 0, st,
-            *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count, w.tile_fill, (const float4 *)w.records,
-            b->gt_hwc, b->gt_u8_hwc, (float *)nullptr, b->grads, b->stats, (float *)nullptr, (const float *)nullptr);
+        launch_raster<RasterMode::Fit>(true, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count,
+            w.tile_fill, (const float4 *)w.records, b->gt_hwc, b->gt_u8_hwc, nullptr, b->grads, b->stats, nullptr,
+            nullptr);
     cudaEventRecord(e1, st);
     // nothing pending (the accumulated gradient is garbage), loss accumulators back to zero
     cudaMemsetAsync(b->stats + kStatPending, 0, sizeof(double), st);
@@ -1107,19 +1378,20 @@ extern "C" int gi2d_measure_fp32_peak(float *tflops_host, gi2d_stream_t stream) 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int iters = 1 << 14, grid = sms * 8;
+    const int iters = 1 << 10, grid = sms * 8;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     float best = 0.f;
-    for (int rep = 0; rep < 5; ++rep) {
+    for (int rep = 0; rep < 6; ++rep) {
         cudaEventRecord(e0, st);
-        fma_peak_kernel<<<grid, 256, 0, st>>>(d, iters);
+        fma_peak_kernel<<<grid, 256, 0, st>>>(d, iters, 1.0000001f, 1e-7f);
         cudaEventRecord(e1, st);
         cudaEventSynchronize(e1);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        const float tf = (float)((double)grid * 256.0 * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12);
+        // 512 packed FMAs per trip and thread = 2048 FLOP
+        const float tf = (float)((double)grid * 256.0 * iters * 512.0 * 4.0 / (ms * 1e-3) / 1e12);
         if (rep > 0 && tf > best) best = tf;
     }
     cudaEventDestroy(e0);
@@ -1136,7 +1408,8 @@ extern "C" int gi2d_fit_input_grads(const gi2d_fit_params *p, const gi2d_fit_buf
     GI2D_REQUIRE(b->grads && out, "null buffer");
     if (p->num_points == 0) return GI2D_OK;
     launch_pdl(fit_input_grads_kernel, dim3(cdiv(p->num_points, 256)), dim3(256), 0, (cudaStream_t)stream,
-               p->num_points, (const float4 *)b->proj, (const float4 *)b->grads, (float4 *)out);
+               p->num_points, (const float4 *)b->proj, (const float4 *)b->grads, (float4 *)out,
+               (const double *)b->stats);
     return check_launch(__func__);
 }
 

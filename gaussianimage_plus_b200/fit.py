@@ -116,6 +116,7 @@ class GaussianImageFitter:
         self.cholesky_bound = torch.tensor([lp, 0, lp], **f).view(1, 3).repeat(num_points, 1).contiguous()
         self.gt_hwc = None
         self._step0 = 0
+        self._expected_step = 0
         self._alloc_state(zero_moments=True)
 
     # ------------------------------------------------------------------ buffers
@@ -185,6 +186,7 @@ class GaussianImageFitter:
             _lib.check(self.lib.gi2d_fit_reset(C.byref(self.params), C.byref(self.buffers), int(step),
                                                _stream(self.device)), "fit_reset")
         self._dirty = False
+        self._expected_step = int(step)   # training steps requested so far (the device counts the ones that happened)
 
     def sync_params(self, force: bool = False):
         """Apply a pending optimiser step now (asynchronous; no-op when nothing is pending).  `force`
@@ -265,6 +267,7 @@ class GaussianImageFitter:
         if rc != 0:
             _lib.check(rc, "fit_step_host")
         self._dirty = True
+        self._expected_step += 1
         return self._slot.value
 
     def _setup_host_pipe(self, host_img, host_stats):
@@ -328,6 +331,7 @@ class GaussianImageFitter:
         if self.gt_hwc is None:
             raise RuntimeError("set_target() first")
         self._dirty = not self.external_optimizer
+        self._expected_step += 1
         with torch.cuda.device(self.device):
             self._train_iter_enqueue(want_error_map)
             if getattr(self, "_gt_alt", None) is not None:   # double-buffered targets: this buffer is free after the step
@@ -389,6 +393,7 @@ class GaussianImageFitter:
                     self._multi_graphs[key] = g
                 for _ in range(n // unroll):
                     g.replay()
+            self._expected_step += (n // unroll) * unroll
             self._dirty = not self.external_optimizer
             n %= unroll
         for _ in range(n):
@@ -474,17 +479,36 @@ class GaussianImageFitter:
         return _sse_total(host_slot) / (3.0 * H * W)
 
     def ensure_capacity(self, st: Optional[dict] = None) -> bool:
-        """Host check of the overflow flag; grows the intersection buffers when it tripped.
-        Returns True when a regrow happened (the overflowing step's gradient is dropped, not applied).
+        """Host check of the overflow flag; grows the intersection buffers when it tripped.  Returns True when a
+        regrow happened.  A step that overflows is a no-op on the device (no Adam update, step counter / bias
+        correction / StepLR untouched: gi2d_fit.cu step_bookkeeping_warp0), so nothing has to be rewound; the
+        iterations that did not happen are re-run by `catch_up()`.
         `st`: a stats() result the caller already has (saves the read-back)."""
         st = st if st is not None else self.stats()
         if not st["overflow"]:
             return False
+        expected = self._expected_step
         self._capacity_hint = int(st["num_intersects"] * 2)
-        self._step0 = st["step"] - 1  # the overflowing step did not update the parameters
+        self._step0 = st["step"]
         self._alloc_state(zero_moments=False)
         self._reset_keep_best(self._step0, st)
+        self._expected_step = expected
         return True
+
+    def catch_up(self, st: Optional[dict] = None) -> dict:
+        """Re-run the training iterations that were requested but did not happen because the intersection
+        buffers overflowed (each was a no-op on the device): grow the buffers, run `requested - done` more steps,
+        until the device step counter has caught up.  Synchronises (one stats read-back per round); `fit()` calls
+        it at every host checkpoint, direct users of train_iter()/train_iters() call it before they read results."""
+        st = st if st is not None else self.stats()
+        while st["step"] < self._expected_step:
+            lost = self._expected_step - st["step"]
+            if not self.ensure_capacity(st):
+                raise _lib.Gi2dError(f"{lost} training steps are missing but no overflow is flagged")
+            self._expected_step -= lost
+            self.train_iters(lost)
+            st = self.stats()
+        return st
 
     def _reset_keep_best(self, step: int, st: dict):
         """reset_stats() that carries the best-so-far squared error / step over (the snapshot stays valid)."""
@@ -553,8 +577,12 @@ class GaussianImageFitter:
         self.sync_params(force=True)
         st = self.stats()
         # the same read-back tells whether the intersection buffers overflowed since the last look (the steps since
-        # then were vetoed on the device): grow them here, so that a long fit() never stalls silently
-        self.ensure_capacity(st)
+        # then were no-ops on the device): grow them and re-run those iterations, so that a long fit() neither stalls
+        # nor loses iterations
+        if st["step"] < self._expected_step:
+            self.catch_up(st)
+            self.sync_params(force=True)
+            st = self.stats()
         if st["non_psd"] == 0:
             return 0, self.cur_num_points
         n_bad, valid = self.check_non_semi_definite()
@@ -666,8 +694,7 @@ class GaussianImageFitter:
                     self.non_semi_definite_prune()
                 if grow:
                     self.add_sample_positions(max_num_points, last=(it == iterations - grow_iter), errors=self.err_map)
-            self.sync_params()
-            return self.stats()
+            return self._finish_fit()
         for it in range(1, iterations + 1):
             grow = adaptive_add and it % grow_iter == 0 and it < iterations
             self.train_iter(want_error_map=grow)
@@ -677,5 +704,13 @@ class GaussianImageFitter:
                 self.add_sample_positions(max_num_points, last=(it == iterations - grow_iter), errors=self.err_map)
             if callback is not None:
                 callback(it, self)
+        return self._finish_fit()
+
+    def _finish_fit(self) -> dict:
         self.sync_params()
-        return self.stats()
+        st = self.stats()
+        if st["step"] < self._expected_step:   # iterations lost to an intersection-buffer overflow: re-run them
+            self.catch_up(st)
+            self.sync_params()
+            st = self.stats()
+        return st

@@ -153,6 +153,37 @@ def test_fit_loop_grows_the_intersection_buffers_by_itself():
     assert st["psnr"] > 15 and st["num_intersects"] > 6000
 
 
+def test_overflow_steps_are_noops_and_are_rerun():
+    """Several iterations pass between an overflow and the host's next look at the flag: every one of
+    them must be a no-op on the device -- parameters, step counter, Adam bias correction and StepLR untouched --
+    and `catch_up()` / `fit()` must re-run exactly those iterations after growing the buffers."""
+    a, _ = make_fitter(3000, 256, 384, seed=3, colors="zeros", use_graph=True, keep_render=False, isect_capacity=6000)
+    b, _ = make_fitter(3000, 256, 384, seed=3, colors="zeros", use_graph=True, keep_render=False)
+    x0 = a._xyz.clone()
+    a.train_iters(12)
+    st = a.stats()
+    assert st["overflow"] and st["step"] == 0 and st["lr"] == b.stats()["lr"]
+    assert torch.equal(x0, a._xyz)
+    st = a.catch_up()
+    assert st["step"] == 12 and not st["overflow"] and a.isect_capacity > 6000
+    b.train_iters(12)
+    sb = b.stats()
+    assert sb["step"] == 12 and st["num_intersects"] == sb["num_intersects"]
+    assert abs(st["mse"] - sb["mse"]) <= 1e-4 * sb["mse"]
+    assert torch.allclose(a._xyz, b._xyz, atol=5e-3)
+    # an overflow that appears in the middle of a run (the Gaussians grow): fit() without prune checkpoints only
+    # looks at the end, and must still deliver every iteration
+    i0 = sb["num_intersects"]
+    sb = b.fit(288, prune=False, adaptive_add=False)
+    assert sb["step"] == 300
+    if sb["num_intersects"] > i0 + 16:
+        c, _ = make_fitter(3000, 256, 384, seed=3, colors="zeros", use_graph=True, keep_render=False,
+                           isect_capacity=(i0 + sb["num_intersects"]) // 2)
+        sc = c.fit(300, prune=False, adaptive_add=False)
+        assert sc["step"] == 300 and not sc["overflow"] and sc["lr"] == sb["lr"]
+        assert abs(sc["psnr"] - sb["psnr"]) < 0.1, (sc["psnr"], sb["psnr"])
+
+
 def test_prune_and_densify_keep_state_consistent():
     fit, _ = make_fitter(2000, 256, 384, seed=6, colors="zeros", use_graph=True)
     for _ in range(20):
