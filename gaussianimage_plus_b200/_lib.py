@@ -47,6 +47,19 @@ class FitBuffers(C.Structure):
     ]
 
 
+MAX_RANKS = 8
+
+
+class TileRow(C.Structure):
+    """struct gi2d_tilerow (include/gi2d.h)"""
+    _fields_ = [
+        ("rank", C.c_int32), ("world", C.c_int32), ("band_edge", C.c_int32 * (MAX_RANKS + 1)),
+        ("own_begin", C.c_int32), ("own_end", C.c_int32), ("sync", C.c_int32),
+        ("peer_grads", _P * MAX_RANKS), ("peer_proj", _P * MAX_RANKS), ("peer_boxes", _P * MAX_RANKS),
+        ("peer_flags", _P * MAX_RANKS), ("ctrl", _P),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/gi2d.h declares
 SIGNATURES = {
     "gi2d_abi_version": (_I, []),
@@ -74,8 +87,8 @@ SIGNATURES = {
     "gi2d_fit_profile_raster": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, C.POINTER(C.c_float), _P]),
     "gi2d_measure_fp32_peak": (_I, [C.POINTER(C.c_float), _P]),
     "gi2d_fit_input_grads": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _P, _P]),
-    "gi2d_fit_exchange_adam": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _I, C.POINTER(_P),
-                                   C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P]),
+    "gi2d_tilerow_init": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), C.POINTER(TileRow), _P]),
+    "gi2d_tilerow_step": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), C.POINTER(TileRow), _I, _I, _P]),
     "gi2d_ssim_workspace_size": (_SZ, [_I, _I]),
     "gi2d_image_loss_grad": (_I, [_I, _I, _P, _P, _P, _F, _F, _F, _P, _P, _P, _SZ, _P]),
     "gi2d_ms_ssim_workspace_size": (_SZ, [_I, _I]),

@@ -203,10 +203,16 @@ __device__ __forceinline__ void adam_load(const AdamPtrs &a, int g, const float4
     }
 }
 
+__device__ __forceinline__ void adam_apply_scalars(const gi2d_fit_params &p, const AdamPtrs &a, int g, AdamRegs &r,
+                                                   float step_size, float bc2_sqrt);
+
 __device__ __forceinline__ void adam_apply(const gi2d_fit_params &p, const AdamPtrs &a, int g, AdamRegs &r,
                                            const double *__restrict__ stats) {
-    const float step_size = (float)__ldcg(stats + kStatStepSize);
-    const float bc2_sqrt = (float)__ldcg(stats + kStatBc2Sqrt);
+    adam_apply_scalars(p, a, g, r, (float)__ldcg(stats + kStatStepSize), (float)__ldcg(stats + kStatBc2Sqrt));
+}
+
+__device__ __forceinline__ void adam_apply_scalars(const gi2d_fit_params &p, const AdamPtrs &a, int g, AdamRegs &r,
+                                                   float step_size, float bc2_sqrt) {
     const float w1 = (float)(1.0 - (double)p.beta1), w2 = (float)(1.0 - (double)p.beta2);
     float gc[3];
     conic_vjp(r.p0.z, r.p0.w, r.p1.x, r.g0.z, r.g0.w, r.g1.x, gc[0], gc[1], gc[2]);
@@ -364,7 +370,7 @@ __device__ __forceinline__ void step_bookkeeping_warp0(const gi2d_fit_params &p,
             stats[GI2D_STAT_ABS_SUM] = 0.0;
         }
         stats[kStatPending] = (with_backward && !p.external_optimizer && !overflow) ? 1.0 : 0.0;
-        if (with_backward && !overflow) {
+        if (with_backward && !overflow && p.external_optimizer != 2) {
             const double step = stats[GI2D_STAT_STEP] + 1.0;
             stats[GI2D_STAT_STEP] = step;
             stats[kStatB1Pow] *= (double)p.beta1;
@@ -755,13 +761,16 @@ fit_raster_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_
 
 // ------------------------------------------------------------------------------------ K3, round 2
 // The same work as fit_raster_kernel, reorganised around what the hardware issues fastest (gi2d_raster_quad.cuh):
-// one CTA per tile of kWarps warps (1 or 2), every warp owning 4 / kWarps quadrants of 8x8 pixels with its lanes
-// holding pixel PAIRS as f32x2, so that the sweeps are packed FFMA2 / FMUL2 / FADD2; the loss gradient of a
-// lane's pixels stays in its registers between the forward and the backward sweep; one block barrier (after
-// the rank sort), none between the passes.  Results: tile ranges, sorted keys and the image are bit-identical
-// to fit_raster_kernel (same operations per pixel, same order); gradients agree to fp32 summation order.
+// one CTA per tile of kWarps warps (1, 2 or 4), every warp owning 4 / kWarps quadrants of 8x8 pixels with its
+// lanes holding pixel PAIRS as f32x2, so that the sweeps are packed FFMA2 / FMUL2 / FADD2; the backward works on
+// four Gaussians per warp at a time (8 lanes each) over pixel rows.  With 1 or 2 warps per tile a warp keeps its
+// own region from the forward to the backward sweep (dL/d(out) changes layout through a per-warp shared-memory
+// copy, one __syncwarp); with 4 warps per tile the backward region is the whole tile and the groups of four
+// Gaussians are dealt to the warps (one more block barrier, twice the warps to hide latency with).
+// Results: tile ranges, sorted keys and the image are bit-identical to fit_raster_kernel (same operations per
+// pixel, same order); gradients agree to fp32 summation order.
 template <RasterMode kMode, int kWarps>
-__global__ void __launch_bounds__(32 * kWarps, kWarps == 1 ? 16 : 10)
+__global__ void __launch_bounds__(32 * kWarps, kWarps == 1 ? 16 : (kWarps == 2 ? 10 : 8))
 fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_t *__restrict__ keys_tmp,
                    const int32_t *__restrict__ tile_bins, int32_t *__restrict__ tile_count,
                    int32_t *__restrict__ tile_fill, const float4 *__restrict__ records,
@@ -771,21 +780,30 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     constexpr bool kHasFwd = kMode != RasterMode::FitBackward;
     constexpr bool kHasLoss = kMode == RasterMode::Fit || kMode == RasterMode::FitForward;
     constexpr bool kHasBwd = kMode == RasterMode::Fit || kMode == RasterMode::FitBackward;
-    constexpr int kNQ = kQuads / kWarps;   // quadrants per warp
+    constexpr int kNQ = kQuads / kWarps;            // quadrants per warp
+    constexpr int kCols = QuadGeom<kNQ>::kCols;
     constexpr int kThreads = 32 * kWarps;
+    constexpr bool kTileWide = kWarps == 4;         // backward region: the whole tile, groups dealt to the warps
+    constexpr int kRegions = kTileWide ? 1 : kWarps;
+    constexpr int kRegionRows = kTile / kRegions;
     __shared__ QuadRecords sg;
     __shared__ int s_ids[kMaxPerTile];
     __shared__ __align__(16) int s_sort[kMaxPerTile + 4];
+    __shared__ __align__(16) WarpGrad<kRegionRows> s_wg[kRegions];
+    __shared__ unsigned char s_list[kWarps][kMaxPerTile];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_y = p.tile_row_begin + blockIdx.y;
     const int tile_id = tile_y * p.tiles_x + blockIdx.x;
     pdl_launch_dependents();
-    const int qrow0 = kWarps == 2 ? warp : 0;   // first quadrant row of this warp
-    const int qshift = 2 * qrow0;
-    const int px0 = blockIdx.x * kTile + (lane & 7);
-    const int py0 = tile_y * kTile + 8 * qrow0 + (lane >> 3);
-    const QuadLane<kNQ> ln = quad_lane<kNQ>(blockIdx.x * kTile, tile_y * kTile, qrow0);
-    // pixel (quadrant qi, pair element e) of this lane: (px0 + 8*(qi&1), py0 + 8*(qi>>1) + 4*e)
+    // the warp's first quadrant (column, row) and its bit in the reach masks
+    const int qcol0 = kWarps == 4 ? (warp & 1) : 0;
+    const int qrow0 = kWarps == 4 ? (warp >> 1) : (kWarps == 2 ? warp : 0);
+    const int qshift = 2 * qrow0 + qcol0;
+    const int lx0 = 8 * qcol0 + (lane & 7), ly0 = 8 * qrow0 + (lane >> 3);   // tile-relative
+    const int px0 = blockIdx.x * kTile + lx0;
+    const int py0 = tile_y * kTile + ly0;
+    const QuadLane<kNQ> ln = quad_lane<kNQ>(px0, py0);
+    // pixel (quadrant qi, pair element e) of this lane: (px0 + 8*(qi % kCols), py0 + 8*(qi / kCols) + 4*e)
     const bool full_tile = (blockIdx.x + 1) * kTile <= p.img_width && (tile_y + 1) * kTile <= p.img_height;
     unsigned outside = 0;
     if (!full_tile) {
@@ -793,7 +811,7 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
         for (int qi = 0; qi < kNQ; ++qi)
 #pragma unroll
             for (int e = 0; e < 2; ++e)
-                if (px0 + 8 * (qi & 1) >= p.img_width || py0 + 8 * (qi >> 1) + 4 * e >= p.img_height)
+                if (px0 + 8 * (qi % kCols) >= p.img_width || py0 + 8 * (qi / kCols) + 4 * e >= p.img_height)
                     outside |= 1u << (2 * qi + e);
     }
     // the target pixels are written by no kernel of the step: pull their lines towards L2 while the predecessor
@@ -806,7 +824,7 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
 #pragma unroll
             for (int e = 0; e < 2; ++e)
                 if (!((outside >> (2 * qi + e)) & 1u) && (lane & 7) == 0) {
-                    const size_t pix = (size_t)(py0 + 8 * (qi >> 1) + 4 * e) * p.img_width + px0 + 8 * (qi & 1);
+                    const size_t pix = (size_t)(py0 + 8 * (qi / kCols) + 4 * e) * p.img_width + px0 + 8 * (qi % kCols);
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(base + pix * bpp));
                 }
     }
@@ -879,25 +897,28 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     f32x2 accR[kNQ], accG[kNQ], accB[kNQ];
 #pragma unroll
     for (int qi = 0; qi < kNQ; ++qi) accR[qi] = accG[qi] = accB[qi] = 0ull;
-    if (kHasFwd) quad_forward<kNQ, false>(sg, cnt, ln, qshift, 0u, accR, accG, accB);
+    if (kHasFwd) quad_forward<kNQ>(sg, cnt, ln, qshift, accR, accG, accB);
     // no intersection in the whole image: the reference returns ones * background (== 1) and no gradient
     // (rasterize_sum_plus.py:110-118); a band of a tile-row split cannot know, and renders its (empty) sum
     const bool ones = n_isect == 0.0 && p.tile_row_begin == 0 && p.tile_row_end == p.tiles_y;
-    f32x2 vR[kNQ], vG[kNQ], vB[kNQ];
+    // the region whose dL/d(out) this warp fills: its own rows (1, 2 warps per tile) or the whole tile (4)
+    WarpGrad<kRegionRows> &wg = s_wg[kTileWide ? 0 : warp];
+    const int region_row0 = kTileWide ? 0 : 8 * qrow0;
     float se = 0.f, ae = 0.f;
 #pragma unroll
     for (int qi = 0; qi < kNQ; ++qi) {
-        float cr[2], cg[2], cb[2], wr[2], wg[2], wb[2];
+        float cr[2], cg[2], cb[2];
         unpk2(accR[qi], cr[0], cr[1]);
         unpk2(accG[qi], cg[0], cg[1]);
         unpk2(accB[qi], cb[0], cb[1]);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const bool inside = !((outside >> (2 * qi + e)) & 1u);
-            const size_t pix = (size_t)(py0 + 8 * (qi >> 1) + 4 * e) * p.img_width + px0 + 8 * (qi & 1);
+            const int lx = lx0 + 8 * (qi % kCols), ly = ly0 + 8 * (qi / kCols) + 4 * e;   // tile-relative
+            const size_t pix = (size_t)(tile_y * kTile + ly) * p.img_width + blockIdx.x * kTile + lx;
             float r = cr[e], g = cg[e], b = cb[e];
             if (ones) r = g = b = 1.f;
-            wr[e] = wg[e] = wb[e] = 0.f;
+            float wr = 0.f, wgc = 0.f, wb = 0.f;
             if (kMode == RasterMode::Render) {
                 // the model's `render`: clamp to [0,1], CHW planar (gaussianimage_covariance.py:210-211)
                 if (inside && out_img) {
@@ -925,13 +946,13 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
                     const float l1 = p.loss_l1_scale;
                     if (l1 != 0.f) {
                         ae += fabsf(dr) + fabsf(dg) + fabsf(db);
-                        wr[e] = (r >= 0.f && r <= 1.f) ? fmaf(l1, (float)((dr > 0.f) - (dr < 0.f)), p.loss_scale * dr) : 0.f;
-                        wg[e] = (g >= 0.f && g <= 1.f) ? fmaf(l1, (float)((dg > 0.f) - (dg < 0.f)), p.loss_scale * dg) : 0.f;
-                        wb[e] = (b >= 0.f && b <= 1.f) ? fmaf(l1, (float)((db > 0.f) - (db < 0.f)), p.loss_scale * db) : 0.f;
+                        wr = (r >= 0.f && r <= 1.f) ? fmaf(l1, (float)((dr > 0.f) - (dr < 0.f)), p.loss_scale * dr) : 0.f;
+                        wgc = (g >= 0.f && g <= 1.f) ? fmaf(l1, (float)((dg > 0.f) - (dg < 0.f)), p.loss_scale * dg) : 0.f;
+                        wb = (b >= 0.f && b <= 1.f) ? fmaf(l1, (float)((db > 0.f) - (db < 0.f)), p.loss_scale * db) : 0.f;
                     } else {
-                        wr[e] = (r >= 0.f && r <= 1.f) ? p.loss_scale * dr : 0.f;
-                        wg[e] = (g >= 0.f && g <= 1.f) ? p.loss_scale * dg : 0.f;
-                        wb[e] = (b >= 0.f && b <= 1.f) ? p.loss_scale * db : 0.f;
+                        wr = (r >= 0.f && r <= 1.f) ? p.loss_scale * dr : 0.f;
+                        wgc = (g >= 0.f && g <= 1.f) ? p.loss_scale * dg : 0.f;
+                        wb = (b >= 0.f && b <= 1.f) ? p.loss_scale * db : 0.f;
                     }
                     if (out_img) {
                         out_img[3 * pix] = r;
@@ -943,15 +964,17 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
                 }
             } else {   // FitBackward: dL/d(out) computed by the loss kernels between the two halves
                 if (inside && n_isect != 0.0) {
-                    wr[e] = __ldcg(v_out + 3 * pix);
-                    wg[e] = __ldcg(v_out + 3 * pix + 1);
-                    wb[e] = __ldcg(v_out + 3 * pix + 2);
+                    wr = __ldcg(v_out + 3 * pix);
+                    wgc = __ldcg(v_out + 3 * pix + 1);
+                    wb = __ldcg(v_out + 3 * pix + 2);
                 }
             }
+            if (kHasBwd) {   // hand dL/d(out) to the backward's layout (0 outside the image)
+                wg.v[0][ly - region_row0][lx] = wr;
+                wg.v[1][ly - region_row0][lx] = wgc;
+                wg.v[2][ly - region_row0][lx] = wb;
+            }
         }
-        vR[qi] = pk2(wr[0], wr[1]);
-        vG[qi] = pk2(wg[0], wg[1]);
-        vB[qi] = pk2(wb[0], wb[1]);
     }
     if (kMode == RasterMode::Render) return;
     if (kHasLoss) {
@@ -962,20 +985,38 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
             if (p.loss_l1_scale != 0.f) atomicAdd(stats + GI2D_STAT_ABS_SUM, (double)ae);
         }
     }
-    if (!kHasBwd || cnt == 0) return;
-    // ---- backward: the same walk, dL/d(out) in registers
+    if (!kHasBwd || cnt == 0) return;   // (CTA-uniform)
+    // ---- backward: four Gaussians per warp at a time (gi2d_raster_quad.cuh, quad_backward4)
+    // the staged Gaussians that can reach the region, ascending (every warp builds the list it walks)
+    unsigned char *list = s_list[warp];
+    const unsigned region_bits = kTileWide ? 0xFu : (((1u << kNQ) - 1u) << qshift);
+    int n = 0;
+    for (int base = 0; base < cnt; base += 32) {
+        const int t = base + lane;
+        const bool hit = t < cnt && ((unsigned)sg.mask[t] & region_bits) != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) list[n + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)t;
+        n += __popc(bal);
+    }
+    if (kTileWide) __syncthreads(); else __syncwarp();   // dL/d(out) and the list are in shared memory
+    if (n == 0) return;
+    const int region_py0 = tile_y * kTile + region_row0;
+    const int first_group = kTileWide ? warp : 0, group_stride = kTileWide ? kWarps : 1;
     if (full_tile)
-        quad_backward<kNQ, false>(sg, s_ids, cnt, ln, qshift, 0u, vR, vG, vB, grads);
+        quad_backward4<kRegionRows, false>(sg, s_ids, list, n, first_group, group_stride, blockIdx.x * kTile,
+                                           region_py0, region_row0, p.img_width, kRegionRows, wg, grads);
     else
-        quad_backward<kNQ, true>(sg, s_ids, cnt, ln, qshift, outside, vR, vG, vB, grads);
+        quad_backward4<kRegionRows, true>(sg, s_ids, list, n, first_group, group_stride, blockIdx.x * kTile,
+                                          region_py0, region_row0, p.img_width,
+                                          min(kRegionRows, p.img_height - region_py0), wg, grads);
 }
 
-// which rasterizer a step launches: GI2D_RASTER=0 the round-1 kernel (8 warps per tile), 1 / 2 the quadrant
-// kernel with one / two warps per tile (default 2)
+// which rasterizer a step launches: GI2D_RASTER=0 the round-1 kernel (8 warps per tile, scalar math); 1 / 2 / 4 the
+// quadrant kernel with that many warps per tile.  Default: 4 (measured, profiles/README.md).
 int raster_variant() {
     static const int v = [] {
         const char *e = getenv("GI2D_RASTER");
-        return e ? atoi(e) : 2;
+        return e ? atoi(e) : 4;
     }();
     return v;
 }
@@ -993,6 +1034,9 @@ cudaError_t launch_raster(bool pdl, dim3 grid, cudaStream_t st, const gi2d_fit_p
     } else if (v == 2) {
         if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 2>, grid, dim3(64), 0, st, GI2D_RASTER_ARGS);
         fit_rasterq_kernel<kMode, 2><<<grid, 64, 0, st>>>(GI2D_RASTER_ARGS);
+    } else if (v == 4) {
+        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 4>, grid, dim3(128), 0, st, GI2D_RASTER_ARGS);
+        fit_rasterq_kernel<kMode, 4><<<grid, 128, 0, st>>>(GI2D_RASTER_ARGS);
     } else {
         if (pdl) return launch_pdl(fit_raster_kernel<kMode>, grid, dim3(kRasterThreads), 0, st, GI2D_RASTER_ARGS);
         fit_raster_kernel<kMode><<<grid, kRasterThreads, 0, st>>>(GI2D_RASTER_ARGS);
@@ -1052,56 +1096,219 @@ __global__ void fit_clear_pending_kernel(double *__restrict__ stats) {
     }
 }
 
-// --------------------------------------------------------------------- multi-GPU exchange
-// Tile-row split of ONE image over `world` GPUs: every rank rasterized a band and holds
-// PARTIAL per-Gaussian gradients in its own grads[N,8].  Instead of "all-reduce, then a replicated
-// optimiser step", one kernel per rank does the exchange and the math together over NVLink peer
-// memory (symmetric allocations, raw peer pointers):
-//   reduce-scatter : the rank owns the Gaussians [g0,g1); for each it LOADS that row of every peer's
-//                    gradient buffer (P2P LDG.128) and sums them in rank order (same order on every
-//                    rank => the parameters stay bitwise identical everywhere);
-//   optimiser      : projection backward + Adam with the moments of the owned slice only (the
-//                    optimiser state is sharded: 1/world of the moment traffic per GPU);
-//   all-gather     : the 8 updated parameters are STORED into every rank's xyz / cov / rgb (P2P STG).
-// Bytes over NVLink per rank and step: (world-1)/world * N * (32 in + 32 out) -- versus
-// 2 (world-1)/world * N * 32 for a ring all-reduce, plus a full-size replicated Adam.
-// Cross-GPU ordering (peers finished their backward / their stores) is the caller's barrier on the
-// symmetric-memory signal pads before and after this launch.
-struct PeerPtrs {
-    const float4 *grads[8];
-    float *xyz[8], *cov[8], *rgb[8];
-};
+// --------------------------------------------------------------------- multi-GPU tile-row split
+// ONE image over `world` GPUs of an NVSwitch box (the reference is single-GPU, train.py:39).
+// Rank q rasterizes the tile rows [band_edge[q], band_edge[q+1]); the Gaussians are dealt to OWNERS in equal
+// contiguous slices, and only the owner keeps a Gaussian's parameters and Adam moments and projects it
+// (sharded optimiser AND sharded projection -- nothing per-Gaussian is replicated).  What crosses NVLink, per
+// Gaussian and step, goes only between its owner and the ranks whose band its tile box overlaps (1.1 ranks on
+// average, not world-1): the partial gradient row (32 B, P2P load by the owner) and the projected record +
+// tile box (40 B, P2P store by the owner).  One step on a rank is
+//   tr_count_kernel      wait "every peer's records of the previous exchange have landed" (flag spin on
+//                        this rank's own memory) | every Gaussian's tile box clipped to the band -> per-tile
+//                        overlap counts, zeroing of the gradient rows the band will touch
+//   [device-wide scan] + fit_place_kernel + rasterizer on the band     (the single-GPU kernels, unchanged)
+//   tr_exchange_kernel   wait "every peer finished its backward" | owner: sum the partial rows of the ranks
+//                        the box overlaps (fixed rank order), projection backward + Adam, projection, and
+//                        scatter of the new record + box to the ranks the old or the new box overlaps
+// Cross-GPU ordering uses two monotonically increasing flag words per peer in peer-mapped memory (written with
+// st.release.sys after a system fence by the first CTA of the waiting kernel's own grid, read with
+// ld.acquire.sys): no separate barrier launches, no host involvement, the whole step is graph-capturable (the
+// epoch lives in device memory).  A step in which ANY rank overflowed its intersection buffers applies no Adam
+// update anywhere (the overflow bit travels with the flag), so the ranks never diverge.
+constexpr int kTrFlagA = 0, kTrFlagB = GI2D_MAX_RANKS;          // offsets in a rank's flag block (u32[16])
+constexpr int kCtrlEpoch = 0, kCtrlTicketEx = 1, kCtrlExitEx = 2, kCtrlError = 3, kCtrlTicketCnt = 4;
 
-__global__ void __launch_bounds__(256)
-fit_exchange_adam_kernel(gi2d_fit_params p, AdamPtrs local, PeerPtrs peers, int rank, int world, int g0, int g1,
-                         const float4 *__restrict__ proj, const double *__restrict__ stats) {
-    const int g = g0 + blockIdx.x * 256 + threadIdx.x;
-    if (g >= g1) return;
-    const bool veto = __ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0;
-    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-    for (int q = 0; q < world; ++q) {  // fixed order: identical sums on every rank
-        const float4 a0 = __ldcg(peers.grads[q] + 2 * g), a1 = __ldcg(peers.grads[q] + 2 * g + 1);
-        s0.x += a0.x; s0.y += a0.y; s0.z += a0.z; s0.w += a0.w;
-        s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Thread 0 of every CTA: the first CTA of the grid to arrive tells every peer `value` (slot `rank` of their
+// flag group), then everybody waits until every peer's slot in OUR flag block has reached `want`.  Returns the
+// OR of the low bits of the peers' words when `low_bit` (the overflow veto).  Gives up after 20 s (a dead peer
+// must not hang the GPU): ctrl[kCtrlError] is set and the host raises.
+__device__ __forceinline__ uint32_t tr_signal_and_wait(const gi2d_tilerow &tr, uint32_t *ctrl, int ticket_slot,
+                                                       int group, uint32_t value, uint32_t want, bool low_bit) {
+    uint32_t acc = 0;
+    const unsigned ticket = atomicAdd(ctrl + ticket_slot, 1u);
+    if (ticket == 0) {
+        __threadfence_system();
+        for (int q = 0; q < tr.world; ++q)
+            if (q != tr.rank) st_release_sys(tr.peer_flags[q] + group + tr.rank, value);
     }
-    float2 x;
-    float c[3], col[3];
-    AdamRegs r;
-    adam_load(local, g, proj, peers.grads[rank], r);
-    r.g0 = s0;  // the reduced gradient replaces the local partial
-    r.g1 = s1;
-    if (!veto) adam_apply(p, local, g, r, stats);
-    x = r.x;
+    if (ticket == gridDim.x - 1) ctrl[ticket_slot] = 0;   // (the next launch of this kernel starts from 0)
+    const unsigned long long t0 = global_ns();
+    for (int q = 0; q < tr.world; ++q) {
+        if (q == tr.rank) continue;
+        const uint32_t *f = tr.peer_flags[tr.rank] + group + q;
+        uint32_t v = ld_acquire_sys(f);
+        while ((low_bit ? (v >> 1) : v) < want) {
+            __nanosleep(64);
+            if (global_ns() - t0 > 20000000000ull) { atomicExch(ctrl + kCtrlError, 1u); break; }
+            v = ld_acquire_sys(f);
+        }
+        acc |= v & 1u;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ bool box_hits_band(ushort4 bx, int y_begin, int y_end) {
+    return bx.z > bx.x && (int)bx.w > y_begin && (int)bx.y < y_end;
+}
+
+// First kernel of a tile-row step (see above).  boxes_all: this rank's copy of every Gaussian's tile box
+// (written by the owners); boxes_band: the box clipped to the band, for fit_place_kernel.
+__global__ void __launch_bounds__(256)
+tr_count_kernel(gi2d_fit_params p, gi2d_tilerow tr, const ushort4 *__restrict__ boxes_all,
+                ushort4 *__restrict__ boxes_band, int32_t *__restrict__ tile_count, float4 *__restrict__ grads,
+                int with_backward) {
+    pdl_wait();
+    if (tr.sync && threadIdx.x == 0) {
+        const uint32_t epoch = *(volatile uint32_t *)(tr.ctrl + kCtrlEpoch);
+        // every peer's exchange of the previous epoch has landed in our proj / boxes (and has read our grads)
+        tr_signal_and_wait(tr, tr.ctrl, kCtrlTicketCnt, kTrFlagB, epoch - 1, epoch - 1, false);
+    }
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.num_points) return;
+    const ushort4 bx = __ldcg(boxes_all + g);   // (peer-written: never through the non-coherent path)
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    if (box_hits_band(bx, p.tile_row_begin, p.tile_row_end)) {
+        x0 = bx.x; x1 = bx.z;
+        y0 = max((int)bx.y, p.tile_row_begin);
+        y1 = min((int)bx.w, p.tile_row_end);
+        if (with_backward) {   // the rows this band's backward accumulates into (and the owner will read)
+            grads[2 * g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            grads[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    boxes_band[g] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+    for (int ty = y0; ty < y1; ++ty)
+        for (int tx = x0; tx < x1; ++tx) atomicAdd(tile_count + ty * p.tiles_x + tx, 1);
+}
+
+// sync == 0 (ranks emulated on one GPU, ordered by the stream): publish the overflow bit of this rank's band
+// step to the peers at the end of phase 1, so that the veto is global there too
+__global__ void tr_publish_kernel(gi2d_tilerow tr, const double *__restrict__ stats) {
+    const uint32_t epoch = *(volatile uint32_t *)(tr.ctrl + kCtrlEpoch);
+    const uint32_t v = epoch * 2u + (__ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0 ? 1u : 0u);
+    for (int q = 0; q < tr.world; ++q)
+        if (q != tr.rank) tr.peer_flags[q][kTrFlagA + tr.rank] = v;
+}
+
+// Last kernel of a tile-row step: exchange + optimiser + projection of the owned slice.  mode 0: a training
+// step; mode 1: initial projection only (no gradient, no Adam, no flags: the host barriers around it).
+__global__ void __launch_bounds__(256)
+tr_exchange_kernel(gi2d_fit_params p, gi2d_tilerow tr, AdamPtrs a, const float *__restrict__ cov_bound,
+                   double *__restrict__ stats, int mode) {
+    __shared__ uint32_t s_veto;
+    __shared__ float s_step_size, s_bc2;
+    uint32_t *ctrl = tr.ctrl;
+    uint32_t epoch = 0;
+    if (threadIdx.x == 0) {
+        epoch = *(volatile uint32_t *)(ctrl + kCtrlEpoch);
+        uint32_t veto = __ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0 ? 1u : 0u;
+        if (mode == 0 && tr.sync)   // every peer has finished the backward of this epoch
+            veto |= tr_signal_and_wait(tr, ctrl, kCtrlTicketEx, kTrFlagA, epoch * 2u + veto, epoch, true);
+        else if (mode == 0)         // emulated ranks: tr_publish_kernel of every rank ran before (stream order)
+            for (int q = 0; q < tr.world; ++q)
+                if (q != tr.rank) veto |= *(volatile uint32_t *)(tr.peer_flags[tr.rank] + kTrFlagA + q) & 1u;
+        s_veto = veto;
+        // torch.optim.Adam's scalars for step t = STEP + 1, in double like torch; every CTA of every rank
+        // evaluates the same expression (the counters themselves advance once, at the end of this kernel)
+        const double b1 = __ldcg(stats + kStatB1Pow) * (double)p.beta1, b2 = __ldcg(stats + kStatB2Pow) * (double)p.beta2;
+        const long long k = (long long)__ldcg(stats + GI2D_STAT_STEP);   // = t - 1
+        double lr = __ldcg(stats + GI2D_STAT_LR);
+        if (k > 0 && p.lr_step_size > 0 && k % p.lr_step_size == 0) lr *= (double)p.lr_gamma;
+        s_step_size = (float)(lr / (1.0 - b1));
+        s_bc2 = (float)sqrt(1.0 - b2);
+    }
+    __syncthreads();
+    const bool veto = s_veto != 0;
+    const int g = tr.own_begin + blockIdx.x * 256 + threadIdx.x;
+    if (g < tr.own_end) {
+        float4 *proj_own = reinterpret_cast<float4 *>(tr.peer_proj[tr.rank]);
+        ushort4 *boxes_own = reinterpret_cast<ushort4 *>(tr.peer_boxes[tr.rank]);
+        const ushort4 box_old = mode == 0 ? boxes_own[g] : make_ushort4(0, 0, 0, 0);
+        float2 x;
+        float c[3], q[3];
+        if (mode == 0 && !veto) {
+            // reduce: the partial rows of the ranks whose band the box overlapped, in rank order (so that the
+            // sum does not depend on which rank owns the Gaussian)
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+            for (int r = 0; r < tr.world; ++r) {
+                if (!box_hits_band(box_old, tr.band_edge[r], tr.band_edge[r + 1])) continue;
+                const float4 *gp = reinterpret_cast<const float4 *>(tr.peer_grads[r]);
+                const float4 a0 = __ldcg(gp + 2 * g), a1 = __ldcg(gp + 2 * g + 1);
+                s0.x += a0.x; s0.y += a0.y; s0.z += a0.z; s0.w += a0.w;
+                s1.x += a1.x; s1.y += a1.y; s1.z += a1.z; s1.w += a1.w;
+            }
+            AdamRegs r;
+            adam_load(a, g, proj_own, proj_own, r);   // (second pointer: placeholder, the gradient is set below)
+            r.g0 = s0;
+            r.g1 = s1;
+            adam_apply_scalars(p, a, g, r, s_step_size, s_bc2);
+            x = r.x;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { c[k] = r.c[k]; col[k] = r.q[k]; }
-    if (veto) return;
-    for (int q = 0; q < world; ++q) {
-        if (q == rank) continue;  // the local copy was written by adam_update_gaussian
-        reinterpret_cast<float2 *>(peers.xyz[q])[g] = x;
+            for (int k = 0; k < 3; ++k) { c[k] = r.c[k]; q[k] = r.q[k]; }
+        } else {
+            x = reinterpret_cast<const float2 *>(a.xyz)[g];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            peers.cov[q][3 * g + k] = c[k];
-            peers.rgb[q][3 * g + k] = col[k];
+            for (int k = 0; k < 3; ++k) { c[k] = a.cov[3 * g + k]; q[k] = a.rgb[3 * g + k]; }
+        }
+        // projection of the (new) parameters, exactly as fit_project_kernel
+        const float sx = __fadd_rn(c[0], __ldg(cov_bound + 3 * g));
+        const float sxy = __fadd_rn(c[1], __ldg(cov_bound + 3 * g + 1));
+        const float sy = __fadd_rn(c[2], __ldg(cov_bound + 3 * g + 2));
+        float cr = q[0], cg = q[1], cb = q[2];
+        if (p.color_sigmoid) { cr = sigmoidf(cr); cg = sigmoidf(cg); cb = sigmoidf(cb); }
+        const Projected pr = project_cov(x.x, x.y, sx, sxy, sy, p.clip_coe, p.radius_clip, p.tiles_x, p.tiles_y);
+        ushort4 box_new = make_ushort4(0, 0, 0, 0);
+        if (pr.ntiles > 0 && !((float)pr.radius < p.radius_clip))
+            box_new = make_ushort4((unsigned short)pr.box.x0, (unsigned short)pr.box.y0, (unsigned short)pr.box.x1,
+                                   (unsigned short)pr.box.y1);
+        const float4 rec0 = make_float4(pr.x, pr.y, pr.a, pr.b), rec1 = make_float4(pr.c, cr, cg, cb);
+        // scatter: to every rank that saw the Gaussian in its band or will see it (so that a rank it leaves
+        // learns that it left), and to ourselves
+        for (int r = 0; r < tr.world; ++r) {
+            if (r != tr.rank && mode == 0 && !box_hits_band(box_old, tr.band_edge[r], tr.band_edge[r + 1]) &&
+                !box_hits_band(box_new, tr.band_edge[r], tr.band_edge[r + 1]))
+                continue;
+            float4 *pp = reinterpret_cast<float4 *>(tr.peer_proj[r]);
+            pp[2 * g] = rec0;
+            pp[2 * g + 1] = rec1;
+            reinterpret_cast<ushort4 *>(tr.peer_boxes[r])[g] = box_new;
+        }
+    }
+    if (mode != 0) return;
+    // the last CTA to finish advances the epoch (every CTA has read it) and, unless the step was vetoed, the
+    // optimiser's counters
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(ctrl + kCtrlExitEx, 1u) == gridDim.x - 1) {
+            ctrl[kCtrlExitEx] = 0;
+            if (!veto) {
+                const double step = stats[GI2D_STAT_STEP] + 1.0;
+                const long long k = (long long)step - 1;
+                stats[GI2D_STAT_STEP] = step;
+                stats[kStatB1Pow] *= (double)p.beta1;
+                stats[kStatB2Pow] *= (double)p.beta2;
+                if (k > 0 && p.lr_step_size > 0 && k % p.lr_step_size == 0) stats[GI2D_STAT_LR] *= (double)p.lr_gamma;
+            }
+            stats[GI2D_STAT_OVERFLOW] = veto ? 1.0 : 0.0;   // any rank's overflow vetoes (and is visible on) all
+            __threadfence();
+            *(volatile uint32_t *)(ctrl + kCtrlEpoch) = *(volatile uint32_t *)(ctrl + kCtrlEpoch) + 1u;
         }
     }
 }
@@ -1166,7 +1373,7 @@ struct Marks {            // optional per-kernel timing marks (gi2d_fit_profile)
 };
 
 int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int with_backward,
-                              cudaStream_t st, Marks *mk) {
+                              cudaStream_t st, Marks *mk, const gi2d_tilerow *tr = nullptr) {
     const int rc = validate(p, b);
     if (rc != GI2D_OK) return rc;
     GI2D_REQUIRE(p->num_points == 0 || (b->xyz && b->cov && b->cov_bound && b->rgb), "null parameter buffer");
@@ -1183,9 +1390,14 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     if (mk) mk->mark(st);
     const AdamPtrs ap{b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
     const int proj_threads = p->num_points <= (1 << 16) ? 64 : kProjThreads;
-    launch_pdl(fit_project_kernel, dim3(max(1, cdiv(p->num_points, proj_threads))), dim3(proj_threads), 0, st,
-        *p, ap, b->cov_bound, (float4 *)b->proj, (float4 *)b->grads, w.boxes, w.tile_count, b->stats, with_backward,
-        (float4 *)b->best, (with_backward && !p->external_optimizer) ? 1 : 0);
+    if (tr)   // tile-row split: the records and boxes came from their owners; count this band's overlaps
+        tr_count_kernel<<<max(1, cdiv(p->num_points, 256)), 256, 0, st>>>(
+            *p, *tr, (const ushort4 *)tr->peer_boxes[tr->rank], w.boxes, w.tile_count, (float4 *)b->grads,
+            with_backward);
+    else
+        launch_pdl(fit_project_kernel, dim3(max(1, cdiv(p->num_points, proj_threads))), dim3(proj_threads), 0, st,
+            *p, ap, b->cov_bound, (float4 *)b->proj, (float4 *)b->grads, w.boxes, w.tile_count, b->stats, with_backward,
+            (float4 *)b->best, (with_backward && !p->external_optimizer) ? 1 : 0);
     if (mk) mk->mark(st);
     if (!pl.smem_scan) {
         // more tiles than one CTA scans in shared memory: device-wide inclusive prefix sum of the counts
@@ -1413,34 +1625,65 @@ extern "C" int gi2d_fit_input_grads(const gi2d_fit_params *p, const gi2d_fit_buf
     return check_launch(__func__);
 }
 
-// Fused reduce-scatter + optimiser + all-gather over peer memory (see fit_exchange_adam_kernel).
-// peer_* are HOST arrays of `world` device pointers (this rank's own buffer at index `rank`); the
-// caller guarantees, with a cross-GPU barrier on the stream before and after this call, that every
-// peer finished its backward before and sees the stores after.  p->external_optimizer must be 1.
-extern "C" int gi2d_fit_exchange_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int rank, int world,
-                                      const void *const *peer_grads, void *const *peer_xyz, void *const *peer_cov,
-                                      void *const *peer_rgb, gi2d_stream_t stream) {
+// ---- tile-row split entry points (kernels: tr_count_kernel / tr_exchange_kernel above)
+static int validate_tilerow(const gi2d_fit_params *p, const gi2d_fit_buffers *b, const gi2d_tilerow *tr) {
     const int rc = validate(p, b);
     if (rc != GI2D_OK) return rc;
-    GI2D_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad rank/world (<= 8 GPUs of one box)");
-    GI2D_REQUIRE(p->external_optimizer, "set external_optimizer so that the step leaves its gradient to this call");
-    GI2D_REQUIRE(peer_grads && peer_xyz && peer_cov && peer_rgb, "null peer pointer table");
-    GI2D_REQUIRE(b->m_xyz && b->v_xyz && b->m_cov && b->v_cov && b->m_rgb && b->v_rgb, "null moment buffer");
-    if (p->num_points == 0) return GI2D_OK;
-    PeerPtrs pp{};
-    for (int q = 0; q < world; ++q) {
-        pp.grads[q] = (const float4 *)peer_grads[q];
-        pp.xyz[q] = (float *)peer_xyz[q];
-        pp.cov[q] = (float *)peer_cov[q];
-        pp.rgb[q] = (float *)peer_rgb[q];
-        GI2D_REQUIRE(pp.grads[q] && pp.xyz[q] && pp.cov[q] && pp.rgb[q], "null peer pointer");
+    GI2D_REQUIRE(tr, "null tile-row descriptor");
+    GI2D_REQUIRE(tr->world >= 1 && tr->world <= GI2D_MAX_RANKS && tr->rank >= 0 && tr->rank < tr->world,
+                 "bad rank/world (<= 8 GPUs of one box)");
+    GI2D_REQUIRE(p->external_optimizer == 2, "set external_optimizer = 2 (the exchange kernel owns the optimiser)");
+    GI2D_REQUIRE(tr->band_edge[0] == 0 && tr->band_edge[tr->world] == p->tiles_y, "bands must cover the image");
+    for (int q = 0; q < tr->world; ++q) {
+        GI2D_REQUIRE(tr->band_edge[q] <= tr->band_edge[q + 1], "band edges must ascend");
+        GI2D_REQUIRE(tr->peer_grads[q] && tr->peer_proj[q] && tr->peer_boxes[q] && tr->peer_flags[q], "null peer pointer");
     }
-    const int per = cdiv(p->num_points, world);
-    const int g0 = min(p->num_points, rank * per), g1 = min(p->num_points, g0 + per);
-    if (g1 <= g0) return GI2D_OK;
-    const AdamPtrs ap{b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
-    fit_exchange_adam_kernel<<<cdiv(g1 - g0, 256), 256, 0, (cudaStream_t)stream>>>(
-        *p, ap, pp, rank, world, g0, g1, (const float4 *)b->proj, b->stats);
+    GI2D_REQUIRE(p->tile_row_begin == tr->band_edge[tr->rank] && p->tile_row_end == tr->band_edge[tr->rank + 1],
+                 "tile_row_begin/end must be this rank's band");
+    GI2D_REQUIRE(0 <= tr->own_begin && tr->own_begin <= tr->own_end && tr->own_end <= p->num_points, "bad owned slice");
+    GI2D_REQUIRE(tr->ctrl, "null control block");
+    GI2D_REQUIRE(b->grads == tr->peer_grads[tr->rank] && b->proj == tr->peer_proj[tr->rank],
+                 "b->grads / b->proj must be this rank's peer-visible buffers");
+    GI2D_REQUIRE(b->xyz && b->cov && b->cov_bound && b->rgb && b->m_xyz && b->v_xyz && b->m_cov && b->v_cov &&
+                     b->m_rgb && b->v_rgb, "null parameter / moment buffer");
+    return GI2D_OK;
+}
+
+extern "C" int gi2d_tilerow_init(const gi2d_fit_params *p, const gi2d_fit_buffers *b, const gi2d_tilerow *tr,
+                                 gi2d_stream_t stream) {
+    const int rc = validate_tilerow(p, b, tr);
+    if (rc != GI2D_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // control block: epoch 1, tickets 0.  (The peer-visible buffers were zeroed by the caller BEFORE its barrier:
+    // a peer's scatter below may reach our records / boxes before this call even starts.)
+    static const uint32_t ctrl0[8] = {1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    cudaMemcpyAsync(tr->ctrl, ctrl0, sizeof(ctrl0), cudaMemcpyHostToDevice, st);
+    const int n = tr->own_end - tr->own_begin;
+    if (n > 0) {
+        const AdamPtrs ap{b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
+        tr_exchange_kernel<<<cdiv(n, 256), 256, 0, st>>>(*p, *tr, ap, b->cov_bound, b->stats, 1);
+    }
+    return check_launch(__func__);
+}
+
+extern "C" int gi2d_tilerow_step(const gi2d_fit_params *p, const gi2d_fit_buffers *b, const gi2d_tilerow *tr,
+                                 int with_backward, int phase, gi2d_stream_t stream) {
+    int rc = validate_tilerow(p, b, tr);
+    if (rc != GI2D_OK) return rc;
+    GI2D_REQUIRE(phase >= 1 && phase <= 3, "phase: 1 = band step, 2 = exchange, 3 = both");
+    GI2D_REQUIRE(p->loss_ssim_weight == 0.f, "SSIM losses are not available for a tile-row band");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (phase & 1) {
+        rc = fit_forward_backward_impl(p, b, with_backward, st, nullptr, tr);
+        if (rc != GI2D_OK) return rc;
+        if (!tr->sync && with_backward) tr_publish_kernel<<<1, 1, 0, st>>>(*tr, b->stats);
+    }
+    if ((phase & 2) && with_backward) {
+        const int n = tr->own_end - tr->own_begin;
+        const AdamPtrs ap{b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
+        // (every rank launches at least one CTA: it takes part in the flag exchange even with an empty slice)
+        tr_exchange_kernel<<<max(1, cdiv(n, 256)), 256, 0, st>>>(*p, *tr, ap, b->cov_bound, b->stats, 0);
+    }
     return check_launch(__func__);
 }
 

@@ -7,19 +7,21 @@
 // (74.1 of 74.4 TFLOP/s) with half the issue slots of FFMA.  Hence this design:
 //
 // Geometry : the tile is 4 QUADRANTS of 8x8 pixels.  A warp owns whole quadrants (all 4: one warp per tile;
-//            or 2: the top / bottom half, two warps per tile); lane L owns the pixel PAIR (L&7, L>>3) and
+//            2: the top / bottom half, two warps per tile; 1: four warps per tile); lane L owns the pixel PAIR (L&7, L>>3) and
 //            (L&7, (L>>3)+4) of each of its quadrants and keeps it in ONE 64-bit register as f32x2, so every
 //            floating-point instruction of the sweeps is packed and works on 64 pixels of a quadrant at once.
-//            A Gaussian's record is staged in shared memory with every value DUPLICATED (x,x | y,y | ...):
-//            4 broadcast LDS.128 deliver ready-made f32x2 operands, no register moves.
+//            A Gaussian's record is staged in shared memory as it comes (32 bytes, 2 broadcast LDS.128); a
+//            scalar enters the packed math through the scalar-broadcast operand form of FADD2/FMUL2/FFMA2.
 // Forward  : the warp walks the tile's list in ascending order (bit-reproducible image: per pixel the same
 //            operations in the same order as forward.cu:652-668), skipping quadrants outside the Gaussian's
 //            alpha >= 1/255 reach box (warp-uniform mask).  A rejected pair gets weight 0 instead of a branch.
 // Loss     : the lane that rendered a pixel also evaluates its loss gradient; dL/d(out) of its 8 (4) pixels
 //            never leaves the registers -- no shared-memory image, no block barrier between the passes.
-// Backward : the same walk again; per Gaussian 8 packed accumulators, then the 9-shuffle transposed
-//            reduce-scatter (gi2d_raster_core.cuh) and 8 red.global per (warp, Gaussian).
-// The only block-wide synchronisation is the one after the list has been rank-sorted into shared memory.
+// Backward : FOUR Gaussians per warp at a time, 8 lanes each, sweeping pixel rows (see quad_backward4 below): the
+//            cross-lane reduction spans 8 lanes and serves 4 Gaussians at once, every lane ends with exactly one
+//            (Gaussian, component) total -> one RED instruction per group of four.
+// Block-wide synchronisation: one barrier after the list has been rank-sorted into shared memory (and, with four
+// warps per tile, one more where dL/d(out) changes hands between the pixel-owning and the Gaussian-owning warps).
 #pragma once
 #include "gi2d_raster_core.cuh"
 
@@ -53,93 +55,113 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
 
 constexpr int kQuads = 4;   // 8x8-pixel quadrants per tile: bit q <-> (x0, y0) = (8*(q&1), 8*(q>>1))
 
-// Quadrant reach mask of one Gaussian with opacity 1 (same conservative box as reach_mask(): the axis-aligned
-// bounding box of {sigma <= ln 255}, inflated by 0.1 % + 1e-3 px).  (gx,gy) relative to the tile origin.
-__device__ __forceinline__ unsigned reach_mask_quad(float gx, float gy, float a, float b, float c) {
+// Reach of one Gaussian with opacity 1 inside a tile (same conservative box as reach_mask(): the axis-aligned
+// bounding box of {sigma <= ln 255}, inflated by 0.1 % + 1e-3 px): the quadrants it can touch (bits 0..3) and
+// the first / last tile row (0..15) it can touch.  (gx,gy) relative to the tile origin.
+struct QuadReach {
+    unsigned mask;
+    int row_lo, row_hi;
+};
+
+__device__ __forceinline__ QuadReach reach_quad(float gx, float gy, float a, float b, float c) {
+    QuadReach o;
+    o.mask = 0xFu;
+    o.row_lo = 0;
+    o.row_hi = kTile - 1;
     const float det = fmaf(a, c, -b * b);
     const float L = 5.5412635f * 1.001f + 1e-3f;   // ln(255)
-    if (!(det > 1e-3f * a * c && a > 0.f && c > 0.f)) return 0xFu;   // indefinite / NaN / needle: no culling
+    if (!(det > 1e-3f * a * c && a > 0.f && c > 0.f)) return o;   // indefinite / NaN / needle: no culling
     const float k = __fdividef(2.f * L, det);
     const float hx = sqrt_approx(k * c) * 1.001f + 1e-3f;
     const float hy = sqrt_approx(k * a) * 1.001f + 1e-3f;
-    if (!(hx < 1e30f && hy < 1e30f)) return 0xFu;
+    if (!(hx < 1e30f && hy < 1e30f)) return o;
     const float x0 = gx - hx, x1 = gx + hx, y0 = gy - hy, y1 = gy + hy;
     const unsigned cols = ((x0 <= 7.f && x1 >= 0.f) ? 1u : 0u) | ((x0 <= 15.f && x1 >= 8.f) ? 2u : 0u);
     const unsigned rows = ((y0 <= 7.f && y1 >= 0.f) ? 1u : 0u) | ((y0 <= 15.f && y1 >= 8.f) ? 2u : 0u);
     // bit q = col bit (q&1) AND row bit (q>>1)
-    return ((rows & 1u) ? cols : 0u) | ((rows & 2u) ? (cols << 2) : 0u);
+    o.mask = ((rows & 1u) ? cols : 0u) | ((rows & 2u) ? (cols << 2) : 0u);
+    // pixel rows r with y0 <= r <= y1 (pixel centres sit on integers, forward.cu:596-597)
+    o.row_lo = (int)fminf(fmaxf(ceilf(y0), 0.f), 15.f);
+    o.row_hi = (int)fminf(fmaxf(floorf(y1), 0.f), 15.f);
+    return o;
 }
 
-// Shared-memory staging: every value duplicated, so that one LDS.128 yields two f32x2 operands.
+// Shared-memory staging of the tile's list in rank order: the 32-byte projected record of gi2d_fit.cu verbatim.
+// The sweeps turn a scalar into an f32x2 operand with pk2(v, v): ptxas folds that into the scalar-broadcast
+// operand form of FADD2 / FMUL2 / FFMA2, so no register is spent on the copy.
 struct QuadRecords {
-    float4 xy[kMaxPerTile];   // x x y y
-    float4 ab[kMaxPerTile];   // a a b b
-    float4 cr[kMaxPerTile];   // c c r r
-    float4 gb[kMaxPerTile];   // g g b b   (colour g, colour b)
+    float4 xyab[kMaxPerTile];   // x y a b
+    float4 crgb[kMaxPerTile];   // c r g b
     unsigned char mask[kMaxPerTile];
+    unsigned char rows[kMaxPerTile];   // row_lo | row_hi << 4
 };
 
 __device__ __forceinline__ void stage_quad(QuadRecords &s, int slot, float4 p0, float4 p1, float tile_x0,
                                            float tile_y0) {
-    s.xy[slot] = make_float4(p0.x, p0.x, p0.y, p0.y);
-    s.ab[slot] = make_float4(p0.z, p0.z, p0.w, p0.w);
-    s.cr[slot] = make_float4(p1.x, p1.x, p1.y, p1.y);
-    s.gb[slot] = make_float4(p1.z, p1.z, p1.w, p1.w);
-    s.mask[slot] = (unsigned char)reach_mask_quad(p0.x - tile_x0, p0.y - tile_y0, p0.z, p0.w, p1.x);
+    s.xyab[slot] = p0;
+    s.crgb[slot] = p1;
+    const QuadReach rc = reach_quad(p0.x - tile_x0, p0.y - tile_y0, p0.z, p0.w, p1.x);
+    s.mask[slot] = (unsigned char)rc.mask;
+    s.rows[slot] = (unsigned char)(rc.row_lo | (rc.row_hi << 4));
 }
 
-__device__ __forceinline__ void lds_pair(const float4 *p, f32x2 &u, f32x2 &v) {
-    const ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(p);
-    u = w.x;
-    v = w.y;
-}
-
-// Per-lane constants: minus the pixel coordinates of the lane's pairs.  kNQ quadrants owned by the warp
-// (4: all; 2: the row of quadrants `half`), i.e. 2 columns x kNQ/2 quadrant rows.
+// Geometry of a warp that owns kNQ quadrants: kNQ = 4 all of them (2 columns x 2 rows), 2 one ROW of quadrants
+// (2 columns), 1 a single quadrant.  Quadrant qi of the warp sits at column qi % kCols, row qi / kCols
+// relative to the warp's first quadrant.
 template <int kNQ>
-struct QuadLane {
-    f32x2 npx[2];         // (-px, -px) for the left / right quadrant column
-    f32x2 npy[kNQ / 2];   // (-py, -(py+4)) per owned quadrant row
+struct QuadGeom {
+    static constexpr int kCols = kNQ >= 2 ? 2 : 1;
+    static constexpr int kRows = kNQ == 4 ? 2 : 1;
 };
 
+// Per-lane constants: minus the pixel coordinates of the lane's pairs.
 template <int kNQ>
-__device__ __forceinline__ QuadLane<kNQ> quad_lane(int tile_px0, int tile_py0, int half) {
-    const int lane = threadIdx.x & 31;
+struct QuadLane {
+    f32x2 npx[QuadGeom<kNQ>::kCols];   // (-px, -px) per quadrant column
+    f32x2 npy[QuadGeom<kNQ>::kRows];   // (-py, -(py+4)) per quadrant row
+};
+
+// (px0, py0): pixel of this lane in the warp's first quadrant, pair element 0
+template <int kNQ>
+__device__ __forceinline__ QuadLane<kNQ> quad_lane(int px0, int py0) {
     QuadLane<kNQ> g;
-    const float px = (float)(tile_px0 + (lane & 7));
 #pragma unroll
-    for (int k = 0; k < 2; ++k) g.npx[k] = pk2(-(px + 8.f * k), -(px + 8.f * k));
+    for (int k = 0; k < QuadGeom<kNQ>::kCols; ++k) {
+        const float px = (float)(px0 + 8 * k);
+        g.npx[k] = pk2(-px, -px);
+    }
 #pragma unroll
-    for (int j = 0; j < kNQ / 2; ++j) {
-        const float py = (float)(tile_py0 + 8 * (half + j) + (lane >> 3));
+    for (int j = 0; j < QuadGeom<kNQ>::kRows; ++j) {
+        const float py = (float)(py0 + 8 * j);
         g.npy[j] = pk2(-py, -(py + 4.f));
     }
     return g;
 }
 
-// Everything of one staged Gaussian the sweeps share between the quadrants.
+// Everything of one staged Gaussian the forward sweep shares between the warp's quadrants.
 template <int kNQ>
 struct QuadGauss {
-    f32x2 dx[2], adx[2], bdx[2];
-    f32x2 dy[kNQ / 2], dycdy[kNQ / 2];
+    f32x2 dx[QuadGeom<kNQ>::kCols], adx[QuadGeom<kNQ>::kCols], bdx[QuadGeom<kNQ>::kCols];
+    f32x2 dy[QuadGeom<kNQ>::kRows], dycdy[QuadGeom<kNQ>::kRows];
     f32x2 r, g, b;
 };
 
 template <int kNQ>
 __device__ __forceinline__ void quad_load(const QuadRecords &s, int t, const QuadLane<kNQ> &ln, QuadGauss<kNQ> &q) {
-    f32x2 xx, yy, aa, bb, cc;
-    lds_pair(&s.xy[t], xx, yy);
-    lds_pair(&s.ab[t], aa, bb);
-    lds_pair(&s.cr[t], cc, q.r);
-    lds_pair(&s.gb[t], q.g, q.b);
+    const float4 p0 = s.xyab[t], p1 = s.crgb[t];
+    const f32x2 xx = pk2(p0.x, p0.x), yy = pk2(p0.y, p0.y), aa = pk2(p0.z, p0.z), bb = pk2(p0.w, p0.w);
+    const f32x2 cc = pk2(p1.x, p1.x);
+    q.r = pk2(p1.y, p1.y);
+    q.g = pk2(p1.z, p1.z);
+    q.b = pk2(p1.w, p1.w);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < QuadGeom<kNQ>::kCols; ++k) {
         q.dx[k] = add2(xx, ln.npx[k]);        // x - px   (forward.cu:654)
         q.adx[k] = mul2(aa, q.dx[k]);
         q.bdx[k] = mul2(bb, q.dx[k]);
     }
 #pragma unroll
-    for (int j = 0; j < kNQ / 2; ++j) {
+    for (int j = 0; j < QuadGeom<kNQ>::kRows; ++j) {
         q.dy[j] = add2(yy, ln.npy[j]);
         q.dycdy[j] = mul2(q.dy[j], mul2(cc, q.dy[j]));
     }
@@ -157,36 +179,29 @@ __device__ __forceinline__ float accept_weight(float sigma, float vis) {
     return w;
 }
 
-// sigma and the masked weight of the lane's pixel pair in quadrant (column k, row j):
+// sigma and the masked weight of a pixel pair:
 //   sigma = fma(dy, b*dx, 0.5*fma(dx, a*dx, dy*(c*dy)))  (the -O3 SASS order of forward.cu:655-657),
 //   vis = ex2(-sigma*log2e);  weight = vis when sigma >= 0 and vis >= 1/255 (forward.cu:659), else 0.
-// kGuard: lanes whose pixel lies outside the image (bits of `outside`: 2*quadrant + pair element) get weight 0,
-// so that a NaN of a pixel that does not exist cannot reach the gradient sums.
-template <int kNQ, bool kGuard>
-__device__ __forceinline__ f32x2 quad_weight(const QuadGauss<kNQ> &q, int k, int j, unsigned outside, int qi) {
+__device__ __forceinline__ f32x2 pair_weight(f32x2 dx, f32x2 adx, f32x2 bdx, f32x2 dy, f32x2 dycdy) {
     const f32x2 half2 = pk2(0.5f, 0.5f), nl2e = pk2(-1.4426950216293334961f, -1.4426950216293334961f);
-    const f32x2 qq = fma2(q.dx[k], q.adx[k], q.dycdy[j]);
-    const f32x2 sg = fma2(q.dy[j], q.bdx[k], mul2(qq, half2));
+    const f32x2 qq = fma2(dx, adx, dycdy);
+    const f32x2 sg = fma2(dy, bdx, mul2(qq, half2));
     const f32x2 tt = mul2(sg, nl2e);
     float s0, s1, t0, t1, v0, v1;
     unpk2(sg, s0, s1);
     unpk2(tt, t0, t1);
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v0) : "f"(t0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v1) : "f"(t1));
-    float w0 = accept_weight(s0, v0), w1 = accept_weight(s1, v1);
-    if (kGuard) {
-        if ((outside >> (2 * qi)) & 1u) w0 = 0.f;
-        if ((outside >> (2 * qi + 1)) & 1u) w1 = 0.f;
-    }
-    return pk2(w0, w1);
+    return pk2(accept_weight(s0, v0), accept_weight(s1, v1));
 }
 
 // Forward sweep of a warp over the staged list: acc*[qi] += weight * colour for its kNQ quadrants.
-// `qshift`: bit position of the warp's first quadrant in the reach masks (0, or 2 for the bottom half).
-template <int kNQ, bool kGuard>
+// `qshift`: bit position of the warp's first quadrant in the reach masks.  (Pixels outside the image
+// accumulate like any other; nobody reads them.)
+template <int kNQ>
 __device__ __forceinline__ void quad_forward(const QuadRecords &s, int cnt, const QuadLane<kNQ> &ln, int qshift,
-                                             unsigned outside, f32x2 (&accR)[kNQ], f32x2 (&accG)[kNQ],
-                                             f32x2 (&accB)[kNQ]) {
+                                             f32x2 (&accR)[kNQ], f32x2 (&accG)[kNQ], f32x2 (&accB)[kNQ]) {
+    constexpr int kCols = QuadGeom<kNQ>::kCols;
     for (int t = 0; t < cnt; ++t) {
         const unsigned m = ((unsigned)s.mask[t] >> qshift) & ((1u << kNQ) - 1u);
         if (!m) continue;   // warp-uniform
@@ -194,8 +209,9 @@ __device__ __forceinline__ void quad_forward(const QuadRecords &s, int cnt, cons
         quad_load<kNQ>(s, t, ln, q);
 #pragma unroll
         for (int qi = 0; qi < kNQ; ++qi) {
-            if (!((m >> qi) & 1u)) continue;   // warp-uniform
-            const f32x2 w = quad_weight<kNQ, kGuard>(q, qi & 1, qi >> 1, outside, qi);
+            if (kNQ > 1 && !((m >> qi) & 1u)) continue;   // warp-uniform
+            const int k = qi % kCols, j = qi / kCols;
+            const f32x2 w = pair_weight(q.dx[k], q.adx[k], q.bdx[k], q.dy[j], q.dycdy[j]);
             accR[qi] = fma2(w, q.r, accR[qi]);   // out += alpha * rgb, ascending order (forward.cu:662-666)
             accG[qi] = fma2(w, q.g, accG[qi]);
             accB[qi] = fma2(w, q.b, accB[qi]);
@@ -203,55 +219,126 @@ __device__ __forceinline__ void quad_forward(const QuadRecords &s, int cnt, cons
     }
 }
 
-// Backward sweep: per staged Gaussian accumulate over the warp's quadrants, reduce across the warp, and add the
-// 8 components {v_x, v_y, v_a, v_b, v_c, v_r, v_g, v_b} to grads[8*id + k] (backward.cu:1273-1345).
-// vR/vG/vB: dL/d(out) of the lane's pixel pairs (0 outside the image).
-template <int kNQ, bool kGuard>
-__device__ __forceinline__ void quad_backward(const QuadRecords &s, const int *s_ids, int cnt,
-                                              const QuadLane<kNQ> &ln, int qshift, unsigned outside,
-                                              const f32x2 (&vR)[kNQ], const f32x2 (&vG)[kNQ],
-                                              const f32x2 (&vB)[kNQ], float *__restrict__ grads) {
-    const int lane = threadIdx.x & 31;
-    for (int t = 0; t < cnt; ++t) {
-        const unsigned m = ((unsigned)s.mask[t] >> qshift) & ((1u << kNQ) - 1u);
-        if (!m) continue;   // warp-uniform
-        QuadGauss<kNQ> q;
-        quad_load<kNQ>(s, t, ln, q);
-        f32x2 ax = 0ull, ay = 0ull, aa = 0ull, ab = 0ull, ac = 0ull, ar = 0ull, ag = 0ull, abl = 0ull;
+// ---------------------------------------------------------------------------------------------------------
+// Backward sweep, group layout: FOUR Gaussians per warp at a time, 8 lanes each.
+//
+// A warp that walks the list one Gaussian at a time with its lanes on pixels pays per (warp, Gaussian) a 32-lane
+// reduction (9 shuffles + 14 selects + 7 adds, a chain of five dependent shuffle round trips), the record load,
+// the loop control and the atomic set-up: ~95 instructions around ~45 of useful pair math at the list lengths of
+// a 768x512 / 5000-Gaussian scene (ncu of that first version: 36 % of the kernel's instructions, the top stall
+// reasons; profiles/README.md).  Here the region (kRows rows of 16 pixels) is swept row by row with lane j = L&7 of every 8-lane group holding the pixel pair (2j, 2j+1) of the row,
+// and group L>>3 working on its OWN Gaussian: one instruction still evaluates 64 pairs, but the fixed part is
+// paid once per FOUR Gaussians, the reduction spans 8 lanes (7 shuffles for 4 Gaussians at once), and after
+// it every one of the 32 lanes holds exactly one (Gaussian, component) total: one RED instruction.
+// dL/d(out) comes from a per-warp shared-memory copy (3 broadcast LDS.64 per row, identical addresses in the
+// four groups).  The row range swept is the union of the four reach boxes (warp-uniform, redux.sync).
+// `list`: ranks of the staged Gaussians this warp reaches (n of them), ascending.
+template <int kRows>
+struct WarpGrad {                      // dL/d(out) of the warp's region, planar, row stride 16
+    float v[3][kRows][kTile];
+};
+
+__device__ __forceinline__ float group_reduce_scatter8(float (&v)[8]) {
+    // transposed butterfly over lane bits 2,1,0: on return lane j (= L&7) of every group holds component j
+    const unsigned lane = threadIdx.x & 31u;
 #pragma unroll
-        for (int qi = 0; qi < kNQ; ++qi) {
-            if (!((m >> qi) & 1u)) continue;   // warp-uniform
-            const int k = qi & 1, j = qi >> 1;
-            const f32x2 w = quad_weight<kNQ, kGuard>(q, k, j, outside, qi);
-            ar = fma2(w, vR[qi], ar);     // v_rgb += alpha * v_out
-            ag = fma2(w, vG[qi], ag);
-            abl = fma2(w, vB[qi], abl);
-            const f32x2 va = fma2(q.b, vB[qi], fma2(q.g, vG[qi], mul2(q.r, vR[qi])));   // v_alpha = rgb . v_out
-            const f32x2 u = mul2(w, va);  // vis * v_alpha = -v_sigma
-            const f32x2 t1 = mul2(u, q.dx[k]), t2 = mul2(u, q.dy[j]);
-            aa = fma2(t1, q.dx[k], aa);
-            ab = fma2(t1, q.dy[j], ab);
-            ac = fma2(t2, q.dy[j], ac);
-            ax = add2(ax, t1);
-            ay = add2(ay, t2);
+    for (int half = 4; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
         }
-        float l0, l1;
-        float acc[8];
-        // sums over the pair, with the sign of v_sigma = -u restored
-        unpk2(ax, l0, l1); const float sx = -(l0 + l1);
-        unpk2(ay, l0, l1); const float sy = -(l0 + l1);
-        // conic a, b, c of this Gaussian: re-read (broadcast LDS) instead of holding six more registers
-        const float ca = s.ab[t].x, cb = s.ab[t].z, cc = s.cr[t].x;
-        acc[0] = fmaf(ca, sx, cb * sy);   // v_xy = C * sum(v_sigma * delta)
-        acc[1] = fmaf(cb, sx, cc * sy);
-        unpk2(aa, l0, l1); acc[2] = -0.5f * (l0 + l1);
-        unpk2(ab, l0, l1); acc[3] = -0.5f * (l0 + l1);
-        unpk2(ac, l0, l1); acc[4] = -0.5f * (l0 + l1);
-        unpk2(ar, l0, l1); acc[5] = l0 + l1;
-        unpk2(ag, l0, l1); acc[6] = l0 + l1;
-        unpk2(abl, l0, l1); acc[7] = l0 + l1;
-        const float total = warp_reduce_scatter8(acc);
-        if ((lane & 3) == 0 && total != 0.f) atomicAdd(grads + 8 * (size_t)s_ids[t] + (lane >> 2), total);
+    }
+    return v[0];
+}
+
+// one row of the sweep: accumulate the pair (2j, 2j+1) of region row r
+struct GroupAcc {
+    f32x2 ax, ay, sa, sb, sc, ar, ag, abl;
+};
+
+template <int kRows, bool kGuard>
+__device__ __forceinline__ void group_row(GroupAcc &A, int r, int region_py0, int j, bool xin0, bool xin1,
+                                          const WarpGrad<kRows> &wg, f32x2 yy, f32x2 cc, f32x2 dx, f32x2 adx,
+                                          f32x2 bdx, f32x2 cr, f32x2 cg, f32x2 cb) {
+    const float npy = -(float)(region_py0 + r);
+    const f32x2 dy = add2(yy, pk2(npy, npy));
+    const f32x2 dycdy = mul2(dy, mul2(cc, dy));
+    f32x2 w = pair_weight(dx, adx, bdx, dy, dycdy);
+    if (kGuard) {   // a NaN of a pixel that does not exist must not reach the sums
+        float w0, w1;
+        unpk2(w, w0, w1);
+        w = pk2(xin0 ? w0 : 0.f, xin1 ? w1 : 0.f);
+    }
+    const f32x2 vr = *reinterpret_cast<const f32x2 *>(&wg.v[0][r][2 * j]);
+    const f32x2 vg = *reinterpret_cast<const f32x2 *>(&wg.v[1][r][2 * j]);
+    const f32x2 vb = *reinterpret_cast<const f32x2 *>(&wg.v[2][r][2 * j]);
+    A.ar = fma2(w, vr, A.ar);     // v_rgb += alpha * v_out
+    A.ag = fma2(w, vg, A.ag);
+    A.abl = fma2(w, vb, A.abl);
+    const f32x2 va = fma2(cb, vb, fma2(cg, vg, mul2(cr, vr)));   // v_alpha = rgb . v_out
+    const f32x2 u = mul2(w, va);   // vis * v_alpha = -v_sigma
+    const f32x2 t1x = mul2(u, dx), t2y = mul2(u, dy);
+    A.sa = fma2(t1x, dx, A.sa);
+    A.sb = fma2(t1x, dy, A.sb);
+    A.sc = fma2(t2y, dy, A.sc);
+    A.ax = add2(A.ax, t1x);
+    A.ay = add2(A.ay, t2y);
+}
+
+// `list`: ranks of the staged Gaussians that reach the region (n of them, ascending).  The warp takes the
+// groups first_group, first_group + group_stride, ...  (region = the warp's own rows: 0, 1; region = the whole
+// tile shared by the CTA's warps: warp, #warps).
+template <int kRows, bool kGuard>
+__device__ __forceinline__ void quad_backward4(const QuadRecords &s, const int *s_ids, const unsigned char *list,
+                                               int n, int first_group, int group_stride, int tile_px0,
+                                               int region_py0, int region_row0, int img_w, int rows_inside,
+                                               const WarpGrad<kRows> &wg, float *__restrict__ grads) {
+    const int lane = threadIdx.x & 31, j = lane & 7, grp = lane >> 3;
+    const float px = (float)(tile_px0 + 2 * j);
+    const f32x2 npx = pk2(-px, -(px + 1.f));
+    bool xin0 = true, xin1 = true;
+    if (kGuard) {
+        xin0 = tile_px0 + 2 * j < img_w;
+        xin1 = tile_px0 + 2 * j + 1 < img_w;
+    }
+    for (int base = 4 * first_group; base < n; base += 4 * group_stride) {
+        const bool valid = base + grp < n;
+        const int t = list[valid ? base + grp : n - 1];
+        const float4 p0 = s.xyab[t], p1 = s.crgb[t];
+        const unsigned rw = s.rows[t];
+        // rows of the region the group's Gaussian can reach; union over the warp
+        int lo = max((int)(rw & 15u) - region_row0, 0), hi = min((int)(rw >> 4) - region_row0, kRows - 1);
+        if (!valid) { lo = kRows; hi = -1; }
+        const int ulo = __reduce_min_sync(0xffffffffu, lo);
+        int uhi = __reduce_max_sync(0xffffffffu, hi);
+        if (kGuard) uhi = min(uhi, rows_inside - 1);
+        const f32x2 xx = pk2(p0.x, p0.x), yy = pk2(p0.y, p0.y), aa = pk2(p0.z, p0.z), bb = pk2(p0.w, p0.w);
+        const f32x2 cc = pk2(p1.x, p1.x), cr = pk2(p1.y, p1.y), cg = pk2(p1.z, p1.z), cb = pk2(p1.w, p1.w);
+        const f32x2 dx = add2(xx, npx), adx = mul2(aa, dx), bdx = mul2(bb, dx);
+        // two rows per trip with separate accumulators: two independent dependency chains per warp
+        GroupAcc A{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull}, B = A;
+        int r = ulo;
+        for (; r + 1 <= uhi; r += 2) {   // warp-uniform
+            group_row<kRows, kGuard>(A, r, region_py0, j, xin0, xin1, wg, yy, cc, dx, adx, bdx, cr, cg, cb);
+            group_row<kRows, kGuard>(B, r + 1, region_py0, j, xin0, xin1, wg, yy, cc, dx, adx, bdx, cr, cg, cb);
+        }
+        if (r <= uhi) group_row<kRows, kGuard>(A, r, region_py0, j, xin0, xin1, wg, yy, cc, dx, adx, bdx, cr, cg, cb);
+        float l0, l1, m0, m1, acc[8];
+        unpk2(A.ax, l0, l1); unpk2(B.ax, m0, m1); const float sx = -((l0 + l1) + (m0 + m1));
+        unpk2(A.ay, l0, l1); unpk2(B.ay, m0, m1); const float sy = -((l0 + l1) + (m0 + m1));
+        acc[0] = fmaf(p0.z, sx, p0.w * sy);   // v_xy = C * sum(v_sigma * delta)
+        acc[1] = fmaf(p0.w, sx, p1.x * sy);
+        unpk2(A.sa, l0, l1); unpk2(B.sa, m0, m1); acc[2] = -0.5f * ((l0 + l1) + (m0 + m1));
+        unpk2(A.sb, l0, l1); unpk2(B.sb, m0, m1); acc[3] = -0.5f * ((l0 + l1) + (m0 + m1));
+        unpk2(A.sc, l0, l1); unpk2(B.sc, m0, m1); acc[4] = -0.5f * ((l0 + l1) + (m0 + m1));
+        unpk2(A.ar, l0, l1); unpk2(B.ar, m0, m1); acc[5] = (l0 + l1) + (m0 + m1);
+        unpk2(A.ag, l0, l1); unpk2(B.ag, m0, m1); acc[6] = (l0 + l1) + (m0 + m1);
+        unpk2(A.abl, l0, l1); unpk2(B.abl, m0, m1); acc[7] = (l0 + l1) + (m0 + m1);
+        const float total = group_reduce_scatter8(acc);
+        if (valid && total != 0.f) atomicAdd(grads + 8 * (size_t)s_ids[t] + j, total);
     }
 }
 

@@ -100,7 +100,7 @@ class GaussianImageFitter:
         self.grad_hook = grad_hook  # called right after the backward of every step (multi-GPU all-reduce)
         self._capacity_hint = isect_capacity
         self._dirty = False         # a gradient is pending on the device
-        self.external_optimizer = False  # True: grad_hook applies the gradients itself (parallel.FusedTileRowExchange)
+        self.external_optimizer = 0  # 1: the caller applies the gradients (codec.py); 2: parallel.TileRowFit
         self.keep_render = False    # tests: also store the unclamped [H,W,3] render of every train_iter
         self.eager_steps_after_resize = 150
         self.track_best = True      # keep the parameters of the best-PSNR step on the device (train.py:132-137)
@@ -136,8 +136,9 @@ class GaussianImageFitter:
         tiles = self.tile_bounds[0] * self.tile_bounds[1]
         cap = self._capacity_hint or max(1 << 16, 32 * n)
         self.isect_capacity = int(min(cap, max(n, 1) * tiles, 2 ** 31 - 1024))
-        self.grads = torch.zeros(n, 8, **f)
-        self.proj = torch.zeros(n, 8, **f)
+        if not getattr(self, "_keep_exchange_buffers", False):   # (parallel.TileRowFit homes them in peer memory)
+            self.grads = torch.zeros(n, 8, **f)
+            self.proj = torch.zeros(n, 8, **f)
         if getattr(self, "best", None) is None or self.best.shape[0] != n:
             self.best = torch.zeros(n, 8, **f)   # device-side best-state snapshot (train.py:132-137)
         if not hasattr(self, "err_map"):
@@ -152,7 +153,7 @@ class GaussianImageFitter:
             n, self.W, self.H, self.tile_bounds[0], self.tile_bounds[1], self.tile_rows[0], self.tile_rows[1],
             self.isect_capacity, self.clip_coe, self.radius_clip, self.lr, 0.9, 0.999, 1e-15, 20000, 0.5,
             int(self.color_norm), 2.0 * self.loss_w[0] / (3.0 * self.H * self.W),
-            1 if self.external_optimizer else 0, self.loss_w[1] / (3.0 * self.H * self.W), self.loss_w[2])
+            int(self.external_optimizer), self.loss_w[1] / (3.0 * self.H * self.W), self.loss_w[2])
         ws_bytes = self.lib.gi2d_fit_workspace_size(C.byref(self.params))
         self.workspace = torch.zeros(max(ws_bytes, 256), dtype=torch.uint8, device=self.device)
         self._invalidate_graphs()

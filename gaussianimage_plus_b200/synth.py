@@ -72,3 +72,35 @@ def scale_rot_inputs(N: int, H: int, W: int, seed: int = 3047):
     rot = (rng.random((N, 1)) * 2 * math.pi).astype(np.float32)
     colors = rng.random((N, 3), np.float32)
     return means, scales, rot, colors
+
+
+def target_image_u8_torch(H: int, W: int, seed: int = 3047, device="cuda"):
+    """u8[H,W,3] on `device`: the same family of targets as target_image() (64 anisotropic blobs + 8 half-plane
+    steps + 2 % noise, clamp, 8-bit), evaluated with torch on the device -- for the 8192^2 workload, whose 67 M
+    pixels take minutes in numpy on a host core.  The blob / step parameters come from the same numpy stream as
+    target_image(); only the per-pixel noise differs (torch generator).  Deterministic for a given seed."""
+    import torch
+
+    rng = np.random.default_rng(seed)
+    dev = torch.device(device)
+    yy = torch.arange(H, device=dev, dtype=torch.float32).view(H, 1)
+    xx = torch.arange(W, device=dev, dtype=torch.float32).view(1, W)
+    img = torch.zeros(H, W, 3, device=dev)
+    for _ in range(64):
+        cx, cy = rng.uniform(0, W), rng.uniform(0, H)
+        sx, sy = rng.uniform(0.02, 0.15) * W, rng.uniform(0.02, 0.15) * H
+        th = rng.uniform(0, math.pi)
+        c, s = math.cos(th), math.sin(th)
+        col = torch.tensor(rng.uniform(0.1, 0.6, 3).astype(np.float32), device=dev)
+        u = (xx - cx) * c + (yy - cy) * s
+        v = -(xx - cx) * s + (yy - cy) * c
+        img += torch.exp(-0.5 * ((u / sx) ** 2 + (v / sy) ** 2)).unsqueeze(-1) * col
+    for _ in range(8):
+        nx, ny = rng.normal(size=2)
+        d = rng.uniform(-0.3, 0.3) * max(H, W)
+        col = torch.tensor(rng.uniform(-0.25, 0.25, 3).astype(np.float32), device=dev)
+        img += (((xx - W / 2) * nx + (yy - H / 2) * ny) > d).float().unsqueeze(-1) * col
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    img += (torch.rand(H, W, 3, device=dev, generator=g) - 0.5) * 0.04
+    return (img.clamp_(0.0, 1.0) * 255.0).round_().to(torch.uint8)

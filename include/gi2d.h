@@ -184,8 +184,9 @@ typedef struct gi2d_fit_params {
     float lr_gamma;
     int32_t color_sigmoid;      /* 1: colours = sigmoid(features) (the reference's color_norm) */
     float loss_scale;           /* dL/d(out) = loss_scale * (clamp(out) - gt); 2/(3*H*W) for mse */
-    int32_t external_optimizer; /* 1: a training step leaves b->grads alone (nothing pending); the caller applies
-                                   them with gi2d_fit_exchange_adam (multi-GPU tile-row split) */
+    int32_t external_optimizer; /* 1: a training step leaves b->grads alone (nothing pending): the caller reads
+                                   them with gi2d_fit_input_grads and runs its own optimiser; 2: tile-row split
+                                   (gi2d_tilerow_step: the exchange kernel owns optimiser and step counters) */
     /* loss_fn of models/utils.py:60-80 as three weights:  loss = w2 * mse + w1 * l1 + ws * (1 - ssim)
      *   L2 (1,0,0)  L1 (0,1,0)  SSIM (0,0,1)  Fusion1 (l,0,1-l)  Fusion2 (0,l,1-l)  Fusion3 (l,1-l,0),  l = 0.7
      * loss_scale = 2 w2 / (3HW) (above), loss_l1_scale = w1 / (3HW), loss_ssim_weight = ws.  With ws == 0 the
@@ -267,14 +268,45 @@ int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, gi2d_stre
  * syy, r, g, b) -- b->grads pushed through the projection backward (-X G X, backward2d.cu:157-214). */
 int gi2d_fit_input_grads(const gi2d_fit_params *p, const gi2d_fit_buffers *b, float *out, gi2d_stream_t stream);
 
-/* Multi-GPU tile-row split: fused reduce-scatter of the partial gradients + projection
- * backward + Adam on the owned slice (sharded optimiser state) + all-gather of the updated parameters,
- * ONE kernel over NVLink peer memory.  peer_* are HOST arrays of `world` device pointers to every
- * rank's grads f32[N,8] / xyz / cov / rgb (symmetric allocations; own buffers at index `rank`).
- * The caller brackets the call with a cross-GPU barrier on `stream`.  Requires external_optimizer. */
-int gi2d_fit_exchange_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int rank, int world,
-                           const void *const *peer_grads, void *const *peer_xyz, void *const *peer_cov,
-                           void *const *peer_rgb, gi2d_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU tile-row split of ONE image (the reference is single-GPU, train.py:39).
+ * Rank q rasterizes tile rows [band_edge[q], band_edge[q+1]).  Every Gaussian has ONE owner rank (equal
+ * contiguous slices [own_begin, own_end)): only the owner holds its parameters and Adam moments, applies
+ * projection backward + Adam to it and projects it.  Per step and Gaussian the owner loads the partial
+ * gradient rows of the ranks whose band the Gaussian's tile box overlaps (P2P loads, fixed rank order) and
+ * stores the new projected record + tile box to the ranks whose band the old or the new box overlaps (P2P
+ * stores): about 1.1 x 72 bytes per Gaussian cross NVLink, not (world-1) x 64.  Cross-GPU ordering is two flag
+ * words per peer inside the kernels (st.release.sys / ld.acquire.sys on peer-mapped memory): no barrier
+ * launches, no host involvement, graph-capturable.  A step in which any rank overflowed its intersection
+ * buffers updates nothing anywhere (GI2D_STAT_OVERFLOW is then set on every rank and GI2D_STAT_STEP does not
+ * advance).  p->external_optimizer must be 2; b->grads / b->proj must be peer_grads[rank] / peer_proj[rank];
+ * p->tile_row_begin/end must be the rank's band.  All peer_* buffers are peer-mapped device memory
+ * (symmetric allocations); sync = 0 switches the in-kernel flags off for a caller that orders the ranks
+ * itself (several ranks emulated on ONE GPU, stream-ordered: phase 1 for every rank, then phase 2).
+ * ------------------------------------------------------------------------------------------ */
+#define GI2D_MAX_RANKS 8
+typedef struct gi2d_tilerow {
+    int32_t rank, world;
+    int32_t band_edge[GI2D_MAX_RANKS + 1];
+    int32_t own_begin, own_end;
+    int32_t sync;
+    float *peer_grads[GI2D_MAX_RANKS];     /* f32[N,8] partial gradients of each rank's band */
+    float *peer_proj[GI2D_MAX_RANKS];      /* f32[N,8] projected records (every rank holds all of them) */
+    void *peer_boxes[GI2D_MAX_RANKS];      /* u16[N,4] tile box (x0,y0,x1,y1) of every Gaussian, unclipped */
+    uint32_t *peer_flags[GI2D_MAX_RANKS];  /* u32[16]: [q] "rank q finished the backward of epoch e" (e*2 + overflow),
+                                              [8+q] "rank q's exchange of epoch e has landed" */
+    uint32_t *ctrl;                        /* u32[8], this rank only: epoch, tickets, [3] != 0: a flag wait timed out */
+} gi2d_tilerow;
+
+/* Set the control block (epoch 1) and project + scatter the owned slice.  Before the call every rank has ZEROED
+ * its peer-visible buffers and the caller has put a cross-rank barrier (host side); another barrier follows the
+ * call (every rank's records have landed everywhere). */
+int gi2d_tilerow_init(const gi2d_fit_params *p, const gi2d_fit_buffers *b, const gi2d_tilerow *tr,
+                      gi2d_stream_t stream);
+/* One step.  phase 1: count + place + rasterize the band (with_backward: + loss gradient + backward into
+ * b->grads); phase 2: exchange + Adam + projection of the owned slice; 3: both. */
+int gi2d_tilerow_step(const gi2d_fit_params *p, const gi2d_fit_buffers *b, const gi2d_tilerow *tr,
+                      int with_backward, int phase, gi2d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Training steps fed from HOST memory (bench.py's `e2e`): one C call per step does what a driver that gets a
