@@ -222,12 +222,14 @@ def make_fitter(torch, synth, name, dev, seed_img=3047, tile_rows=None, use_grap
     return fit, (xyz, cov, bound, rgb), gt_u8, gt_host
 
 
-def roofline_record(torch, lib, _lib, fit, flush, name, peak_tf, n_warm=200, n_flushed=50, barrier=lambda: None):
+def roofline_record(torch, lib, _lib, fit, flush, name, peak_tf, n_warm=200, n_flushed=50, barrier=None):
     """Roofline of the rasterize kernel at the fitter's CURRENT state: pairs of the scene, the kernel's duration
     from back-to-back replays, its share of a back-to-back step, and that share of an L2-flushed step."""
     import ctypes as C
 
     dev = fit.device
+    if barrier is None:
+        barrier = lambda: torch.cuda.synchronize(dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fit.train_iters(16)
     barrier()
@@ -556,17 +558,8 @@ def main():
                 except Exception as e:
                     dropin = {"error": repr(e)[:300]}
 
-    # ---------------- N > 1: ONE 8192^2 / 1M image split by tile rows over the ranks (configs[4])
+    # ---------------- N > 1: ONE 8192^2 / 1M image split by tile rows over the ranks (configs[4]) -- see below
     tilerow = None
-    if world > 1 and not args.no_extra:
-        try:
-            del fit
-        except NameError:
-            pass
-        del flush
-        torch.cuda.empty_cache()
-        tilerow = tilerow_leg(torch, dist, synth, _lib, dev, rank, world, "big_1m", 60, 10, "fused")
-
     if rank == 0:
         line = {
             "metric": "fit_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": Wm,
@@ -602,7 +595,7 @@ def main():
             "gpu_launches": launches_per_step * K,
             "launches_per_step": launches_per_step,
             "clocks": clk.summary(), "roofline": roofline, "workloads": workloads, "cpu_baseline": cpu,
-            "ref_cuda": ref_cuda, "dropin": dropin, "fit_loop": fit_loop, "tilerow": tilerow,
+            "ref_cuda": ref_cuda, "dropin": dropin, "fit_loop": fit_loop, "tilerow": None,
         }
         if ref_cuda and isinstance(ref_cuda.get("fastmath"), dict) and "fit_it_s" in ref_cuda["fastmath"]:
             line["ref_ext_it_s"] = ref_cuda["fastmath"]["fit_it_s"]
@@ -610,14 +603,54 @@ def main():
             line["dropin_it_s"] = dropin["dropin_it_s"]
         if fit_loop and "it_s" in fit_loop:
             line["fit_loop_it_s"] = fit_loop["it_s"]
-        sys.stdout.flush()
-        print(json.dumps(line), flush=True)
+    else:
+        line = None
+
+    def emit(tr):
+        if rank == 0:
+            line["tilerow"] = tr
+            sys.stdout.flush()
+            print(json.dumps(line), flush=True)
+
+    if world > 1 and not args.no_extra:
+        # The tile-row leg: the headline numbers above are final; whatever happens below -- a failed in-run assert on
+        # one rank, a peer that never arrives -- rank 0 still prints its ONE line (with the error in `tilerow`).
+        # (a watchdog THREAD: a signal handler would not run while the main thread sits in a CUDA / NCCL wait)
+        def on_timeout():
+            emit({"error": "the tile-row leg did not finish within 300 s"})
+            os._exit(0)
+
+        watchdog = threading.Timer(300.0, on_timeout)
+        watchdog.daemon = True
+        watchdog.start()
+        try:
+            del fit, flush
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        try:
+            tilerow = tilerow_leg(torch, dist, synth, _lib, dev, rank, world, "big_1m", 60, 10, "fused")
+            failed = 0
+        except BaseException as e:  # noqa: BLE001
+            tilerow, failed = {"error": repr(e)[:400]}, 1
+        try:   # every rank learns whether any rank failed (a rank that died in a collective trips the alarm instead)
+            f = torch.tensor([failed], dtype=torch.int32, device=dev)
+            dist.all_reduce(f, op=dist.ReduceOp.MAX)
+            if int(f.item()) and not failed:
+                tilerow = {"error": "another rank failed an in-run check", "partial": tilerow}
+        except BaseException:  # noqa: BLE001
+            pass
+        watchdog.cancel()
+    emit(tilerow)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except BaseException:  # noqa: BLE001
+            pass
 
 
-STAT_COUNT_BYTES = 80 * 8
+STAT_COUNT_BYTES = 96 * 8
 
 
 # ------------------------------------------------------------------------------------------------ tile rows
@@ -843,7 +876,61 @@ def bench_dropin(torch, dev, xyz, cov, bound, rgb, gt, H, W, iters=300, warm=30)
     for _ in range(iters):
         psnr = train_iter()
     torch.cuda.synchronize(dev)
-    return {"dropin_it_s": iters / (time.perf_counter() - t0), "psnr_after": psnr, "iters": iters + warm,
+    rate = iters / (time.perf_counter() - t0)
+
+    # The same protocol with operators that COST NOTHING (autograd Functions handing back tensors computed once):
+    # what torch's eager glue -- autograd graph, mse_loss, clamp / permute, torch.optim.Adam, two .item() syncs --
+    # allows by itself.  No operator library can make this loop faster than that.
+    class _Proj(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, m, c):
+            ctx.mark_non_differentiable(*_cache["proj"][1:3], _cache["proj"][4])
+            return _cache["proj"]
+
+        @staticmethod
+        def backward(ctx, *g):
+            return _cache["g_xyz"], _cache["g_cov"]
+
+    class _Rast(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, xys, conics, colors):
+            return _cache["img"]
+
+        @staticmethod
+        def backward(ctx, g):
+            return _cache["g_xys"], _cache["g_conics"], _cache["g_rgb"]
+
+    with torch.no_grad():
+        pr = project_gaussians_2d_covariance(p_xyz, p_cov + bnd, H, W, tb)
+        _cache = {"proj": tuple(t.detach() for t in pr),
+                  "img": rasterize_gaussians_plus(*pr, p_rgb, opacity, H, W, 16, 16).detach(),
+                  "g_xyz": torch.zeros_like(p_xyz), "g_cov": torch.zeros_like(p_cov), "g_rgb": torch.zeros_like(p_rgb),
+                  "g_xys": torch.zeros(N, 2, device=dev), "g_conics": torch.zeros(N, 3, device=dev)}
+
+    def glue_iter():
+        xys, depths, radii, conics, nth = _Proj.apply(p_xyz, p_cov + bnd)
+        out = _Rast.apply(xys, conics, p_rgb)
+        image = torch.clamp(out, 0, 1).view(-1, H, W, 3).permute(0, 3, 1, 2).contiguous()
+        loss = torch.nn.functional.mse_loss(image, gt_chw)
+        loss.backward()
+        with torch.no_grad():
+            ps = 10 * math.log10(1.0 / torch.nn.functional.mse_loss(image, gt_chw).item())
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        sched.step()
+        return ps
+
+    for _ in range(warm):
+        glue_iter()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        glue_iter()
+    torch.cuda.synchronize(dev)
+    ceiling = iters / (time.perf_counter() - t0)
+    return {"dropin_it_s": rate, "protocol_ceiling_it_s": ceiling, "psnr_after": psnr, "iters": iters + warm,
+            "protocol_ceiling_note": "the identical loop with zero-cost operators (tensors computed once): the rate "
+                                     "torch's eager autograd + mse_loss + torch.optim.Adam + two .item() syncs allow",
             "protocol": "models/gaussianimage_covariance.py:187-259 unchanged (autograd glue, torch.optim.Adam, two "
                         ".item() syncs per iteration); only `gsplat` is this repo's package"}
 

@@ -31,7 +31,7 @@ class FitParams(C.Structure):
         ("lr0", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("lr_step_size", C.c_int32), ("lr_gamma", C.c_float),
         ("color_sigmoid", C.c_int32), ("loss_scale", C.c_float), ("external_optimizer", C.c_int32),
-        ("loss_l1_scale", C.c_float), ("loss_ssim_weight", C.c_float),
+        ("loss_l1_scale", C.c_float), ("loss_ssim_weight", C.c_float), ("dynamic_points", C.c_int32),
     ]
 
 
@@ -43,7 +43,7 @@ class FitBuffers(C.Structure):
         ("gt_hwc", _P), ("out_img", _P),
         ("grads", _P), ("proj", _P), ("sorted_keys", _P), ("tile_bins", _P), ("stats", _P),
         ("workspace", _P), ("workspace_bytes", _SZ), ("gt_u8_hwc", _P),
-        ("best", _P), ("err_map", _P),
+        ("best", _P), ("err_map", _P), ("best_bound", _P),
     ]
 
 
@@ -77,7 +77,10 @@ SIGNATURES = {
     "gi2d_sort_workspace_size": (_SZ, [_I]),
     "gi2d_sort_pairs_i64": (_I, [_I, _P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "gi2d_get_tile_bin_edges": (_I, [_I, _P, _P, _I, _P]),
+    "gi2d_bin_sort_workspace_size": (_SZ, [_I, _I, _I, _I]),
+    "gi2d_bin_sort": (_I, [_I, _P, _P, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "gi2d_rasterize_sum_fwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gi2d_rasterize_sum_fwd_dev": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gi2d_rasterize_sum_bwd": (_I, [_I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gi2d_fit_workspace_size": (_SZ, [C.POINTER(FitParams)]),
     "gi2d_fit_forward_backward": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _P]),
@@ -98,6 +101,11 @@ SIGNATURES = {
     "gi2d_fit_step_host": (_I, [_P, C.POINTER(FitParams), C.POINTER(FitBuffers), _P, _SZ, _P, _P, C.POINTER(_I)]),
     "gi2d_host_pipe_wait": (_I, [_P, _I]),
     "gi2d_fit_reset": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _P]),
+    "gi2d_fit_set_num_points": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _P]),
+    "gi2d_fit_prune_workspace_size": (_SZ, [_I]),
+    "gi2d_fit_prune": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _P, _SZ, _P]),
+    "gi2d_fit_densify_workspace_size": (_SZ, [_I, _I]),
+    "gi2d_fit_densify": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, _P, _I, _P, _SZ, _P]),
 }
 
 _lib = None

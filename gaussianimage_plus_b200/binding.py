@@ -269,6 +269,100 @@ def get_tile_bin_edges(num_intersects, isect_ids_sorted, num_rows: Optional[int]
 
 
 # ------------------------------------------------------------------------------- rasterize
+_BIN_CAP = {}      # device index -> intersection capacity that has been enough so far
+_BIN_PENDING = {}  # device index -> (pinned info, event) of the last gi2d_bin_sort call
+_BIN_RING = {}     # device index -> [8 pinned i32[3] buffers, next]
+
+
+class BinSortResult:
+    """Outputs of `bin_sort`: the reference's (isect_ids_sorted, gaussian_ids_sorted, tile_bins) with `capacity`
+    rows, `info` i32[3] on the device = {rows written, num_intersects, overflow}, and a pinned host copy of it that
+    `check()` waits for (no synchronisation unless somebody asks)."""
+    __slots__ = ("isect_ids_sorted", "gaussian_ids_sorted", "tile_bins", "info", "_host", "_event", "_dev", "capacity")
+
+    def check(self, block: bool = True):
+        """This call's counters: raises if the buffers overflowed (the render was built from a truncated list), else
+        returns num_intersects.  The capacity for later calls grows with what has been seen.  `block=False`: only
+        if the counters have already arrived (returns None otherwise) -- the autograd backward uses that, so the
+        operator path never stalls the host; a late overflow is then caught by the next call."""
+        if not block and not self._event.query():
+            return None
+        self._event.synchronize()
+        rows, total, ovf = (int(v) for v in self._host)
+        idx = self._dev
+        _BIN_CAP[idx] = max(_BIN_CAP.get(idx, 0), 2 * total)
+        if ovf:
+            raise _lib.Gi2dError(f"bin_sort: {total} intersections did not fit the {self.capacity} rows allocated "
+                                 "(the capacity has been raised; run the step again)")
+        return total
+
+
+def bin_sort(num_points, xys, depths, radii, tile_bounds, radius_clip=1.0) -> BinSortResult:
+    """gi2d_bin_sort: compute_cumulative_intersects + bin_and_sort_gaussians (gsplat/utils.py:231-311) in ONE call with
+    num_intersects kept on the device -- no `.item()`.  Requires depths that all share one bit pattern (the 2-D
+    projections of this package emit 0.0 and say so)."""
+    lib = _lib.load()
+    _check_input(xys, "xys", f32)
+    _check_input(radii, "radii", i32)
+    dev = xys.device
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    n = int(num_points)
+    tx, ty = int(tile_bounds[0]), int(tile_bounds[1])
+    prev = _BIN_PENDING.get(idx)
+    if prev is not None and prev[1].query():     # the previous call's counters have arrived: size from them
+        _BIN_CAP[idx] = max(_BIN_CAP.get(idx, 0), 2 * int(prev[0][1]))
+        if int(prev[0][2]):
+            _BIN_PENDING.pop(idx, None)
+            raise _lib.Gi2dError(f"bin_sort: the previous call overflowed its {prev[2]} rows ({int(prev[0][1])} "
+                                 "intersections); the capacity has been raised -- run the step again")
+    cap = int(min(max(_BIN_CAP.get(idx, 0), 1 << 16, 32 * n), max(n, 1) * tx * ty, 2 ** 31 - 1024))
+    res = BinSortResult()
+    res.isect_ids_sorted = torch.empty(cap, dtype=i64, device=dev)
+    res.gaussian_ids_sorted = torch.empty(cap, dtype=i32, device=dev)
+    res.tile_bins = torch.empty((tx * ty, 2), dtype=i32, device=dev)
+    res.info = torch.empty(3, dtype=i32, device=dev)
+    res.capacity, res._dev = cap, idx
+    ws = _workspace(lib.gi2d_bin_sort_workspace_size(n, tx, ty, cap), dev)
+    with _on(dev):
+        _lib.check(lib.gi2d_bin_sort(n, _p(xys), _p(depths), _p(radii), tx, ty, float(radius_clip), cap,
+                                     _p(res.isect_ids_sorted), _p(res.gaussian_ids_sorted), _p(res.tile_bins),
+                                     _p(res.info), _p(ws), ws.numel(), _stream(dev)), "bin_sort")
+        ring = _BIN_RING.setdefault(idx, [[torch.zeros(3, dtype=i32).pin_memory() for _ in range(8)], 0])
+        res._host = ring[0][ring[1] & 7]     # (pinned allocations cost ~50 us each: a small ring, reused)
+        ring[1] += 1
+        res._host.copy_(res.info, non_blocking=True)
+        res._event = torch.cuda.Event()
+        res._event.record(torch.cuda.current_stream(dev))
+    _BIN_PENDING[idx] = (res._host, res._event, cap)
+    return res
+
+
+def rasterize_sum_plus_forward_dev(tile_bounds, block, img_size, bins: BinSortResult, xys, conics, colors, opacities,
+                                   background):
+    """rasterize_sum_plus_forward on the outputs of `bin_sort` (num_intersects on the device: the constant
+    background image of rasterize_sum_plus.py:110-118 is the kernel's branch, not the host's)."""
+    lib = _lib.load()
+    _check_tiles(block)
+    for t, nme, dt in ((xys, "xys", f32), (conics, "conics", f32), (colors, "colors", f32), (opacities, "opacities", f32)):
+        _check_input(t, nme, dt)
+    if colors.shape[-1] != 3:
+        raise ValueError("rasterize_sum kernels render 3 channels")
+    dev = xys.device
+    W, H = int(img_size[0]), int(img_size[1])
+    out_img = torch.empty((H, W, 3), dtype=f32, device=dev)
+    final_Ts = torch.empty((H, W), dtype=f32, device=dev)
+    bg = None
+    if background is not None:
+        bg = _check_input(background.to(device=dev, dtype=f32).contiguous(), "background", f32)
+    with _on(dev):
+        _lib.check(lib.gi2d_rasterize_sum_fwd_dev(int(tile_bounds[0]), int(tile_bounds[1]), W, H,
+                                                  _p(bins.gaussian_ids_sorted), _p(bins.tile_bins),
+                                                  int(bins.tile_bins.shape[0]), _p(xys), _p(conics), _p(colors),
+                                                  _p(opacities), _p(out_img), _p(final_Ts), None,
+                                                  _p(bins.info[1:2]), _p(bg), _stream(dev)), "rasterize_sum_fwd_dev")
+    return out_img, final_Ts
+
+
 def _check_tiles(block):
     if int(block[0]) != TILE or int(block[1]) != TILE:
         # the reference silently mis-bins for any other block size (SURVEY R8): refuse instead
@@ -321,10 +415,10 @@ def rasterize_sum_plus_backward(img_height, img_width, BLOCK_H, BLOCK_W, gaussia
     dev, n = xys.device, xys.shape[0]
     H, W = int(img_height), int(img_width)
     tb = ((W + TILE - 1) // TILE, (H + TILE - 1) // TILE)
-    v_xy = torch.empty((n, 2), dtype=f32, device=dev)
-    v_conic = torch.empty((n, 3), dtype=f32, device=dev)
-    v_colors = torch.empty((n, 3), dtype=f32, device=dev)
-    v_opacity = torch.empty((n, 1), dtype=f32, device=dev)
+    # the four outputs back to back in ONE allocation: the library zero-fills them with one memset
+    block = torch.empty(9 * n, dtype=f32, device=dev)
+    v_xy, v_conic = block[:2 * n].view(n, 2), block[2 * n:5 * n].view(n, 3)
+    v_colors, v_opacity = block[5 * n:8 * n].view(n, 3), block[8 * n:].view(n, 1)
     with _on(dev):
         _lib.check(lib.gi2d_rasterize_sum_bwd(n, tb[0], tb[1], W, H, _p(gaussian_ids_sorted), _p(tile_bins),
                                               int(tile_bins.shape[0]), _p(xys), _p(conics), _p(colors),

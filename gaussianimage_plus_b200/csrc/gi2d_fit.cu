@@ -72,6 +72,12 @@ constexpr int kStatNonPsdAcc = 12;  // accumulator behind GI2D_STAT_NON_PSD (mov
 #define GI2D_CHECK(stats, cond) do { } while (0)
 #endif
 
+// Live Gaussian count: the launch-time num_points, or (dynamic_points) the device-side count that
+// gi2d_fit_prune / gi2d_fit_densify maintain -- num_points is then the CAPACITY of the per-Gaussian arrays.
+__device__ __forceinline__ int live_points(const gi2d_fit_params &p, const double *__restrict__ stats) {
+    return p.dynamic_points ? (int)__ldcg(stats + GI2D_STAT_NUM_POINTS) : p.num_points;
+}
+
 // Squared error of the last training step: the 64 partials summed by ONE warp in a fixed order, so that
 // every CTA of the optimiser kernel and the bookkeeping thread take the same best-so-far decision.
 __device__ __forceinline__ double sse_total_warp(const double *__restrict__ stats) {
@@ -98,6 +104,7 @@ __device__ __forceinline__ void best_commit_warp0(double *__restrict__ stats) {
         tot < stats[GI2D_STAT_BEST_SSE]) {
         stats[GI2D_STAT_BEST_SSE] = tot;
         stats[GI2D_STAT_BEST_STEP] = stats[GI2D_STAT_STEP];
+        stats[GI2D_STAT_BEST_N] = stats[GI2D_STAT_NUM_POINTS];   // (rows of the snapshot the optimiser threads wrote)
     }
 }
 
@@ -272,29 +279,34 @@ __global__ void __launch_bounds__(kProjThreads)
 fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bound,
                    float4 *__restrict__ proj, float4 *__restrict__ grads, ushort4 *__restrict__ boxes,
                    int32_t *__restrict__ tile_count, const double *__restrict__ stats, int with_backward,
-                   float4 *__restrict__ best, int expect_pending) {
+                   float4 *__restrict__ best, int expect_pending, float *__restrict__ best_bound) {
     __shared__ int s_best;
     pdl_launch_dependents();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool mine = g < p.num_points;
+    const bool in_cap = g < p.num_points;   // a row of the arrays (the live count comes back with the flags below)
     pdl_wait();  // the previous step's rasterizer wrote grads (and read proj, and zeroed tile_count)
     // A training step nearly always finds a gradient pending: issue every load of the optimiser BEFORE the
     // flags that say so come back (one L2 round trip less on this latency-bound kernel); a render-only call
     // (expect_pending == 0) loads lazily.
-    const bool early = expect_pending && a.m_xyz != nullptr && mine;
+    const bool early = expect_pending && a.m_xyz != nullptr && in_cap;
     AdamRegs r;
     if (early) adam_load(a, g, proj, grads, r);
     float bnd[3] = {0.f, 0.f, 0.f};
-    if (mine) {
+    if (in_cap) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) bnd[k] = __ldg(cov_bound + 3 * g + k);
+        for (int k = 0; k < 3; ++k) bnd[k] = __ldcg(cov_bound + 3 * g + k);   // (prune / densify rewrite the bounds)
     }
+    const bool mine = g < live_points(p, stats);
     const bool pending = a.m_xyz != nullptr && __ldcg(stats + kStatPending) != 0.0;
     const bool veto = __ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0;  // that step overflowed: the host re-runs it
     best_flag_warp0(stats, best != nullptr && pending && !veto, &s_best);
     __syncthreads();
     const bool snapshot = s_best != 0;
-    if (!mine) return;
+    if (!mine) {
+        // a row beyond the live count: an empty box keeps it out of the placement kernel's walk
+        if (in_cap) boxes[g] = make_ushort4(0, 0, 0, 0);
+        return;
+    }
     float2 m;
     float c[3], q[3];
     if (pending) {
@@ -306,6 +318,10 @@ fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_
         if (snapshot) {  // the state dict right after optimizer.step() of the best iteration (train.py:132-137)
             best[2 * g] = make_float4(m.x, m.y, c[0], c[1]);
             best[2 * g + 1] = make_float4(c[2], q[0], q[1], q[2]);
+            if (best_bound) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) best_bound[3 * g + k] = bnd[k];
+            }
         }
     } else if (early) {
         m = r.x;
@@ -460,7 +476,7 @@ __device__ __forceinline__ void walk_intersections(int g_begin, int g_end, int t
 // slot inside its tile's range is handed out by an atomic cursor: the order within a tile is arbitrary
 // here and fixed by the rank sort of K3.  CTA 0 also publishes the tile ranges (forward.cu:211-233;
 // empty tiles keep the reference's (0,0)) and does the bookkeeping.
-template <bool kSmemScan>
+template <bool kSmemScan, bool kFit = true>
 __global__ void __launch_bounds__(kPlaceThreads)
 fit_place_kernel(gi2d_fit_params p, int with_backward, int gpb, int num_tiles,
                  const ushort4 *__restrict__ boxes, const int32_t *__restrict__ tile_count,
@@ -488,37 +504,108 @@ fit_place_kernel(gi2d_fit_params p, int with_backward, int gpb, int num_tiles,
     if (kSmemScan) {
         for (int t = blockIdx.x * kPlaceThreads + threadIdx.x; t < num_tiles; t += gridDim.x * kPlaceThreads) {
             const int c = __ldcg(tile_count + t);
-            reinterpret_cast<int2 *>(tile_bins)[t] = c ? make_int2(s_base[t], s_base[t] + c) : make_int2(0, 0);
+            int2 rg = c ? make_int2(s_base[t], s_base[t] + c) : make_int2(0, 0);
+            if (!kFit) { rg.x = min(rg.x, p.isect_capacity); rg.y = min(rg.y, p.isect_capacity); }   // rows that exist
+            reinterpret_cast<int2 *>(tile_bins)[t] = rg;
         }
     } else {
         for (int t = blockIdx.x * kPlaceThreads + threadIdx.x; t < num_tiles; t += gridDim.x * kPlaceThreads) {
             const int e = __ldcg(tile_incl + t), c = __ldcg(tile_count + t);
-            reinterpret_cast<int2 *>(tile_bins)[t] = c ? make_int2(e - c, e) : make_int2(0, 0);
+            int2 rg = c ? make_int2(e - c, e) : make_int2(0, 0);
+            if (!kFit) { rg.x = min(rg.x, p.isect_capacity); rg.y = min(rg.y, p.isect_capacity); }
+            reinterpret_cast<int2 *>(tile_bins)[t] = rg;
         }
     }
     if (blockIdx.x == 0 && warp == 0) {
-        step_bookkeeping_warp0(p, with_backward, stats, total > p.isect_capacity);
+        if (kFit) step_bookkeeping_warp0(p, with_backward, stats, total > p.isect_capacity);
         if (lane == 0) {
-            stats[GI2D_STAT_ISECTS] = (double)total;
-            *n_isect = total > p.isect_capacity ? p.isect_capacity : total;
+            if (kFit) stats[GI2D_STAT_ISECTS] = (double)total;
+            n_isect[0] = total > p.isect_capacity ? p.isect_capacity : total;
+            if (!kFit) {   // gi2d_bin_sort: {clamped count, true count, overflow}
+                n_isect[1] = total;
+                n_isect[2] = total > p.isect_capacity ? 1 : 0;
+            }
         }
     }
     walk_intersections(g_begin, g_end, p.tiles_x, boxes, first_box, [&](bool valid, int tile, int g) {
         if (valid) {
             // (record loads and the cursor atomic are independent: all in flight together)
-            const float4 r0 = __ldcg(proj + 2 * g), r1 = __ldcg(proj + 2 * g + 1);
+            float4 r0, r1;
+            if (kFit) { r0 = __ldcg(proj + 2 * g); r1 = __ldcg(proj + 2 * g + 1); }
             const int start = kSmemScan ? s_base[tile] : (__ldcg(tile_incl + tile) - __ldcg(tile_count + tile));
             const int slot = atomicAdd(tile_fill + tile, 1);
             const int pos = start + slot;
-            GI2D_CHECK(stats, tile >= 0 && tile < num_tiles && g >= 0 && g < p.num_points && start >= 0 &&
+            if (kFit) GI2D_CHECK(stats, tile >= 0 && tile < num_tiles && g >= 0 && g < p.num_points && start >= 0 &&
                                   slot >= 0 && slot < __ldcg(tile_count + tile));
             if (pos < p.isect_capacity) {
                 keys_out[pos] = ((uint64_t)(uint32_t)tile << 32) | (uint32_t)g;
-                records[2 * (size_t)pos] = r0;
-                records[2 * (size_t)pos + 1] = r1;
+                if (kFit) {
+                    records[2 * (size_t)pos] = r0;
+                    records[2 * (size_t)pos + 1] = r1;
+                }
             }
         }
     });
+}
+
+// ------------------------------------------------------------------------------------------- gi2d_bin_sort
+// The reference's binning (utils.py:231-311: cumsum -> .item() -> map_gaussian_to_intersects -> torch.sort ->
+// gather -> get_tile_bin_edges) as ONE call with num_intersects kept on the device: per-tile counts (one
+// red.global per touched tile), prefix sum, counting-sort placement, in-tile rank sort -- the fit step's scheme,
+// emitting the reference's arrays.  Valid when every depth has the same bit pattern (the 2-D projections emit
+// 0.0): the keys then order by tile, then by Gaussian id (stable sort of Gaussian-major keys).
+__global__ void __launch_bounds__(256)
+bs_count_kernel(int n, const float *__restrict__ xys, const int32_t *__restrict__ radii, int tiles_x, int tiles_y,
+                float radius_clip, ushort4 *__restrict__ boxes, int32_t *__restrict__ tile_count) {
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= n) return;
+    const int r = radii[g];
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    if (!((float)r < radius_clip)) {   // forward.cu:161 (int radius promoted to float)
+        const float2 c = reinterpret_cast<const float2 *>(xys)[g];
+        const TileBox b = tile_bbox(c.x, c.y, (float)r, tiles_x, tiles_y);   // helpers.cuh:43-47 on radii[idx]
+        if (b.x1 > b.x0 && b.y1 > b.y0) { x0 = b.x0; x1 = b.x1; y0 = b.y0; y1 = b.y1; }
+    }
+    boxes[g] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+    for (int ty = y0; ty < y1; ++ty)
+        for (int tx = x0; tx < x1; ++tx) atomicAdd(tile_count + ty * tiles_x + tx, 1);
+}
+
+// one CTA per tile: rank the tile's entries by gaussian id, emit isect_ids_sorted (tile << 32 | depth bits) and
+// gaussian_ids_sorted
+__global__ void __launch_bounds__(64)
+bs_tile_sort_kernel(int capacity, const int32_t *__restrict__ tile_bins, const uint64_t *__restrict__ keys,
+                    int64_t depth_bits, int64_t *__restrict__ isect_ids_sorted,
+                    int32_t *__restrict__ gaussian_ids_sorted) {
+    __shared__ __align__(16) int s_id[kMaxPerTile + 4];
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int2 range = __ldcg(reinterpret_cast<const int2 *>(tile_bins) + tile);
+    const int cnt = max(0, min(range.y, capacity) - range.x);
+    if (cnt == 0) return;
+    const int64_t hi = ((int64_t)tile << 32) | depth_bits;
+    if (cnt <= kMaxPerTile) {
+        for (int e = tid; e < cnt; e += 64) s_id[e] = (int)(uint32_t)__ldcg(keys + range.x + e);
+        if (tid < 4) s_id[cnt + tid] = 0x7fffffff;
+        __syncthreads();
+        for (int e = tid; e < cnt; e += 64) {
+            const int id = s_id[e];
+            int rank = 0;
+            for (int j = 0; j < cnt; j += 4) {
+                const int4 o = *reinterpret_cast<const int4 *>(s_id + j);
+                rank += (o.x < id) + (o.y < id) + (o.z < id) + (o.w < id);
+            }
+            isect_ids_sorted[range.x + rank] = hi;
+            gaussian_ids_sorted[range.x + rank] = id;
+        }
+    } else {
+        for (int e = tid; e < cnt; e += 64) {
+            const int id = (int)(uint32_t)__ldcg(keys + range.x + e);
+            int rank = 0;
+            for (int j = 0; j < cnt; ++j) rank += ((int)(uint32_t)__ldcg(keys + range.x + j) < id) ? 1 : 0;
+            isect_ids_sorted[range.x + rank] = hi;
+            gaussian_ids_sorted[range.x + rank] = id;
+        }
+    }
 }
 
 // ---- optional TMA staging of a tile's records (-DGI2D_TMA_STAGE; measured, not the default: DESIGN.md 2).
@@ -1012,13 +1099,16 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
 }
 
 // which rasterizer a step launches: GI2D_RASTER=0 the round-1 kernel (8 warps per tile, scalar math); 1 / 2 / 4 the
-// quadrant kernel with that many warps per tile.  Default: 4 (measured, profiles/README.md).
-int raster_variant() {
-    static const int v = [] {
+// quadrant kernel with that many warps per tile.  Default (measured on the B200, profiles/README.md): 4 warps per
+// tile while the whole grid fits the GPU in about one wave (768x512: 1536 tiles -- the extra warps hide latency),
+// 2 warps per tile beyond (2040x1356, 8192^2: fewer instructions per pair win once there are many waves).
+int raster_variant(int num_tiles) {
+    static const int forced = [] {
         const char *e = getenv("GI2D_RASTER");
-        return e ? atoi(e) : 4;
+        return e ? atoi(e) : -1;
     }();
-    return v;
+    if (forced >= 0) return forced;
+    return num_tiles <= 4096 ? 4 : 2;
 }
 
 template <RasterMode kMode>
@@ -1026,7 +1116,7 @@ cudaError_t launch_raster(bool pdl, dim3 grid, cudaStream_t st, const gi2d_fit_p
                           uint64_t *keys_tmp, const int32_t *tile_bins, int32_t *tile_count, int32_t *tile_fill,
                           const float4 *records, const float *gt, const uint8_t *gt_u8, float *out_img, float *grads,
                           double *stats, float *err_map, const float *v_out) {
-    const int v = raster_variant();
+    const int v = raster_variant((int)(grid.x * grid.y));
 #define GI2D_RASTER_ARGS p, sorted_keys, keys_tmp, tile_bins, tile_count, tile_fill, records, gt, gt_u8, out_img, grads, stats, err_map, v_out
     if (v == 1) {
         if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 1>, grid, dim3(32), 0, st, GI2D_RASTER_ARGS);
@@ -1051,17 +1141,19 @@ cudaError_t launch_raster(bool pdl, dim3 grid, cudaStream_t st, const gi2d_fit_p
 // next step's K1 does the same work.
 __global__ void __launch_bounds__(256)
 fit_adam_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bound, const float4 *__restrict__ proj,
-                const float4 *__restrict__ grads, double *__restrict__ stats, float4 *__restrict__ best) {
+                const float4 *__restrict__ grads, double *__restrict__ stats, float4 *__restrict__ best,
+                float *__restrict__ best_bound) {
     __shared__ int s_best;
     pdl_launch_dependents();
     pdl_wait();
     const int g = blockIdx.x * 256 + threadIdx.x;
+    const int n_live = live_points(p, stats);
     const bool pending = __ldcg(stats + kStatPending) != 0.0;
     const bool veto = __ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0;
     best_flag_warp0(stats, best != nullptr && pending && !veto, &s_best);
     __syncthreads();
     bool bad = false;
-    if (g < p.num_points) {
+    if (g < n_live) {
         float c[3];
         if (pending) {
             float2 x;
@@ -1070,14 +1162,18 @@ fit_adam_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bou
             if (s_best) {
                 best[2 * g] = make_float4(x.x, x.y, c[0], c[1]);
                 best[2 * g + 1] = make_float4(c[2], q[0], q[1], q[2]);
+                if (best_bound) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) best_bound[3 * g + k] = __ldcg(cov_bound + 3 * g + k);
+                }
             }
         } else {
 #pragma unroll
             for (int k = 0; k < 3; ++k) c[k] = a.cov[3 * g + k];
         }
         // check_non_semi_definite (gaussianimage_covariance.py:373-382) on cov + bound, torch's op order
-        const float sx = __fadd_rn(c[0], cov_bound[3 * g]), sxy = __fadd_rn(c[1], cov_bound[3 * g + 1]);
-        const float sy = __fadd_rn(c[2], cov_bound[3 * g + 2]);
+        const float sx = __fadd_rn(c[0], __ldcg(cov_bound + 3 * g)), sxy = __fadd_rn(c[1], __ldcg(cov_bound + 3 * g + 1));
+        const float sy = __fadd_rn(c[2], __ldcg(cov_bound + 3 * g + 2));
         const float det = __fsub_rn(__fmul_rn(sx, sy), __fmul_rn(sxy, sxy));
         bad = !((det > 0.f) && (sx > 0.f) && (sy > 0.f));
     }
@@ -1316,12 +1412,12 @@ tr_exchange_kernel(gi2d_fit_params p, gi2d_tilerow tr, AdamPtrs a, const float *
 // d loss / d (the step's inputs) for callers with their own optimiser: projection backward only
 __global__ void __launch_bounds__(256)
 fit_input_grads_kernel(int n, const float4 *__restrict__ proj, const float4 *__restrict__ grads,
-                       float4 *__restrict__ out, const double *__restrict__ stats) {
+                       float4 *__restrict__ out, const double *__restrict__ stats, int dynamic) {
     pdl_launch_dependents();
     pdl_wait();
     const int g = blockIdx.x * 256 + threadIdx.x;
     if (g >= n) return;
-    if (__ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0) {   // truncated list: the caller's optimiser step becomes a no-op
+    if (__ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0 || (dynamic && g >= (int)__ldcg(stats + GI2D_STAT_NUM_POINTS))) {   // truncated list: the caller's optimiser step becomes a no-op
         out[2 * g] = out[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
@@ -1336,6 +1432,10 @@ fit_input_grads_kernel(int n, const float4 *__restrict__ proj, const float4 *__r
 __global__ void fit_reset_kernel(gi2d_fit_params p, double *stats, int step) {
     const int i = threadIdx.x;
     if (i >= GI2D_STAT_COUNT) return;
+    if (i == GI2D_STAT_NUM_POINTS) {   // the live count is not a statistic: kept when the device owns it
+        if (!p.dynamic_points) stats[i] = (double)p.num_points;
+        return;
+    }
     double v = 0.0;
     if (i == GI2D_STAT_STEP) v = (double)step;
     if (i == GI2D_STAT_BEST_SSE) v = __longlong_as_double(0x7ff0000000000000LL);  // +inf: nothing seen yet
@@ -1347,6 +1447,172 @@ __global__ void fit_reset_kernel(gi2d_fit_params p, double *stats, int step) {
                                 (step >= 1 && p.lr_step_size > 0) ? floor((double)(step - 1) / p.lr_step_size) : 0.0);
     stats[i] = v;
 }
+
+// ------------------------------------------------------------------- prune / densify on the device
+//   The model's size changes in place: the per-Gaussian arrays hold `capacity` rows, the live
+// count is stats[GI2D_STAT_NUM_POINTS], and these kernels move rows and the count -- no reallocation, no host
+// round trip, the captured step graph stays valid.
+struct ModelPtrs {
+    float *xyz, *cov, *rgb, *bound, *m_xyz, *v_xyz, *m_cov, *v_cov, *m_rgb, *v_rgb;
+};
+constexpr int kRowFloats = 27;   // xyz 2 + cov 3 + rgb 3 + bound 3 + m (2+3+3) + v (2+3+3)
+
+__device__ __forceinline__ void load_row(const ModelPtrs &m, int g, float (&r)[kRowFloats]) {
+    r[0] = m.xyz[2 * g]; r[1] = m.xyz[2 * g + 1];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r[2 + k] = m.cov[3 * g + k]; r[5 + k] = m.rgb[3 * g + k]; r[8 + k] = m.bound[3 * g + k];
+        r[13 + k] = m.m_cov[3 * g + k]; r[16 + k] = m.m_rgb[3 * g + k];
+        r[21 + k] = m.v_cov[3 * g + k]; r[24 + k] = m.v_rgb[3 * g + k];
+    }
+    r[11] = m.m_xyz[2 * g]; r[12] = m.m_xyz[2 * g + 1];
+    r[19] = m.v_xyz[2 * g]; r[20] = m.v_xyz[2 * g + 1];
+}
+
+__device__ __forceinline__ void store_row(const ModelPtrs &m, int g, const float (&r)[kRowFloats]) {
+    m.xyz[2 * g] = r[0]; m.xyz[2 * g + 1] = r[1];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        m.cov[3 * g + k] = r[2 + k]; m.rgb[3 * g + k] = r[5 + k]; m.bound[3 * g + k] = r[8 + k];
+        m.m_cov[3 * g + k] = r[13 + k]; m.m_rgb[3 * g + k] = r[16 + k];
+        m.v_cov[3 * g + k] = r[21 + k]; m.v_rgb[3 * g + k] = r[24 + k];
+    }
+    m.m_xyz[2 * g] = r[11]; m.m_xyz[2 * g + 1] = r[12];
+    m.v_xyz[2 * g] = r[19]; m.v_xyz[2 * g + 1] = r[20];
+}
+
+// check_non_semi_definite (gaussianimage_covariance.py:373-382) on (sxx, sxy, syy), torch's operation order
+__device__ __forceinline__ bool is_pos_def(float sx, float sxy, float sy) {
+    const float det = __fsub_rn(__fmul_rn(sx, sy), __fmul_rn(sxy, sxy));
+    return (det > 0.f) && (sx > 0.f) && (sy > 0.f);
+}
+
+// keep[g] = 1 for the live rows whose covariance + bound is positive definite
+__global__ void __launch_bounds__(256)
+prune_flag_kernel(gi2d_fit_params p, ModelPtrs m, const double *__restrict__ stats, int32_t *__restrict__ keep) {
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= p.num_points) return;
+    int k = 0;
+    if (g < live_points(p, stats))
+        k = is_pos_def(__fadd_rn(m.cov[3 * g], m.bound[3 * g]), __fadd_rn(m.cov[3 * g + 1], m.bound[3 * g + 1]),
+                       __fadd_rn(m.cov[3 * g + 2], m.bound[3 * g + 2])) ? 1 : 0;
+    keep[g] = k;
+}
+
+// stable compaction, first half: survivors to their new row of the scratch copy
+__global__ void __launch_bounds__(256)
+prune_gather_kernel(gi2d_fit_params p, ModelPtrs m, const double *__restrict__ stats, const int32_t *__restrict__ keep,
+                    const int32_t *__restrict__ incl, float *__restrict__ scratch) {
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    const int n = live_points(p, stats);
+    const int kept = p.num_points > 0 ? incl[p.num_points - 1] : 0;
+    if (kept == n || kept == 0) return;    // nothing to prune / `cur - to_prune > 0` fails: leave everything
+    if (g >= n || !keep[g]) return;
+    float r[kRowFloats];
+    load_row(m, g, r);
+    float *dst = scratch + (size_t)(incl[g] - 1) * kRowFloats;
+#pragma unroll
+    for (int k = 0; k < kRowFloats; ++k) dst[k] = r[k];
+}
+
+// second half: scratch back to the arrays, new live count
+__global__ void __launch_bounds__(256)
+prune_scatter_kernel(gi2d_fit_params p, ModelPtrs m, double *__restrict__ stats, const int32_t *__restrict__ incl,
+                     const float *__restrict__ scratch) {
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    const int n = live_points(p, stats);
+    const int kept = p.num_points > 0 ? incl[p.num_points - 1] : 0;
+    const bool moved = !(kept == n || kept == 0);
+    if (moved && g < kept) {
+        float r[kRowFloats];
+        const float *src = scratch + (size_t)g * kRowFloats;
+#pragma unroll
+        for (int k = 0; k < kRowFloats; ++k) r[k] = src[k];
+        store_row(m, g, r);
+    }
+    // (every thread has read the old count above; the last block to finish publishes the new one)
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd((unsigned *)(stats + GI2D_STAT_COUNT - 1), 1u) == gridDim.x - 1;   // ticket in the last (unused) slot
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        *(unsigned *)(stats + GI2D_STAT_COUNT - 1) = 0u;
+        stats[GI2D_STAT_PRUNED] = moved ? (double)(n - kept) : 0.0;
+        if (moved && p.dynamic_points) stats[GI2D_STAT_NUM_POINTS] = (double)kept;
+    }
+}
+
+// error map -> sortable keys: descending error, ties by ascending pixel index
+__global__ void __launch_bounds__(256)
+densify_keys_kernel(int n_pix, const float *__restrict__ err, int64_t *__restrict__ keys, int32_t *__restrict__ vals) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_pix) return;
+    const float e = __ldcg(err + i);
+    uint32_t bits = __float_as_uint(e);
+    if (!(e >= 0.f)) bits = 0;                      // (NaN / negative cannot occur in a sum of absolute values)
+    if (bits > 0x7F800000u) bits = 0x7F800000u;
+    keys[i] = ((int64_t)(0x7FFFFFFFu - bits) << 32) | (uint32_t)i;
+    vals[i] = i;
+}
+
+// the first k sorted candidates become new Gaussians (train.py:99-112 + densification_postfix); ONE CTA
+__global__ void __launch_bounds__(1024)
+densify_append_kernel(gi2d_fit_params p, ModelPtrs m, double *__restrict__ stats, const int32_t *__restrict__ sorted_pix,
+                      const float *__restrict__ new_cov, int k_rows, int slv) {
+    __shared__ int s_warp[32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x;
+    const int n = live_points(p, stats);
+    const int k = max(0, min(k_rows, p.num_points - n));
+    // pass 1: how many candidates have a positive-definite covariance (the bound is not added: the reference tests
+    // new_cov2d itself, gaussianimage_covariance.py:309)
+    int mine = 0;
+    for (int i = tid; i < k; i += 1024)
+        mine += is_pos_def(new_cov[3 * i], new_cov[3 * i + 1], new_cov[3 * i + 2]) ? 1 : 0;
+    int tot;
+    block_scan_inclusive<1024>(mine, s_warp, &tot);
+    if (tid == 0) s_total = tot;
+    __syncthreads();
+    const int n_new = n + s_total;
+    // low_pass = min(H*W / (9*pi*cur_num_points), 300) evaluated in double like the Python expression, then float32
+    const float lp = slv ? (float)fmin((double)p.img_height * (double)p.img_width / (9.0 * 3.141592653589793 * (double)n_new), 300.0)
+                         : 0.5f;
+    // pass 2: append in candidate order (chunks of 1024, running base)
+    int base = n;
+    for (int c0 = 0; c0 < k; c0 += 1024) {
+        const int i = c0 + tid;
+        float cx = 0.f, cxy = 0.f, cy = 0.f;
+        bool ok = false;
+        if (i < k) {
+            cx = new_cov[3 * i]; cxy = new_cov[3 * i + 1]; cy = new_cov[3 * i + 2];
+            ok = is_pos_def(cx, cxy, cy);
+        }
+        int chunk;
+        const int incl = block_scan_inclusive<1024>(ok ? 1 : 0, s_warp, &chunk);
+        if (ok) {
+            const int g = base + incl - 1;
+            const int pix = sorted_pix[i];
+            float r[kRowFloats];
+#pragma unroll
+            for (int q = 0; q < kRowFloats; ++q) r[q] = 0.f;
+            r[0] = (float)(pix % p.img_width);
+            r[1] = (float)(pix / p.img_width);
+            r[2] = cx; r[3] = cxy; r[4] = cy;
+            r[8] = lp; r[9] = 0.f; r[10] = lp;
+            store_row(m, g, r);
+        }
+        base += chunk;
+    }
+    if (tid == 0) {
+        stats[GI2D_STAT_ADDED] = (double)s_total;
+        if (p.dynamic_points) stats[GI2D_STAT_NUM_POINTS] = (double)n_new;
+    }
+}
+
+__global__ void set_stat_kernel(double *stats, int slot, double v) { stats[slot] = v; }
 
 int validate(const gi2d_fit_params *p, const gi2d_fit_buffers *b) {
     GI2D_REQUIRE(p && b, "null params");
@@ -1397,7 +1663,7 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     else
         launch_pdl(fit_project_kernel, dim3(max(1, cdiv(p->num_points, proj_threads))), dim3(proj_threads), 0, st,
             *p, ap, b->cov_bound, (float4 *)b->proj, (float4 *)b->grads, w.boxes, w.tile_count, b->stats, with_backward,
-            (float4 *)b->best, (with_backward && !p->external_optimizer) ? 1 : 0);
+            (float4 *)b->best, (with_backward && !p->external_optimizer) ? 1 : 0, b->best_bound);
     if (mk) mk->mark(st);
     if (!pl.smem_scan) {
         // more tiles than one CTA scans in shared memory: device-wide inclusive prefix sum of the counts
@@ -1520,8 +1786,138 @@ extern "C" int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b
     const AdamPtrs ap{b->xyz, b->cov, b->rgb, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
     launch_pdl(fit_adam_kernel, dim3(cdiv(p->num_points, 256)), dim3(256), 0, (cudaStream_t)stream, *p, ap,
                (const float *)b->cov_bound, (const float4 *)b->proj, (const float4 *)b->grads, b->stats,
-               (float4 *)b->best);
+               (float4 *)b->best, b->best_bound);
     fit_clear_pending_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(b->stats);
+    return check_launch(__func__);
+}
+
+extern "C" int gi2d_fit_set_num_points(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int n,
+                                       gi2d_stream_t stream) {
+    GI2D_REQUIRE(p && b && b->stats, "null stats");
+    GI2D_REQUIRE(n >= 0 && n <= p->num_points, "count outside [0, capacity]");
+    set_stat_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(b->stats, GI2D_STAT_NUM_POINTS, (double)n);
+    return check_launch(__func__);
+}
+
+static ModelPtrs model_ptrs(const gi2d_fit_buffers *b) {
+    return ModelPtrs{b->xyz, b->cov, b->rgb, b->cov_bound, b->m_xyz, b->v_xyz, b->m_cov, b->v_cov, b->m_rgb, b->v_rgb};
+}
+
+extern "C" size_t gi2d_fit_prune_workspace_size(int capacity) {
+    const size_t n = (size_t)(capacity > 0 ? capacity : 1);
+    return 2 * align_up(n * 4) + align_up(cumsum_i32_workspace((int)n)) + align_up(n * kRowFloats * 4);
+}
+
+extern "C" int gi2d_fit_prune(const gi2d_fit_params *p, const gi2d_fit_buffers *b, void *workspace,
+                              size_t workspace_bytes, gi2d_stream_t stream) {
+    int rc = gi2d_fit_adam(p, b, stream);   // (validates; applies a pending step; counts the non-PSD rows)
+    if (rc != GI2D_OK) return rc;
+    if (p->num_points == 0) return GI2D_OK;
+    if (!workspace || workspace_bytes < gi2d_fit_prune_workspace_size(p->num_points)) {
+        set_error("%s: workspace too small", __func__);
+        return GI2D_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)p->num_points;
+    char *c = (char *)workspace;
+    int32_t *keep = (int32_t *)c;   c += align_up(n * 4);
+    int32_t *incl = (int32_t *)c;   c += align_up(n * 4);
+    int32_t *scan_ws = (int32_t *)c; c += align_up(cumsum_i32_workspace((int)n));
+    float *scratch = (float *)c;
+    const ModelPtrs m = model_ptrs(b);
+    const int grid = cdiv(p->num_points, 256);
+    prune_flag_kernel<<<grid, 256, 0, st>>>(*p, m, b->stats, keep);
+    rc = cumsum_i32_launch(p->num_points, keep, incl, nullptr, scan_ws, st);
+    if (rc != GI2D_OK) return rc;
+    prune_gather_kernel<<<grid, 256, 0, st>>>(*p, m, b->stats, keep, incl, scratch);
+    prune_scatter_kernel<<<grid, 256, 0, st>>>(*p, m, b->stats, incl, scratch);
+    return check_launch(__func__);
+}
+
+extern "C" size_t gi2d_fit_densify_workspace_size(int img_height, int img_width) {
+    const size_t n = (size_t)img_height * img_width;
+    return 2 * align_up(n * 8) + 2 * align_up(n * 4) + align_up(gi2d_sort_workspace_size((int)n));
+}
+
+extern "C" int gi2d_fit_densify(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int k_rows,
+                                const float *new_cov2d, int slv, void *workspace, size_t workspace_bytes,
+                                gi2d_stream_t stream) {
+    int rc = gi2d_fit_adam(p, b, stream);   // (validates; nothing may be pending while rows are appended)
+    if (rc != GI2D_OK) return rc;
+    GI2D_REQUIRE(p->dynamic_points, "densification needs dynamic_points (capacity-sized arrays)");
+    GI2D_REQUIRE(b->err_map, "no error map bound (a training step writes it when b->err_map is set)");
+    GI2D_REQUIRE(k_rows >= 0 && (k_rows == 0 || new_cov2d), "bad candidate block");
+    const size_t n = (size_t)p->img_height * p->img_width;
+    GI2D_REQUIRE(n < ((size_t)1 << 31), "image too large for 32-bit pixel indices");
+    if (k_rows == 0) return GI2D_OK;
+    if (!workspace || workspace_bytes < gi2d_fit_densify_workspace_size(p->img_height, p->img_width)) {
+        set_error("%s: workspace too small", __func__);
+        return GI2D_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char *c = (char *)workspace;
+    int64_t *keys = (int64_t *)c;     c += align_up(n * 8);
+    int64_t *keys_s = (int64_t *)c;   c += align_up(n * 8);
+    int32_t *vals = (int32_t *)c;     c += align_up(n * 4);
+    int32_t *vals_s = (int32_t *)c;   c += align_up(n * 4);
+    void *sort_ws = c;
+    densify_keys_kernel<<<cdiv((long long)n, 256), 256, 0, st>>>((int)n, b->err_map, keys, vals);
+    rc = gi2d_sort_pairs_i64((int)n, keys, vals, keys_s, vals_s, 0, 63, sort_ws, gi2d_sort_workspace_size((int)n), stream);
+    if (rc != GI2D_OK) return rc;
+    densify_append_kernel<<<1, 1024, 0, st>>>(*p, model_ptrs(b), b->stats, vals_s, new_cov2d, k_rows, slv);
+    return check_launch(__func__);
+}
+
+extern "C" size_t gi2d_bin_sort_workspace_size(int num_points, int tiles_x, int tiles_y, int capacity) {
+    const size_t T = (size_t)(tiles_x > 0 && tiles_y > 0 ? (size_t)tiles_x * tiles_y : 1);
+    const size_t n = (size_t)(num_points > 0 ? num_points : 1);
+    return 3 * align_up(T * 4) + align_up(cumsum_i32_workspace((int)T)) + align_up(n * 8) +
+           align_up((size_t)(capacity > 0 ? capacity : 1) * 8);
+}
+
+extern "C" int gi2d_bin_sort(int num_points, const float *xys, const float *depths, const int32_t *radii,
+                             int tiles_x, int tiles_y, float radius_clip, int capacity,
+                             int64_t *isect_ids_sorted, int32_t *gaussian_ids_sorted, int32_t *tile_bins,
+                             int32_t *info, void *workspace, size_t workspace_bytes, gi2d_stream_t stream) {
+    GI2D_REQUIRE(num_points >= 0 && tiles_x > 0 && tiles_y > 0 && capacity > 0, "bad sizes");
+    GI2D_REQUIRE(tiles_x <= 65535 && tiles_y <= 65535, "image too large");
+    GI2D_REQUIRE(isect_ids_sorted && gaussian_ids_sorted && tile_bins && info, "null output");
+    GI2D_REQUIRE(num_points == 0 || (xys && radii), "null input");
+    if (!workspace || workspace_bytes < gi2d_bin_sort_workspace_size(num_points, tiles_x, tiles_y, capacity)) {
+        set_error("%s: workspace too small", __func__);
+        return GI2D_ERR_WORKSPACE;
+    }
+    (void)depths;   // every depth shares one bit pattern by contract (0.0 from the 2-D projections): low key word 0
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = tiles_x * tiles_y;
+    char *c = (char *)workspace;
+    int32_t *tile_count = (int32_t *)c;  c += align_up((size_t)T * 4);
+    int32_t *tile_fill = (int32_t *)c;   c += align_up((size_t)T * 4);
+    int32_t *tile_incl = (int32_t *)c;   c += align_up((size_t)T * 4);
+    int32_t *scan_ws = (int32_t *)c;     c += align_up(cumsum_i32_workspace(T));
+    ushort4 *boxes = (ushort4 *)c;       c += align_up((size_t)(num_points > 0 ? num_points : 1) * 8);
+    uint64_t *keys = (uint64_t *)c;
+    cudaMemsetAsync(tile_count, 0, (char *)tile_incl - (char *)tile_count, st);   // counts + cursors
+    gi2d_fit_params p{};
+    p.num_points = num_points;
+    p.tiles_x = tiles_x;
+    p.tiles_y = tiles_y;
+    p.tile_row_end = tiles_y;
+    p.isect_capacity = capacity;
+    if (num_points > 0)
+        bs_count_kernel<<<cdiv(num_points, 256), 256, 0, st>>>(num_points, xys, radii, tiles_x, tiles_y, radius_clip,
+                                                               boxes, tile_count);
+    const Plan pl = make_plan(p);
+    if (pl.smem_scan) {
+        fit_place_kernel<true, false><<<pl.nblocks, kPlaceThreads, 0, st>>>(
+            p, 0, pl.gpb, T, boxes, tile_count, tile_incl, tile_fill, keys, nullptr, nullptr, tile_bins, info, nullptr);
+    } else {
+        const int rc = cumsum_i32_launch(T, tile_count, tile_incl, nullptr, scan_ws, st);
+        if (rc != GI2D_OK) return rc;
+        fit_place_kernel<false, false><<<pl.nblocks, kPlaceThreads, 0, st>>>(
+            p, 0, pl.gpb, T, boxes, tile_count, tile_incl, tile_fill, keys, nullptr, nullptr, tile_bins, info, nullptr);
+    }
+    bs_tile_sort_kernel<<<T, 64, 0, st>>>(capacity, tile_bins, keys, (int64_t)0, isect_ids_sorted, gaussian_ids_sorted);
     return check_launch(__func__);
 }
 
@@ -1621,7 +2017,7 @@ extern "C" int gi2d_fit_input_grads(const gi2d_fit_params *p, const gi2d_fit_buf
     if (p->num_points == 0) return GI2D_OK;
     launch_pdl(fit_input_grads_kernel, dim3(cdiv(p->num_points, 256)), dim3(256), 0, (cudaStream_t)stream,
                p->num_points, (const float4 *)b->proj, (const float4 *)b->grads, (float4 *)out,
-               (const double *)b->stats);
+               (const double *)b->stats, p->dynamic_points);
     return check_launch(__func__);
 }
 

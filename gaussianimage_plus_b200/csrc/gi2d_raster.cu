@@ -19,7 +19,8 @@ raster_fwd_kernel(int tiles_x, int img_w, int img_h, const int32_t *__restrict__
                   const int32_t *__restrict__ tile_bins, int rows, const float *__restrict__ xys,
                   const float *__restrict__ conics, const float *__restrict__ colors,
                   const float *__restrict__ opacities, float *__restrict__ out_img,
-                  float *__restrict__ final_Ts, int32_t *__restrict__ final_idx) {
+                  float *__restrict__ final_Ts, int32_t *__restrict__ final_idx,
+                  const int32_t *__restrict__ num_intersects_dev, const float *__restrict__ background) {
     __shared__ TileGaussians sg;
     const int tid = threadIdx.x;
     const int tile_id = blockIdx.y * tiles_x + blockIdx.x;
@@ -37,6 +38,13 @@ raster_fwd_kernel(int tiles_x, int img_w, int img_h, const int32_t *__restrict__
     float r = 0.f, g = 0.f, b = 0.f;
     int last = -1;
     forward_sweep(sg, cnt, blk, inside, (float)j, (float)i, r, g, b, last);
+    // rasterize_sum_plus.py:110-118: with no intersection at all the operator returns ones * background; the
+    // caller that kept num_intersects on the device (gi2d_bin_sort) lets the kernel take that branch
+    if (num_intersects_dev && __ldg(num_intersects_dev) < 1) {
+        r = background ? __ldg(background) : 1.f;
+        g = background ? __ldg(background + 1) : 1.f;
+        b = background ? __ldg(background + 2) : 1.f;
+    }
     if (inside) {
         const size_t pix = (size_t)i * img_w + j;
         out_img[3 * pix] = r;
@@ -99,11 +107,29 @@ raster_bwd_kernel(int tiles_x, int img_w, int img_h, const int32_t *__restrict__
 
 using namespace gi2d;
 
+extern "C" int gi2d_rasterize_sum_fwd_dev(int tiles_x, int tiles_y, int img_width, int img_height,
+                                          const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                                          int num_bins_rows, const float *xys, const float *conics,
+                                          const float *colors, const float *opacities, float *out_img,
+                                          float *final_Ts, int32_t *final_idx, const int32_t *num_intersects_dev,
+                                          const float *background, gi2d_stream_t stream);
+
 extern "C" int gi2d_rasterize_sum_fwd(int tiles_x, int tiles_y, int img_width, int img_height,
                                       const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
                                       int num_bins_rows, const float *xys, const float *conics,
                                       const float *colors, const float *opacities, float *out_img,
                                       float *final_Ts, int32_t *final_idx, gi2d_stream_t stream) {
+    return gi2d_rasterize_sum_fwd_dev(tiles_x, tiles_y, img_width, img_height, gaussian_ids_sorted, tile_bins,
+                                      num_bins_rows, xys, conics, colors, opacities, out_img, final_Ts, final_idx,
+                                      nullptr, nullptr, stream);
+}
+
+extern "C" int gi2d_rasterize_sum_fwd_dev(int tiles_x, int tiles_y, int img_width, int img_height,
+                                          const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                                          int num_bins_rows, const float *xys, const float *conics,
+                                          const float *colors, const float *opacities, float *out_img,
+                                          float *final_Ts, int32_t *final_idx, const int32_t *num_intersects_dev,
+                                          const float *background, gi2d_stream_t stream) {
     GI2D_REQUIRE(tiles_x >= 0 && tiles_y >= 0 && img_width >= 0 && img_height >= 0, "negative size");
     GI2D_REQUIRE(num_bins_rows >= 0, "negative num_bins_rows");
     if (tiles_x == 0 || tiles_y == 0 || img_width == 0 || img_height == 0) return GI2D_OK;
@@ -115,7 +141,7 @@ extern "C" int gi2d_rasterize_sum_fwd(int tiles_x, int tiles_y, int img_width, i
     dim3 grid(tiles_x, tiles_y);
     raster_fwd_kernel<<<grid, kTilePixels, 0, (cudaStream_t)stream>>>(
         tiles_x, img_width, img_height, gaussian_ids_sorted, tile_bins, num_bins_rows, xys, conics,
-        colors, opacities, out_img, final_Ts, final_idx);
+        colors, opacities, out_img, final_Ts, final_idx, num_intersects_dev, background);
     return check_launch(__func__);
 }
 
@@ -131,10 +157,16 @@ extern "C" int gi2d_rasterize_sum_bwd(int num_points, int tiles_x, int tiles_y, 
     if (num_points == 0) return GI2D_OK;
     GI2D_REQUIRE(v_xy && v_conic && v_colors, "null gradient output");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(v_xy, 0, (size_t)num_points * 2 * sizeof(float), st);
-    cudaMemsetAsync(v_conic, 0, (size_t)num_points * 3 * sizeof(float), st);
-    cudaMemsetAsync(v_colors, 0, (size_t)num_points * 3 * sizeof(float), st);
-    if (v_opacity) cudaMemsetAsync(v_opacity, 0, (size_t)num_points * sizeof(float), st);
+    const size_t n = (size_t)num_points;
+    if (v_conic == v_xy + 2 * n && v_colors == v_conic + 3 * n && (!v_opacity || v_opacity == v_colors + 3 * n)) {
+        // one block (the binding allocates the four outputs back to back): one fill instead of four
+        cudaMemsetAsync(v_xy, 0, n * (v_opacity ? 9 : 8) * sizeof(float), st);
+    } else {
+        cudaMemsetAsync(v_xy, 0, n * 2 * sizeof(float), st);
+        cudaMemsetAsync(v_conic, 0, n * 3 * sizeof(float), st);
+        cudaMemsetAsync(v_colors, 0, n * 3 * sizeof(float), st);
+        if (v_opacity) cudaMemsetAsync(v_opacity, 0, n * sizeof(float), st);
+    }
     if (tiles_x == 0 || tiles_y == 0 || num_bins_rows == 0) return check_launch(__func__);
     GI2D_REQUIRE(gaussian_ids_sorted && tile_bins && xys && conics && colors && v_output, "null pointer");
     GI2D_REQUIRE(tiles_x * kTile >= img_width && tiles_y * kTile >= img_height,

@@ -30,7 +30,8 @@ from .binding import TILE, _stream
 
 STAT_STEP, STAT_ISECTS, STAT_OVERFLOW, STAT_LR, STAT_SSE, STAT_SSE_SLOTS = 0, 1, 2, 3, 16, 64
 STAT_BEST_SSE, STAT_BEST_STEP, STAT_NON_PSD, STAT_SSIM_SUM, STAT_ABS_SUM = 9, 10, 11, 13, 14
-STAT_COUNT = STAT_SSE + STAT_SSE_SLOTS
+STAT_NUM_POINTS, STAT_BEST_N, STAT_PRUNED, STAT_ADDED = 80, 81, 82, 83
+STAT_COUNT = 96
 _NAMES = ("xyz", "cov2d", "f_dc")  # the reference's optimiser group names (gaussianimage_covariance.py:93-96)
 
 
@@ -63,13 +64,25 @@ def _sse_total(s) -> float:
 
 
 def _flushed(attr):
-    """Property over a private attribute whose getter first applies a pending optimiser step."""
+    """Property over a private capacity-sized tensor (or dict of tensors): the getter first applies a pending
+    optimiser step and returns the LIVE rows [0, cur_num_points) as a view, so in-place edits reach the device
+    arrays; the setter copies into the live rows (or swaps the model in when the row count differs)."""
     def get(self):
         self.sync_params()
-        return getattr(self, attr)
+        n = self.cur_num_points
+        v = getattr(self, attr)
+        return {k: t[:n] for k, t in v.items()} if isinstance(v, dict) else v[:n]
 
     def set_(self, value):
-        setattr(self, attr, value)
+        cur = getattr(self, attr, None)
+        if cur is None or isinstance(cur, dict) or isinstance(value, dict):
+            setattr(self, attr, value)
+            return
+        n = self.cur_num_points
+        if value.shape[0] != n:
+            raise ValueError(f"{attr}: {value.shape[0]} rows for a model of {n} Gaussians (use _replace())")
+        self.sync_params()
+        cur[:n].copy_(value)
 
     return property(get, set_)
 
@@ -80,12 +93,16 @@ class GaussianImageFitter:
     _features_dc = _flushed("_t_f_dc")       # f32[N,3] colours
     exp_avg = _flushed("_t_m")               # Adam first moments, dict keyed like the reference's groups
     exp_avg_sq = _flushed("_t_v")            # Adam second moments
+    cholesky_bound = _flushed("_t_bound")    # f32[N,3] SLV bound added to the covariance parameters
 
     def __init__(self, num_points: int, H: int, W: int, device="cuda:0", lr: float = 0.018,
                  clip_coe: float = 3.0, radius_clip: float = 1.0, color_norm: bool = False,
                  SLV_init: bool = True, tile_rows: Optional[Tuple[int, int]] = None,
                  isect_capacity: Optional[int] = None, use_graph: bool = True,
-                 grad_hook=None, loss_type: str = "L2", lambda_value: float = 0.7):
+                 grad_hook=None, loss_type: str = "L2", lambda_value: float = 0.7,
+                 max_num_points: Optional[int] = None):
+        """`max_num_points`: rows to allocate for (the model can grow to it by densification with no
+        reallocation and no new CUDA graph); default: num_points."""
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -102,18 +119,24 @@ class GaussianImageFitter:
         self._dirty = False         # a gradient is pending on the device
         self.external_optimizer = 0  # 1: the caller applies the gradients (codec.py); 2: parallel.TileRowFit
         self.keep_render = False    # tests: also store the unclamped [H,W,3] render of every train_iter
-        self.eager_steps_after_resize = 150
         self.track_best = True      # keep the parameters of the best-PSNR step on the device (train.py:132-137)
-        self._best_frozen = None    # best state of an EARLIER Gaussian count (prune/densify happened since)
         f = dict(dtype=torch.float32, device=self.device)
+        # The per-Gaussian arrays hold `capacity` rows; the LIVE count is kept ON THE DEVICE (stats slot
+        # NUM_POINTS: prune / densify change it there) and mirrored on the host lazily (`cur_num_points`).
+        self.capacity = max(int(num_points), int(max_num_points or 0))
+        self._n, self._n_stale = int(num_points), False
+        cap, n = self.capacity, self._n
         # reference init, gaussianimage_covariance.py:52-66
-        w_init = torch.rand(num_points, 1, **f) * self.W
-        h_init = torch.rand(num_points, 1, **f) * self.H
-        self._t_xyz = torch.cat((w_init, h_init), dim=1).contiguous()
-        self._t_cov2d = torch.rand((num_points, 3), **f)
-        self._t_f_dc = torch.zeros(num_points, 3, **f)
-        lp = slv_bound(self.H, self.W, num_points) if self.SLV else 0.5
-        self.cholesky_bound = torch.tensor([lp, 0, lp], **f).view(1, 3).repeat(num_points, 1).contiguous()
+        w_init = torch.rand(n, 1, **f) * self.W
+        h_init = torch.rand(n, 1, **f) * self.H
+        self._t_xyz = torch.zeros(cap, 2, **f)
+        self._t_xyz[:n] = torch.cat((w_init, h_init), dim=1)
+        self._t_cov2d = torch.zeros(cap, 3, **f)
+        self._t_cov2d[:n] = torch.rand((n, 3), **f)
+        self._t_f_dc = torch.zeros(cap, 3, **f)
+        lp = slv_bound(self.H, self.W, n) if self.SLV else 0.5
+        self._t_bound = torch.zeros(cap, 3, **f)
+        self._t_bound[:n] = torch.tensor([lp, 0, lp], **f)
         self.gt_hwc = None
         self._step0 = 0
         self._expected_step = 0
@@ -122,13 +145,19 @@ class GaussianImageFitter:
     # ------------------------------------------------------------------ buffers
     @property
     def cur_num_points(self) -> int:
-        return self._t_xyz.shape[0]
+        """The live Gaussian count.  After a device-side prune / densify the host's copy is stale: the first read
+        fetches it (one 8-byte read-back; synchronises)."""
+        if self._n_stale:
+            self._n = int(self.stats_buf[STAT_NUM_POINTS].item())
+            self._n_stale = False
+        return self._n
 
     def _raw_params(self):
         return {"xyz": self._t_xyz, "cov2d": self._t_cov2d, "f_dc": self._t_f_dc}
 
     def _alloc_state(self, zero_moments: bool, eager_steps: int = 1):
-        n = self.cur_num_points
+        """(Re)allocate everything that is sized by the capacity or the intersection capacity."""
+        n = self.capacity
         f = dict(dtype=torch.float32, device=self.device)
         if zero_moments:
             self._t_m = {k: torch.zeros_like(t) for k, t in self._raw_params().items()}
@@ -140,27 +169,33 @@ class GaussianImageFitter:
             self.grads = torch.zeros(n, 8, **f)
             self.proj = torch.zeros(n, 8, **f)
         if getattr(self, "best", None) is None or self.best.shape[0] != n:
-            self.best = torch.zeros(n, 8, **f)   # device-side best-state snapshot (train.py:132-137)
+            old, oldb = getattr(self, "best", None), getattr(self, "best_bound", None)
+            self.best = torch.zeros(n, 8, **f)          # device-side best-state snapshot (train.py:132-137)
+            self.best_bound = torch.zeros(n, 3, **f)    # ... and its slv_bound (train.py:136)
+            if old is not None:                          # (capacity grew: the snapshot stays valid)
+                k = min(old.shape[0], n)
+                self.best[:k], self.best_bound[:k] = old[:k], oldb[:k]
         if not hasattr(self, "err_map"):
             self.err_map = torch.zeros(self.H, self.W, **f)
         self.sorted_keys = torch.zeros(self.isect_capacity, dtype=torch.int64, device=self.device)
         self.tile_bins = torch.zeros(tiles, 2, dtype=torch.int32, device=self.device)
         if not hasattr(self, "stats_buf"):
             self.stats_buf = torch.zeros(STAT_COUNT, dtype=torch.float64, device=self.device)
+            self.stats_buf[STAT_NUM_POINTS] = float(self._n)
         self.out_hwc = torch.zeros(self.H, self.W, 3, **f)
         self.render_chw = torch.zeros(3, self.H, self.W, **f)
         self.params = _lib.FitParams(
             n, self.W, self.H, self.tile_bounds[0], self.tile_bounds[1], self.tile_rows[0], self.tile_rows[1],
             self.isect_capacity, self.clip_coe, self.radius_clip, self.lr, 0.9, 0.999, 1e-15, 20000, 0.5,
             int(self.color_norm), 2.0 * self.loss_w[0] / (3.0 * self.H * self.W),
-            int(self.external_optimizer), self.loss_w[1] / (3.0 * self.H * self.W), self.loss_w[2])
+            int(self.external_optimizer), self.loss_w[1] / (3.0 * self.H * self.W), self.loss_w[2], 1)
         ws_bytes = self.lib.gi2d_fit_workspace_size(C.byref(self.params))
         self.workspace = torch.zeros(max(ws_bytes, 256), dtype=torch.uint8, device=self.device)
+        self._prune_ws = None
+        self._densify_ws = None
         self._invalidate_graphs()
         # steps to run un-graphed before the next capture: 1 loads the kernels (lazy module loading cannot be
-        # captured); after a change of the Gaussian count more, because torch's graph capture costs ~3 ms (two
-        # graphs per count) while pruning can change the count every 100 iterations -- an eager step (3
-        # launches with programmatic edges) costs only ~2 us more than a replay
+        # captured)
         self._eager_left = eager_steps
         self._dirty = False
         self._bind()
@@ -171,7 +206,7 @@ class GaussianImageFitter:
             out_img = self.out_hwc.data_ptr()
         gt = self.gt_hwc
         self.buffers = _lib.FitBuffers(
-            self._t_xyz.data_ptr(), self._t_cov2d.data_ptr(), self.cholesky_bound.data_ptr(), self._t_f_dc.data_ptr(),
+            self._t_xyz.data_ptr(), self._t_cov2d.data_ptr(), self._t_bound.data_ptr(), self._t_f_dc.data_ptr(),
             m["xyz"].data_ptr(), v["xyz"].data_ptr(), m["cov2d"].data_ptr(), v["cov2d"].data_ptr(),
             m["f_dc"].data_ptr(), v["f_dc"].data_ptr(),
             gt.data_ptr() if (gt is not None and gt.dtype == torch.float32) else None,
@@ -179,7 +214,8 @@ class GaussianImageFitter:
             self.tile_bins.data_ptr(), self.stats_buf.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(),
             gt.data_ptr() if (gt is not None and gt.dtype == torch.uint8) else None,
             self.best.data_ptr() if self.track_best else None,
-            self.err_map.data_ptr() if err_map else None)
+            self.err_map.data_ptr() if err_map else None,
+            self.best_bound.data_ptr() if self.track_best else None)
 
     def reset_stats(self, step: int = 0):
         """Zero the device-side statistics (drops a pending gradient) and set the Adam step counter."""
@@ -431,6 +467,7 @@ class GaussianImageFitter:
         """Synchronises.  mse/psnr refer to the render of the LAST train_iter (before its Adam update),
         like the reference's per-iteration psnr (gaussianimage_covariance.py:256-257)."""
         s = self.stats_buf.cpu()
+        self._n, self._n_stale = int(s[STAT_NUM_POINTS]), False   # (the live count rides along for free)
         sse = _sse_total(s)
         mse = sse / (3.0 * self.H * self.W)
         best_mse = float(s[STAT_BEST_SSE]) / (3.0 * self.H * self.W)
@@ -446,7 +483,7 @@ class GaussianImageFitter:
                 "best_sse": float(s[STAT_BEST_SSE]), "best_step": int(s[STAT_BEST_STEP]),
                 "best_psnr": (10 * math.log10(1.0 / best_mse) if 0 < best_mse < float("inf") else
                               (0.0 if best_mse > 0 else float("inf"))),
-                "non_psd": int(s[STAT_NON_PSD])}
+                "non_psd": int(s[STAT_NON_PSD]), "num_points": self._n}
 
     def psnr(self) -> float:
         return self.stats()["psnr"]
@@ -514,37 +551,36 @@ class GaussianImageFitter:
     def _reset_keep_best(self, step: int, st: dict):
         """reset_stats() that carries the best-so-far squared error / step over (the snapshot stays valid)."""
         keep = self.stats_buf[STAT_SSE:STAT_SSE + STAT_SSE_SLOTS].clone()   # the last step's squared error
+        best_n = self.stats_buf[STAT_BEST_N].clone()
         self.reset_stats(step)
         self.stats_buf[STAT_BEST_SSE:STAT_BEST_STEP + 1] = torch.tensor(
             [st["best_sse"], float(st["best_step"])], dtype=torch.float64, device=self.device)
+        self.stats_buf[STAT_BEST_N] = best_n
         self.stats_buf[STAT_SSE:STAT_SSE + STAT_SSE_SLOTS] = keep
 
     def best_state(self) -> dict:
         """The reference's `best_model_dict` + `slv_bound` (train.py:132-137,159-164): parameters right after
-        the optimiser step of the best-PSNR iteration, and the SLV bound of that moment.  Synchronises."""
+        the optimiser step of the best-PSNR iteration, and the SLV bound of that moment -- the device-side
+        snapshot (rows [0, best_n) of `best` / `best_bound`; its row count is the model's size at that
+        iteration, whatever prune / densify did since).  Synchronises."""
         self.sync_params()
         st = self.stats()
-        fr = self._best_frozen
-        if fr is not None and fr["best_step"] >= st["best_step"]:
-            return dict(fr)
         if st["best_step"] == 0:
             raise RuntimeError("no training step has completed yet")
-        b = self.best
+        n = int(self.stats_buf[STAT_BEST_N].item())
+        b = self.best[:n]
         return {"_xyz": b[:, 0:2].clone(), "_cov2d": b[:, 2:5].clone(), "_features_dc": b[:, 5:8].clone(),
-                "cholesky_bound": self.cholesky_bound.clone(), "best_step": st["best_step"],
+                "cholesky_bound": self.best_bound[:n].clone(), "best_step": st["best_step"],
                 "best_psnr": st["best_psnr"]}
 
     def load_best_state(self):
         """train.py:158-164: continue (evaluate) from the best state."""
         bs = self.best_state()
-        st = self.stats()
         n = bs["_xyz"].shape[0]
-        zeros = lambda t: torch.zeros_like(t)
-        self._best_frozen = bs
+        z = lambda t: torch.zeros_like(t)
         self._replace(bs["_xyz"], bs["_cov2d"], bs["_features_dc"], bs["cholesky_bound"],
-                      {"xyz": zeros(bs["_xyz"]), "cov2d": zeros(bs["_cov2d"]), "f_dc": zeros(bs["_features_dc"])},
-                      {"xyz": zeros(bs["_xyz"]), "cov2d": zeros(bs["_cov2d"]), "f_dc": zeros(bs["_features_dc"])},
-                      _stats=st)
+                      {"xyz": z(bs["_xyz"]), "cov2d": z(bs["_cov2d"]), "f_dc": z(bs["_features_dc"])},
+                      {"xyz": z(bs["_xyz"]), "cov2d": z(bs["_cov2d"]), "f_dc": z(bs["_features_dc"])})
         return n
 
     # ------------------------------------------------------------------ N-changing operations
@@ -554,84 +590,131 @@ class GaussianImageFitter:
         valid = (c[:, 0] * c[:, 2] - c[:, 1] ** 2 > 0) & (c[:, 0] > 0) & (c[:, 2] > 0)
         return int((~valid).sum().item()), valid
 
-    def _replace(self, xyz, cov, rgb, bound, m, v, _stats=None):
-        """Swap in parameter/moment tensors of a different Gaussian count.  The best-state snapshot of the old
-        count is frozen first (the reference keeps its deep copy across prune/densify the same way)."""
+    def _set_num_points(self, n: int):
+        self._n, self._n_stale = int(n), False
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gi2d_fit_set_num_points(C.byref(self.params), C.byref(self.buffers), int(n),
+                                                        _stream(self.device)), "fit_set_num_points")
+
+    def _grow_capacity(self, new_cap: int):
+        """More rows than were allocated for: the one case that reallocates (and drops the captured graphs)."""
         self.sync_params()
-        st = _stats or self.stats()
-        step = st["step"]
-        if self.track_best and st["best_step"] > 0 and (
-                self._best_frozen is None or self._best_frozen["best_step"] < st["best_step"]):
-            self._best_frozen = self.best_state()
-        self._t_xyz, self._t_cov2d, self._t_f_dc, self.cholesky_bound = (
-            t.contiguous() for t in (xyz, cov, rgb, bound))
-        self._t_m, self._t_v = m, v
-        self._step0 = step
-        self._alloc_state(zero_moments=False, eager_steps=self.eager_steps_after_resize)
-        self._reset_keep_best(step, st)
+        n = self.cur_num_points
+        st = self.stats()
+        expected = self._expected_step
+
+        def grown(t):
+            out = torch.zeros(new_cap, t.shape[1], dtype=t.dtype, device=t.device)
+            out[:n] = t[:n]
+            return out
+
+        self._t_xyz, self._t_cov2d, self._t_f_dc, self._t_bound = (
+            grown(t) for t in (self._t_xyz, self._t_cov2d, self._t_f_dc, self._t_bound))
+        self._t_m = {k: grown(t) for k, t in self._t_m.items()}
+        self._t_v = {k: grown(t) for k, t in self._t_v.items()}
+        self.capacity = int(new_cap)
+        self._alloc_state(zero_moments=False)
+        self._set_num_points(n)
+        self._expected_step = expected
+        del st
+
+    def _replace(self, xyz, cov, rgb, bound, m, v):
+        """Swap in a model of a different size: rows are copied into the capacity-sized arrays (grown first if
+        they do not fit), the live count is set, the optimiser's step counter and the best state stay."""
+        self.sync_params()
+        n = xyz.shape[0]
+        if n > self.capacity:
+            self._grow_capacity(n)
+        for dst, src in ((self._t_xyz, xyz), (self._t_cov2d, cov), (self._t_f_dc, rgb), (self._t_bound, bound)):
+            dst[:n].copy_(src)
+        for k in _NAMES:
+            self._t_m[k][:n].copy_(m[k])
+            self._t_v[k][:n].copy_(v[k])
+        self._set_num_points(n)
+
+    def prune_async(self):
+        """`non_semi_definite_prune` (gaussianimage_covariance.py:354-382) entirely on the device: flush the
+        pending step, drop the rows whose covariance + bound is not positive definite (stable compaction of
+        parameters, both Adam moments and bounds), update the live count there.  No read-back, no reallocation,
+        the step graph stays valid; `cur_num_points` fetches the new count when somebody asks."""
+        if self._prune_ws is None:
+            nbytes = self.lib.gi2d_fit_prune_workspace_size(self.capacity)
+            self._prune_ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+        self._dirty = False
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gi2d_fit_prune(C.byref(self.params), C.byref(self.buffers), self._prune_ws.data_ptr(),
+                                               self._prune_ws.numel(), _stream(self.device)), "fit_prune")
+        self._n_stale = True
 
     def non_semi_definite_prune(self):
-        """gaussianimage_covariance.py:354-371: drop Gaussians whose covariance is not positive definite
-        (parameters, Adam moments and SLV bounds are masked together)."""
-        # the flush kernel counts the non-PSD Gaussians while it applies the pending step: the common
-        # "nothing to prune" outcome costs that launch + one small read-back, no torch ops
-        self.sync_params(force=True)
-        st = self.stats()
-        # the same read-back tells whether the intersection buffers overflowed since the last look (the steps since
-        # then were no-ops on the device): grow them and re-run those iterations, so that a long fit() neither stalls
-        # nor loses iterations
-        if st["step"] < self._expected_step:
-            self.catch_up(st)
-            self.sync_params(force=True)
-            st = self.stats()
-        if st["non_psd"] == 0:
-            return 0, self.cur_num_points
-        n_bad, valid = self.check_non_semi_definite()
-        if n_bad and self.cur_num_points - n_bad > 0:
-            m = {k: t[valid].contiguous() for k, t in self.exp_avg.items()}
-            v = {k: t[valid].contiguous() for k, t in self.exp_avg_sq.items()}
-            self._replace(self._xyz[valid], self._cov2d[valid], self._features_dc[valid],
-                          self.cholesky_bound[valid], m, v)
-        return n_bad, self.cur_num_points
+        """gaussianimage_covariance.py:354-371 with the reference's return value (pruned, remaining): the device
+        prune + one read-back of the two counts.  `fit()` uses prune_async() and never reads them."""
+        self.prune_async()
+        s = self.stats_buf.cpu()
+        self._n, self._n_stale = int(s[STAT_NUM_POINTS]), False
+        return int(s[STAT_NON_PSD]), self._n
 
     def densification_postfix(self, new_xyz, new_features_dc, new_cov2d):
-        """gaussianimage_covariance.py:307-334: append Gaussians (zero Adam moments, new SLV bound)."""
+        """gaussianimage_covariance.py:307-334: append the given Gaussians (zero Adam moments, new SLV bound).
+        (Arbitrary candidates: a torch-side append into the capacity-sized arrays.  The training loop's own
+        densification, `add_sample_positions`, selects and appends on the device.)"""
         n_bad, valid = self.check_non_semi_definite(new_cov2d)
         new_xyz, new_features_dc, new_cov2d = new_xyz[valid], new_features_dc[valid], new_cov2d[valid]
         k = new_xyz.shape[0]
-        cat = lambda a, b: torch.cat((a, b.to(a)), dim=0)
-        n_new = self.cur_num_points + k
+        self.sync_params()
+        n = self.cur_num_points
+        n_new = n + k
+        if n_new > self.capacity:
+            self._grow_capacity(n_new)
         lp = slv_bound(self.H, self.W, n_new) if self.SLV else 0.5
-        new_bound = torch.tensor([lp, 0, lp], dtype=torch.float32, device=self.device).view(1, 3).repeat(k, 1)
-        names = dict(xyz=new_xyz, cov2d=new_cov2d, f_dc=new_features_dc)
-        m = {kk: cat(t, torch.zeros_like(names[kk])) for kk, t in self.exp_avg.items()}
-        v = {kk: cat(t, torch.zeros_like(names[kk])) for kk, t in self.exp_avg_sq.items()}
-        self._replace(cat(self._xyz, new_xyz), cat(self._cov2d, new_cov2d), cat(self._features_dc, new_features_dc),
-                      cat(self.cholesky_bound, new_bound), m, v)
+        self._t_xyz[n:n_new] = new_xyz.to(self._t_xyz)
+        self._t_cov2d[n:n_new] = new_cov2d.to(self._t_cov2d)
+        self._t_f_dc[n:n_new] = new_features_dc.to(self._t_f_dc)
+        self._t_bound[n:n_new] = torch.tensor([lp, 0, lp], dtype=torch.float32, device=self.device)
+        for k_ in _NAMES:
+            self._t_m[k_][n:n_new] = 0
+            self._t_v[k_][n:n_new] = 0
+        self._set_num_points(n_new)
         return n_new, n_bad
 
     def add_sample_positions(self, max_num_points: int, base_num_samples: int = 1000, last: bool = False,
-                             errors: Optional[torch.Tensor] = None):
-        """train.py:85-118: new Gaussians at the pixels of largest L1 error.  `errors` f32[H,W] is the map a
-        `train_iter(want_error_map=True)` left behind (the reference passes that iteration's render); without
-        it the current parameters are rendered first."""
+                             errors: Optional[torch.Tensor] = None, new_cov2d: Optional[torch.Tensor] = None):
+        """train.py:85-118: new Gaussians at the pixels of largest L1 error, selected AND appended on the device
+        (gi2d_fit_densify: a 64-bit radix sort of (error, pixel) keys, the positive-definite filter and the
+        append of rows, moments and bounds).  `errors` f32[H,W]: the map a `train_iter(want_error_map=True)` left
+        in `self.err_map` (the reference passes that iteration's render); without it the current parameters are
+        rendered first.  The candidates' covariances are drawn like the reference does, on the CPU generator
+        (train.py:110-112), so the host needs the live count once here: one small read-back per densification.
+        `new_cov2d` f32[>=k,3] replaces that draw (parity tests feed the oracle the same numbers)."""
         if errors is None:
             render = self.forward()["render"]
             gt = self.gt_hwc.permute(2, 0, 1).unsqueeze(0)
             if gt.dtype == torch.uint8:
                 gt = gt.float() / 255
             errors = torch.abs(render - gt).sum(dim=1)
-        p_flat = (errors / torch.sum(errors)).view(-1)
+        if errors.data_ptr() != self.err_map.data_ptr():
+            self.err_map.copy_(errors.reshape(self.H, self.W))
+        self.sync_params()
         room = max(0, max_num_points - self.cur_num_points)
         k = room if last else min(base_num_samples, room)
         if not k:
             return 0
-        _, idx = torch.topk(p_flat, k)
-        xyz = torch.stack([idx % self.W, idx // self.W], dim=1).float()
-        color = torch.zeros(k, 3, device=self.device)
-        # the reference draws on the CPU generator and moves the sample over (train.py:110-112)
-        cov = torch.rand(k, 3).to(self.device) + torch.tensor([0.5, 0, 0.5], device=self.device)
-        self.densification_postfix(xyz, color, cov)
+        if max_num_points > self.capacity:
+            self._grow_capacity(max_num_points)
+        if new_cov2d is None:
+            new_cov2d = torch.rand(k, 3) + torch.tensor([0.5, 0, 0.5])
+        cov = new_cov2d[:k].to(self.device, torch.float32).contiguous()
+        if self._densify_ws is None:
+            nbytes = self.lib.gi2d_fit_densify_workspace_size(self.H, self.W)
+            self._densify_ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+        self._bind(err_map=True)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gi2d_fit_densify(C.byref(self.params), C.byref(self.buffers), int(k), cov.data_ptr(),
+                                                 1 if self.SLV else 0, self._densify_ws.data_ptr(),
+                                                 self._densify_ws.numel(), _stream(self.device)), "fit_densify")
+        self._bind()
+        self._n_stale = True
+        self._keepalive = cov      # (read by the kernel just enqueued)
         return k
 
     # ------------------------------------------------------------------ checkpoint (train.py:61-77,173-175)
@@ -671,18 +754,24 @@ class GaussianImageFitter:
 
     # ------------------------------------------------------------------ the training loop
     def fit(self, iterations: int, max_num_points: Optional[int] = None, prune_iter: int = 100,
-            grow_iter: int = 5000, adaptive_add: bool = True, prune: bool = True, callback=None) -> dict:
-        """`SimpleTrainer2d.train` (train.py:120-176) without its per-iteration host work: every iteration is
-        one graph replay; the best state is snapshotted by the kernels; the host looks at the device only
-        every `prune_iter` iterations (non-PSD count, one small read-back) and every `grow_iter` iterations
-        (densification).  Returns the final stats (incl. best_psnr / best_step); `best_state()` has the
-        parameters.  `callback(iteration, self)` runs after every iteration when given (tests, logging)."""
+            grow_iter: int = 5000, adaptive_add: bool = True, prune: bool = True, callback=None,
+            check_iter: int = 1000) -> dict:
+        """`SimpleTrainer2d.train` (train.py:120-176) without its per-iteration host work: every iteration is one
+        graph replay; the best state is snapshotted by the kernels; pruning (every `prune_iter`) compacts the model
+        on the device with no read-back; densification (every `grow_iter`) selects and appends on the device after
+        ONE small read-back (the live count, for the reference's CPU-generator draw).  The arrays are allocated
+        for `max_num_points` up front, so neither changes a pointer nor drops the captured graph.  Every
+        `check_iter` iterations (and at the end) the host reads the stats block once to catch an intersection-buffer
+        overflow.  Returns the final stats (incl. best_psnr / best_step); `best_state()` has the parameters.
+        `callback(iteration, self)` runs after every iteration when given (tests, logging)."""
         max_num_points = max_num_points if max_num_points is not None else self.cur_num_points
+        if adaptive_add and max_num_points > self.capacity:
+            self._grow_capacity(max_num_points)
         if callback is None:
-            # between two host interventions (prune / grow / the end) the steps are replayed in unrolled graphs
+            # between two host interventions (prune / grow / check / the end) the steps are replayed in unrolled graphs
             it = 0
             while it < iterations:
-                nxt = iterations
+                nxt = min(iterations, (it // check_iter + 1) * check_iter)
                 if prune:
                     nxt = min(nxt, (it // prune_iter + 1) * prune_iter)
                 if adaptive_add:
@@ -692,15 +781,19 @@ class GaussianImageFitter:
                 self.train_iter(want_error_map=grow)
                 it = nxt
                 if prune and it % prune_iter == 0:
-                    self.non_semi_definite_prune()
+                    self.prune_async()
                 if grow:
                     self.add_sample_positions(max_num_points, last=(it == iterations - grow_iter), errors=self.err_map)
+                if it % check_iter == 0 and it < iterations:
+                    st = self.stats()
+                    if st["step"] < self._expected_step:
+                        self.catch_up(st)
             return self._finish_fit()
         for it in range(1, iterations + 1):
             grow = adaptive_add and it % grow_iter == 0 and it < iterations
             self.train_iter(want_error_map=grow)
             if prune and it % prune_iter == 0:
-                self.non_semi_definite_prune()
+                self.prune_async()
             if grow:
                 self.add_sample_positions(max_num_points, last=(it == iterations - grow_iter), errors=self.err_map)
             if callback is not None:

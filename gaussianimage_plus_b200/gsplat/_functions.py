@@ -12,7 +12,8 @@ import torch
 from torch.autograd import Function
 
 from . import cuda as _C
-from .utils import bin_and_sort_gaussians, compute_cumulative_intersects, cumulative_intersects_and_depth_flag
+from .. import binding as _b
+from .utils import bin_and_sort_gaussians, cumulative_intersects_and_depth_flag
 
 
 class ProjectCovariance(Function):
@@ -106,9 +107,19 @@ class RasterizeSum(Function):
                 BLOCK_W, background, radius_clip, isprint, depths_zero=None):
         n = xys.size(0)
         tile_bounds = ((img_width + BLOCK_W - 1) // BLOCK_W, (img_height + BLOCK_H - 1) // BLOCK_H, 1)
-        if depths_zero:    # depths straight from one of this package's 2-D projections: known to be all 0.0
-            num_intersects, cum_tiles_hit = compute_cumulative_intersects(num_tiles_hit)
-            uniform = True
+        if depths_zero:
+            # depths straight from one of this package's 2-D projections (known to be all 0.0): ONE binning call
+            # with num_intersects kept on the device (gi2d_bin_sort) -- no .item(), no torch.sort -- and the
+            # rasterizer takes the "no intersection" branch of rasterize_sum_plus.py:110-118 by itself
+            res = _b.bin_sort(n, xys, depths.view(-1), radii.view(-1), tile_bounds, radius_clip)
+            out_img, final_Ts = _b.rasterize_sum_plus_forward_dev(
+                tile_bounds, (BLOCK_W, BLOCK_H, 1), (img_width, img_height, 1), res, xys, conics, colors, opacity,
+                background)
+            ctx.meta = (img_height, img_width, BLOCK_H, BLOCK_W, 1)
+            ctx.bins = res
+            ctx.save_for_backward(res.gaussian_ids_sorted, res.tile_bins, xys, conics, colors, opacity)
+            ctx.final_Ts = final_Ts
+            return out_img
         else:
             num_intersects, cum_tiles_hit, uniform = cumulative_intersects_and_depth_flag(num_tiles_hit, depths)
         if num_intersects < 1:
@@ -124,6 +135,7 @@ class RasterizeSum(Function):
                 tile_bounds, (BLOCK_W, BLOCK_H, 1), (img_width, img_height, 1), ids, bins, xys, conics, colors,
                 opacity, background, isprint)
         ctx.meta = (img_height, img_width, BLOCK_H, BLOCK_W, num_intersects)
+        ctx.bins = None
         ctx.save_for_backward(ids, bins, xys, conics, colors, opacity)
         ctx.final_Ts = final_Ts
         return out_img
@@ -132,6 +144,8 @@ class RasterizeSum(Function):
     def backward(ctx, v_out_img):
         H, W, BH, BW, num_intersects = ctx.meta
         ids, bins, xys, conics, colors, opacity = ctx.saved_tensors
+        if ctx.bins is not None:
+            ctx.bins.check(block=False)   # (raises if the forward worked on a truncated list; never waits)
         if num_intersects < 1:
             grads = tuple(torch.zeros_like(t) for t in (xys, conics, colors, opacity))
         else:

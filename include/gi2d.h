@@ -130,6 +130,20 @@ int gi2d_sort_pairs_i64(int num_items, const int64_t *keys_in, const int32_t *va
                         int64_t *keys_out, int32_t *vals_out, int begin_bit, int end_bit,
                         void *workspace, size_t workspace_bytes, gi2d_stream_t stream);
 
+/* Replaces the whole of `compute_cumulative_intersects` + `bin_and_sort_gaussians` (gsplat/utils.py:231-311:
+ * torch.cumsum, the `.item()` host synchronisation, map_gaussian_to_intersects, torch.sort, torch.gather,
+ * get_tile_bin_edges) by ONE call that keeps num_intersects ON THE DEVICE: per-tile overlap counts,
+ * prefix sum, counting-sort placement, in-tile rank sort by Gaussian id.  Contract: every depth has the same bit
+ * pattern (the 2-D projections emit 0.0), so the reference's stable sort of Gaussian-major keys orders by tile, then
+ * by Gaussian id.  Outputs have `capacity` rows (tile_bins: tiles_x*tiles_y rows, empty tiles (0,0));
+ * info i32[3] (device) = {rows written = min(num_intersects, capacity), num_intersects, overflow flag}.
+ * Bit-identical to the multi-call path on rows [0, num_intersects). */
+size_t gi2d_bin_sort_workspace_size(int num_points, int tiles_x, int tiles_y, int capacity);
+int gi2d_bin_sort(int num_points, const float *xys, const float *depths, const int32_t *radii,
+                  int tiles_x, int tiles_y, float radius_clip, int capacity,
+                  int64_t *isect_ids_sorted, int32_t *gaussian_ids_sorted, int32_t *tile_bins,
+                  int32_t *info, void *workspace, size_t workspace_bytes, gi2d_stream_t stream);
+
 /* Replaces `get_tile_bin_edges` (ext.cpp:66, bindings.cu:368-383, kernel forward.cu:211-233).
  * tile_bins i32[num_bins_rows,2] is zero-filled first (the reference's torch::zeros), rows
  * whose tile id is >= num_bins_rows are skipped instead of written out of bounds. */
@@ -151,9 +165,21 @@ int gi2d_rasterize_sum_fwd(int tiles_x, int tiles_y, int img_width, int img_heig
                            float *out_img, float *final_Ts, int32_t *final_idx,
                            gi2d_stream_t stream);
 
+/* The same with num_intersects on the DEVICE (info[1] of gi2d_bin_sort): when it is < 1 the kernel writes
+ * `background` (f32[3], nullable = ones) to every pixel -- the branch rasterize_sum_plus.py:110-118 takes on the
+ * host after its `.item()`. */
+int gi2d_rasterize_sum_fwd_dev(int tiles_x, int tiles_y, int img_width, int img_height,
+                               const int32_t *gaussian_ids_sorted, const int32_t *tile_bins,
+                               int num_bins_rows, const float *xys, const float *conics,
+                               const float *colors, const float *opacities,
+                               float *out_img, float *final_Ts, int32_t *final_idx,
+                               const int32_t *num_intersects_dev, const float *background,
+                               gi2d_stream_t stream);
+
 /* Replaces `rasterize_sum_plus_backward` / `rasterize_sum_backward` (ext.cpp:24,17,
  * bindings.cu:1241-1314, kernel backward.cu:1168-1350).  v_xy f32[N,2], v_conic f32[N,3],
- * v_colors f32[N,3], v_opacity f32[N] are zero-filled by the call, then accumulated. */
+ * v_colors f32[N,3], v_opacity f32[N] are zero-filled by the call (ONE fill when the four lie back to back in one
+ * allocation, as the binding allocates them), then accumulated. */
 int gi2d_rasterize_sum_bwd(int num_points, int tiles_x, int tiles_y, int img_width,
                            int img_height, const int32_t *gaussian_ids_sorted,
                            const int32_t *tile_bins, int num_bins_rows, const float *xys,
@@ -194,6 +220,9 @@ typedef struct gi2d_fit_params {
      * SSIM gradient (2 kernels, gi2d_loss.cu) / backward. */
     float loss_l1_scale;
     float loss_ssim_weight;
+    int32_t dynamic_points;     /* 1: the per-Gaussian arrays hold num_points ROWS (a capacity) and the live count is
+                                   stats[GI2D_STAT_NUM_POINTS]: gi2d_fit_prune / gi2d_fit_densify change the model's
+                                   size on the device, with no reallocation, no host round trip and no new graph */
 } gi2d_fit_params;
 
 /* stats layout (f64): the device-side step counter makes the step graph-replayable with no
@@ -209,7 +238,11 @@ typedef struct gi2d_fit_params {
 #define GI2D_STAT_ABS_SUM 14    /* sum |clamp(out)-gt| of the last step (w1 != 0) */
 #define GI2D_STAT_SSE 16        /* 64 partial sums of squared error of the clamped render */
 #define GI2D_STAT_SSE_SLOTS 64
-#define GI2D_STAT_COUNT (GI2D_STAT_SSE + GI2D_STAT_SSE_SLOTS)
+#define GI2D_STAT_NUM_POINTS 80 /* the Gaussian count when p->dynamic_points: prune / densify change it ON THE DEVICE */
+#define GI2D_STAT_BEST_N 81     /* Gaussian count of the best-state snapshot (rows of b->best / b->best_bound) */
+#define GI2D_STAT_PRUNED 82     /* Gaussians removed by the last gi2d_fit_prune */
+#define GI2D_STAT_ADDED 83      /* Gaussians appended by the last gi2d_fit_densify */
+#define GI2D_STAT_COUNT 96
 
 typedef struct gi2d_fit_buffers {
     /* parameters + optimiser state (updated in place) */
@@ -239,6 +272,8 @@ typedef struct gi2d_fit_buffers {
                        a new minimum (GI2D_STAT_BEST_SSE / _STEP) -- no host round trip, no extra launch */
     float *err_map; /* nullable f32[H,W]: a training step also writes the per-pixel L1 error of its clamped
                        render, sum_c |clamp(out)-gt| (the `errors` map of train.py:87 that drives densification) */
+    float *best_bound; /* nullable f32[N,3]: cov_bound rows of the best-state snapshot (the `slv_bound` copy of
+                          train.py:136), written together with b->best */
 } gi2d_fit_buffers;
 
 size_t gi2d_fit_workspace_size(const gi2d_fit_params *p);
@@ -261,6 +296,35 @@ int gi2d_fit_forward_backward(const gi2d_fit_params *p, const gi2d_fit_buffers *
  * Gaussians whose covariance cov+cov_bound is not positive definite into GI2D_STAT_NON_PSD (the test of
  * gaussianimage_covariance.py:373-382), so the prune decision costs no extra launch. */
 int gi2d_fit_adam(const gi2d_fit_params *p, const gi2d_fit_buffers *b, gi2d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Changing the model's size on the device (p->dynamic_points).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Set the live Gaussian count (rows [0,n) of the per-Gaussian arrays are the model). */
+int gi2d_fit_set_num_points(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int n, gi2d_stream_t stream);
+
+/* `non_semi_definite_prune` (models/gaussianimage_covariance.py:354-382): flush a pending optimiser step, then
+ * drop every Gaussian whose covariance cov + cov_bound is not positive definite (det > 0, sxx > 0, syy > 0 in
+ * torch's operation order), keeping the order of the survivors: parameters, both Adam moments and the bound rows
+ * are compacted together (stable, through a scratch copy), the live count and GI2D_STAT_PRUNED are updated.
+ * Nothing moves when no row fails or when every row would fail (`if to_prune_nums and cur - to_prune > 0`).
+ * Asynchronous, no host round trip.  workspace: gi2d_fit_prune_workspace_size(p->num_points) bytes. */
+size_t gi2d_fit_prune_workspace_size(int capacity);
+int gi2d_fit_prune(const gi2d_fit_params *p, const gi2d_fit_buffers *b, void *workspace, size_t workspace_bytes,
+                   gi2d_stream_t stream);
+
+/* `add_sample_positions` + `densification_postfix` (train.py:85-118, models/gaussianimage_covariance.py:307-334):
+ * the k pixels of largest error in b->err_map (f32[H,W], written by a training step; descending, ties by the
+ * smaller pixel index -- a full 64-bit radix sort of (error, index) keys) become new Gaussians at (x, y) with
+ * zero colour, zero Adam moments and covariance new_cov2d[i] (f32[k_rows,3], the caller's random draw + (0.5,0,0.5):
+ * the reference draws it on the CPU generator); candidates whose covariance is not positive definite are skipped;
+ * every appended row gets the bound (lp, 0, lp), lp = min(HW / (9 pi n_new), 300) of the NEW count (slv != 0), and
+ * the live count and GI2D_STAT_ADDED are updated.  k = min(k_rows, p->num_points - live count).
+ * A pending optimiser step is flushed first.  workspace: gi2d_fit_densify_workspace_size(H, W) bytes. */
+size_t gi2d_fit_densify_workspace_size(int img_height, int img_width);
+int gi2d_fit_densify(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int k_rows, const float *new_cov2d,
+                     int slv, void *workspace, size_t workspace_bytes, gi2d_stream_t stream);
 
 /* Gradients of the last training step with respect to the step's INPUTS, for a caller that keeps its own
  * parameters and optimiser (p->external_optimizer: the quantisation-aware pass feeds de-quantised means /

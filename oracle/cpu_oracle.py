@@ -227,3 +227,54 @@ class FitState:
                                  _p(self.v[2]), _p(self.gt), _p(img), C.byref(ni))
         self.num_intersects = ni.value
         return (mse, img) if want_image else mse
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The two operations that change the model's size, restated in numpy.  float32 arithmetic in
+# torch's operation order; test infrastructure like everything else in this module.
+def check_non_semi_definite(cov2d):
+    """models/gaussianimage_covariance.py:373-382: valid = (c0*c2 - c1**2 > 0) & (c0 > 0) & (c2 > 0), float32.
+    Returns (number to prune, valid mask)."""
+    c = np.asarray(cov2d, np.float32)
+    det = (c[:, 0] * c[:, 2]).astype(np.float32) - (c[:, 1] * c[:, 1]).astype(np.float32)
+    valid = (det > 0) & (c[:, 0] > 0) & (c[:, 2] > 0)
+    return int((~valid).sum()), valid
+
+
+def non_semi_definite_prune(xyz, cov, rgb, bound, m, v):
+    """models/gaussianimage_covariance.py:336-371 (`_prune_optimizer` + `non_semi_definite_prune`): when some but
+    not all Gaussians fail the test on get_cov2d_elements (= _cov2d + cholesky_bound, :169), parameters, both Adam
+    moments (dicts xyz / cov2d / f_dc) and the bound rows are masked together, order kept.
+    Returns (to_prune, xyz, cov, rgb, bound, m, v)."""
+    n_bad, valid = check_non_semi_definite(np.asarray(cov, np.float32) + np.asarray(bound, np.float32))
+    if n_bad and xyz.shape[0] - n_bad > 0:
+        return (n_bad, xyz[valid], cov[valid], rgb[valid], bound[valid],
+                {k: t[valid] for k, t in m.items()}, {k: t[valid] for k, t in v.items()})
+    return n_bad, xyz, cov, rgb, bound, m, v
+
+
+def add_sample_positions(errors, cur_num_points, max_num_points, new_cov2d_draw, W, H, base_num_samples=1000,
+                         last=False, slv=True):
+    """train.py:85-118 + models/gaussianimage_covariance.py:307-334.  `errors` f32[H,W] = |render - gt| summed over
+    the channels (train.py:87); k = max - cur when `last` (iter == iterations - grow_iter) else min(1000, max - cur)
+    (:93-97); the k pixels of largest error, descending (torch.topk, :101; ties -- which torch leaves unspecified
+    -- by the smaller index); new_xyz = (idx % W, idx // W) as float (:104-108), colour 0 (:106), covariance =
+    the caller's `torch.rand(k, 3) + (0.5, 0, 0.5)` draw (:110-112; passed in so that both sides use the same
+    numbers); candidates whose covariance fails check_non_semi_definite are dropped (:309-314); the appended rows
+    get the bound (lp, 0, lp) with lp = min(H*W / (9 pi n_new), 300) of the NEW count (:326-330).
+    (Dividing the errors by their sum, :89, does not change the order.)
+    Returns (k, chosen pixel indices [k], valid mask [k], new_xyz, new_cov, new_bound rows of the valid ones)."""
+    import math
+
+    room = max(0, max_num_points - cur_num_points)
+    k = room if last else min(base_num_samples, room)
+    e = np.asarray(errors, np.float32).reshape(-1)
+    order = np.lexsort((np.arange(e.size), -e.astype(np.float64)))[:k]   # value descending, index ascending
+    cov = np.asarray(new_cov2d_draw, np.float32)[:k]
+    _, valid = check_non_semi_definite(cov)
+    idx = order[valid]
+    new_xyz = np.stack([idx % W, idx // W], axis=1).astype(np.float32)
+    n_new = cur_num_points + int(valid.sum())
+    lp = np.float32(min(H * W / (9 * math.pi * n_new), 300)) if slv else np.float32(0.5)
+    new_bound = np.tile(np.array([lp, 0, lp], np.float32), (int(valid.sum()), 1))
+    return k, order, valid, new_xyz, cov[valid], new_bound

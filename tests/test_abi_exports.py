@@ -38,11 +38,28 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().gi2d_abi_version() == 1
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """The ctypes mirrors of the C structs against what gcc makes of include/gi2d.h: sizes and every offset."""
+    import subprocess
+
     from gaussianimage_plus_b200 import _lib
 
-    assert ctypes.sizeof(_lib.FitParams) == 21 * 4
-    assert ctypes.sizeof(_lib.FitBuffers) == 22 * 8
+    structs = {"gi2d_fit_params": _lib.FitParams, "gi2d_fit_buffers": _lib.FitBuffers, "gi2d_tilerow": _lib.TileRow}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gi2d.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
 
 
 def test_no_cpu_fallback_in_product():

@@ -202,6 +202,90 @@ def test_prune_and_densify_keep_state_consistent():
     assert st["step"] == 70 and np.isfinite(st["psnr"]) and st["psnr"] > p0 - 1
 
 
+def test_device_prune_matches_oracle(oracle):
+    """gi2d_fit_prune == the oracle's restatement of non_semi_definite_prune (gaussianimage_covariance.py:336-382):
+    the same rows survive, in the same order, with their Adam moments and bounds, bit for bit; the live count and
+    the reference's return value; nothing moves when nothing fails or everything would."""
+    fit, _ = make_fitter(3000, 256, 384, seed=6, colors="zeros", use_graph=True, keep_render=False)
+    fit.train_iters(12)
+    g = torch.Generator().manual_seed(5)
+    bad = torch.randperm(3000, generator=g)[:137]
+    cov = fit._cov2d
+    cov[bad[:50], 0] = -5.0                      # sxx < 0
+    cov[bad[50:100], 1] = 1e4                    # det < 0
+    cov[bad[100:], 2] = -fit.cholesky_bound[bad[100:], 2]   # syy == 0 exactly (singular)
+    state = lambda: (N_(fit._xyz), N_(fit._cov2d), N_(fit._features_dc), N_(fit.cholesky_bound),
+                     {k: N_(t) for k, t in fit.exp_avg.items()}, {k: N_(t) for k, t in fit.exp_avg_sq.items()})
+    before = state()
+    n_bad, *want = oracle.non_semi_definite_prune(*before)
+    ptrs = (fit._t_xyz.data_ptr(), fit._t_m["cov2d"].data_ptr(), fit.grads.data_ptr())
+    got_bad, n_now = fit.non_semi_definite_prune()
+    assert (got_bad, n_now) == (n_bad, 3000 - 137) == (137, fit.cur_num_points)
+    assert ptrs == (fit._t_xyz.data_ptr(), fit._t_m["cov2d"].data_ptr(), fit.grads.data_ptr())   # nothing reallocated
+    after = state()
+    for a, b in zip(after[:4], want[:4]):
+        np.testing.assert_array_equal(a, b)
+    for a, b in zip(after[4:], want[4:]):
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])
+    # a second prune finds nothing and moves nothing
+    assert fit.non_semi_definite_prune() == (0, 3000 - 137)
+    for a, b in zip(state()[:4], want[:4]):
+        np.testing.assert_array_equal(a, b)
+    # every row invalid: `cur_num_points - to_prune_nums > 0` fails, the model stays
+    fit._cov2d[:, 0] = -1000.0
+    keep = state()
+    assert fit.non_semi_definite_prune() == (3000 - 137, 3000 - 137)
+    for a, b in zip(state()[:4], keep[:4]):
+        np.testing.assert_array_equal(a, b)
+    # the training step keeps working on the compacted model, replayed from the SAME graph
+    fit._cov2d.copy_(torch.from_numpy(want[1]))
+    fit.train_iters(20)
+    st = fit.stats()
+    assert st["step"] == 32 and st["num_points"] == 3000 - 137 and np.isfinite(st["psnr"])
+
+
+def test_device_densify_matches_oracle(oracle):
+    """gi2d_fit_densify == the oracle's restatement of add_sample_positions + densification_postfix (train.py:85-118,
+    gaussianimage_covariance.py:307-334): the same pixels in the same order, the same rows appended (positions,
+    covariances, zero colour / moments, the bound of the NEW count), candidates with a non-positive-definite draw
+    skipped, nothing reallocated."""
+    H, W = 256, 384
+    fit, _ = make_fitter(2000, H, W, seed=6, colors="zeros", use_graph=True, keep_render=False, max_num_points=3000)
+    fit.train_iters(30)
+    fit.train_iter(want_error_map=True)
+    torch.cuda.synchronize()
+    errors = N_(fit.err_map)
+    before = (N_(fit._xyz), N_(fit._cov2d), N_(fit._features_dc), N_(fit.cholesky_bound))
+    ptrs = (fit._t_xyz.data_ptr(), fit._t_bound.data_ptr(), fit.sorted_keys.data_ptr())
+    torch.manual_seed(77)
+    draw = (torch.rand(700, 3) + torch.tensor([0.5, 0, 0.5])).numpy()
+    draw[::9, 1] = 3.0                                                    # (make some of them indefinite)
+    added = fit.add_sample_positions(max_num_points=3000, base_num_samples=700, errors=fit.err_map,
+                                     new_cov2d=torch.from_numpy(draw))
+    k, order, valid, new_xyz, new_cov, new_bound = oracle.add_sample_positions(
+        errors, 2000, 3000, draw, W, H, base_num_samples=700)
+    assert added == k == 700 and 0 < valid.sum() < 700
+    n_new = 2000 + int(valid.sum())
+    assert fit.cur_num_points == n_new and ptrs == (fit._t_xyz.data_ptr(), fit._t_bound.data_ptr(), fit.sorted_keys.data_ptr())
+    np.testing.assert_array_equal(N_(fit._xyz)[:2000], before[0])
+    np.testing.assert_array_equal(N_(fit._xyz)[2000:], new_xyz)
+    np.testing.assert_array_equal(N_(fit._cov2d)[2000:], new_cov)
+    np.testing.assert_array_equal(N_(fit.cholesky_bound)[:2000], before[3])
+    np.testing.assert_array_equal(N_(fit.cholesky_bound)[2000:], new_bound)
+    assert not N_(fit._features_dc)[2000:].any()
+    for d in (fit.exp_avg, fit.exp_avg_sq):
+        for t in d.values():
+            assert not N_(t)[2000:].any()
+    # the last growth fills up to max_num_points (train.py:93-94), and the fit goes on from the same graph
+    fit.train_iter(want_error_map=True)
+    added = fit.add_sample_positions(max_num_points=3000, last=True, errors=fit.err_map)
+    assert added == 3000 - n_new and n_new < fit.cur_num_points <= 3000
+    fit.train_iters(20)
+    st = fit.stats()
+    assert st["num_points"] == fit.cur_num_points and np.isfinite(st["psnr"]) and st["step"] == 52
+
+
 @pytest.mark.parametrize("graph", [False, True])
 def test_best_state_snapshot_matches_host_tracking(graph):
     """train.py:132-137 (`if best_psnr < psnr: deepcopy(state_dict)`): the device-side snapshot taken by the

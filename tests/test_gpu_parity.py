@@ -254,6 +254,50 @@ def test_rasterize_empty_and_ragged(B):
                                      z(0, 2, dt=torch.int32), z(1, 2), z(1, 3), z(1, 3), z(1, 1))
 
 
+@pytest.mark.parametrize("N,H,W,scale", [(400, 96, 128, 1.0), (5000, 512, 768, 1.0), (5000, 512, 768, 4.0),
+                                          (20000, 1356, 2040, 1.0), (3000, 64, 64, 3.0)])
+def test_bin_sort_single_call_matches_oracle(oracle, B, N, H, W, scale):
+    """gi2d_bin_sort (ONE call, num_intersects on the device) == the oracle's restatement of
+    compute_cumulative_intersects + bin_and_sort_gaussians (utils.py:231-311) bit for bit: sorted keys, sorted
+    Gaussian ids, tile ranges and the count -- the same arrays the multi-call path of this package yields."""
+    xyz, cov, rgb = scene(N, H, W, seed=N + W, cov_scale=scale)
+    tb = oracle.tile_bounds(H, W)
+    xys, depths, radii, conics, nth = oracle.project_cov_fwd(xyz, cov, H, W, tb)
+    total, cum, ids, gids, ids_s, gids_s, bins = oracle.bin_and_sort(xys, depths, radii, nth, tb)
+    res = B.bin_sort(N, T(xys), T(depths), T(radii), tb, 1.0)
+    assert res.check() == total
+    np.testing.assert_array_equal(N_(res.isect_ids_sorted[:total]), ids_s)
+    np.testing.assert_array_equal(N_(res.gaussian_ids_sorted[:total]), gids_s)
+    tiles = tb[0] * tb[1]
+    ref_bins = np.zeros((tiles, 2), np.int32)
+    ref_bins[:min(tiles, bins.shape[0])] = bins[:tiles]
+    np.testing.assert_array_equal(N_(res.tile_bins), ref_bins)
+    assert N_(res.info).tolist() == [total, total, 0]
+
+
+def test_bin_sort_overflow_is_flagged_not_silent(oracle, B):
+    from gaussianimage_plus_b200 import _lib
+
+    N, H, W = 5000, 512, 768
+    xyz, cov, rgb = scene(N, H, W, seed=3, cov_scale=4.0)
+    tb = oracle.tile_bounds(H, W)
+    xys, depths, radii, conics, nth = oracle.project_cov_fwd(xyz, cov, H, W, tb)
+    total = int(nth.sum())
+    lib = _lib.load()
+    cap = total // 2
+    out_k = torch.empty(cap, dtype=torch.int64, device=DEV)
+    out_g = torch.empty(cap, dtype=torch.int32, device=DEV)
+    bins = torch.empty(tb[0] * tb[1], 2, dtype=torch.int32, device=DEV)
+    info = torch.zeros(3, dtype=torch.int32, device=DEV)
+    ws = torch.empty(lib.gi2d_bin_sort_workspace_size(N, tb[0], tb[1], cap), dtype=torch.uint8, device=DEV)
+    rc = lib.gi2d_bin_sort(N, T(xys).data_ptr(), T(depths).data_ptr(), T(radii).data_ptr(), tb[0], tb[1], 1.0, cap,
+                           out_k.data_ptr(), out_g.data_ptr(), bins.data_ptr(), info.data_ptr(), ws.data_ptr(),
+                           ws.numel(), None)
+    assert rc == 0
+    assert N_(info).tolist() == [cap, total, 1]
+    assert int(bins.max()) <= cap            # the ranges never point past the rows that exist
+
+
 # --------------------------------------------------------------------------- autograd operators
 def test_gsplat_operators_autograd_vs_oracle(oracle):
     """The reference-facing Python API end to end: project_gaussians_2d_covariance ->
