@@ -432,7 +432,7 @@ class TileRowFit:
             if self.group is not None:
                 src = dist.get_global_rank(self.group, q)
                 dist.broadcast(rec, src=src, group=self.group)
-                dist.broadcast(box, src=src, group=self.group)
+                dist.broadcast(box.view(torch.int32), src=src, group=self.group)   # (NCCL has no 16-bit integer type)
             b = box.to(torch.int32) & 0xFFFF
             hit = (b[:, 2] > b[:, 0]) & (b[:, 3] > lo) & (b[:, 1] < hi)
             same = (fit.proj[g0:g1].view(torch.int32) == rec.view(torch.int32)).all(dim=1) & \

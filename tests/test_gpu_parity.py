@@ -282,7 +282,7 @@ def test_bin_sort_overflow_is_flagged_not_silent(oracle, B):
     xyz, cov, rgb = scene(N, H, W, seed=3, cov_scale=4.0)
     tb = oracle.tile_bounds(H, W)
     xys, depths, radii, conics, nth = oracle.project_cov_fwd(xyz, cov, H, W, tb)
-    total = int(nth.sum())
+    total = oracle.bin_and_sort(xys, depths, radii, nth, tb)[0]
     lib = _lib.load()
     cap = total // 2
     out_k = torch.empty(cap, dtype=torch.int64, device=DEV)
