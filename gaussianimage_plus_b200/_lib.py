@@ -60,6 +60,26 @@ class TileRow(C.Structure):
     ]
 
 
+class QuantParams(C.Structure):
+    """struct gi2d_quant_params (include/gi2d.h)"""
+    _fields_ = [
+        ("num_points", C.c_int32), ("xy_qmax", C.c_int32), ("cov_qmax", C.c_int32), ("color_qmax", C.c_int32),
+        ("color_sigmoid", C.c_int32), ("lr0", C.c_float), ("lr_step", C.c_int32), ("lr_q0", C.c_float),
+        ("lr_q_step", C.c_int32), ("lr_gamma", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+        ("eps", C.c_float), ("eps_xyz_q", C.c_float),
+    ]
+
+
+class QuantBuffers(C.Structure):
+    """struct gi2d_quant_buffers (include/gi2d.h)"""
+    _fields_ = [
+        ("xyz", _P), ("cov", _P), ("rgb", _P), ("bound", _P),
+        ("m_xyz", _P), ("v_xyz", _P), ("m_cov", _P), ("v_cov", _P), ("m_rgb", _P), ("v_rgb", _P),
+        ("qparams", _P), ("qm", _P), ("qv", _P), ("qstats", _P),
+        ("out_xyz", _P), ("out_cov", _P), ("out_rgb", _P), ("in_grads", _P), ("dbg_grads", _P),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/gi2d.h declares
 SIGNATURES = {
     "gi2d_abi_version": (_I, []),
@@ -90,6 +110,9 @@ SIGNATURES = {
     "gi2d_fit_profile_raster": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, C.POINTER(C.c_float), _P]),
     "gi2d_measure_fp32_peak": (_I, [C.POINTER(C.c_float), _P]),
     "gi2d_fit_input_grads": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _P, _P]),
+    "gi2d_quant_init": (_I, [C.POINTER(QuantParams), C.POINTER(QuantBuffers), _P]),
+    "gi2d_quant_forward": (_I, [C.POINTER(QuantParams), C.POINTER(QuantBuffers), _P]),
+    "gi2d_quant_backward_step": (_I, [C.POINTER(QuantParams), C.POINTER(QuantBuffers), _P]),
     "gi2d_tilerow_init": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), C.POINTER(TileRow), _P]),
     "gi2d_tilerow_step": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), C.POINTER(TileRow), _I, _I, _P]),
     "gi2d_ssim_workspace_size": (_SZ, [_I, _I]),

@@ -343,3 +343,152 @@ class FusedQuantizedTrainer(QuantizedGaussianImage):
     def psnr(self) -> float:
         """PSNR of the render of the LAST iteration (before its update); synchronises."""
         return self._fit.stats()["psnr"]
+
+
+# ----------------------------------------------------------------------------------- QAT as kernels
+class KernelQuantizedTrainer(QuantizedGaussianImage):
+    """The quantisation-aware iteration with the quantisers, their straight-through backward and the four
+    optimisers as KERNELS (csrc/gi2d_quant.cu) around the fused fit step:
+
+        gi2d_quant_forward (2 launches)  ->  fit step, external_optimizer (3)  ->  gi2d_fit_input_grads (1)
+        ->  gi2d_quant_backward_step (2)
+
+    eight launches replayed from one CUDA graph, no torch autograd, no torch.optim; the learning-rate schedules
+    are evaluated on the device from the iteration counter, so the graph is captured once.  The attributes are
+    the parent class's nn.Parameters (updated in place), the 12 quantiser parameters live in `qparams` and are
+    copied into the parent's quantiser modules by `sync_quantizers()` (compress_wo_ec does it for you)."""
+
+    def __init__(self, *a, use_graph: bool = True, debug_grads: bool = False, **kw):
+        super().__init__(*a, **kw)
+        import ctypes as C
+
+        from . import _lib
+        from .fit import GaussianImageFitter
+
+        dev = self._xyz.device
+        n = self._xyz.shape[0]
+        fit = GaussianImageFitter(n, self.H, self.W, device=dev, lr=0.0, clip_coe=self.gs_clip_coe,
+                                  radius_clip=self.radius_clip, color_norm=False, use_graph=False,
+                                  loss_type=self.loss_type)
+        fit.external_optimizer = True
+        fit.track_best = False
+        fit.params.external_optimizer = 1
+        fit.cholesky_bound.zero_()             # the inputs are complete covariances (bound already added)
+        fit._bind()
+        self._fit = fit
+        f = dict(device=dev, dtype=torch.float32)
+        self._gbuf = torch.zeros(n, 8, **f)
+        self._moments = {k: torch.zeros_like(p) for k, p in
+                         (("m_xyz", self._xyz), ("v_xyz", self._xyz), ("m_cov", self._cov2d), ("v_cov", self._cov2d),
+                          ("m_rgb", self._features_dc), ("v_rgb", self._features_dc))}
+        self.qparams = torch.zeros(12, **f)
+        self._qm, self._qv = torch.zeros(12, **f), torch.zeros(12, **f)
+        self.qstats = torch.zeros(32, device=dev, dtype=torch.float64)
+        self.dbg_grads = torch.zeros(n, 8, **f) if debug_grads else None
+        lr = float(self.optimizer.param_groups[0]["lr"])
+        self._qp = _lib.QuantParams(n, self.xyz_quantizer.qmax, self.cholesky_quantizer.cov_quantizer.qmax,
+                                    self.features_dc_quantizer.qmax, int(self.color_norm), lr, 20000, 0.001, 10000,
+                                    0.5, 0.9, 0.999, 1e-15, 1e-8)
+        if self.cholesky_quantizer.var_quantizer.qmax != self.cholesky_quantizer.cov_quantizer.qmax:
+            raise NotImplementedError("the kernels assume bits == cov_bits in HybirdQuant (the reference's setting)")
+        bound = self.cholesky_bound.contiguous()
+        self.cholesky_bound = bound
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        self._qb = _lib.QuantBuffers(
+            ptr(self._xyz.data), ptr(self._cov2d.data), ptr(self._features_dc.data), ptr(bound),
+            *(ptr(self._moments[k]) for k in ("m_xyz", "v_xyz", "m_cov", "v_cov", "m_rgb", "v_rgb")),
+            ptr(self.qparams), ptr(self._qm), ptr(self._qv), ptr(self.qstats),
+            ptr(fit._t_xyz), ptr(fit._t_cov2d), ptr(fit._t_f_dc), ptr(self._gbuf), ptr(self.dbg_grads))
+        self._C = C
+        self.use_graph = use_graph
+        self._graph = None
+        self._warm = 0
+        self._initialised = False
+        self.iterations = 0
+
+    def set_target(self, gt_hwc: torch.Tensor):
+        self._fit.set_target(gt_hwc)
+
+    def _enqueue_iteration(self):
+        from . import _lib
+        from .binding import _stream
+
+        C, fit = self._C, self._fit
+        st = _stream(fit.device)
+        _lib.check(fit.lib.gi2d_quant_forward(C.byref(self._qp), C.byref(self._qb), st), "quant_forward")
+        fit._enqueue_step()
+        _lib.check(fit.lib.gi2d_fit_input_grads(C.byref(fit.params), C.byref(fit.buffers), self._gbuf.data_ptr(), st),
+                   "fit_input_grads")
+        _lib.check(fit.lib.gi2d_quant_backward_step(C.byref(self._qp), C.byref(self._qb), st), "quant_backward_step")
+
+    def init_quantizers(self):
+        """`_init_data` of the three quantisers from the current attributes (first call of the reference's
+        forward_quantize, quantize.py:72-80 / 352-354)."""
+        from . import _lib
+        from .binding import _stream
+
+        _lib.check(self._fit.lib.gi2d_quant_init(self._C.byref(self._qp), self._C.byref(self._qb),
+                                                 _stream(self._fit.device)), "quant_init")
+        self._initialised = True
+
+    def train_iter_quantize(self, gt_hwc: Optional[torch.Tensor] = None):
+        """One quantisation-aware iteration (gaussianimage_covariance.py:219-247), asynchronous.  Returns
+        nothing: read `psnr()` / `loss()` when needed."""
+        if gt_hwc is not None:
+            self._fit.set_target(gt_hwc)
+        dev = self._xyz.device
+        with torch.cuda.device(dev):
+            if not self._initialised:
+                self.init_quantizers()
+            if not self.use_graph or self._warm < 2:
+                self._warm += 1
+                self._enqueue_iteration()
+            else:
+                if self._graph is None:
+                    self._graph = torch.cuda.CUDAGraph()
+                    s = torch.cuda.Stream(device=dev)
+                    s.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(s):
+                        with torch.cuda.graph(self._graph, stream=s):
+                            self._enqueue_iteration()
+                    torch.cuda.current_stream(dev).wait_stream(s)
+                self._graph.replay()
+        self.iterations += 1
+
+    def psnr(self) -> float:
+        """PSNR of the render of the LAST iteration (before its update); synchronises.  Also the place where an
+        overflow of the intersection buffers is noticed (the iteration then applied zero gradients)."""
+        st = self._fit.stats()
+        if st["overflow"]:
+            raise RuntimeError("intersection buffers overflowed during quantisation-aware training: construct the "
+                               "trainer's fitter with a larger capacity")
+        return st["psnr"]
+
+    def loss(self) -> float:
+        return float(self._loss_from_stats())
+
+    _loss_from_stats = FusedQuantizedTrainer._loss_from_stats
+
+    @torch.no_grad()
+    def sync_quantizers(self):
+        """qparams -> the scale / beta parameters of the parent's quantiser modules (state-dict compatible)."""
+        if not self._initialised:
+            self.init_quantizers()
+        q = self.qparams
+        self.xyz_quantizer.scale.data.copy_(q[0:2])
+        self.xyz_quantizer.beta.data.copy_(q[2:4])
+        self.cholesky_quantizer.cov_quantizer.scale.data.copy_(q[4:5])
+        self.cholesky_quantizer.cov_quantizer.beta.data.copy_(q[5:6])
+        self.features_dc_quantizer.scale.data.copy_(q[6:9])
+        self.features_dc_quantizer.beta.data.copy_(q[9:12])
+        for m in (self.xyz_quantizer, self.cholesky_quantizer, self.cholesky_quantizer.cov_quantizer,
+                  self.cholesky_quantizer.var_quantizer, self.features_dc_quantizer):
+            m.init_state = 1
+
+    def forward_quantize(self) -> Dict:
+        self.sync_quantizers()
+        return super().forward_quantize()
+
+    def compress_wo_ec(self) -> Dict:
+        self.sync_quantizers()
+        return super().compress_wo_ec()

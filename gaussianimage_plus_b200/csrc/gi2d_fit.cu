@@ -108,9 +108,19 @@ __device__ __forceinline__ void best_commit_warp0(double *__restrict__ stats) {
     }
 }
 
+// GI2D_TILE_ORDER=0 switches the heaviest-first work list off (A/B timing)
+bool tile_order_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("GI2D_TILE_ORDER");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+
 struct Plan {
     int num_tiles;
     bool smem_scan;    // tile starts fit the in-kernel scan
+    bool ordered;      // K2 also emits the heaviest-first work list the rasterizer's CTAs follow
     int gpb;           // Gaussians per CTA of K2
     int nblocks;       // CTAs of K2
 };
@@ -119,6 +129,9 @@ Plan make_plan(const gi2d_fit_params &p) {
     Plan pl;
     pl.num_tiles = p.tiles_x * p.tiles_y;
     pl.smem_scan = pl.num_tiles <= kMaxSmemTiles;
+    // heaviest-first tile order: only where the grid is a wave or two (beyond, the tail is a few per cent and a
+    // band of a tile-row split keeps its launch order)
+    pl.ordered = pl.smem_scan && p.tile_row_begin == 0 && p.tile_row_end == p.tiles_y && tile_order_enabled();
     // at most ~16 CTAs per SM of K2: beyond that, more Gaussians per CTA
     int gpb = kPlaceWarps * kPlaceGpw;
     while ((long long)gpb * 2368 < p.num_points) gpb *= 2;
@@ -136,6 +149,7 @@ struct Workspace {
     int32_t *scan_ws;     //     block sums of that scan
     ushort4 *boxes;       // [N] clipped tile box per Gaussian
     int32_t *n_isect;     // [1] device copy of num_intersects (clamped to capacity)
+    int4 *tile_work;      // [T] heaviest-first work list of the rasterizer (only up to kMaxSmemTiles tiles)
     float4 *records;      // [capacity][2] projected record of every intersection, tile order
     uint64_t *keys_tmp;   // [capacity] scratch for tiles with more than 256 entries (full in-tile sort)
     float *loss_render;   // [H,W,3] unclamped render   } only with loss_ssim_weight != 0:
@@ -160,6 +174,8 @@ Workspace carve(const gi2d_fit_params &p, const Plan &pl, void *base) {
     }
     w.boxes = (ushort4 *)(c + off);       off += align_up((size_t)(p.num_points > 0 ? p.num_points : 1) * 8);
     w.n_isect = (int32_t *)(c + off);     off += 256;
+    w.tile_work = nullptr;
+    if (pl.smem_scan) { w.tile_work = (int4 *)(c + off); off += align_up(T * 16); }
     w.records = (float4 *)(c + off);      off += align_up((size_t)p.isect_capacity * 32);
     w.keys_tmp = (uint64_t *)(c + off);   off += align_up((size_t)p.isect_capacity * 8);
     w.loss_render = w.loss_dm = w.loss_vout = nullptr;
@@ -482,9 +498,11 @@ fit_place_kernel(gi2d_fit_params p, int with_backward, int gpb, int num_tiles,
                  const ushort4 *__restrict__ boxes, const int32_t *__restrict__ tile_count,
                  const int32_t *__restrict__ tile_incl, int32_t *__restrict__ tile_fill,
                  uint64_t *__restrict__ keys_out, const float4 *__restrict__ proj, float4 *__restrict__ records,
-                 int32_t *__restrict__ tile_bins, int32_t *__restrict__ n_isect, double *__restrict__ stats) {
+                 int32_t *__restrict__ tile_bins, int32_t *__restrict__ n_isect, double *__restrict__ stats,
+                 int4 *__restrict__ tile_work) {
     __shared__ int s_base[kSmemScan ? kMaxSmemTiles : 1];
     __shared__ int s_warp[kPlaceWarps];
+    __shared__ int s_bin[kSmemScan ? kPlaceThreads : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     pdl_launch_dependents();
     const int gpw = gpb / kPlaceWarps;
@@ -514,6 +532,27 @@ fit_place_kernel(gi2d_fit_params p, int with_backward, int gpb, int num_tiles,
             int2 rg = c ? make_int2(e - c, e) : make_int2(0, 0);
             if (!kFit) { rg.x = min(rg.x, p.isect_capacity); rg.y = min(rg.y, p.isect_capacity); }
             reinterpret_cast<int2 *>(tile_bins)[t] = rg;
+        }
+    }
+    // the rasterizer's work list: tiles by descending count (counting sort over min(count, 255), ties in any
+    // order), written by the LAST CTA (the one with the fewest Gaussians to place)
+    if (kSmemScan && tile_work && blockIdx.x == gridDim.x - 1) {
+        s_bin[threadIdx.x] = 0;
+        __syncthreads();
+        for (int t = threadIdx.x; t < num_tiles; t += kPlaceThreads)
+            atomicAdd(&s_bin[kPlaceThreads - 1 - min(__ldcg(tile_count + t), kPlaceThreads - 1)], 1);
+        __syncthreads();
+        const int mine = s_bin[threadIdx.x];
+        int tot;
+        const int incl = block_scan_inclusive<kPlaceThreads>(mine, s_warp, &tot);
+        __syncthreads();
+        s_bin[threadIdx.x] = incl - mine;
+        __syncthreads();
+        for (int t = threadIdx.x; t < num_tiles; t += kPlaceThreads) {
+            const int c = __ldcg(tile_count + t);
+            const int pos = atomicAdd(&s_bin[kPlaceThreads - 1 - min(c, kPlaceThreads - 1)], 1);
+            const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+            tile_work[pos] = c ? make_int4(tx | (ty << 16), s_base[t], s_base[t] + c, c) : make_int4(tx | (ty << 16), 0, 0, 0);
         }
     }
     if (blockIdx.x == 0 && warp == 0) {
@@ -856,14 +895,18 @@ fit_raster_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_
 // Gaussians are dealt to the warps (one more block barrier, twice the warps to hide latency with).
 // Results: tile ranges, sorted keys and the image are bit-identical to fit_raster_kernel (same operations per
 // pixel, same order); gradients agree to fp32 summation order.
+#ifndef GI2D_RQ4_MINBLOCKS
+#define GI2D_RQ4_MINBLOCKS 7
+#endif
 template <RasterMode kMode, int kWarps>
-__global__ void __launch_bounds__(32 * kWarps, kWarps == 1 ? 16 : (kWarps == 2 ? 10 : 8))
+__global__ void __launch_bounds__(32 * kWarps, kWarps == 1 ? 16 : (kWarps == 2 ? 10 : GI2D_RQ4_MINBLOCKS))
 fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_t *__restrict__ keys_tmp,
                    const int32_t *__restrict__ tile_bins, int32_t *__restrict__ tile_count,
                    int32_t *__restrict__ tile_fill, const float4 *__restrict__ records,
                    const float *__restrict__ gt, const uint8_t *__restrict__ gt_u8,
                    float *__restrict__ out_img, float *__restrict__ grads, double *__restrict__ stats,
-                   float *__restrict__ err_map, const float *__restrict__ v_out) {
+                   float *__restrict__ err_map, const float *__restrict__ v_out,
+                   const int4 *__restrict__ tile_work) {
     constexpr bool kHasFwd = kMode != RasterMode::FitBackward;
     constexpr bool kHasLoss = kMode == RasterMode::Fit || kMode == RasterMode::FitForward;
     constexpr bool kHasBwd = kMode == RasterMode::Fit || kMode == RasterMode::FitBackward;
@@ -879,19 +922,34 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     __shared__ __align__(16) WarpGrad<kRegionRows> s_wg[kRegions];
     __shared__ unsigned char s_list[kWarps][kMaxPerTile];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile_y = p.tile_row_begin + blockIdx.y;
-    const int tile_id = tile_y * p.tiles_x + blockIdx.x;
     pdl_launch_dependents();
     // the warp's first quadrant (column, row) and its bit in the reach masks
     const int qcol0 = kWarps == 4 ? (warp & 1) : 0;
     const int qrow0 = kWarps == 4 ? (warp >> 1) : (kWarps == 2 ? warp : 0);
     const int qshift = 2 * qrow0 + qcol0;
     const int lx0 = 8 * qcol0 + (lane & 7), ly0 = 8 * qrow0 + (lane >> 3);   // tile-relative
-    const int px0 = blockIdx.x * kTile + lx0;
+    pdl_wait();
+    // which tile: the launch order (tile_work == nullptr) or the placement kernel's heaviest-first work list
+    // (one entry per CTA: tile x | y << 16, range begin, range end) -- the long tiles start first, the short ones
+    // fill the tail of the grid's last wave
+    int tile_x, tile_y;
+    int2 range;
+    if (tile_work) {
+        const int4 wk = __ldcg(tile_work + blockIdx.y * gridDim.x + blockIdx.x);
+        tile_x = wk.x & 0xffff;
+        tile_y = (int)((unsigned)wk.x >> 16);
+        range = make_int2(wk.y, wk.z);
+    } else {
+        tile_x = blockIdx.x;
+        tile_y = p.tile_row_begin + blockIdx.y;
+        range = __ldcg(reinterpret_cast<const int2 *>(tile_bins) + tile_y * p.tiles_x + tile_x);
+    }
+    const int tile_id = tile_y * p.tiles_x + tile_x;
+    const int px0 = tile_x * kTile + lx0;
     const int py0 = tile_y * kTile + ly0;
     const QuadLane<kNQ> ln = quad_lane<kNQ>(px0, py0);
     // pixel (quadrant qi, pair element e) of this lane: (px0 + 8*(qi % kCols), py0 + 8*(qi / kCols) + 4*e)
-    const bool full_tile = (blockIdx.x + 1) * kTile <= p.img_width && (tile_y + 1) * kTile <= p.img_height;
+    const bool full_tile = (tile_x + 1) * kTile <= p.img_width && (tile_y + 1) * kTile <= p.img_height;
     unsigned outside = 0;
     if (!full_tile) {
 #pragma unroll
@@ -901,8 +959,8 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
                 if (px0 + 8 * (qi % kCols) >= p.img_width || py0 + 8 * (qi / kCols) + 4 * e >= p.img_height)
                     outside |= 1u << (2 * qi + e);
     }
-    // the target pixels are written by no kernel of the step: pull their lines towards L2 while the predecessor
-    // drains and the list is staged (they are loaded after the forward sweep, so they cost no registers here)
+    // the target pixels are written by no kernel of the step: pull their lines towards L2 while the list is
+    // staged (they are loaded after the forward sweep, so they cost no registers here)
     if (kHasLoss) {
         const int bpp = gt ? 12 : 3;
         const char *base = gt ? (const char *)gt : (const char *)gt_u8;
@@ -915,9 +973,7 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(base + pix * bpp));
                 }
     }
-    pdl_wait();
     const double n_isect = __ldcg(stats + GI2D_STAT_ISECTS);
-    const int2 range = __ldcg(reinterpret_cast<const int2 *>(tile_bins) + tile_id);
     const int total_cnt = max(0, min(range.y, p.isect_capacity) - range.x);
     const int cnt = min(kMaxPerTile, total_cnt);
     if (kHasFwd && tid == 0) {   // the counters of this tile go back to K1 / K2 of the next step zeroed
@@ -928,7 +984,7 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     }
     // ---- finish the key sort (see fit_raster_kernel): rank by gaussian id, stage at the rank
     constexpr bool kWriteBack = kMode != RasterMode::FitForward;
-    const float tx0 = (float)(blockIdx.x * kTile), ty0 = (float)(tile_y * kTile);
+    const float tx0 = (float)(tile_x * kTile), ty0 = (float)(tile_y * kTile);
     if (total_cnt <= kMaxPerTile) {
         uint64_t key0 = 0;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), b0 = a0;
@@ -1002,7 +1058,7 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
         for (int e = 0; e < 2; ++e) {
             const bool inside = !((outside >> (2 * qi + e)) & 1u);
             const int lx = lx0 + 8 * (qi % kCols), ly = ly0 + 8 * (qi / kCols) + 4 * e;   // tile-relative
-            const size_t pix = (size_t)(tile_y * kTile + ly) * p.img_width + blockIdx.x * kTile + lx;
+            const size_t pix = (size_t)(tile_y * kTile + ly) * p.img_width + tile_x * kTile + lx;
             float r = cr[e], g = cg[e], b = cb[e];
             if (ones) r = g = b = 1.f;
             float wr = 0.f, wgc = 0.f, wb = 0.f;
@@ -1077,23 +1133,21 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     // the staged Gaussians that can reach the region, ascending (every warp builds the list it walks)
     unsigned char *list = s_list[warp];
     const unsigned region_bits = kTileWide ? 0xFu : (((1u << kNQ) - 1u) << qshift);
-    int n = 0;
-    for (int base = 0; base < cnt; base += 32) {
-        const int t = base + lane;
-        const bool hit = t < cnt && ((unsigned)sg.mask[t] & region_bits) != 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) list[n + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)t;
-        n += __popc(bal);
+    const int n = build_group_list<kRegionRows>(sg, cnt, region_bits, region_row0, list);
+    if (lane < kTile && (!kTileWide || warp == 0)) {   // the all-zero row a group reads past its own rows
+        wg.v[0][kRegionRows][lane] = 0.f;
+        wg.v[1][kRegionRows][lane] = 0.f;
+        wg.v[2][kRegionRows][lane] = 0.f;
     }
     if (kTileWide) __syncthreads(); else __syncwarp();   // dL/d(out) and the list are in shared memory
     if (n == 0) return;
     const int region_py0 = tile_y * kTile + region_row0;
     const int first_group = kTileWide ? warp : 0, group_stride = kTileWide ? kWarps : 1;
     if (full_tile)
-        quad_backward4<kRegionRows, false>(sg, s_ids, list, n, first_group, group_stride, blockIdx.x * kTile,
+        quad_backward4<kRegionRows, false>(sg, s_ids, list, n, first_group, group_stride, tile_x * kTile,
                                            region_py0, region_row0, p.img_width, kRegionRows, wg, grads);
     else
-        quad_backward4<kRegionRows, true>(sg, s_ids, list, n, first_group, group_stride, blockIdx.x * kTile,
+        quad_backward4<kRegionRows, true>(sg, s_ids, list, n, first_group, group_stride, tile_x * kTile,
                                           region_py0, region_row0, p.img_width,
                                           min(kRegionRows, p.img_height - region_py0), wg, grads);
 }
@@ -1115,18 +1169,18 @@ template <RasterMode kMode>
 cudaError_t launch_raster(bool pdl, dim3 grid, cudaStream_t st, const gi2d_fit_params &p, uint64_t *sorted_keys,
                           uint64_t *keys_tmp, const int32_t *tile_bins, int32_t *tile_count, int32_t *tile_fill,
                           const float4 *records, const float *gt, const uint8_t *gt_u8, float *out_img, float *grads,
-                          double *stats, float *err_map, const float *v_out) {
+                          double *stats, float *err_map, const float *v_out, const int4 *tile_work) {
     const int v = raster_variant((int)(grid.x * grid.y));
 #define GI2D_RASTER_ARGS p, sorted_keys, keys_tmp, tile_bins, tile_count, tile_fill, records, gt, gt_u8, out_img, grads, stats, err_map, v_out
     if (v == 1) {
-        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 1>, grid, dim3(32), 0, st, GI2D_RASTER_ARGS);
-        fit_rasterq_kernel<kMode, 1><<<grid, 32, 0, st>>>(GI2D_RASTER_ARGS);
+        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 1>, grid, dim3(32), 0, st, GI2D_RASTER_ARGS, tile_work);
+        fit_rasterq_kernel<kMode, 1><<<grid, 32, 0, st>>>(GI2D_RASTER_ARGS, tile_work);
     } else if (v == 2) {
-        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 2>, grid, dim3(64), 0, st, GI2D_RASTER_ARGS);
-        fit_rasterq_kernel<kMode, 2><<<grid, 64, 0, st>>>(GI2D_RASTER_ARGS);
+        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 2>, grid, dim3(64), 0, st, GI2D_RASTER_ARGS, tile_work);
+        fit_rasterq_kernel<kMode, 2><<<grid, 64, 0, st>>>(GI2D_RASTER_ARGS, tile_work);
     } else if (v == 4) {
-        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 4>, grid, dim3(128), 0, st, GI2D_RASTER_ARGS);
-        fit_rasterq_kernel<kMode, 4><<<grid, 128, 0, st>>>(GI2D_RASTER_ARGS);
+        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 4>, grid, dim3(128), 0, st, GI2D_RASTER_ARGS, tile_work);
+        fit_rasterq_kernel<kMode, 4><<<grid, 128, 0, st>>>(GI2D_RASTER_ARGS, tile_work);
     } else {
         if (pdl) return launch_pdl(fit_raster_kernel<kMode>, grid, dim3(kRasterThreads), 0, st, GI2D_RASTER_ARGS);
         fit_raster_kernel<kMode><<<grid, kRasterThreads, 0, st>>>(GI2D_RASTER_ARGS);
@@ -1674,11 +1728,11 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     if (pl.smem_scan)
         launch_pdl(fit_place_kernel<true>, dim3(pl.nblocks), dim3(kPlaceThreads), 0, st,
             *p, with_backward, pl.gpb, num_tiles, w.boxes, w.tile_count, w.tile_incl, w.tile_fill, b->sorted_keys,
-            (const float4 *)b->proj, w.records, b->tile_bins, w.n_isect, b->stats);
+            (const float4 *)b->proj, w.records, b->tile_bins, w.n_isect, b->stats, pl.ordered ? w.tile_work : nullptr);
     else
         launch_pdl(fit_place_kernel<false>, dim3(pl.nblocks), dim3(kPlaceThreads), 0, st,
             *p, with_backward, pl.gpb, num_tiles, w.boxes, w.tile_count, w.tile_incl, w.tile_fill, b->sorted_keys,
-            (const float4 *)b->proj, w.records, b->tile_bins, w.n_isect, b->stats);
+            (const float4 *)b->proj, w.records, b->tile_bins, w.n_isect, b->stats, pl.ordered ? w.tile_work : nullptr);
     if (mk) mk->mark(st);
     const int band = p->tile_row_end - p->tile_row_begin;
     if (band > 0) {
@@ -1688,7 +1742,7 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
             // the backward half.  (Band-split multi-GPU runs would need a halo exchange of the render.)
             launch_raster<RasterMode::FitForward>(false, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins,
                 w.tile_count, w.tile_fill, (const float4 *)w.records, b->gt_hwc, b->gt_u8_hwc, w.loss_render, nullptr,
-                b->stats, b->err_map, nullptr);
+                b->stats, b->err_map, nullptr, pl.ordered ? w.tile_work : nullptr);
             if (b->out_img)
                 cudaMemcpyAsync(b->out_img, w.loss_render, (size_t)p->img_width * p->img_height * 12,
                                 cudaMemcpyDeviceToDevice, st);
@@ -1697,15 +1751,15 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
                              b->stats + GI2D_STAT_SSIM_SUM, st);
             launch_raster<RasterMode::FitBackward>(false, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins,
                 w.tile_count, w.tile_fill, (const float4 *)w.records, nullptr, nullptr, nullptr, b->grads, b->stats,
-                nullptr, w.loss_vout);
+                nullptr, w.loss_vout, pl.ordered ? w.tile_work : nullptr);
         } else if (with_backward)
             launch_raster<RasterMode::Fit>(true, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count,
                 w.tile_fill, (const float4 *)w.records, b->gt_hwc, b->gt_u8_hwc, b->out_img, b->grads, b->stats,
-                b->err_map, nullptr);
+                b->err_map, nullptr, pl.ordered ? w.tile_work : nullptr);
         else
             launch_raster<RasterMode::Render>(true, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins,
                 w.tile_count, w.tile_fill, (const float4 *)w.records, nullptr, nullptr, b->out_img, nullptr, b->stats,
-                nullptr, nullptr);
+                nullptr, nullptr, pl.ordered ? w.tile_work : nullptr);
     }
     if (mk) mk->mark(st);
     return check_launch("gi2d_fit_forward_backward");
@@ -1910,12 +1964,12 @@ extern "C" int gi2d_bin_sort(int num_points, const float *xys, const float *dept
     const Plan pl = make_plan(p);
     if (pl.smem_scan) {
         fit_place_kernel<true, false><<<pl.nblocks, kPlaceThreads, 0, st>>>(
-            p, 0, pl.gpb, T, boxes, tile_count, tile_incl, tile_fill, keys, nullptr, nullptr, tile_bins, info, nullptr);
+            p, 0, pl.gpb, T, boxes, tile_count, tile_incl, tile_fill, keys, nullptr, nullptr, tile_bins, info, nullptr, nullptr);
     } else {
         const int rc = cumsum_i32_launch(T, tile_count, tile_incl, nullptr, scan_ws, st);
         if (rc != GI2D_OK) return rc;
         fit_place_kernel<false, false><<<pl.nblocks, kPlaceThreads, 0, st>>>(
-            p, 0, pl.gpb, T, boxes, tile_count, tile_incl, tile_fill, keys, nullptr, nullptr, tile_bins, info, nullptr);
+            p, 0, pl.gpb, T, boxes, tile_count, tile_incl, tile_fill, keys, nullptr, nullptr, tile_bins, info, nullptr, nullptr);
     }
     bs_tile_sort_kernel<<<T, 64, 0, st>>>(capacity, tile_bins, keys, (int64_t)0, isect_ids_sorted, gaussian_ids_sorted);
     return check_launch(__func__);
@@ -1960,7 +2014,7 @@ extern "C" int gi2d_fit_profile_raster(const gi2d_fit_params *p, const gi2d_fit_
     for (int i = 0; i < reps; ++i)
         launch_raster<RasterMode::Fit>(true, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count,
             w.tile_fill, (const float4 *)w.records, b->gt_hwc, b->gt_u8_hwc, nullptr, b->grads, b->stats, nullptr,
-            nullptr);
+            nullptr, pl.ordered ? w.tile_work : nullptr);
     cudaEventRecord(e1, st);
     // nothing pending (the accumulated gradient is garbage), loss accumulators back to zero
     cudaMemsetAsync(b->stats + kStatPending, 0, sizeof(double), st);

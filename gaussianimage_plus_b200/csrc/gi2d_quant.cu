@@ -44,8 +44,7 @@ __device__ __forceinline__ Lsq lsq(float x, float s, float beta, float qmax) {
     o.code = __fdiv_rn(__fsub_rn(x, beta), s);
     o.inside = o.code >= 0.f && o.code <= qmax;
     o.r = rintf(fminf(fmaxf(o.code, 0.f), qmax));
-    o.y = __fmaf_rn(o.r, s, beta) == __fadd_rn(__fmul_rn(o.r, s), beta) ? __fadd_rn(__fmul_rn(o.r, s), beta)
-                                                                        : __fadd_rn(__fmul_rn(o.r, s), beta);
+    o.y = __fadd_rn(__fmul_rn(o.r, s), beta);   // torch: r * scale + beta, two roundings
     return o;
 }
 
@@ -117,7 +116,7 @@ __device__ __forceinline__ LogQ logq(float x, float beta, float mx, float qmax) 
     LogQ o;
     o.beta = beta;
     o.mx = mx;
-    o.scale = __fdiv_rn(__fsub_rn(mx, beta), qmax);
+    o.scale = __fmul_rn(__fsub_rn(mx, beta), __fdiv_rn(1.f, qmax));   // (torch divides by a host scalar as x * (1 / s))
     o.L = logf(fabsf(x) + 1e-6f);
     o.code = __fdiv_rn(__fsub_rn(o.L, beta), o.scale);
     o.inside = o.code >= 0.f && o.code <= qmax;
@@ -249,6 +248,7 @@ quant_update_kernel(gi2d_quant_params p, gi2d_quant_buffers b) {
             const float x = b.xyz[2 * g + k];
             const Lsq o = lsq(x, q[k], q[2 + k], (float)p.xy_qmax);
             const float gx = o.inside ? gin[k] : 0.f;
+            if (b.dbg_grads) b.dbg_grads[8 * g + k] = gx;
             b.xyz[2 * g + k] = adam1(x, b.m_xyz[2 * g + k], b.v_xyz[2 * g + k], gx, p.beta1, p.beta2, step_a, bc2s, p.eps);
         }
         // covariance parameters (the bound is a constant: d(cov + bound)/d cov = 1)
@@ -268,6 +268,7 @@ quant_update_kernel(gi2d_quant_params p, gi2d_quant_buffers b) {
                 const float sgn = (e > 0.f) - (e < 0.f);
                 gx = gL * sgn / (fabsf(e) + 1e-6f);
             }
+            if (b.dbg_grads) b.dbg_grads[8 * g + 2 + k] = gx;
             b.cov[3 * g + k] = adam1(c, b.m_cov[3 * g + k], b.v_cov[3 * g + k], gx, p.beta1, p.beta2, step_a, bc2s, p.eps);
         }
         // colours
@@ -278,6 +279,7 @@ quant_update_kernel(gi2d_quant_params p, gi2d_quant_buffers b) {
             if (p.color_sigmoid) { f = sigmoid_(raw); df = f * (1.f - f); }
             const Lsq o = lsq(f, q[6 + k], q[9 + k], (float)p.color_qmax);
             const float gx = o.inside ? gin[5 + k] * df : 0.f;
+            if (b.dbg_grads) b.dbg_grads[8 * g + 5 + k] = gx;
             b.rgb[3 * g + k] = adam1(raw, b.m_rgb[3 * g + k], b.v_rgb[3 * g + k], gx, p.beta1, p.beta2, step_a, bc2s, p.eps);
         }
     }
@@ -344,7 +346,8 @@ quant_init_kernel(gi2d_quant_params p, gi2d_quant_buffers b) {
         float a = s_min[tid][0], z = s_max[tid][0];
         for (int w = 1; w < 32; ++w) { a = fminf(a, s_min[tid][w]); z = fmaxf(z, s_max[tid][w]); }
         const float qmax = tid < 2 ? (float)p.xy_qmax : (tid == 2 ? (float)p.cov_qmax : (float)p.color_qmax);
-        const float scale = __fdiv_rn(__fsub_rn(z, a), qmax);          // (t_max - t_min) / (qmax - qmin), qmin = 0
+        // (t_max - t_min) / (qmax - qmin), qmin = 0; torch divides by a host scalar as x * (1 / s)
+        const float scale = __fmul_rn(__fsub_rn(z, a), __fdiv_rn(1.f, qmax));
         const int si = tid < 2 ? tid : (tid == 2 ? 4 : 6 + (tid - 3));
         const int bi = tid < 2 ? 2 + tid : (tid == 2 ? 5 : 9 + (tid - 3));
         b.qparams[si] = scale;

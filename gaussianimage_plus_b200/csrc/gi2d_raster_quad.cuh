@@ -61,6 +61,7 @@ constexpr int kQuads = 4;   // 8x8-pixel quadrants per tile: bit q <-> (x0, y0) 
 struct QuadReach {
     unsigned mask;
     int row_lo, row_hi;
+    int col_lo, col_hi;
 };
 
 __device__ __forceinline__ QuadReach reach_quad(float gx, float gy, float a, float b, float c) {
@@ -68,6 +69,8 @@ __device__ __forceinline__ QuadReach reach_quad(float gx, float gy, float a, flo
     o.mask = 0xFu;
     o.row_lo = 0;
     o.row_hi = kTile - 1;
+    o.col_lo = 0;
+    o.col_hi = kTile - 1;
     const float det = fmaf(a, c, -b * b);
     const float L = 5.5412635f * 1.001f + 1e-3f;   // ln(255)
     if (!(det > 1e-3f * a * c && a > 0.f && c > 0.f)) return o;   // indefinite / NaN / needle: no culling
@@ -83,6 +86,8 @@ __device__ __forceinline__ QuadReach reach_quad(float gx, float gy, float a, flo
     // pixel rows r with y0 <= r <= y1 (pixel centres sit on integers, forward.cu:596-597)
     o.row_lo = (int)fminf(fmaxf(ceilf(y0), 0.f), 15.f);
     o.row_hi = (int)fminf(fmaxf(floorf(y1), 0.f), 15.f);
+    o.col_lo = (int)fminf(fmaxf(ceilf(x0), 0.f), 15.f);
+    o.col_hi = (int)fminf(fmaxf(floorf(x1), 0.f), 15.f);
     return o;
 }
 
@@ -94,6 +99,7 @@ struct QuadRecords {
     float4 crgb[kMaxPerTile];   // c r g b
     unsigned char mask[kMaxPerTile];
     unsigned char rows[kMaxPerTile];   // row_lo | row_hi << 4
+    unsigned char cols[kMaxPerTile];   // col_lo | col_hi << 4
 };
 
 __device__ __forceinline__ void stage_quad(QuadRecords &s, int slot, float4 p0, float4 p1, float tile_x0,
@@ -103,6 +109,7 @@ __device__ __forceinline__ void stage_quad(QuadRecords &s, int slot, float4 p0, 
     const QuadReach rc = reach_quad(p0.x - tile_x0, p0.y - tile_y0, p0.z, p0.w, p1.x);
     s.mask[slot] = (unsigned char)rc.mask;
     s.rows[slot] = (unsigned char)(rc.row_lo | (rc.row_hi << 4));
+    s.cols[slot] = (unsigned char)(rc.col_lo | (rc.col_hi << 4));
 }
 
 // Geometry of a warp that owns kNQ quadrants: kNQ = 4 all of them (2 columns x 2 rows), 2 one ROW of quadrants
@@ -225,18 +232,83 @@ __device__ __forceinline__ void quad_forward(const QuadRecords &s, int cnt, cons
 // A warp that walks the list one Gaussian at a time with its lanes on pixels pays per (warp, Gaussian) a 32-lane
 // reduction (9 shuffles + 14 selects + 7 adds, a chain of five dependent shuffle round trips), the record load,
 // the loop control and the atomic set-up: ~95 instructions around ~45 of useful pair math at the list lengths of
-// a 768x512 / 5000-Gaussian scene (ncu of that first version: 36 % of the kernel's instructions, the top stall
-// reasons; profiles/README.md).  Here the region (kRows rows of 16 pixels) is swept row by row with lane j = L&7 of every 8-lane group holding the pixel pair (2j, 2j+1) of the row,
-// and group L>>3 working on its OWN Gaussian: one instruction still evaluates 64 pairs, but the fixed part is
-// paid once per FOUR Gaussians, the reduction spans 8 lanes (7 shuffles for 4 Gaussians at once), and after
-// it every one of the 32 lanes holds exactly one (Gaussian, component) total: one RED instruction.
-// dL/d(out) comes from a per-warp shared-memory copy (3 broadcast LDS.64 per row, identical addresses in the
-// four groups).  The row range swept is the union of the four reach boxes (warp-uniform, redux.sync).
-// `list`: ranks of the staged Gaussians this warp reaches (n of them), ascending.
+// a 768x512 / 5000-Gaussian scene.  Here every 8-lane group (L>>3) works on its OWN Gaussian and sweeps that
+// Gaussian's OWN reach box inside the region (kRows rows of 16 pixels): one instruction still evaluates 64
+// pairs, but the fixed part is paid once per FOUR Gaussians, the reduction spans 8 lanes (7 shuffles for 4
+// Gaussians at once), and after it every one of the 32 lanes holds exactly one (Gaussian, component) total: one
+// RED instruction.
+//
+// Shape of a group's sweep (all of it per-lane DATA, so four different shapes run in one warp without a
+// divergent branch): the 8 lanes hold 8 pixel pairs (x, x+1) laid out as
+//     8 pairs x 1 row   (reach wider than 8 columns)          1 row  per trip
+//     4 pairs x 2 rows  (reach within 8 columns)              2 rows per trip
+//     2 pairs x 4 rows  (reach within 4 columns)              4 rows per trip
+// starting at the reach box's first row / first (even) column.  The trip count of the warp is the largest of its
+// four groups; the list is ordered by trip count (build_group_list) so that the four are alike.  A group that
+// runs past its own rows reads dL/d(out) from an all-zero extra row (its weights there are below 1/255 anyway).
+// At 768x512 / 5000 Gaussians a reach box covers ~9 of a tile's 16 rows and ~9 of its 16 columns: sweeping the
+// union of four boxes over all 16 columns (the first version of this kernel) evaluated ~2x the pairs.
 template <int kRows>
-struct WarpGrad {                      // dL/d(out) of the warp's region, planar, row stride 16
-    float v[3][kRows][kTile];
+struct WarpGrad {                      // dL/d(out) of the region, planar, row stride 16; row kRows stays zero
+    float v[3][kRows + 1][kTile];
 };
+
+struct GroupShape {
+    int lo;      // first region row
+    int c0;      // first column (even)
+    int lg;      // log2(pairs per row): 3, 2, 1
+    int trips;   // ceil(rows / rows per trip); 0: nothing to sweep
+};
+
+template <int kRows>
+__device__ __forceinline__ GroupShape group_shape(unsigned rw, unsigned cw, int region_row0) {
+    GroupShape g;
+    g.lo = max((int)(rw & 15u) - region_row0, 0);
+    const int hi = min((int)(rw >> 4) - region_row0, kRows - 1);
+    const int chi = (int)(cw >> 4);
+    g.c0 = (int)(cw & 14u);
+    const int w = chi - g.c0;   // columns c0 .. c0 + w
+    if (w < 4) { g.lg = 1; g.c0 = min(g.c0, 12); }
+    else if (w < 8) { g.lg = 2; g.c0 = min(g.c0, 8); }
+    else { g.lg = 3; g.c0 = 0; }
+    g.trips = max(0, (hi - g.lo + (8 >> g.lg)) >> (3 - g.lg));
+    return g;
+}
+
+// The staged Gaussians that reach the region (quadrant bits `region_bits`), longest sweep first: four buckets of
+// trip counts (> 8, 5-8, 3-4, 1-2) filled by ballots.  Every lane of the warp calls it; returns the list length.
+template <int kRows>
+__device__ __forceinline__ int build_group_list(const QuadRecords &s, int cnt, unsigned region_bits, int region_row0,
+                                                unsigned char *list) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    auto bucket_of = [&](int t) -> int {
+        if (t >= cnt || !((unsigned)s.mask[t] & region_bits)) return -1;
+        const int trips = group_shape<kRows>(s.rows[t], s.cols[t], region_row0).trips;
+        return trips > 8 ? 0 : (trips > 4 ? 1 : (trips > 2 ? 2 : (trips > 0 ? 3 : -1)));
+    };
+    int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+    int b_first = bucket_of(lane);   // (lists of up to 32 entries -- the common case -- classify once)
+    for (int base = 0; base < cnt; base += 32) {
+        const int b = base == 0 ? b_first : bucket_of(base + lane);
+        n0 += __popc(__ballot_sync(0xffffffffu, b == 0));
+        n1 += __popc(__ballot_sync(0xffffffffu, b == 1));
+        n2 += __popc(__ballot_sync(0xffffffffu, b == 2));
+        n3 += __popc(__ballot_sync(0xffffffffu, b == 3));
+    }
+    int o0 = 0, o1 = n0, o2 = n0 + n1, o3 = n0 + n1 + n2;
+    const int n = o3 + n3;
+    for (int base = 0; base < cnt; base += 32) {
+        const int b = base == 0 ? b_first : bucket_of(base + lane);
+        const unsigned m0 = __ballot_sync(0xffffffffu, b == 0), m1 = __ballot_sync(0xffffffffu, b == 1);
+        const unsigned m2 = __ballot_sync(0xffffffffu, b == 2), m3 = __ballot_sync(0xffffffffu, b == 3);
+        const unsigned mine = b == 0 ? m0 : (b == 1 ? m1 : (b == 2 ? m2 : m3));
+        const int off = b == 0 ? o0 : (b == 1 ? o1 : (b == 2 ? o2 : o3));
+        if (b >= 0) list[off + __popc(mine & lt)] = (unsigned char)(base + lane);
+        o0 += __popc(m0); o1 += __popc(m1); o2 += __popc(m2); o3 += __popc(m3);
+    }
+    return n;
+}
 
 __device__ __forceinline__ float group_reduce_scatter8(float (&v)[8]) {
     // transposed butterfly over lane bits 2,1,0: on return lane j (= L&7) of every group holds component j
@@ -254,27 +326,29 @@ __device__ __forceinline__ float group_reduce_scatter8(float (&v)[8]) {
     return v[0];
 }
 
-// one row of the sweep: accumulate the pair (2j, 2j+1) of region row r
 struct GroupAcc {
     f32x2 ax, ay, sa, sb, sc, ar, ag, abl;
 };
 
+// one trip of a lane: the pixel pair (px, px+1) of the row at byte offset `off` of the region (fy = its y)
 template <int kRows, bool kGuard>
-__device__ __forceinline__ void group_row(GroupAcc &A, int r, int region_py0, int j, bool xin0, bool xin1,
-                                          const WarpGrad<kRows> &wg, f32x2 yy, f32x2 cc, f32x2 dx, f32x2 adx,
-                                          f32x2 bdx, f32x2 cr, f32x2 cg, f32x2 cb) {
-    const float npy = -(float)(region_py0 + r);
-    const f32x2 dy = add2(yy, pk2(npy, npy));
-    const f32x2 dycdy = mul2(dy, mul2(cc, dy));
-    f32x2 w = pair_weight(dx, adx, bdx, dy, dycdy);
+__device__ __forceinline__ void group_trip(GroupAcc &A, const char *wg_base, int off, int zoff, float fy, bool in0,
+                                           bool in1, float y, float c, f32x2 dx, f32x2 adx, f32x2 bdx, f32x2 cr,
+                                           f32x2 cg, f32x2 cb) {
+    constexpr int kPlane = (kRows + 1) * kTile * 4;
+    const float dyf = y - fy;
+    const float dycdyf = dyf * (c * dyf);
+    const f32x2 dy = pk2(dyf, dyf);
+    f32x2 w = pair_weight(dx, adx, bdx, dy, pk2(dycdyf, dycdyf));
     if (kGuard) {   // a NaN of a pixel that does not exist must not reach the sums
         float w0, w1;
         unpk2(w, w0, w1);
-        w = pk2(xin0 ? w0 : 0.f, xin1 ? w1 : 0.f);
+        w = pk2(in0 ? w0 : 0.f, in1 ? w1 : 0.f);
     }
-    const f32x2 vr = *reinterpret_cast<const f32x2 *>(&wg.v[0][r][2 * j]);
-    const f32x2 vg = *reinterpret_cast<const f32x2 *>(&wg.v[1][r][2 * j]);
-    const f32x2 vb = *reinterpret_cast<const f32x2 *>(&wg.v[2][r][2 * j]);
+    const char *src = wg_base + min(off, zoff);   // past the region: the zero row
+    const f32x2 vr = *reinterpret_cast<const f32x2 *>(src);
+    const f32x2 vg = *reinterpret_cast<const f32x2 *>(src + kPlane);
+    const f32x2 vb = *reinterpret_cast<const f32x2 *>(src + 2 * kPlane);
     A.ar = fma2(w, vr, A.ar);     // v_rgb += alpha * v_out
     A.ag = fma2(w, vg, A.ag);
     A.abl = fma2(w, vb, A.abl);
@@ -288,44 +362,64 @@ __device__ __forceinline__ void group_row(GroupAcc &A, int r, int region_py0, in
     A.ay = add2(A.ay, t2y);
 }
 
-// `list`: ranks of the staged Gaussians that reach the region (n of them, ascending).  The warp takes the
-// groups first_group, first_group + group_stride, ...  (region = the warp's own rows: 0, 1; region = the whole
-// tile shared by the CTA's warps: warp, #warps).
+// `list`: ranks of the staged Gaussians that reach the region (n of them, build_group_list order).  The warp
+// takes the groups first_group, first_group + group_stride, ...  (region = the warp's own rows: 0, 1; region =
+// the whole tile shared by the CTA's warps: warp, #warps).
 template <int kRows, bool kGuard>
 __device__ __forceinline__ void quad_backward4(const QuadRecords &s, const int *s_ids, const unsigned char *list,
                                                int n, int first_group, int group_stride, int tile_px0,
                                                int region_py0, int region_row0, int img_w, int rows_inside,
                                                const WarpGrad<kRows> &wg, float *__restrict__ grads) {
     const int lane = threadIdx.x & 31, j = lane & 7, grp = lane >> 3;
-    const float px = (float)(tile_px0 + 2 * j);
-    const f32x2 npx = pk2(-px, -(px + 1.f));
-    bool xin0 = true, xin1 = true;
-    if (kGuard) {
-        xin0 = tile_px0 + 2 * j < img_w;
-        xin1 = tile_px0 + 2 * j + 1 < img_w;
-    }
+    const char *wg_base = reinterpret_cast<const char *>(&wg.v[0][0][0]);
     for (int base = 4 * first_group; base < n; base += 4 * group_stride) {
         const bool valid = base + grp < n;
         const int t = list[valid ? base + grp : n - 1];
         const float4 p0 = s.xyab[t], p1 = s.crgb[t];
-        const unsigned rw = s.rows[t];
-        // rows of the region the group's Gaussian can reach; union over the warp
-        int lo = max((int)(rw & 15u) - region_row0, 0), hi = min((int)(rw >> 4) - region_row0, kRows - 1);
-        if (!valid) { lo = kRows; hi = -1; }
-        const int ulo = __reduce_min_sync(0xffffffffu, lo);
-        int uhi = __reduce_max_sync(0xffffffffu, hi);
-        if (kGuard) uhi = min(uhi, rows_inside - 1);
-        const f32x2 xx = pk2(p0.x, p0.x), yy = pk2(p0.y, p0.y), aa = pk2(p0.z, p0.z), bb = pk2(p0.w, p0.w);
-        const f32x2 cc = pk2(p1.x, p1.x), cr = pk2(p1.y, p1.y), cg = pk2(p1.z, p1.z), cb = pk2(p1.w, p1.w);
-        const f32x2 dx = add2(xx, npx), adx = mul2(aa, dx), bdx = mul2(bb, dx);
-        // two rows per trip with separate accumulators: two independent dependency chains per warp
-        GroupAcc A{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull}, B = A;
-        int r = ulo;
-        for (; r + 1 <= uhi; r += 2) {   // warp-uniform
-            group_row<kRows, kGuard>(A, r, region_py0, j, xin0, xin1, wg, yy, cc, dx, adx, bdx, cr, cg, cb);
-            group_row<kRows, kGuard>(B, r + 1, region_py0, j, xin0, xin1, wg, yy, cc, dx, adx, bdx, cr, cg, cb);
+        GroupShape sh = group_shape<kRows>(s.rows[t], s.cols[t], region_row0);
+        if (!valid) sh.trips = 0;
+        const int T = __reduce_max_sync(0xffffffffu, sh.trips);   // warp-uniform
+        const int rpt = 8 >> sh.lg;                                // rows per trip
+        const int col = sh.c0 + 2 * (j & ((1 << sh.lg) - 1));
+        int row = sh.lo + (j >> sh.lg);
+        const int px = tile_px0 + col;
+        bool in0 = true, in1 = true;
+        if (kGuard) {
+            in0 = px < img_w;
+            in1 = px + 1 < img_w;
         }
-        if (r <= uhi) group_row<kRows, kGuard>(A, r, region_py0, j, xin0, xin1, wg, yy, cc, dx, adx, bdx, cr, cg, cb);
+        const f32x2 xx = pk2(p0.x, p0.x), aa = pk2(p0.z, p0.z), bb = pk2(p0.w, p0.w);
+        const f32x2 cr = pk2(p1.y, p1.y), cg = pk2(p1.z, p1.z), cb = pk2(p1.w, p1.w);
+        const f32x2 npx = pk2(-(float)px, -((float)px + 1.f));
+        const f32x2 dx = add2(xx, npx), adx = mul2(aa, dx), bdx = mul2(bb, dx);
+        float fy = (float)(region_py0 + row);
+        const float frpt = (float)rpt;
+        int off = (row * kTile + col) * 4;
+        const int zoff = (kRows * kTile + col) * 4, doff = rpt * kTile * 4;
+        // two trips per loop iteration with separate accumulators: two independent dependency chains per warp
+        GroupAcc A{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull}, B = A;
+        int i = 0;
+        for (; i + 1 < T; i += 2) {   // warp-uniform
+            bool y0 = in0, y1 = in1, z0 = in0, z1 = in1;
+            if (kGuard) {
+                const bool ra = row < rows_inside, rb = row + rpt < rows_inside;
+                y0 = in0 && ra; y1 = in1 && ra; z0 = in0 && rb; z1 = in1 && rb;
+                row += 2 * rpt;
+            }
+            group_trip<kRows, kGuard>(A, wg_base, off, zoff, fy, y0, y1, p0.y, p1.x, dx, adx, bdx, cr, cg, cb);
+            group_trip<kRows, kGuard>(B, wg_base, off + doff, zoff, fy + frpt, z0, z1, p0.y, p1.x, dx, adx, bdx, cr,
+                                      cg, cb);
+            off += 2 * doff;
+            fy += 2.f * frpt;
+        }
+        if (i < T) {
+            bool y0 = in0, y1 = in1;
+            if (kGuard) {
+                const bool ra = row < rows_inside;
+                y0 = in0 && ra; y1 = in1 && ra;
+            }
+            group_trip<kRows, kGuard>(A, wg_base, off, zoff, fy, y0, y1, p0.y, p1.x, dx, adx, bdx, cr, cg, cb);
+        }
         float l0, l1, m0, m1, acc[8];
         unpk2(A.ax, l0, l1); unpk2(B.ax, m0, m1); const float sx = -((l0 + l1) + (m0 + m1));
         unpk2(A.ay, l0, l1); unpk2(B.ay, m0, m1); const float sy = -((l0 + l1) + (m0 + m1));

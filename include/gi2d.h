@@ -333,6 +333,56 @@ int gi2d_fit_densify(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int k_
 int gi2d_fit_input_grads(const gi2d_fit_params *p, const gi2d_fit_buffers *b, float *out, gi2d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Quantisation-aware iteration of the compression pass, default `lsq` quantisers:
+ * GaussianImage_Covariance.forward_quantize / train_iter_quantize (models/gaussianimage_covariance.py:219-247,
+ * 384-410) = UniformQuantizer (LSQ+, quantize.py:39-156) on positions (2 channels) and colours (3 channels),
+ * HybirdQuant (quantize.py:336-389) on the covariance: the two variances through LogQuantizer(learned=False), whose
+ * range is the min / max of log(|x|+1e-6) over the whole tensor ON EVERY CALL with gradients through min and max
+ * (quantize.py:223-235), the off-diagonal through a 1-channel UniformQuantizer; plus the reference's four
+ * torch.optim.Adam + StepLR (attributes: eps 1e-15, StepLR(20000); the three quantisers: lr 1e-3, StepLR(10000),
+ * eps 1e-15 except the position quantiser's, which keeps torch's default 1e-8; :116-146).
+ * One iteration = gi2d_quant_forward -> a gi2d_fit_forward_backward training step with external_optimizer = 1 on
+ * the de-quantised attributes (b->out_* are the fit step's xyz / cov / rgb, cov_bound of the fit step all zero)
+ * -> gi2d_fit_input_grads -> gi2d_quant_backward_step; eight launches, no host round trip, graph-capturable.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gi2d_quant_params {
+    int32_t num_points;
+    int32_t xy_qmax, cov_qmax, color_qmax; /* 2^bits - 1 (unsigned ranges: qmin = 0) */
+    int32_t color_sigmoid;                 /* 1: colours = sigmoid(features) before quantisation (color_norm) */
+    float lr0;                             /* attributes: lr = lr0 * gamma^floor((step-1)/lr_step) */
+    int32_t lr_step;
+    float lr_q0;                           /* quantiser parameters, same schedule with lr_q_step */
+    int32_t lr_q_step;
+    float lr_gamma;
+    float beta1, beta2;
+    float eps;                             /* Adam eps of the attributes, the covariance and the colour quantiser */
+    float eps_xyz_q;                       /* Adam eps of the position quantiser */
+} gi2d_quant_params;
+
+typedef struct gi2d_quant_buffers {
+    float *xyz, *cov, *rgb;                /* f32[N,2] [N,3] [N,3] raw attributes, updated in place */
+    const float *bound;                    /* f32[N,3] cholesky_bound (cov + bound is what gets quantised) */
+    float *m_xyz, *v_xyz, *m_cov, *v_cov, *m_rgb, *v_rgb; /* Adam moments of the attributes */
+    float *qparams;                        /* f32[12] scale_xyz[2] beta_xyz[2] scale_cov beta_cov scale_rgb[3] beta_rgb[3] */
+    float *qm, *qv;                        /* f32[12] their Adam moments */
+    double *qstats;                        /* f64[32]: [0] iterations done, [1] min [2] max of the log range,
+                                              [3] [4] how many elements are the min / the max, [5..18] the
+                                              quantiser-parameter gradients of the last iteration (log scale, log
+                                              beta, 6 LSQ scales, 6 LSQ betas; channels xyz 0,1 | cov | rgb 0,1,2) */
+    float *out_xyz, *out_cov, *out_rgb;    /* de-quantised attributes (the fit step's inputs) */
+    const float *in_grads;                 /* f32[N,8] from gi2d_fit_input_grads */
+    float *dbg_grads;                      /* optional f32[N,8]: gradient of the raw attributes (tests) */
+} gi2d_quant_buffers;
+
+/* UniformQuantizer._init_data / HybirdQuant._init_data (quantize.py:72-80, 352-354): scale / beta of the learned
+ * quantisers from the per-channel min / max of the current attributes; zeroes qm, qv and qstats. */
+int gi2d_quant_init(const gi2d_quant_params *p, const gi2d_quant_buffers *b, gi2d_stream_t stream);
+/* forward_quantize up to the rasterizer's inputs: log range (1 launch) + quantise / de-quantise (1 launch). */
+int gi2d_quant_forward(const gi2d_quant_params *p, const gi2d_quant_buffers *b, gi2d_stream_t stream);
+/* Straight-through backward of the quantisers + the four optimiser steps (2 launches). */
+int gi2d_quant_backward_step(const gi2d_quant_params *p, const gi2d_quant_buffers *b, gi2d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-GPU tile-row split of ONE image (the reference is single-GPU, train.py:39).
  * Rank q rasterizes tile rows [band_edge[q], band_edge[q+1]).  Every Gaussian has ONE owner rank (equal
  * contiguous slices [own_begin, own_end)): only the owner holds its parameters and Adam moments, applies

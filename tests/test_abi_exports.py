@@ -44,7 +44,8 @@ def test_struct_layout_matches_header(tmp_path):
 
     from gaussianimage_plus_b200 import _lib
 
-    structs = {"gi2d_fit_params": _lib.FitParams, "gi2d_fit_buffers": _lib.FitBuffers, "gi2d_tilerow": _lib.TileRow}
+    structs = {"gi2d_fit_params": _lib.FitParams, "gi2d_fit_buffers": _lib.FitBuffers, "gi2d_tilerow": _lib.TileRow,
+               "gi2d_quant_params": _lib.QuantParams, "gi2d_quant_buffers": _lib.QuantBuffers}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gi2d.h"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')

@@ -290,7 +290,8 @@ def test_bin_sort_overflow_is_flagged_not_silent(oracle, B):
     bins = torch.empty(tb[0] * tb[1], 2, dtype=torch.int32, device=DEV)
     info = torch.zeros(3, dtype=torch.int32, device=DEV)
     ws = torch.empty(lib.gi2d_bin_sort_workspace_size(N, tb[0], tb[1], cap), dtype=torch.uint8, device=DEV)
-    rc = lib.gi2d_bin_sort(N, T(xys).data_ptr(), T(depths).data_ptr(), T(radii).data_ptr(), tb[0], tb[1], 1.0, cap,
+    d_xys, d_depths, d_radii = T(xys), T(depths), T(radii)   # (kept alive: the call takes raw pointers)
+    rc = lib.gi2d_bin_sort(N, d_xys.data_ptr(), d_depths.data_ptr(), d_radii.data_ptr(), tb[0], tb[1], 1.0, cap,
                            out_k.data_ptr(), out_g.data_ptr(), bins.data_ptr(), info.data_ptr(), ws.data_ptr(),
                            ws.numel(), None)
     assert rc == 0
