@@ -109,6 +109,8 @@ SIGNATURES = {
     "gi2d_fit_profile": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), C.POINTER(C.c_float), _P]),
     "gi2d_fit_profile_raster": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _I, C.POINTER(C.c_float), _P]),
     "gi2d_measure_fp32_peak": (_I, [C.POINTER(C.c_float), _P]),
+    "gi2d_fit_bucket_capacity": (_I, [C.POINTER(FitParams)]),
+    "gi2d_fit_export_binning": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _P, _P, _P]),
     "gi2d_fit_input_grads": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), _P, _P]),
     "gi2d_quant_init": (_I, [C.POINTER(QuantParams), C.POINTER(QuantBuffers), _P]),
     "gi2d_quant_forward": (_I, [C.POINTER(QuantParams), C.POINTER(QuantBuffers), _P]),

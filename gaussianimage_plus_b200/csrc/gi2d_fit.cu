@@ -45,6 +45,7 @@ int ssim_grad_launch(int H, int W, const float *render, const float *gt, const u
 namespace {
 
 constexpr int kMaxSmemTiles = 2048;               // tile starts are scanned in shared memory up to here
+constexpr int kOrderPerThread = 32;                 // tiles per thread of the CTA that orders the rasterizer's work list
 constexpr int kProjThreads = 256;                   // launch bound; small scenes launch 64-thread CTAs (latency bound:
                                                     // spread over the SMs), large ones 256
 constexpr int kPlaceWarps = 8;
@@ -62,7 +63,11 @@ constexpr int kStatPending = 8;   // != 0: grads of the last step have not been 
                                   // into the NEXT step's projection kernel, or flushed by gi2d_fit_adam)
 
 [[maybe_unused]] constexpr int kStatDebug = 15;      // GI2D_DEBUG_CHECKS builds: number of violated device-side invariants (stays 0)
-constexpr int kStatNonPsdAcc = 12;  // accumulator behind GI2D_STAT_NON_PSD (moved + zeroed by the clear kernel)
+constexpr int kStatNonPsdAcc = 12;
+// bucketed binning (see fit_project_kernel<true>): which of the two per-tile counter arrays holds the counts of
+// the most recent forward, the intersection / largest-tile accumulators of the forward in flight (integers in
+// the slots' 8 bytes) and the ticket that elects the last CTA of K1
+constexpr int kStatBank = 85, kStatMaxFillAcc = 87, kStatTicket = 88;  // accumulator behind GI2D_STAT_NON_PSD (moved + zeroed by the clear kernel)
 
 // compute-sanitizer is closed on the development pool: a -DGI2D_DEBUG_CHECKS build counts violated index /
 // range invariants of the binning and staging code into stats[kStatDebug] instead (tools/debug_checks.py).
@@ -89,12 +94,15 @@ __device__ __forceinline__ double sse_total_warp(const double *__restrict__ stat
 }
 
 // Was the step whose gradient is pending a new best (train.py:132: `if best_psnr < psnr`)?  Warp 0 of the
-// CTA evaluates, everybody reads s_flag after the caller's __syncthreads().
-__device__ __forceinline__ void best_flag_warp0(const double *__restrict__ stats, bool candidate, int *s_flag) {
+// CTA evaluates, everybody reads s_flag after the caller's __syncthreads().  Returns the squared error of
+// that step (in warp 0; 0 elsewhere).
+__device__ __forceinline__ double best_flag_warp0(const double *__restrict__ stats, bool candidate, int *s_flag) {
+    double tot = 0.0;
     if (threadIdx.x < 32) {
-        const double tot = sse_total_warp(stats);
+        tot = sse_total_warp(stats);
         if (threadIdx.x == 0) *s_flag = (candidate && tot < __ldcg(stats + GI2D_STAT_BEST_SSE)) ? 1 : 0;
     }
+    return tot;
 }
 
 // Bookkeeping half of the same decision, by warp 0 of ONE CTA after every optimiser thread has read it.
@@ -117,10 +125,25 @@ bool tile_order_enabled() {
     return on;
 }
 
+int raster_variant(int num_tiles);
+
+// GI2D_BUCKET=0 switches the bucketed binning off (A/B timing; the scan + placement path is also what the
+// tile-row split and gi2d_bin_sort use)
+bool bucket_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("GI2D_BUCKET");
+        const char *r = getenv("GI2D_RASTER");
+        return (!e || atoi(e) != 0) && !(r && atoi(r) == 0);
+    }();
+    return on;
+}
+
 struct Plan {
     int num_tiles;
     bool smem_scan;    // tile starts fit the in-kernel scan
     bool ordered;      // K2 also emits the heaviest-first work list the rasterizer's CTAs follow
+    int bucket_cap;    // > 0: bucketed binning -- tile t owns rows [t * bucket_cap, (t+1) * bucket_cap) of the key /
+                       // record arrays, K1 places straight into them and there is no scan and no K2
     int gpb;           // Gaussians per CTA of K2
     int nblocks;       // CTAs of K2
 };
@@ -131,7 +154,14 @@ Plan make_plan(const gi2d_fit_params &p) {
     pl.smem_scan = pl.num_tiles <= kMaxSmemTiles;
     // heaviest-first tile order: only where the grid is a wave or two (beyond, the tail is a few per cent and a
     // band of a tile-row split keeps its launch order)
-    pl.ordered = pl.smem_scan && p.tile_row_begin == 0 && p.tile_row_end == p.tiles_y && tile_order_enabled();
+    // bucketed binning: everywhere except the tile-row exchange (whose owners scatter records across GPUs) and
+    // the round-1 rasterizer; needs at least 8 rows per tile (tiny capacities -- overflow tests -- keep the scan)
+    pl.bucket_cap = 0;
+    if (p.external_optimizer != 2 && bucket_enabled() && pl.num_tiles > 0 && p.isect_capacity / pl.num_tiles >= 8)
+        pl.bucket_cap = p.isect_capacity / pl.num_tiles;
+    // (bucketed: an extra CTA of K1 builds the list from the PREVIOUS forward's counts; up to 16384 tiles)
+    pl.ordered = (pl.bucket_cap ? pl.num_tiles <= kOrderPerThread * 64 : pl.smem_scan) && p.tile_row_begin == 0 &&
+                 p.tile_row_end == p.tiles_y && tile_order_enabled();
     // at most ~16 CTAs per SM of K2: beyond that, more Gaussians per CTA
     int gpb = kPlaceWarps * kPlaceGpw;
     while ((long long)gpb * 2368 < p.num_points) gpb *= 2;
@@ -175,7 +205,7 @@ Workspace carve(const gi2d_fit_params &p, const Plan &pl, void *base) {
     w.boxes = (ushort4 *)(c + off);       off += align_up((size_t)(p.num_points > 0 ? p.num_points : 1) * 8);
     w.n_isect = (int32_t *)(c + off);     off += 256;
     w.tile_work = nullptr;
-    if (pl.smem_scan) { w.tile_work = (int4 *)(c + off); off += align_up(T * 16); }
+    if (pl.smem_scan || pl.bucket_cap) { w.tile_work = (int4 *)(c + off); off += align_up(T * 16); }
     w.records = (float4 *)(c + off);      off += align_up((size_t)p.isect_capacity * 32);
     w.keys_tmp = (uint64_t *)(c + off);   off += align_up((size_t)p.isect_capacity * 8);
     w.loss_render = w.loss_dm = w.loss_vout = nullptr;
@@ -284,99 +314,6 @@ __device__ __forceinline__ void adam_update_gaussian(const gi2d_fit_params &p, c
     for (int k = 0; k < 3; ++k) { c[k] = r.c[k]; q[k] = r.q[k]; }
 }
 
-// ------------------------------------------------------------------------------------ K1
-// Optimiser of the PREVIOUS step + projection of THIS step, per Gaussian, in one launch: the thread
-// that owns Gaussian g first applies projection-backward + Adam to it when a gradient is pending
-// (stats[kStatPending]; the overflow flag of that step vetoes it), then projects the fresh parameters,
-// writes the 32-B record, zeroes the gradient row for the coming backward and adds 1 to the overlap
-// count of every tile its box touches ("per-tile overlap counts", one fire-and-forget red.global each).
-// This kernel only READS the stats block; the bookkeeping for the step in flight is done by K2.
-__global__ void __launch_bounds__(kProjThreads)
-fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bound,
-                   float4 *__restrict__ proj, float4 *__restrict__ grads, ushort4 *__restrict__ boxes,
-                   int32_t *__restrict__ tile_count, const double *__restrict__ stats, int with_backward,
-                   float4 *__restrict__ best, int expect_pending, float *__restrict__ best_bound) {
-    __shared__ int s_best;
-    pdl_launch_dependents();
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in_cap = g < p.num_points;   // a row of the arrays (the live count comes back with the flags below)
-    pdl_wait();  // the previous step's rasterizer wrote grads (and read proj, and zeroed tile_count)
-    // A training step nearly always finds a gradient pending: issue every load of the optimiser BEFORE the
-    // flags that say so come back (one L2 round trip less on this latency-bound kernel); a render-only call
-    // (expect_pending == 0) loads lazily.
-    const bool early = expect_pending && a.m_xyz != nullptr && in_cap;
-    AdamRegs r;
-    if (early) adam_load(a, g, proj, grads, r);
-    float bnd[3] = {0.f, 0.f, 0.f};
-    if (in_cap) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) bnd[k] = __ldcg(cov_bound + 3 * g + k);   // (prune / densify rewrite the bounds)
-    }
-    const bool mine = g < live_points(p, stats);
-    const bool pending = a.m_xyz != nullptr && __ldcg(stats + kStatPending) != 0.0;
-    const bool veto = __ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0;  // that step overflowed: the host re-runs it
-    best_flag_warp0(stats, best != nullptr && pending && !veto, &s_best);
-    __syncthreads();
-    const bool snapshot = s_best != 0;
-    if (!mine) {
-        // a row beyond the live count: an empty box keeps it out of the placement kernel's walk
-        if (in_cap) boxes[g] = make_ushort4(0, 0, 0, 0);
-        return;
-    }
-    float2 m;
-    float c[3], q[3];
-    if (pending) {
-        if (!early) adam_load(a, g, proj, grads, r);
-        if (!veto) adam_apply(p, a, g, r, stats);
-        m = r.x;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { c[k] = r.c[k]; q[k] = r.q[k]; }
-        if (snapshot) {  // the state dict right after optimizer.step() of the best iteration (train.py:132-137)
-            best[2 * g] = make_float4(m.x, m.y, c[0], c[1]);
-            best[2 * g + 1] = make_float4(c[2], q[0], q[1], q[2]);
-            if (best_bound) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) best_bound[3 * g + k] = bnd[k];
-            }
-        }
-    } else if (early) {
-        m = r.x;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { c[k] = r.c[k]; q[k] = r.q[k]; }
-    } else {
-        m = reinterpret_cast<const float2 *>(a.xyz)[g];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { c[k] = a.cov[3 * g + k]; q[k] = a.rgb[3 * g + k]; }
-    }
-    // get_cov2d_elements = _cov2d + cholesky_bound (gaussianimage_covariance.py:169)
-    const float sx = __fadd_rn(c[0], bnd[0]);
-    const float sxy = __fadd_rn(c[1], bnd[1]);
-    const float sy = __fadd_rn(c[2], bnd[2]);
-    float cr = q[0], cg = q[1], cb = q[2];
-    if (p.color_sigmoid) { cr = sigmoidf(cr); cg = sigmoidf(cg); cb = sigmoidf(cb); }
-    const Projected pr = project_cov(m.x, m.y, sx, sxy, sy, p.clip_coe, p.radius_clip, p.tiles_x, p.tiles_y);
-    proj[2 * g] = make_float4(pr.x, pr.y, pr.a, pr.b);
-    proj[2 * g + 1] = make_float4(pr.c, cr, cg, cb);
-    if (with_backward) {
-        grads[2 * g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        grads[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    // the map kernel's own cull (forward.cu:161) and the band owned by this rank
-    int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-    if (pr.ntiles > 0 && !((float)pr.radius < p.radius_clip)) {
-        x0 = pr.box.x0; x1 = pr.box.x1;
-        y0 = max(pr.box.y0, p.tile_row_begin);
-        y1 = min(pr.box.y1, p.tile_row_end);
-        if (y1 <= y0) { x0 = x1 = y0 = y1 = 0; }
-    }
-    boxes[g] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
-    for (int ty = y0; ty < y1; ++ty)
-        for (int tx = x0; tx < x1; ++tx) {
-            GI2D_CHECK(const_cast<double *>(stats), ty >= p.tile_row_begin && ty < p.tile_row_end && tx >= 0 && tx < p.tiles_x);
-            atomicAdd(tile_count + ty * p.tiles_x + tx, 1);
-        }
-}
-
 // Bookkeeping of the step in flight, by warp 0 of ONE CTA of K2 (K1 has already consumed the previous
 // step's values; K3 has not started): commit the best-so-far decision, zero the loss accumulators and
 // the overflow flag, and -- for a training step -- advance the step counter, the bias-correction powers
@@ -412,6 +349,327 @@ __device__ __forceinline__ void step_bookkeeping_warp0(const gi2d_fit_params &p,
             stats[kStatStepSize] = stats[GI2D_STAT_LR] / (1.0 - stats[kStatB1Pow]);
             stats[kStatBc2Sqrt] = sqrt(1.0 - stats[kStatB2Pow]);
         }
+    }
+}
+
+// The same bookkeeping by ONE thread from values it loaded before anybody could have changed them (the
+// bucketed K1: its last CTA is known only after a ticket atomic, and every load after that atomic would be one
+// more L2 round trip on the step's critical path).
+struct BookInputs {
+    double pending, overflow_prev, best_sse, step, num_points, b1pow, b2pow, lr, sse_total;
+};
+
+__device__ __forceinline__ BookInputs book_inputs_load(const double *__restrict__ stats) {
+    BookInputs k;
+    k.pending = __ldcg(stats + kStatPending);
+    k.overflow_prev = __ldcg(stats + GI2D_STAT_OVERFLOW);
+    k.best_sse = __ldcg(stats + GI2D_STAT_BEST_SSE);
+    k.step = __ldcg(stats + GI2D_STAT_STEP);
+    k.num_points = __ldcg(stats + GI2D_STAT_NUM_POINTS);
+    k.b1pow = __ldcg(stats + kStatB1Pow);
+    k.b2pow = __ldcg(stats + kStatB2Pow);
+    k.lr = __ldcg(stats + GI2D_STAT_LR);
+    k.sse_total = 0.0;
+    return k;
+}
+
+__device__ __forceinline__ void step_bookkeeping_values(const gi2d_fit_params &p, int with_backward,
+                                                        double *__restrict__ stats, bool overflow,
+                                                        const BookInputs &k) {
+    if (k.pending != 0.0 && k.overflow_prev == 0.0 && k.sse_total < k.best_sse) {   // best_commit_warp0
+        stats[GI2D_STAT_BEST_SSE] = k.sse_total;
+        stats[GI2D_STAT_BEST_STEP] = k.step;
+        stats[GI2D_STAT_BEST_N] = k.num_points;
+    }
+    stats[GI2D_STAT_OVERFLOW] = overflow ? 1.0 : 0.0;
+    if (with_backward) {
+#pragma unroll 8
+        for (int i = 0; i < GI2D_STAT_SSE_SLOTS; ++i) stats[GI2D_STAT_SSE + i] = 0.0;
+        stats[GI2D_STAT_SSIM_SUM] = 0.0;
+        stats[GI2D_STAT_ABS_SUM] = 0.0;
+    }
+    stats[kStatPending] = (with_backward && !p.external_optimizer && !overflow) ? 1.0 : 0.0;
+    if (with_backward && !overflow && p.external_optimizer != 2) {
+        const double step = k.step + 1.0;
+        stats[GI2D_STAT_STEP] = step;
+        const double b1 = k.b1pow * (double)p.beta1, b2 = k.b2pow * (double)p.beta2;
+        stats[kStatB1Pow] = b1;
+        stats[kStatB2Pow] = b2;
+        double lr = k.lr;
+        const long long kk = (long long)step - 1;
+        if (kk > 0 && p.lr_step_size > 0 && kk % p.lr_step_size == 0) lr *= (double)p.lr_gamma;
+        stats[GI2D_STAT_LR] = lr;
+        stats[kStatStepSize] = lr / (1.0 - b1);
+        stats[kStatBc2Sqrt] = sqrt(1.0 - b2);
+    }
+}
+
+// Ticket of the bucketed K1 (thread 0 of every CTA): ONE returning atomic carries the ticket (bits 0-19), the
+// CTA's intersection count (bits 20-62) and "a tile overflowed" (bit 63, added by the first CTA to raise
+// kStatMaxFillAcc from zero); the old value it returns holds the totals of all the others, and whoever sees the
+// count complete does the step's bookkeeping from values it loaded before anybody could change them: the tail
+// of the kernel is one L2 round trip.
+__device__ __forceinline__ void k1_ticket(const gi2d_fit_params &p, int with_backward, double *__restrict__ stats,
+                                          int bank, unsigned long long isects, bool first_overflow,
+                                          const BookInputs &bk) {
+    const unsigned long long word = 1ull | (isects << 20) | (first_overflow ? (1ull << 63) : 0ull);
+    const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(stats + kStatTicket), word);
+    const unsigned long long sum = old + word;
+    if ((sum & 0xFFFFFull) != (unsigned long long)gridDim.x) return;
+    const bool overflow = (sum >> 63) != 0ull;
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(stats);
+    step_bookkeeping_values(p, with_backward, stats, overflow, bk);
+    stats[GI2D_STAT_ISECTS] = (double)((sum >> 20) & ((1ull << 43) - 1ull));
+    stats[GI2D_STAT_MAX_TILE] = overflow ? (double)__ldcg(acc + kStatMaxFillAcc) : 0.0;
+    stats[kStatBank] = (double)bank;
+    if (overflow) acc[kStatMaxFillAcc] = 0ull;
+    acc[kStatTicket] = 0ull;
+}
+
+// The extra CTA of the bucketed K1 that orders the rasterizer's work list: tiles by descending count of the
+// PREVIOUS forward (that counter array is read-only while K1 runs; K3 zeroes it afterwards) -- a counting sort
+// over min(count, 255), ties in any order.  Counts move slowly from step to step: the long tiles start first,
+// the short ones fill the tail of the rasterizer's last wave.  Every global load is issued up front (both
+// counter arrays: which one is the previous forward's comes back with the same round trip).
+__device__ __forceinline__ void k1_order_cta(const gi2d_fit_params &p, int with_backward, double *__restrict__ stats,
+                                             const int32_t *__restrict__ tile_count,
+                                             const int32_t *__restrict__ tile_fill, int32_t *__restrict__ tile_order,
+                                             int *s_bin) {
+    const int lane = threadIdx.x & 31;
+    const int T = p.tiles_x * p.tiles_y;   // <= kOrderPerThread * blockDim.x (make_plan)
+    int ca[kOrderPerThread], cb[kOrderPerThread];
+#pragma unroll
+    for (int k = 0; k < kOrderPerThread; ++k) {
+        const int t = k * blockDim.x + threadIdx.x;
+        ca[k] = t < T ? __ldcg(tile_count + t) : -1;
+        cb[k] = t < T ? __ldcg(tile_fill + t) : -1;
+    }
+    const int bank = 1 - (int)__ldcg(stats + kStatBank);   // the array this forward fills; the other is `prev`
+    BookInputs bk;
+    if (threadIdx.x == 0) bk = book_inputs_load(stats);
+    double sse_tot = 0.0;
+    if (threadIdx.x < 32) sse_tot = sse_total_warp(stats);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bin[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kOrderPerThread; ++k) {
+        ca[k] = min(bank ? ca[k] : cb[k], 255);
+        if (ca[k] >= 0) atomicAdd(&s_bin[255 - ca[k]], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[k] = s_bin[8 * lane + k]; sum += v[k]; }
+        int run = warp_scan_inclusive(sum) - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s_bin[8 * lane + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kOrderPerThread; ++k)
+        if (ca[k] >= 0) {
+            const int t = k * blockDim.x + threadIdx.x;
+            const int pos = atomicAdd(&s_bin[255 - ca[k]], 1);
+            const int ty = t / p.tiles_x;
+            tile_order[pos] = (t - ty * p.tiles_x) | (ty << 16);
+        }
+    if (threadIdx.x == 0) {
+        bk.sse_total = sse_tot;
+        k1_ticket(p, with_backward, stats, bank, 0ull, false, bk);
+    }
+}
+
+// ------------------------------------------------------------------------------------ K1
+// Optimiser of the PREVIOUS step + projection of THIS step, per Gaussian, in one launch: the thread
+// that owns Gaussian g first applies projection-backward + Adam to it when a gradient is pending
+// (stats[kStatPending]; the overflow flag of that step vetoes it), then projects the fresh parameters,
+// writes the 32-B record and zeroes the gradient row for the coming backward.  Then
+//   kBucket == false: adds 1 to the overlap count of every tile its box touches ("per-tile overlap counts", one
+//       fire-and-forget red.global each); the scan + placement kernel (K2) follows and does the bookkeeping;
+//   kBucket == true : PLACES the intersections itself.  Tile t owns the rows [t * C, (t+1) * C) of the key / record
+//       arrays (C = capacity / #tiles), so a slot is just the tile's cursor atomic -- no prefix sum, no second
+//       kernel: the warp walks the intersections of its 32 Gaussians cooperatively (lane = intersection, owner by
+//       shuffle search, the owner's record by shuffles), all cursor atomics of up to 256 intersections in flight
+//       before the first dependent store.  The order inside a tile is arbitrary and fixed by the rank sort of K3.
+//       The cursors are double-buffered (stats[kStatBank]): this forward fills one array, K3 reads it and zeroes
+//       the OTHER one for the next forward, so K3 can be replayed and the counts outlive the step.  A tile with
+//       more than C overlaps raises the overflow flag (the step becomes an optimiser no-op, the host regrows).
+//       The LAST CTA to finish (ticket) does the bookkeeping K2 does otherwise.
+template <bool kBucket>
+__global__ void __launch_bounds__(kProjThreads)
+fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bound,
+                   float4 *__restrict__ proj, float4 *__restrict__ grads, ushort4 *__restrict__ boxes,
+                   int32_t *__restrict__ tile_count, double *__restrict__ stats, int with_backward,
+                   float4 *__restrict__ best, int expect_pending, float *__restrict__ best_bound,
+                   int32_t *__restrict__ tile_fill, uint64_t *__restrict__ keys_out, float4 *__restrict__ records,
+                   int bucket_cap, int32_t *__restrict__ tile_order) {
+    __shared__ int s_best;
+    __shared__ int s_ovf;
+    __shared__ int s_bin[kBucket ? 256 : 1];
+    __shared__ int s_isect[kProjThreads / 32];
+    pdl_launch_dependents();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (kBucket && threadIdx.x == 0) s_ovf = 0;
+    const bool in_cap = g < p.num_points;   // a row of the arrays (the live count comes back with the flags below)
+    pdl_wait();  // the previous step's rasterizer wrote grads (and read proj, and zeroed the tile counters)
+    if (kBucket && tile_order && blockIdx.x == gridDim.x - 1) {   // (CTA-uniform: the extra CTA has no Gaussians)
+        k1_order_cta(p, with_backward, stats, tile_count, tile_fill, tile_order, s_bin);
+        return;
+    }
+    // A training step nearly always finds a gradient pending: issue every load of the optimiser BEFORE the
+    // flags that say so come back (one L2 round trip less on this latency-bound kernel); a render-only call
+    // (expect_pending == 0) loads lazily.
+    const bool early = expect_pending && a.m_xyz != nullptr && in_cap;
+    AdamRegs r;
+    if (early) adam_load(a, g, proj, grads, r);
+    float bnd[3] = {0.f, 0.f, 0.f};
+    if (in_cap) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bnd[k] = __ldcg(cov_bound + 3 * g + k);   // (prune / densify rewrite the bounds)
+    }
+    const bool mine = g < live_points(p, stats);
+    const bool pending = a.m_xyz != nullptr && __ldcg(stats + kStatPending) != 0.0;
+    const bool veto = __ldcg(stats + GI2D_STAT_OVERFLOW) != 0.0;  // that step overflowed: the host re-runs it
+    const int bank = kBucket ? (1 - (int)__ldcg(stats + kStatBank)) : 0;   // the counter array this forward fills
+    BookInputs bk;
+    if (kBucket && threadIdx.x == 0) bk = book_inputs_load(stats);   // (thread 0 may turn out to be the bookkeeper)
+    const double sse_tot = best_flag_warp0(stats, best != nullptr && pending && !veto, &s_best);
+    if (kBucket && threadIdx.x == 0) bk.sse_total = sse_tot;
+    __syncthreads();
+    const bool snapshot = s_best != 0;
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    float4 rec0 = make_float4(0.f, 0.f, 0.f, 0.f), rec1 = rec0;
+    if (mine) {
+        float2 m;
+        float c[3], q[3];
+        if (pending) {
+            if (!early) adam_load(a, g, proj, grads, r);
+            if (!veto) adam_apply(p, a, g, r, stats);
+            m = r.x;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { c[k] = r.c[k]; q[k] = r.q[k]; }
+            if (snapshot) {  // the state dict right after optimizer.step() of the best iteration (train.py:132-137)
+                best[2 * g] = make_float4(m.x, m.y, c[0], c[1]);
+                best[2 * g + 1] = make_float4(c[2], q[0], q[1], q[2]);
+                if (best_bound) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) best_bound[3 * g + k] = bnd[k];
+                }
+            }
+        } else if (early) {
+            m = r.x;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { c[k] = r.c[k]; q[k] = r.q[k]; }
+        } else {
+            m = reinterpret_cast<const float2 *>(a.xyz)[g];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { c[k] = a.cov[3 * g + k]; q[k] = a.rgb[3 * g + k]; }
+        }
+        // get_cov2d_elements = _cov2d + cholesky_bound (gaussianimage_covariance.py:169)
+        const float sx = __fadd_rn(c[0], bnd[0]);
+        const float sxy = __fadd_rn(c[1], bnd[1]);
+        const float sy = __fadd_rn(c[2], bnd[2]);
+        float cr = q[0], cg = q[1], cb = q[2];
+        if (p.color_sigmoid) { cr = sigmoidf(cr); cg = sigmoidf(cg); cb = sigmoidf(cb); }
+        const Projected pr = project_cov(m.x, m.y, sx, sxy, sy, p.clip_coe, p.radius_clip, p.tiles_x, p.tiles_y);
+        rec0 = make_float4(pr.x, pr.y, pr.a, pr.b);
+        rec1 = make_float4(pr.c, cr, cg, cb);
+        proj[2 * g] = rec0;
+        proj[2 * g + 1] = rec1;
+        if (with_backward) {
+            grads[2 * g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            grads[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // the map kernel's own cull (forward.cu:161) and the band owned by this rank
+        if (pr.ntiles > 0 && !((float)pr.radius < p.radius_clip)) {
+            x0 = pr.box.x0; x1 = pr.box.x1;
+            y0 = max(pr.box.y0, p.tile_row_begin);
+            y1 = min(pr.box.y1, p.tile_row_end);
+            if (y1 <= y0) { x0 = x1 = y0 = y1 = 0; }
+        }
+    }
+    // (a row beyond the live count keeps an empty box: it stays out of every walk)
+    if (in_cap) boxes[g] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+    if (!kBucket) {
+        for (int ty = y0; ty < y1; ++ty)
+            for (int tx = x0; tx < x1; ++tx) {
+                GI2D_CHECK(stats, ty >= p.tile_row_begin && ty < p.tile_row_end && tx >= 0 && tx < p.tiles_x);
+                atomicAdd(tile_count + ty * p.tiles_x + tx, 1);
+            }
+        return;
+    }
+    // ---- placement (warp-converged from here on)
+    int32_t *cursor = bank ? tile_fill : tile_count;
+    const int bw = x1 - x0;
+    const int n = bw * (y1 - y0);
+    const int incl = warp_scan_inclusive(n);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int max_fill = 0;
+    for (int batch = 0; batch < total; batch += 256) {
+        int slot[8], tile[8], owner[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            slot[k] = 0; tile[k] = 0; owner[k] = 0;
+            if (batch + 32 * k < total) {   // warp-uniform
+                const int it = batch + 32 * k + lane;
+                int lo = 0;   // owner = smallest j with incl_j > it
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+                    if (probe <= it) lo += step;
+                }
+                const int ow = min(lo, 31);
+                const int o_incl = __shfl_sync(0xffffffffu, incl, ow);
+                const int o_n = __shfl_sync(0xffffffffu, n, ow);
+                const int o_w = __shfl_sync(0xffffffffu, bw, ow);
+                const int o_x0 = __shfl_sync(0xffffffffu, x0, ow);
+                const int o_y0 = __shfl_sync(0xffffffffu, y0, ow);
+                owner[k] = ow;
+                if (it < total) {
+                    const int kk = it - (o_incl - o_n);
+                    const int ry = kk / o_w;
+                    tile[k] = (o_y0 + ry) * p.tiles_x + o_x0 + (kk - ry * o_w);
+                    GI2D_CHECK(stats, tile[k] >= 0 && tile[k] < p.tiles_x * p.tiles_y);
+                    slot[k] = atomicAdd(cursor + tile[k], 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (batch + 32 * k < total) {   // warp-uniform
+                const int ow = owner[k];
+                float4 q0, q1;
+                q0.x = __shfl_sync(0xffffffffu, rec0.x, ow); q0.y = __shfl_sync(0xffffffffu, rec0.y, ow);
+                q0.z = __shfl_sync(0xffffffffu, rec0.z, ow); q0.w = __shfl_sync(0xffffffffu, rec0.w, ow);
+                q1.x = __shfl_sync(0xffffffffu, rec1.x, ow); q1.y = __shfl_sync(0xffffffffu, rec1.y, ow);
+                q1.z = __shfl_sync(0xffffffffu, rec1.z, ow); q1.w = __shfl_sync(0xffffffffu, rec1.w, ow);
+                if (batch + 32 * k + lane < total) {
+                    if (slot[k] < bucket_cap) {
+                        const size_t pos = (size_t)tile[k] * bucket_cap + slot[k];
+                        keys_out[pos] = ((uint64_t)(uint32_t)tile[k] << 32) | (uint32_t)(g - lane + ow);
+                        records[2 * pos] = q0;
+                        records[2 * pos + 1] = q1;
+                    }
+                    max_fill = max(max_fill, slot[k] + 1);
+                }
+            }
+        }
+    }
+    // ---- ticket: the last CTA to get here does the bookkeeping of the step in flight (k1_ticket)
+    max_fill = __reduce_max_sync(0xffffffffu, max_fill);
+    if (lane == 0) s_isect[threadIdx.x >> 5] = total;
+    if (lane == 0 && max_fill > bucket_cap) {   // (rare) largest count seen, for the host's regrow
+        const unsigned long long old =
+            atomicMax(reinterpret_cast<unsigned long long *>(stats + kStatMaxFillAcc), (unsigned long long)max_fill);
+        if (old == 0ull) s_ovf = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long mine_isects = 0ull;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mine_isects += (unsigned long long)s_isect[w];
+        k1_ticket(p, with_backward, stats, bank, mine_isects, s_ovf != 0, bk);
     }
 }
 
@@ -906,7 +1164,7 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
                    const float *__restrict__ gt, const uint8_t *__restrict__ gt_u8,
                    float *__restrict__ out_img, float *__restrict__ grads, double *__restrict__ stats,
                    float *__restrict__ err_map, const float *__restrict__ v_out,
-                   const int4 *__restrict__ tile_work) {
+                   const int4 *__restrict__ tile_work, int bucket_cap) {
     constexpr bool kHasFwd = kMode != RasterMode::FitBackward;
     constexpr bool kHasLoss = kMode == RasterMode::Fit || kMode == RasterMode::FitForward;
     constexpr bool kHasBwd = kMode == RasterMode::Fit || kMode == RasterMode::FitBackward;
@@ -934,7 +1192,38 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     // fill the tail of the grid's last wave
     int tile_x, tile_y;
     int2 range;
-    if (tile_work) {
+    int32_t *zero_a = tile_count, *zero_b = tile_fill;   // the counters this CTA hands back zeroed
+    // first trip of the staging loop: key and record of entry `tid` stay in registers (one round trip)
+    uint64_t key0 = 0;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), b0 = a0;
+    bool have0 = false;
+    if (bucket_cap > 0) {
+        // bucketed binning: the tile's rows start at tile * bucket_cap, its count is the cursor K1 left in the
+        // counter array of this forward (stats[kStatBank]); the OTHER array is zeroed for the next forward.
+        // Nothing here depends on anything else: the flag, both counters and -- speculatively, the rows exist
+        // whatever the count is -- the first 32 entries are all in flight together.
+        tile_x = blockIdx.x;
+        tile_y = p.tile_row_begin + blockIdx.y;
+        if (tile_work) {   // (bucketed: one int per CTA, tile x | y << 16, K1's heaviest-first list)
+            const int wk = __ldcg(reinterpret_cast<const int32_t *>(tile_work) + blockIdx.y * gridDim.x + blockIdx.x);
+            tile_x = wk & 0xffff;
+            tile_y = (int)((unsigned)wk >> 16);
+        }
+        const int t = tile_y * p.tiles_x + tile_x;
+        const double bankd = __ldcg(stats + kStatBank);
+        const int c0 = __ldcg(tile_count + t), c1 = __ldcg(tile_fill + t);
+        if (tid < min(bucket_cap, 32)) {
+            const size_t row = (size_t)t * bucket_cap + tid;
+            key0 = __ldcg(sorted_keys + row);
+            a0 = __ldcg(records + 2 * row);
+            b0 = __ldcg(records + 2 * row + 1);
+            have0 = true;
+        }
+        const bool bank = bankd != 0.0;
+        const int c = bank ? c1 : c0;
+        range = make_int2(t * bucket_cap, t * bucket_cap + min(c, bucket_cap));
+        zero_a = zero_b = bank ? tile_count : tile_fill;
+    } else if (tile_work) {
         const int4 wk = __ldcg(tile_work + blockIdx.y * gridDim.x + blockIdx.x);
         tile_x = wk.x & 0xffff;
         tile_y = (int)((unsigned)wk.x >> 16);
@@ -977,21 +1266,22 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     const int total_cnt = max(0, min(range.y, p.isect_capacity) - range.x);
     const int cnt = min(kMaxPerTile, total_cnt);
     if (kHasFwd && tid == 0) {   // the counters of this tile go back to K1 / K2 of the next step zeroed
-        GI2D_CHECK(stats, range.x >= 0 && range.y >= range.x && tile_fill[tile_id] == tile_count[tile_id] &&
-                              (range.y - range.x == tile_count[tile_id] || n_isect > (double)p.isect_capacity));
-        tile_count[tile_id] = 0;
-        tile_fill[tile_id] = 0;
+        GI2D_CHECK(stats, range.x >= 0 && range.y >= range.x &&
+                              (bucket_cap > 0 || (tile_fill[tile_id] == tile_count[tile_id] &&
+                               (range.y - range.x == tile_count[tile_id] || n_isect > (double)p.isect_capacity))));
+        zero_a[tile_id] = 0;
+        if (zero_b != zero_a) zero_b[tile_id] = 0;
     }
     // ---- finish the key sort (see fit_raster_kernel): rank by gaussian id, stage at the rank
     constexpr bool kWriteBack = kMode != RasterMode::FitForward;
     const float tx0 = (float)(tile_x * kTile), ty0 = (float)(tile_y * kTile);
     if (total_cnt <= kMaxPerTile) {
-        uint64_t key0 = 0;
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), b0 = a0;
-        if (tid < cnt) {   // first trip: key and record stay in registers (one round trip)
-            key0 = __ldcg(sorted_keys + range.x + tid);
-            a0 = __ldcg(records + 2 * (size_t)(range.x + tid));
-            b0 = __ldcg(records + 2 * (size_t)(range.x + tid) + 1);
+        if (tid < cnt) {
+            if (!have0) {
+                key0 = __ldcg(sorted_keys + range.x + tid);
+                a0 = __ldcg(records + 2 * (size_t)(range.x + tid));
+                b0 = __ldcg(records + 2 * (size_t)(range.x + tid) + 1);
+            }
             s_sort[tid] = (int)(uint32_t)key0;
         }
         for (int e = tid + kThreads; e < cnt; e += kThreads) s_sort[e] = (int)(uint32_t)__ldcg(sorted_keys + range.x + e);
@@ -1169,18 +1459,18 @@ template <RasterMode kMode>
 cudaError_t launch_raster(bool pdl, dim3 grid, cudaStream_t st, const gi2d_fit_params &p, uint64_t *sorted_keys,
                           uint64_t *keys_tmp, const int32_t *tile_bins, int32_t *tile_count, int32_t *tile_fill,
                           const float4 *records, const float *gt, const uint8_t *gt_u8, float *out_img, float *grads,
-                          double *stats, float *err_map, const float *v_out, const int4 *tile_work) {
+                          double *stats, float *err_map, const float *v_out, const int4 *tile_work, int bucket_cap) {
     const int v = raster_variant((int)(grid.x * grid.y));
 #define GI2D_RASTER_ARGS p, sorted_keys, keys_tmp, tile_bins, tile_count, tile_fill, records, gt, gt_u8, out_img, grads, stats, err_map, v_out
     if (v == 1) {
-        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 1>, grid, dim3(32), 0, st, GI2D_RASTER_ARGS, tile_work);
-        fit_rasterq_kernel<kMode, 1><<<grid, 32, 0, st>>>(GI2D_RASTER_ARGS, tile_work);
+        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 1>, grid, dim3(32), 0, st, GI2D_RASTER_ARGS, tile_work, bucket_cap);
+        fit_rasterq_kernel<kMode, 1><<<grid, 32, 0, st>>>(GI2D_RASTER_ARGS, tile_work, bucket_cap);
     } else if (v == 2) {
-        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 2>, grid, dim3(64), 0, st, GI2D_RASTER_ARGS, tile_work);
-        fit_rasterq_kernel<kMode, 2><<<grid, 64, 0, st>>>(GI2D_RASTER_ARGS, tile_work);
+        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 2>, grid, dim3(64), 0, st, GI2D_RASTER_ARGS, tile_work, bucket_cap);
+        fit_rasterq_kernel<kMode, 2><<<grid, 64, 0, st>>>(GI2D_RASTER_ARGS, tile_work, bucket_cap);
     } else if (v == 4) {
-        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 4>, grid, dim3(128), 0, st, GI2D_RASTER_ARGS, tile_work);
-        fit_rasterq_kernel<kMode, 4><<<grid, 128, 0, st>>>(GI2D_RASTER_ARGS, tile_work);
+        if (pdl) return launch_pdl(fit_rasterq_kernel<kMode, 4>, grid, dim3(128), 0, st, GI2D_RASTER_ARGS, tile_work, bucket_cap);
+        fit_rasterq_kernel<kMode, 4><<<grid, 128, 0, st>>>(GI2D_RASTER_ARGS, tile_work, bucket_cap);
     } else {
         if (pdl) return launch_pdl(fit_raster_kernel<kMode>, grid, dim3(kRasterThreads), 0, st, GI2D_RASTER_ARGS);
         fit_raster_kernel<kMode><<<grid, kRasterThreads, 0, st>>>(GI2D_RASTER_ARGS);
@@ -1486,6 +1776,7 @@ fit_input_grads_kernel(int n, const float4 *__restrict__ proj, const float4 *__r
 __global__ void fit_reset_kernel(gi2d_fit_params p, double *stats, int step) {
     const int i = threadIdx.x;
     if (i >= GI2D_STAT_COUNT) return;
+    if (i == kStatBank) return;        // which counter array the last forward filled: not a statistic either
     if (i == GI2D_STAT_NUM_POINTS) {   // the live count is not a statistic: kept when the device owns it
         if (!p.dynamic_points) stats[i] = (double)p.num_points;
         return;
@@ -1668,6 +1959,34 @@ densify_append_kernel(gi2d_fit_params p, ModelPtrs m, double *__restrict__ stats
 
 __global__ void set_stat_kernel(double *stats, int slot, double v) { stats[slot] = v; }
 
+// ------------------------------------------------------------------------------- export of the binning
+// The bucketed layout keeps a tile's (sorted) keys at tile * C; the reference's arrays -- isect_ids_sorted /
+// gaussian_ids_sorted as ONE ascending key array and tile_bins (forward.cu:211-233) -- are produced on demand:
+// one CTA scans the counts of the last forward into tile ranges, then one CTA per tile copies its keys.
+__global__ void __launch_bounds__(1024)
+export_ranges_kernel(int num_tiles, int bucket_cap, const int32_t *__restrict__ count, int32_t *__restrict__ tile_bins) {
+    __shared__ int s_warp[32];
+    int carry = 0;
+    for (int base = 0; base < num_tiles; base += 1024) {
+        const int t = base + threadIdx.x;
+        const int c = t < num_tiles ? min(__ldcg(count + t), bucket_cap) : 0;
+        int tot;
+        const int incl = block_scan_inclusive<1024>(c, s_warp, &tot);
+        if (t < num_tiles)
+            reinterpret_cast<int2 *>(tile_bins)[t] = c ? make_int2(carry + incl - c, carry + incl) : make_int2(0, 0);
+        carry += tot;
+    }
+}
+
+__global__ void __launch_bounds__(64)
+export_keys_kernel(int bucket_cap, const int32_t *__restrict__ tile_bins, const uint64_t *__restrict__ bucket_keys,
+                   uint64_t *__restrict__ keys_out) {
+    const int tile = blockIdx.x;
+    const int2 range = __ldcg(reinterpret_cast<const int2 *>(tile_bins) + tile);
+    for (int e = threadIdx.x; e < range.y - range.x; e += 64)
+        keys_out[range.x + e] = __ldcg(bucket_keys + (size_t)tile * bucket_cap + e);
+}
+
 int validate(const gi2d_fit_params *p, const gi2d_fit_buffers *b) {
     GI2D_REQUIRE(p && b, "null params");
     GI2D_REQUIRE(p->num_points >= 0 && p->img_width > 0 && p->img_height > 0, "bad sizes");
@@ -1714,18 +2033,27 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
         tr_count_kernel<<<max(1, cdiv(p->num_points, 256)), 256, 0, st>>>(
             *p, *tr, (const ushort4 *)tr->peer_boxes[tr->rank], w.boxes, w.tile_count, (float4 *)b->grads,
             with_backward);
-    else
-        launch_pdl(fit_project_kernel, dim3(max(1, cdiv(p->num_points, proj_threads))), dim3(proj_threads), 0, st,
+    else if (pl.bucket_cap)
+        launch_pdl(fit_project_kernel<true>, dim3(max(1, cdiv(p->num_points, proj_threads)) + (pl.ordered ? 1 : 0)),
+            dim3(proj_threads), 0, st,
             *p, ap, b->cov_bound, (float4 *)b->proj, (float4 *)b->grads, w.boxes, w.tile_count, b->stats, with_backward,
-            (float4 *)b->best, (with_backward && !p->external_optimizer) ? 1 : 0, b->best_bound);
+            (float4 *)b->best, (with_backward && !p->external_optimizer) ? 1 : 0, b->best_bound, w.tile_fill,
+            b->sorted_keys, w.records, pl.bucket_cap, pl.ordered ? (int32_t *)w.tile_work : (int32_t *)nullptr);
+    else
+        launch_pdl(fit_project_kernel<false>, dim3(max(1, cdiv(p->num_points, proj_threads))), dim3(proj_threads), 0, st,
+            *p, ap, b->cov_bound, (float4 *)b->proj, (float4 *)b->grads, w.boxes, w.tile_count, b->stats, with_backward,
+            (float4 *)b->best, (with_backward && !p->external_optimizer) ? 1 : 0, b->best_bound, (int32_t *)nullptr,
+            (uint64_t *)nullptr, (float4 *)nullptr, 0, (int32_t *)nullptr);
     if (mk) mk->mark(st);
-    if (!pl.smem_scan) {
+    if (!pl.bucket_cap && !pl.smem_scan) {
         // more tiles than one CTA scans in shared memory: device-wide inclusive prefix sum of the counts
         const int r2 = cumsum_i32_launch(num_tiles, w.tile_count, w.tile_incl, nullptr, w.scan_ws, st);
         if (r2 != GI2D_OK) return r2;
     }
     if (mk) mk->mark(st);
-    if (pl.smem_scan)
+    if (pl.bucket_cap) {
+        // (no scan, no placement kernel)
+    } else if (pl.smem_scan)
         launch_pdl(fit_place_kernel<true>, dim3(pl.nblocks), dim3(kPlaceThreads), 0, st,
             *p, with_backward, pl.gpb, num_tiles, w.boxes, w.tile_count, w.tile_incl, w.tile_fill, b->sorted_keys,
             (const float4 *)b->proj, w.records, b->tile_bins, w.n_isect, b->stats, pl.ordered ? w.tile_work : nullptr);
@@ -1742,7 +2070,7 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
             // the backward half.  (Band-split multi-GPU runs would need a halo exchange of the render.)
             launch_raster<RasterMode::FitForward>(false, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins,
                 w.tile_count, w.tile_fill, (const float4 *)w.records, b->gt_hwc, b->gt_u8_hwc, w.loss_render, nullptr,
-                b->stats, b->err_map, nullptr, pl.ordered ? w.tile_work : nullptr);
+                b->stats, b->err_map, nullptr, pl.ordered ? w.tile_work : nullptr, pl.bucket_cap);
             if (b->out_img)
                 cudaMemcpyAsync(b->out_img, w.loss_render, (size_t)p->img_width * p->img_height * 12,
                                 cudaMemcpyDeviceToDevice, st);
@@ -1751,15 +2079,15 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
                              b->stats + GI2D_STAT_SSIM_SUM, st);
             launch_raster<RasterMode::FitBackward>(false, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins,
                 w.tile_count, w.tile_fill, (const float4 *)w.records, nullptr, nullptr, nullptr, b->grads, b->stats,
-                nullptr, w.loss_vout, pl.ordered ? w.tile_work : nullptr);
+                nullptr, w.loss_vout, pl.ordered ? w.tile_work : nullptr, pl.bucket_cap);
         } else if (with_backward)
             launch_raster<RasterMode::Fit>(true, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count,
                 w.tile_fill, (const float4 *)w.records, b->gt_hwc, b->gt_u8_hwc, b->out_img, b->grads, b->stats,
-                b->err_map, nullptr, pl.ordered ? w.tile_work : nullptr);
+                b->err_map, nullptr, pl.ordered ? w.tile_work : nullptr, pl.bucket_cap);
         else
             launch_raster<RasterMode::Render>(true, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins,
                 w.tile_count, w.tile_fill, (const float4 *)w.records, nullptr, nullptr, b->out_img, nullptr, b->stats,
-                nullptr, nullptr, pl.ordered ? w.tile_work : nullptr);
+                nullptr, nullptr, pl.ordered ? w.tile_work : nullptr, pl.bucket_cap);
     }
     if (mk) mk->mark(st);
     return check_launch("gi2d_fit_forward_backward");
@@ -1805,10 +2133,37 @@ extern "C" size_t gi2d_fit_workspace_size(const gi2d_fit_params *p) {
 extern "C" int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward) {
     if (!p) return 0;
     const Plan pl = make_plan(*p);
-    int n = 3;  // project(+Adam), place, raster
-    if (!pl.smem_scan) n += cdiv(pl.num_tiles, 2048) > 1 ? 3 : 1;  // device-wide scan of the tile counts
+    int n = pl.bucket_cap ? 2 : 3;  // project(+Adam)[+place], [place,] raster
+    if (!pl.bucket_cap && !pl.smem_scan) n += cdiv(pl.num_tiles, 2048) > 1 ? 3 : 1;  // device-wide scan of the tile counts
     if (with_backward && p->loss_ssim_weight != 0.f) n += 3;  // forward / SSIM stats / SSIM gradient / backward
     return n;
+}
+
+extern "C" int gi2d_fit_bucket_capacity(const gi2d_fit_params *p) {
+    if (!p) return 0;
+    return make_plan(*p).bucket_cap;
+}
+
+extern "C" int gi2d_fit_export_binning(const gi2d_fit_params *p, const gi2d_fit_buffers *b, uint64_t *sorted_keys_out,
+                                       int32_t *tile_bins_out, gi2d_stream_t stream) {
+    const int rc = validate(p, b);
+    if (rc != GI2D_OK) return rc;
+    GI2D_REQUIRE(sorted_keys_out && tile_bins_out, "null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Plan pl = make_plan(*p);
+    const Workspace w = carve(*p, pl, b->workspace);
+    if (!pl.bucket_cap) {   // the compact arrays are what the step produces
+        cudaMemcpyAsync(sorted_keys_out, b->sorted_keys, (size_t)p->isect_capacity * 8, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(tile_bins_out, b->tile_bins, (size_t)pl.num_tiles * 8, cudaMemcpyDeviceToDevice, st);
+        return check_launch(__func__);
+    }
+    double bank = 0.0;   // (host read of one flag: this is a diagnostic / test entry point, it synchronises)
+    cudaStreamSynchronize(st);
+    cudaMemcpy(&bank, b->stats + kStatBank, sizeof(double), cudaMemcpyDeviceToHost);
+    const int32_t *count = bank != 0.0 ? w.tile_fill : w.tile_count;
+    export_ranges_kernel<<<1, 1024, 0, st>>>(pl.num_tiles, pl.bucket_cap, count, tile_bins_out);
+    export_keys_kernel<<<pl.num_tiles, 64, 0, st>>>(pl.bucket_cap, tile_bins_out, b->sorted_keys, sorted_keys_out);
+    return check_launch(__func__);
 }
 
 extern "C" int gi2d_fit_reset(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int step,
@@ -2014,7 +2369,7 @@ extern "C" int gi2d_fit_profile_raster(const gi2d_fit_params *p, const gi2d_fit_
     for (int i = 0; i < reps; ++i)
         launch_raster<RasterMode::Fit>(true, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins, w.tile_count,
             w.tile_fill, (const float4 *)w.records, b->gt_hwc, b->gt_u8_hwc, nullptr, b->grads, b->stats, nullptr,
-            nullptr, pl.ordered ? w.tile_work : nullptr);
+            nullptr, pl.ordered ? w.tile_work : nullptr, pl.bucket_cap);
     cudaEventRecord(e1, st);
     // nothing pending (the accumulated gradient is garbage), loss accumulators back to zero
     cudaMemsetAsync(b->stats + kStatPending, 0, sizeof(double), st);

@@ -31,6 +31,7 @@ from .binding import TILE, _stream
 STAT_STEP, STAT_ISECTS, STAT_OVERFLOW, STAT_LR, STAT_SSE, STAT_SSE_SLOTS = 0, 1, 2, 3, 16, 64
 STAT_BEST_SSE, STAT_BEST_STEP, STAT_NON_PSD, STAT_SSIM_SUM, STAT_ABS_SUM = 9, 10, 11, 13, 14
 STAT_NUM_POINTS, STAT_BEST_N, STAT_PRUNED, STAT_ADDED = 80, 81, 82, 83
+STAT_MAX_TILE = 84
 STAT_COUNT = 96
 _NAMES = ("xyz", "cov2d", "f_dc")  # the reference's optimiser group names (gaussianimage_covariance.py:93-96)
 
@@ -177,8 +178,8 @@ class GaussianImageFitter:
                 self.best[:k], self.best_bound[:k] = old[:k], oldb[:k]
         if not hasattr(self, "err_map"):
             self.err_map = torch.zeros(self.H, self.W, **f)
-        self.sorted_keys = torch.zeros(self.isect_capacity, dtype=torch.int64, device=self.device)
-        self.tile_bins = torch.zeros(tiles, 2, dtype=torch.int32, device=self.device)
+        self._keys_buf = torch.zeros(self.isect_capacity, dtype=torch.int64, device=self.device)
+        self._bins_buf = torch.zeros(tiles, 2, dtype=torch.int32, device=self.device)
         if not hasattr(self, "stats_buf"):
             self.stats_buf = torch.zeros(STAT_COUNT, dtype=torch.float64, device=self.device)
             self.stats_buf[STAT_NUM_POINTS] = float(self._n)
@@ -190,6 +191,8 @@ class GaussianImageFitter:
             int(self.color_norm), 2.0 * self.loss_w[0] / (3.0 * self.H * self.W),
             int(self.external_optimizer), self.loss_w[1] / (3.0 * self.H * self.W), self.loss_w[2], 1)
         ws_bytes = self.lib.gi2d_fit_workspace_size(C.byref(self.params))
+        # rows per tile of the bucketed binning (0: the scan + placement path is in use, include/gi2d.h)
+        self.bucket_cap = int(self.lib.gi2d_fit_bucket_capacity(C.byref(self.params)))
         self.workspace = torch.zeros(max(ws_bytes, 256), dtype=torch.uint8, device=self.device)
         self._prune_ws = None
         self._densify_ws = None
@@ -210,12 +213,32 @@ class GaussianImageFitter:
             m["xyz"].data_ptr(), v["xyz"].data_ptr(), m["cov2d"].data_ptr(), v["cov2d"].data_ptr(),
             m["f_dc"].data_ptr(), v["f_dc"].data_ptr(),
             gt.data_ptr() if (gt is not None and gt.dtype == torch.float32) else None,
-            out_img, self.grads.data_ptr(), self.proj.data_ptr(), self.sorted_keys.data_ptr(),
-            self.tile_bins.data_ptr(), self.stats_buf.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(),
+            out_img, self.grads.data_ptr(), self.proj.data_ptr(), self._keys_buf.data_ptr(),
+            self._bins_buf.data_ptr(), self.stats_buf.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(),
             gt.data_ptr() if (gt is not None and gt.dtype == torch.uint8) else None,
             self.best.data_ptr() if self.track_best else None,
             self.err_map.data_ptr() if err_map else None,
             self.best_bound.data_ptr() if self.track_best else None)
+
+    def _export_binning(self):
+        """The reference's view of the last forward's binning (utils.py:301-302 / forward.cu:211-233): one
+        ascending key array i64[capacity] (tile << 32 | gaussian) and tile_bins i32[tiles,2].  With the bucketed
+        layout they are compacted on demand (gi2d_fit_export_binning; synchronises)."""
+        if not self.bucket_cap:
+            return self._keys_buf, self._bins_buf
+        keys, bins = torch.zeros_like(self._keys_buf), torch.zeros_like(self._bins_buf)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gi2d_fit_export_binning(C.byref(self.params), C.byref(self.buffers), keys.data_ptr(),
+                                                        bins.data_ptr(), _stream(self.device)), "fit_export_binning")
+        return keys, bins
+
+    @property
+    def sorted_keys(self) -> torch.Tensor:
+        return self._export_binning()[0]
+
+    @property
+    def tile_bins(self) -> torch.Tensor:
+        return self._export_binning()[1]
 
     def reset_stats(self, step: int = 0):
         """Zero the device-side statistics (drops a pending gradient) and set the Adam step counter."""
@@ -483,7 +506,7 @@ class GaussianImageFitter:
                 "best_sse": float(s[STAT_BEST_SSE]), "best_step": int(s[STAT_BEST_STEP]),
                 "best_psnr": (10 * math.log10(1.0 / best_mse) if 0 < best_mse < float("inf") else
                               (0.0 if best_mse > 0 else float("inf"))),
-                "non_psd": int(s[STAT_NON_PSD]), "num_points": self._n}
+                "non_psd": int(s[STAT_NON_PSD]), "num_points": self._n, "max_tile": int(s[STAT_MAX_TILE])}
 
     def psnr(self) -> float:
         return self.stats()["psnr"]
@@ -494,7 +517,8 @@ class GaussianImageFitter:
         densification has concentrated the Gaussians (load-balance caveat).  In a band-split run
         every rank sees its own band only: all-reduce (SUM) the result before partitioning.  Synchronises."""
         tx, ty = self.tile_bounds[0], self.tile_bounds[1]
-        cnt = (self.tile_bins[:, 1] - self.tile_bins[:, 0]).clamp(min=0).view(ty, tx)
+        bins = self.tile_bins
+        cnt = (bins[:, 1] - bins[:, 0]).clamp(min=0).view(ty, tx)
         return cnt.sum(dim=1).double().cpu()
 
     def ms_ssim(self) -> float:
@@ -526,7 +550,11 @@ class GaussianImageFitter:
         if not st["overflow"]:
             return False
         expected = self._expected_step
-        self._capacity_hint = int(st["num_intersects"] * 2)
+        tiles = self.tile_bounds[0] * self.tile_bounds[1]
+        # with the bucketed binning EVERY tile's bucket must hold the fullest tile: 1.25 x the largest count when the
+        # device reported it, else (coming from the scan + placement path) 4 x the average; at least twice the count
+        self._capacity_hint = max(int(st["num_intersects"] * (2 if st.get("max_tile", 0) else 4)),
+                                  int(st.get("max_tile", 0) * 1.25 + 8) * tiles)
         self._step0 = st["step"]
         self._alloc_state(zero_moments=False)
         self._reset_keep_best(self._step0, st)

@@ -242,6 +242,8 @@ typedef struct gi2d_fit_params {
 #define GI2D_STAT_BEST_N 81     /* Gaussian count of the best-state snapshot (rows of b->best / b->best_bound) */
 #define GI2D_STAT_PRUNED 82     /* Gaussians removed by the last gi2d_fit_prune */
 #define GI2D_STAT_ADDED 83      /* Gaussians appended by the last gi2d_fit_densify */
+#define GI2D_STAT_MAX_TILE 84   /* != 0: the largest per-tile overlap count of a forward whose bucketed binning
+                                   overflowed (more than isect_capacity / #tiles overlaps in one tile) */
 #define GI2D_STAT_COUNT 96
 
 typedef struct gi2d_fit_buffers {
@@ -325,6 +327,19 @@ int gi2d_fit_prune(const gi2d_fit_params *p, const gi2d_fit_buffers *b, void *wo
 size_t gi2d_fit_densify_workspace_size(int img_height, int img_width);
 int gi2d_fit_densify(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int k_rows, const float *new_cov2d,
                      int slv, void *workspace, size_t workspace_bytes, gi2d_stream_t stream);
+
+/* Bucketed binning (the default of the fit step except for the tile-row exchange): tile t owns the rows
+ * [t * C, (t+1) * C), C = isect_capacity / #tiles, of b->sorted_keys and of the record workspace; the projection
+ * kernel places every intersection with one cursor atomic, so a step is TWO launches (no prefix sum, no placement
+ * kernel).  A tile with more than C overlaps raises GI2D_STAT_OVERFLOW like a full intersection buffer does
+ * (GI2D_STAT_MAX_TILE then holds the largest count).  gi2d_fit_bucket_capacity: C, or 0 when the scan + placement
+ * path is in use.  gi2d_fit_export_binning: the reference's view of the last forward's binning -- ONE ascending key
+ * array u64[isect_capacity] (tile << 32 | gaussian: isect_ids_sorted >> 32 and gaussian_ids_sorted of
+ * utils.py:301-302) and tile_bins i32[#tiles,2] (forward.cu:211-233) -- whichever layout the step used; a
+ * diagnostic entry point, it SYNCHRONISES. */
+int gi2d_fit_bucket_capacity(const gi2d_fit_params *p);
+int gi2d_fit_export_binning(const gi2d_fit_params *p, const gi2d_fit_buffers *b, uint64_t *sorted_keys_out,
+                            int32_t *tile_bins_out, gi2d_stream_t stream);
 
 /* Gradients of the last training step with respect to the step's INPUTS, for a caller that keeps its own
  * parameters and optimiser (p->external_optimizer: the quantisation-aware pass feeds de-quantised means /

@@ -257,7 +257,7 @@ def test_device_densify_matches_oracle(oracle):
     torch.cuda.synchronize()
     errors = N_(fit.err_map)
     before = (N_(fit._xyz), N_(fit._cov2d), N_(fit._features_dc), N_(fit.cholesky_bound))
-    ptrs = (fit._t_xyz.data_ptr(), fit._t_bound.data_ptr(), fit.sorted_keys.data_ptr())
+    ptrs = (fit._t_xyz.data_ptr(), fit._t_bound.data_ptr(), fit._keys_buf.data_ptr())
     torch.manual_seed(77)
     draw = (torch.rand(700, 3) + torch.tensor([0.5, 0, 0.5])).numpy()
     draw[::9, 1] = 3.0                                                    # (make some of them indefinite)
@@ -267,7 +267,7 @@ def test_device_densify_matches_oracle(oracle):
         errors, 2000, 3000, draw, W, H, base_num_samples=700)
     assert added == k == 700 and 0 < valid.sum() < 700
     n_new = 2000 + int(valid.sum())
-    assert fit.cur_num_points == n_new and ptrs == (fit._t_xyz.data_ptr(), fit._t_bound.data_ptr(), fit.sorted_keys.data_ptr())
+    assert fit.cur_num_points == n_new and ptrs == (fit._t_xyz.data_ptr(), fit._t_bound.data_ptr(), fit._keys_buf.data_ptr())
     np.testing.assert_array_equal(N_(fit._xyz)[:2000], before[0])
     np.testing.assert_array_equal(N_(fit._xyz)[2000:], new_xyz)
     np.testing.assert_array_equal(N_(fit._cov2d)[2000:], new_cov)
