@@ -1156,8 +1156,11 @@ fit_raster_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_
 #ifndef GI2D_RQ4_MINBLOCKS
 #define GI2D_RQ4_MINBLOCKS 7
 #endif
+#ifndef GI2D_RQ2_MINBLOCKS
+#define GI2D_RQ2_MINBLOCKS 14
+#endif
 template <RasterMode kMode, int kWarps>
-__global__ void __launch_bounds__(32 * kWarps, kWarps == 1 ? 16 : (kWarps == 2 ? 10 : GI2D_RQ4_MINBLOCKS))
+__global__ void __launch_bounds__(32 * kWarps, kWarps == 1 ? 16 : (kWarps == 2 ? GI2D_RQ2_MINBLOCKS : GI2D_RQ4_MINBLOCKS))
 fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64_t *__restrict__ keys_tmp,
                    const int32_t *__restrict__ tile_bins, int32_t *__restrict__ tile_count,
                    int32_t *__restrict__ tile_fill, const float4 *__restrict__ records,

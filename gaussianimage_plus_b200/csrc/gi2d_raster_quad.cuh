@@ -209,6 +209,9 @@ template <int kNQ>
 __device__ __forceinline__ void quad_forward(const QuadRecords &s, int cnt, const QuadLane<kNQ> &ln, int qshift,
                                              f32x2 (&accR)[kNQ], f32x2 (&accG)[kNQ], f32x2 (&accB)[kNQ]) {
     constexpr int kCols = QuadGeom<kNQ>::kCols;
+    // (not unrolled: the kernel is instruction-cache bound when several CTAs of an SM sit in different phases --
+    // ncu: 0.8 'no instruction' stalls per issue with the compiler's 4x unrolling; 2040x1356 -9 %, 8192^2 -13 %)
+#pragma unroll 1
     for (int t = 0; t < cnt; ++t) {
         const unsigned m = ((unsigned)s.mask[t] >> qshift) & ((1u << kNQ) - 1u);
         if (!m) continue;   // warp-uniform
@@ -399,7 +402,8 @@ __device__ __forceinline__ void quad_backward4(const QuadRecords &s, const int *
         // two trips per loop iteration with separate accumulators: two independent dependency chains per warp
         GroupAcc A{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull}, B = A;
         int i = 0;
-        for (; i + 1 < T; i += 2) {   // warp-uniform
+#pragma unroll 1
+        for (; i + 1 < T; i += 2) {   // warp-uniform (kept rolled: instruction cache, see quad_forward)
             bool y0 = in0, y1 = in1, z0 = in0, z1 = in1;
             if (kGuard) {
                 const bool ra = row < rows_inside, rb = row + rpt < rows_inside;
