@@ -32,6 +32,7 @@ class FitParams(C.Structure):
         ("lr_step_size", C.c_int32), ("lr_gamma", C.c_float),
         ("color_sigmoid", C.c_int32), ("loss_scale", C.c_float), ("external_optimizer", C.c_int32),
         ("loss_l1_scale", C.c_float), ("loss_ssim_weight", C.c_float), ("dynamic_points", C.c_int32),
+        ("loss_msssim_weight", C.c_float), ("loss_msssim_win", C.c_int32),
     ]
 
 
@@ -119,6 +120,8 @@ SIGNATURES = {
     "gi2d_tilerow_step": (_I, [C.POINTER(FitParams), C.POINTER(FitBuffers), C.POINTER(TileRow), _I, _I, _P]),
     "gi2d_ssim_workspace_size": (_SZ, [_I, _I]),
     "gi2d_image_loss_grad": (_I, [_I, _I, _P, _P, _P, _F, _F, _F, _P, _P, _P, _SZ, _P]),
+    "gi2d_msssim_grad_workspace_size": (_SZ, [_I, _I]),
+    "gi2d_image_msssim_loss_grad": (_I, [_I, _I, _I, _P, _P, _P, _F, _F, _P, _P, _P, _SZ, _P]),
     "gi2d_ms_ssim_workspace_size": (_SZ, [_I, _I]),
     "gi2d_ms_ssim": (_I, [_I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "gi2d_host_pipe_create": (_I, [C.POINTER(_P)]),

@@ -437,16 +437,27 @@ def image_loss_grad(render_hwc: torch.Tensor, gt_hwc: torch.Tensor, loss_type: s
     have an SSIM term or are pointwise (L2, L1, SSIM, Fusion1-3), in two kernels (gi2d_loss.cu).
     render f32[H,W,3] (unclamped rasterizer output), gt f32 or u8 [H,W,3].
     Returns (v_out f32[H,W,3], ssim_sum f64[1]); mean SSIM = ssim_sum / (3 (H-10)(W-10))."""
-    from .fit import loss_weights
+    from .fit import loss_weights, msssim_term
 
     lib = _lib.load()
     _check_input(render_hwc, "render", f32)
     _check_input(gt_hwc, "gt")
     H, W, _ = render_hwc.shape
     w2, w1, ws = loss_weights(loss_type, lambda_value)
+    wm, win = msssim_term(loss_type, lambda_value)
     dev = render_hwc.device
     v_out = torch.empty_like(render_hwc)
     ssim_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+    if wm:
+        # Fusion4 / Fusion_hinerv (models/utils.py:76-79): the second return value is ms_ssim itself
+        ws_buf = _workspace(lib.gi2d_msssim_grad_workspace_size(H, W), dev)
+        is_u8 = gt_hwc.dtype == torch.uint8
+        with _on(dev):
+            _lib.check(lib.gi2d_image_msssim_loss_grad(H, W, win, _p(render_hwc), None if is_u8 else _p(gt_hwc),
+                                                       _p(gt_hwc) if is_u8 else None, wm, w1 / (3.0 * H * W),
+                                                       _p(v_out), _p(ssim_sum), _p(ws_buf), ws_buf.numel(),
+                                                       _stream(dev)), "image_msssim_loss_grad")
+        return v_out, ssim_sum
     ws_buf = _workspace(lib.gi2d_ssim_workspace_size(H, W), dev)
     is_u8 = gt_hwc.dtype == torch.uint8
     with _on(dev):

@@ -26,7 +26,7 @@ from typing import Dict, Optional
 import torch
 from torch import nn
 
-from .fit import loss_weights
+from .fit import loss_weights, msssim_term
 from .quantize import HybirdQuant, UniformQuantizer
 
 
@@ -47,6 +47,9 @@ class _ImageLoss(torch.autograd.Function):
         loss = w2 * (d * d).mean() + w1 * d.abs().mean()
         if ws:
             loss = loss + ws * (1.0 - ssim_sum[0].float() / (3.0 * (H - 10) * (W - 10)))
+        wm, _ = msssim_term(loss_type, lambda_value)
+        if wm:                                      # (image_loss_grad hands back ms_ssim itself for these)
+            loss = loss + wm * (1.0 - ssim_sum[0].float())
         ctx.save_for_backward(v)
         return loss
 
@@ -281,6 +284,10 @@ class FusedQuantizedTrainer(QuantizedGaussianImage):
             loss = loss + w1 * s[STAT_ABS_SUM] / px3
         if ws:
             loss = loss + ws * (1.0 - s[STAT_SSIM_SUM] / (3.0 * (self.H - 10) * (self.W - 10)))
+        if f.loss_ms[0]:
+            from .fit import STAT_MSSSIM
+
+            loss = loss + f.loss_ms[0] * (1.0 - s[STAT_MSSSIM])
         return loss.float()
 
     def _iteration(self):

@@ -38,6 +38,9 @@ int cumsum_i32_launch(int n, const int32_t *in, int32_t *out, int32_t *total, in
                       cudaStream_t st);
 size_t cumsum_i32_workspace(int n);
 
+size_t msssim_grad_workspace_floats(int H, int W);
+int msssim_grad_launch(int H, int W, int win, const float *render, const float *gt, const uint8_t *gt_u8, float *ws,
+                       float weight, float l1_scale, float *v_out, double *value, cudaStream_t st);
 int ssim_grad_launch(int H, int W, const float *render, const float *gt, const uint8_t *gt_u8, float *dm_ws,
                      float ssim_weight, float l2_scale, float l1_scale, float *v_out, double *ssim_sum,
                      cudaStream_t st);  // gi2d_loss.cu
@@ -209,10 +212,12 @@ Workspace carve(const gi2d_fit_params &p, const Plan &pl, void *base) {
     w.records = (float4 *)(c + off);      off += align_up((size_t)p.isect_capacity * 32);
     w.keys_tmp = (uint64_t *)(c + off);   off += align_up((size_t)p.isect_capacity * 8);
     w.loss_render = w.loss_dm = w.loss_vout = nullptr;
-    if (p.loss_ssim_weight != 0.f) {
+    if (p.loss_ssim_weight != 0.f || p.loss_msssim_weight != 0.f) {
         const size_t px = (size_t)p.img_width * p.img_height;
         w.loss_render = (float *)(c + off);  off += align_up(px * 3 * 4);
-        w.loss_dm = (float *)(c + off);      off += align_up(px * 9 * 4);
+        // (loss_dm: the 9 derivative planes of SSIM, or the whole workspace of the MS-SSIM gradient)
+        const size_t dm_floats = p.loss_msssim_weight != 0.f ? msssim_grad_workspace_floats(p.img_height, p.img_width) : px * 9;
+        w.loss_dm = (float *)(c + off);      off += align_up(dm_floats * 4);
         w.loss_vout = (float *)(c + off);    off += align_up(px * 3 * 4);
     }
     w.total = off;
@@ -2001,6 +2006,15 @@ int validate(const gi2d_fit_params *p, const gi2d_fit_buffers *b) {
     GI2D_REQUIRE(p->isect_capacity > 0, "isect_capacity must be positive");
     GI2D_REQUIRE(p->loss_ssim_weight == 0.f || (p->img_width >= 11 && p->img_height >= 11),
                  "the SSIM window needs an image of at least 11x11 pixels");
+    GI2D_REQUIRE(p->loss_msssim_weight == 0.f || p->loss_ssim_weight == 0.f, "one of the SSIM / MS-SSIM terms at a time");
+    GI2D_REQUIRE(p->loss_msssim_weight == 0.f || p->loss_msssim_win == 11 || p->loss_msssim_win == 5,
+                 "loss_msssim_win must be 11 or 5");
+    GI2D_REQUIRE(p->loss_msssim_weight == 0.f ||
+                     ((p->img_width < p->img_height ? p->img_width : p->img_height) > (p->loss_msssim_win - 1) * 16 &&
+                      p->loss_scale == 0.f),
+                 "MS-SSIM needs the smaller image side to exceed (win - 1) * 16 pixels, and goes with an l1 term only");
+    GI2D_REQUIRE(p->loss_msssim_weight == 0.f || (p->tile_row_begin == 0 && p->tile_row_end == p->tiles_y),
+                 "SSIM losses are not available for a tile-row band (the window crosses band borders)");
     GI2D_REQUIRE(p->loss_ssim_weight == 0.f || (p->tile_row_begin == 0 && p->tile_row_end == p->tiles_y),
                  "SSIM losses are not available for a tile-row band (the window crosses band borders)");
     GI2D_REQUIRE(b->stats && b->workspace && b->proj && b->sorted_keys && b->tile_bins, "null buffer");
@@ -2068,7 +2082,7 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
     const int band = p->tile_row_end - p->tile_row_begin;
     if (band > 0) {
         dim3 grid(p->tiles_x, band);
-        if (with_backward && p->loss_ssim_weight != 0.f) {
+        if (with_backward && (p->loss_ssim_weight != 0.f || p->loss_msssim_weight != 0.f)) {
             // SSIM couples pixels across tile borders: forward everywhere, then the loss gradient image, then
             // the backward half.  (Band-split multi-GPU runs would need a halo exchange of the render.)
             launch_raster<RasterMode::FitForward>(false, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins,
@@ -2077,9 +2091,14 @@ int fit_forward_backward_impl(const gi2d_fit_params *p, const gi2d_fit_buffers *
             if (b->out_img)
                 cudaMemcpyAsync(b->out_img, w.loss_render, (size_t)p->img_width * p->img_height * 12,
                                 cudaMemcpyDeviceToDevice, st);
-            ssim_grad_launch(p->img_height, p->img_width, w.loss_render, b->gt_hwc, b->gt_u8_hwc, w.loss_dm,
-                             p->loss_ssim_weight, p->loss_scale, p->loss_l1_scale, w.loss_vout,
-                             b->stats + GI2D_STAT_SSIM_SUM, st);
+            if (p->loss_msssim_weight != 0.f)
+                msssim_grad_launch(p->img_height, p->img_width, p->loss_msssim_win, w.loss_render, b->gt_hwc,
+                                   b->gt_u8_hwc, w.loss_dm, p->loss_msssim_weight, p->loss_l1_scale, w.loss_vout,
+                                   b->stats + GI2D_STAT_MSSSIM, st);
+            else
+                ssim_grad_launch(p->img_height, p->img_width, w.loss_render, b->gt_hwc, b->gt_u8_hwc, w.loss_dm,
+                                 p->loss_ssim_weight, p->loss_scale, p->loss_l1_scale, w.loss_vout,
+                                 b->stats + GI2D_STAT_SSIM_SUM, st);
             launch_raster<RasterMode::FitBackward>(false, grid, st, *p, b->sorted_keys, w.keys_tmp, b->tile_bins,
                 w.tile_count, w.tile_fill, (const float4 *)w.records, nullptr, nullptr, nullptr, b->grads, b->stats,
                 nullptr, w.loss_vout, pl.ordered ? w.tile_work : nullptr, pl.bucket_cap);
@@ -2139,6 +2158,7 @@ extern "C" int gi2d_fit_launch_count(const gi2d_fit_params *p, int with_backward
     int n = pl.bucket_cap ? 2 : 3;  // project(+Adam)[+place], [place,] raster
     if (!pl.bucket_cap && !pl.smem_scan) n += cdiv(pl.num_tiles, 2048) > 1 ? 3 : 1;  // device-wide scan of the tile counts
     if (with_backward && p->loss_ssim_weight != 0.f) n += 3;  // forward / SSIM stats / SSIM gradient / backward
+    if (with_backward && p->loss_msssim_weight != 0.f) n += 21; // ... / memset + 19 MS-SSIM launches / ...
     return n;
 }
 
@@ -2356,7 +2376,7 @@ extern "C" int gi2d_fit_profile(const gi2d_fit_params *p, const gi2d_fit_buffers
 extern "C" int gi2d_fit_profile_raster(const gi2d_fit_params *p, const gi2d_fit_buffers *b, int reps, float *ms_host,
                                        gi2d_stream_t stream) {
     GI2D_REQUIRE(ms_host && reps > 0, "bad arguments");
-    GI2D_REQUIRE(p && p->loss_ssim_weight == 0.f, "profiles the single-launch rasterizer (no SSIM term)");
+    GI2D_REQUIRE(p && p->loss_ssim_weight == 0.f && p->loss_msssim_weight == 0.f, "profiles the single-launch rasterizer (no SSIM term)");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = fit_forward_backward_impl(p, b, 1, st, nullptr);
     if (rc != GI2D_OK) return rc;
@@ -2479,7 +2499,7 @@ extern "C" int gi2d_tilerow_step(const gi2d_fit_params *p, const gi2d_fit_buffer
     int rc = validate_tilerow(p, b, tr);
     if (rc != GI2D_OK) return rc;
     GI2D_REQUIRE(phase >= 1 && phase <= 3, "phase: 1 = band step, 2 = exchange, 3 = both");
-    GI2D_REQUIRE(p->loss_ssim_weight == 0.f, "SSIM losses are not available for a tile-row band");
+    GI2D_REQUIRE(p->loss_ssim_weight == 0.f && p->loss_msssim_weight == 0.f, "SSIM losses are not available for a tile-row band");
     cudaStream_t st = (cudaStream_t)stream;
     if (phase & 1) {
         rc = fit_forward_backward_impl(p, b, with_backward, st, nullptr, tr);

@@ -32,6 +32,7 @@ STAT_STEP, STAT_ISECTS, STAT_OVERFLOW, STAT_LR, STAT_SSE, STAT_SSE_SLOTS = 0, 1,
 STAT_BEST_SSE, STAT_BEST_STEP, STAT_NON_PSD, STAT_SSIM_SUM, STAT_ABS_SUM = 9, 10, 11, 13, 14
 STAT_NUM_POINTS, STAT_BEST_N, STAT_PRUNED, STAT_ADDED = 80, 81, 82, 83
 STAT_MAX_TILE = 84
+STAT_MSSSIM = 89
 STAT_COUNT = 96
 _NAMES = ("xyz", "cov2d", "f_dc")  # the reference's optimiser group names (gaussianimage_covariance.py:93-96)
 
@@ -42,15 +43,25 @@ def slv_bound(H: int, W: int, num_points: int) -> float:
 
 
 # loss_fn of models/utils.py:60-80 as (w_mse, w_l1, w_ssim); lambda_value = 0.7 at both call sites
-# (gaussianimage_covariance.py:222,252).  The MS-SSIM variants (Fusion4, Fusion_hinerv) are not built.
+# (gaussianimage_covariance.py:222,252).  The MS-SSIM variants come back from msssim_term().
 def loss_weights(loss_type: str, lambda_value: float = 0.7) -> Tuple[float, float, float]:
     lam = float(lambda_value)
     table = {"L2": (1.0, 0.0, 0.0), "L1": (0.0, 1.0, 0.0), "SSIM": (0.0, 0.0, 1.0),
-             "Fusion1": (lam, 0.0, 1.0 - lam), "Fusion2": (0.0, lam, 1.0 - lam), "Fusion3": (lam, 1.0 - lam, 0.0)}
+             "Fusion1": (lam, 0.0, 1.0 - lam), "Fusion2": (0.0, lam, 1.0 - lam), "Fusion3": (lam, 1.0 - lam, 0.0),
+             "Fusion4": (0.0, lam, 0.0), "Fusion_hinerv": (0.0, lam, 0.0)}
     if loss_type not in table:
-        raise ValueError(f"loss_type {loss_type!r} is not supported (have {sorted(table)}; the MS-SSIM losses "
-                         "Fusion4 / Fusion_hinerv are out of scope)")
+        raise ValueError(f"loss_type {loss_type!r} is not supported (have {sorted(table)})")
     return table[loss_type]
+
+
+def msssim_term(loss_type: str, lambda_value: float = 0.7) -> Tuple[float, int]:
+    """(weight, win_size) of the `1 - ms_ssim` term: Fusion4 = 0.7 l1 + 0.3 (1 - ms_ssim), Fusion_hinerv the same
+    with win_size = 5 (models/utils.py:76-79); (0, 11) for every other loss."""
+    if loss_type == "Fusion4":
+        return 1.0 - float(lambda_value), 11
+    if loss_type == "Fusion_hinerv":
+        return 1.0 - float(lambda_value), 5
+    return 0.0, 11
 
 
 def _sse_total(s) -> float:
@@ -115,6 +126,7 @@ class GaussianImageFitter:
         self.color_norm, self.SLV = bool(color_norm), bool(SLV_init)
         self.use_graph = use_graph
         self.loss_type, self.loss_w = loss_type, loss_weights(loss_type, lambda_value)
+        self.loss_ms = msssim_term(loss_type, lambda_value)
         self.grad_hook = grad_hook  # called right after the backward of every step (multi-GPU all-reduce)
         self._capacity_hint = isect_capacity
         self._dirty = False         # a gradient is pending on the device
@@ -189,7 +201,8 @@ class GaussianImageFitter:
             n, self.W, self.H, self.tile_bounds[0], self.tile_bounds[1], self.tile_rows[0], self.tile_rows[1],
             self.isect_capacity, self.clip_coe, self.radius_clip, self.lr, 0.9, 0.999, 1e-15, 20000, 0.5,
             int(self.color_norm), 2.0 * self.loss_w[0] / (3.0 * self.H * self.W),
-            int(self.external_optimizer), self.loss_w[1] / (3.0 * self.H * self.W), self.loss_w[2], 1)
+            int(self.external_optimizer), self.loss_w[1] / (3.0 * self.H * self.W), self.loss_w[2], 1,
+            self.loss_ms[0], self.loss_ms[1])
         ws_bytes = self.lib.gi2d_fit_workspace_size(C.byref(self.params))
         # rows per tile of the bucketed binning (0: the scan + placement path is in use, include/gi2d.h)
         self.bucket_cap = int(self.lib.gi2d_fit_bucket_capacity(C.byref(self.params)))
@@ -500,6 +513,8 @@ class GaussianImageFitter:
             loss += w1 * float(s[STAT_ABS_SUM]) / (3.0 * self.H * self.W)
         if ws:
             loss += ws * (1.0 - float(s[STAT_SSIM_SUM]) / (3.0 * (self.H - 10) * (self.W - 10)))
+        if self.loss_ms[0]:
+            loss += self.loss_ms[0] * (1.0 - float(s[STAT_MSSSIM]))
         return {"step": int(s[STAT_STEP]), "num_intersects": int(s[STAT_ISECTS]), "overflow": bool(s[STAT_OVERFLOW]),
                 "lr": float(s[STAT_LR]), "sse": sse, "mse": mse, "loss": loss,
                 "psnr": 10 * math.log10(1.0 / mse) if mse > 0 else float("inf"),

@@ -162,7 +162,7 @@ class TileRowFit:
         self.fit, self.partition = fit, partition
         self._lib, self._C = _lib, C
         n = fit.cur_num_points
-        if fit.loss_w[2] != 0:
+        if fit.loss_w[2] != 0 or fit.loss_ms[0] != 0:
             raise ValueError("SSIM losses are not available for a tile-row band (the window crosses band borders)")
         if _emulated is None:
             import torch.distributed as dist

@@ -223,6 +223,10 @@ typedef struct gi2d_fit_params {
     int32_t dynamic_points;     /* 1: the per-Gaussian arrays hold num_points ROWS (a capacity) and the live count is
                                    stats[GI2D_STAT_NUM_POINTS]: gi2d_fit_prune / gi2d_fit_densify change the model's
                                    size on the device, with no reallocation, no host round trip and no new graph */
+    float loss_msssim_weight;   /* wm: loss += wm * (1 - ms_ssim) -- Fusion4 (0, l, 0; wm = 1-l, win 11) and Fusion_hinerv
+                                   (win 5) of models/utils.py:76-79; exclusive with loss_ssim_weight; the rasterize
+                                   launch is split around gi2d_image_msssim_loss_grad's kernels */
+    int32_t loss_msssim_win;    /* 11 or 5 */
 } gi2d_fit_params;
 
 /* stats layout (f64): the device-side step counter makes the step graph-replayable with no
@@ -244,6 +248,7 @@ typedef struct gi2d_fit_params {
 #define GI2D_STAT_ADDED 83      /* Gaussians appended by the last gi2d_fit_densify */
 #define GI2D_STAT_MAX_TILE 84   /* != 0: the largest per-tile overlap count of a forward whose bucketed binning
                                    overflowed (more than isect_capacity / #tiles overlaps in one tile) */
+#define GI2D_STAT_MSSSIM 89     /* ms_ssim of the last training step (loss_msssim_weight != 0) */
 #define GI2D_STAT_COUNT 96
 
 typedef struct gi2d_fit_buffers {
@@ -475,6 +480,17 @@ size_t gi2d_ms_ssim_workspace_size(int img_height, int img_width);
 int gi2d_ms_ssim(int img_height, int img_width, const float *render_hwc, const float *gt_hwc,
                  const uint8_t *gt_u8_hwc, double *level_sums, void *workspace, size_t workspace_bytes,
                  gi2d_stream_t stream);
+
+/* MS-SSIM as a TRAINING loss -- `Fusion4` and `Fusion_hinerv` of models/utils.py:76-79:
+ *   loss = l1_weight * l1 + msssim_weight * (1 - ms_ssim(clamp(render), gt, data_range = 1, win_size = win)),
+ * win = 11 (pytorch_msssim's default) or 5 (Fusion_hinerv).  v_out_hwc f32[H,W,3] = d loss / d render (through
+ * torch.clamp's mask, the five levels, their avg_pool2d chain and the relu / weighted product of ms_ssim);
+ * *ms_value (DEVICE pointer, optional) = ms_ssim.  l1_scale = l1_weight / (3 H W).  The smaller image side must
+ * exceed (win - 1) * 16 pixels (pytorch_msssim's own assertion). */
+size_t gi2d_msssim_grad_workspace_size(int img_height, int img_width);
+int gi2d_image_msssim_loss_grad(int img_height, int img_width, int win, const float *render_hwc, const float *gt_hwc,
+                                const uint8_t *gt_u8_hwc, float msssim_weight, float l1_scale, float *v_out_hwc,
+                                double *ms_value, void *workspace, size_t workspace_bytes, gi2d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement utilities for bench.py (these two SYNCHRONISE; never call them while capturing).

@@ -48,9 +48,9 @@ def ssim(X: torch.Tensor, Y: torch.Tensor, data_range: float = 1.0, K=(0.01, 0.0
     return torch.flatten(ssim_map, 2).mean(-1).mean()
 
 
-def _ssim_and_cs(X, Y, data_range=1.0, K=(0.01, 0.03)):
+def _ssim_and_cs(X, Y, data_range=1.0, K=(0.01, 0.03), win_size: int = 11):
     """pytorch_msssim `_ssim(..., size_average=False)`: per-channel means of the SSIM map and of the cs map."""
-    win = fspecial_gauss_1d()
+    win = fspecial_gauss_1d(win_size)
     C1, C2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
     mu1, mu2 = gaussian_filter(X, win), gaussian_filter(Y, win)
     sigma1_sq = gaussian_filter(X * X, win) - mu1 * mu1
@@ -64,14 +64,16 @@ def _ssim_and_cs(X, Y, data_range=1.0, K=(0.01, 0.03)):
 MS_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
 
 
-def ms_ssim(X: torch.Tensor, Y: torch.Tensor, data_range: float = 1.0) -> torch.Tensor:
-    """pytorch_msssim `ms_ssim(X, Y, data_range, size_average=True)` (the evaluation metric of train.py:190):
-    5 levels, avg_pool2d(kernel 2, padding = size % 2) between them, relu on cs / ssim, weighted product."""
-    assert min(X.shape[-2:]) > (11 - 1) * 2 ** 4
+def ms_ssim(X: torch.Tensor, Y: torch.Tensor, data_range: float = 1.0, win_size: int = 11) -> torch.Tensor:
+    """pytorch_msssim `ms_ssim(X, Y, data_range, size_average=True, win_size=...)` (the evaluation metric of
+    train.py:190 and the `1 - ms_ssim` term of Fusion4 / Fusion_hinerv, models/utils.py:76-79): 5 levels,
+    avg_pool2d(kernel 2, padding = size % 2) between them, relu on cs / ssim, weighted product; the window is
+    `_fspecial_gauss_1d(win_size, 1.5)` (win_sigma keeps its default when only win_size is given)."""
+    assert min(X.shape[-2:]) > (win_size - 1) * 2 ** 4
     w = X.new_tensor(MS_WEIGHTS)
     mcs = []
     for i in range(5):
-        ssim_c, cs = _ssim_and_cs(X, Y, data_range)
+        ssim_c, cs = _ssim_and_cs(X, Y, data_range, win_size=win_size)
         if i < 4:
             mcs.append(torch.relu(cs))
             pad = [s % 2 for s in X.shape[2:]]
@@ -82,7 +84,11 @@ def ms_ssim(X: torch.Tensor, Y: torch.Tensor, data_range: float = 1.0) -> torch.
 
 
 def loss_fn(pred: torch.Tensor, target: torch.Tensor, loss_type: str = "L2", lambda_value: float = 0.7):
-    """models/utils.py:60-80 (without the MS-SSIM variants)."""
+    """models/utils.py:60-80."""
+    if loss_type == "Fusion4":
+        return lambda_value * F.l1_loss(pred, target) + (1 - lambda_value) * (1 - ms_ssim(pred, target))
+    if loss_type == "Fusion_hinerv":
+        return lambda_value * F.l1_loss(pred, target) + (1 - lambda_value) * (1 - ms_ssim(pred, target, win_size=5))
     if loss_type == "L2":
         return F.mse_loss(pred, target)
     if loss_type == "L1":
