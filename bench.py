@@ -275,7 +275,7 @@ def roofline_record(torch, lib, _lib, fit, flush, name, peak_tf, n_warm=200, n_f
     # algorithmic HBM bytes of one step: per Gaussian Adam 224 + record in/out 64 + bound 12 +
     # box 8 + gradient row zeroing 32; per intersection count 4 + cursor 4 + key/record written 40 + record read 32 +
     # key/record read 40 + key write-back 8 + gradient reds 32; per pixel the 8-bit target 3; per tile range + counters 32
-    step_bytes = N * 340 + I * 160 + H * W * 3 + tiles * 32
+    step_bytes = N * 340 + I * (124 if getattr(fit, "bucket_cap", 0) else 160) + H * W * 3 + tiles * 32
     summ = ncu_summary().get(name, {})
     rk = summ.get("fit_rasterq_kernel", {})
     return {
@@ -296,7 +296,11 @@ def roofline_record(torch, lib, _lib, fit, flush, name, peak_tf, n_warm=200, n_f
         "kernel_ms_back_to_back_l2_warm": raster_b2b_ms,
         "frac_back_to_back_l2_warm": flop / (raster_b2b_ms * 1e-3) / 1e12 / peak_tf if peak_tf else None,
         "kernel_ms_event_bracketed_l2_flushed": acc[3],
-        "step_kernel_ms": {"adam+project+count": acc[0], "tile_scan": acc[1], "place": acc[2], "sort+raster": acc[3]},
+        "step_kernel_ms": ({"adam+project+place": acc[0], "(empty bracket)": acc[1], "(empty bracket) ": acc[2],
+                            "sort+raster": acc[3]} if getattr(fit, "bucket_cap", 0) else
+                           {"adam+project+count": acc[0], "tile_scan": acc[1], "place": acc[2], "sort+raster": acc[3]}),
+        "binning": ("bucketed: tile t owns rows [t*C, (t+1)*C), C = %d; the projection kernel places (2 launches per "
+                    "step)" % fit.bucket_cap) if getattr(fit, "bucket_cap", 0) else "scan + placement kernel (3+ launches)",
         "step_kernel_ms_note": "CUDA events between the kernels of one un-graphed step, L2 flushed before each sample "
                                "(each bracket carries a few us of launch / drain latency)",
         "raster_share_of_step": share,
@@ -517,7 +521,7 @@ def main():
     final_stats = fit.stats()
 
     # ---------------- extras on one GPU: the other BASELINE workloads, the drop-in, the whole fit loop
-    workloads, dropin, fit_loop, cpu, ref_cuda = None, None, None, None, None
+    workloads, dropin, fit_loop, cpu, ref_cuda, qat = None, None, None, None, None, None
     if world == 1 and not args.no_extra:
         del fit
         torch.cuda.empty_cache()
@@ -544,6 +548,10 @@ def main():
             fit_loop = bench_fit_loop(torch, synth, dev)
         except Exception as e:
             fit_loop = {"error": repr(e)[:300]}
+        try:
+            qat = bench_qat(torch, synth, dev)
+        except Exception as e:
+            qat = {"error": repr(e)[:300]}
     if rank == 0 and world == 1:
         if not args.no_cpu_baseline:
             rate, n, el, t_pre = cpu_port_rate(H, W, N, args.cpu_seconds, preroll=args.preroll, cov_scale=args.cov_scale)
@@ -582,7 +590,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": int(gt_u8_pinned.numel()),
                     "d2h_bytes_per_step": int(STAT_COUNT_BYTES), "steps": Ke,
                     "how": "one gi2d_fit_step_host call per step: 8-bit HWC target pinned->device (double-buffered, on "
-                           "the library's copy stream), the step's 3 kernels, stats block device->pinned; the host "
+                           "the library's copy stream), the step's kernels (launches_per_step), stats block device->pinned; the host "
                            "reads every step's result one step behind; median of 3 trials",
                     "trials": e2e_trials,
                     "h2d_gb_per_s": e2e_value / images * int(gt_u8_pinned.numel()) / 1e9,
@@ -595,7 +603,7 @@ def main():
             "gpu_launches": launches_per_step * K,
             "launches_per_step": launches_per_step,
             "clocks": clk.summary(), "roofline": roofline, "workloads": workloads, "cpu_baseline": cpu,
-            "ref_cuda": ref_cuda, "dropin": dropin, "fit_loop": fit_loop, "tilerow": None,
+            "ref_cuda": ref_cuda, "dropin": dropin, "fit_loop": fit_loop, "qat": qat, "tilerow": None,
         }
         if ref_cuda and isinstance(ref_cuda.get("fastmath"), dict) and "fit_it_s" in ref_cuda["fastmath"]:
             line["ref_ext_it_s"] = ref_cuda["fastmath"]["fit_it_s"]
@@ -603,6 +611,8 @@ def main():
             line["dropin_it_s"] = dropin["dropin_it_s"]
         if fit_loop and "it_s" in fit_loop:
             line["fit_loop_it_s"] = fit_loop["it_s"]
+        if qat and "kernels" in qat:
+            line["qat_us_per_iteration"] = qat["kernels"]["us_per_iteration"]
     else:
         line = None
 
@@ -790,6 +800,48 @@ def bench_fit_loop(torch, synth, dev, iterations=5000):
             best = rec
         del fit
     return best
+
+
+def bench_qat(torch, synth, dev, warm_fit=1500, iters=400):
+    """The quantisation-aware iteration of the compression pass (train_quantize.py; configs[3] second half) at
+    768x512 / 5000 Gaussians, 12/10/6-bit lsq quantisers, L2: the kernel trainer (gi2d_quant_* around the fused fit
+    step, one CUDA graph of 8 launches) next to round 1's form (torch quantiser modules + four torch.optim.Adam
+    replayed from a graph).  CUDA events, back to back."""
+    import numpy as np
+
+    from gaussianimage_plus_b200.codec import FusedQuantizedTrainer, KernelQuantizedTrainer
+    from gaussianimage_plus_b200.fit import GaussianImageFitter
+
+    H, W, N = synth.CONFIGS["kodak_5000"]
+    xyz, cov, bound, rgb = synth.init_covariance_model(N, H, W, seed=3047, colors="zeros")
+    gt_u8 = torch.from_numpy(np.round(synth.target_image(H, W) * 255.0).astype(np.uint8)).to(dev)
+    fit = GaussianImageFitter(N, H, W, device=dev)
+    for dst, src in ((fit._xyz, xyz), (fit._cov2d, cov), (fit.cholesky_bound, bound), (fit._features_dc, rgb)):
+        dst.copy_(torch.from_numpy(src))
+    fit.set_target(gt_u8)
+    fit.train_iters(warm_fit)
+    fit.catch_up()
+    psnr_fit = fit.stats()["psnr"]
+    out = {"warm_up_fit_iterations": warm_fit, "psnr_before_quantisation": psnr_fit, "iterations": iters}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for key, cls in (("kernels", KernelQuantizedTrainer), ("torch_graph", FusedQuantizedTrainer)):
+        q = cls.from_fitter(fit, best=False)
+        q.set_target(gt_u8)
+        for _ in range(20):
+            q.train_iter_quantize()
+        first = q.psnr()
+        torch.cuda.synchronize(dev)
+        ev0.record()
+        for _ in range(iters):
+            q.train_iter_quantize()
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        out[key] = {"us_per_iteration": ev0.elapsed_time(ev1) * 1e3 / iters, "psnr_after_20": first,
+                    "psnr_after": q.psnr()}
+        del q
+        torch.cuda.empty_cache()
+    out["speedup"] = out["torch_graph"]["us_per_iteration"] / out["kernels"]["us_per_iteration"]
+    return out
 
 
 def _has_capacity_arg():

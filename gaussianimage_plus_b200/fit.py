@@ -176,7 +176,9 @@ class GaussianImageFitter:
             self._t_m = {k: torch.zeros_like(t) for k, t in self._raw_params().items()}
             self._t_v = {k: torch.zeros_like(t) for k, t in self._raw_params().items()}
         tiles = self.tile_bounds[0] * self.tile_bounds[1]
-        cap = self._capacity_hint or max(1 << 16, 32 * n)
+        # default: 32 intersections per Gaussian, and -- for the bucketed binning, whose tiles each own capacity / #tiles
+        # rows -- at least the 256 entries per tile the rasterizer stages (densification clusters new Gaussians)
+        cap = self._capacity_hint or max(1 << 16, 32 * n, 256 * tiles)
         self.isect_capacity = int(min(cap, max(n, 1) * tiles, 2 ** 31 - 1024))
         if not getattr(self, "_keep_exchange_buffers", False):   # (parallel.TileRowFit homes them in peer memory)
             self.grads = torch.zeros(n, 8, **f)
