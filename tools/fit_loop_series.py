@@ -29,3 +29,13 @@ for k in range(50):
     st=fit.stats()
     rows.append((it, round(t_step,1), round(t_prune), round(t_grow), st['num_points'], st['num_intersects'], st['overflow'], round(st['psnr'],2)))
 for r in rows[::3]: print(r)
+bins = fit.tile_bins
+cnt = (bins[:, 1] - bins[:, 0]).clamp(min=0)
+top = torch.sort(cnt, descending=True).values[:12].tolist()
+print("largest tile counts at the end:", top, "mean", float(cnt.float().mean()))
+import bench, ctypes as C
+from gaussianimage_plus_b200 import _lib
+lib = _lib.load()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+rec = bench.roofline_record(torch, lib, _lib, fit, flush, "kodak_5000", 74.4)
+print({k: rec[k] for k in ("step_ms", "kernel_ms_back_to_back_l2_warm", "step_kernel_ms", "pairs_per_launch", "num_intersects")})

@@ -24,9 +24,12 @@ WANT = {
     "dram_read_bytes": "dram__bytes_read.sum",
     "dram_write_bytes": "dram__bytes_write.sum",
     "inst_executed": "smsp__inst_executed.sum",
-    "fadd_thread_ops": "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
-    "fmul_thread_ops": "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
-    "ffma_thread_ops": "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
+    # (`--set full` reports these three as a rate: thread-level instructions per elapsed cycle, summed over the GPU)
+    "fadd_thread_inst_per_cycle": "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed",
+    "fmul_thread_inst_per_cycle": "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed",
+    "ffma_thread_inst_per_cycle": "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed",
+    "l2_hit_pct": "lts__t_sector_hit_rate.pct",
+    "dram_throughput_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "pipe_fma_pct_of_active": "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "pipe_fma_pct_of_elapsed": "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "pipe_alu_pct_of_active": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
