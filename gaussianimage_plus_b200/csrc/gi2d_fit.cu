@@ -501,8 +501,11 @@ __device__ __forceinline__ void k1_order_cta(const gi2d_fit_params &p, int with_
 //       the OTHER one for the next forward, so K3 can be replayed and the counts outlive the step.  A tile with
 //       more than C overlaps raises the overflow flag (the step becomes an optimiser no-op, the host regrows).
 //       The LAST CTA to finish (ticket) does the bookkeeping K2 does otherwise.
+#ifndef GI2D_K1_MINBLOCKS
+#define GI2D_K1_MINBLOCKS 2
+#endif
 template <bool kBucket>
-__global__ void __launch_bounds__(kProjThreads)
+__global__ void __launch_bounds__(kProjThreads, GI2D_K1_MINBLOCKS)
 fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_bound,
                    float4 *__restrict__ proj, float4 *__restrict__ grads, ushort4 *__restrict__ boxes,
                    int32_t *__restrict__ tile_count, double *__restrict__ stats, int with_backward,
