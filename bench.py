@@ -490,7 +490,8 @@ def main():
         assert len(mses) == Ke and all(m > 0 for m in mses)
         return Ke * images / dt
 
-    Ke = min(K, 2000)
+    # (at least 500 steps per trial: a 20-step run would time the pipe's fill and drain, not its rate)
+    Ke = min(max(K, 500), 2000)
     _ring = [torch.zeros(fit.stats_buf.numel(), dtype=torch.float64).pin_memory() for _ in range(2)]
     for i in range(4):     # untimed: creates the host pipe, its two device buffers and the bound argument blocks
         fit.wait_host_result(fit.step_from_host(gt_u8_pinned, _ring[i & 1]))
