@@ -154,8 +154,15 @@ struct QuadGauss {
 };
 
 template <int kNQ>
+__device__ __forceinline__ void quad_setup(float4 p0, float4 p1, const QuadLane<kNQ> &ln, QuadGauss<kNQ> &q);
+
+template <int kNQ>
 __device__ __forceinline__ void quad_load(const QuadRecords &s, int t, const QuadLane<kNQ> &ln, QuadGauss<kNQ> &q) {
-    const float4 p0 = s.xyab[t], p1 = s.crgb[t];
+    quad_setup<kNQ>(s.xyab[t], s.crgb[t], ln, q);
+}
+
+template <int kNQ>
+__device__ __forceinline__ void quad_setup(float4 p0, float4 p1, const QuadLane<kNQ> &ln, QuadGauss<kNQ> &q) {
     const f32x2 xx = pk2(p0.x, p0.x), yy = pk2(p0.y, p0.y), aa = pk2(p0.z, p0.z), bb = pk2(p0.w, p0.w);
     const f32x2 cc = pk2(p1.x, p1.x);
     q.r = pk2(p1.y, p1.y);
@@ -211,12 +218,32 @@ __device__ __forceinline__ void quad_forward(const QuadRecords &s, int cnt, cons
     constexpr int kCols = QuadGeom<kNQ>::kCols;
     // (not unrolled: the kernel is instruction-cache bound when several CTAs of an SM sit in different phases --
     // ncu: 0.8 'no instruction' stalls per issue with the compiler's 4x unrolling; 2040x1356 -9 %, 8192^2 -13 %)
+#ifdef GI2D_FWD_PREFETCH
+    // software pipeline: the next entry's mask and record are in flight while this one is evaluated (a warp
+    // that is alone on its scheduler -- the long tile at the end of the grid -- otherwise pays the shared-memory
+    // round trip on top of every Gaussian's dependency chain)
+    if (cnt <= 0) return;
+    unsigned m_next = s.mask[0];
+    float4 p0n = s.xyab[0], p1n = s.crgb[0];
+#pragma unroll 1
+    for (int t = 0; t < cnt; ++t) {
+        const unsigned m = (m_next >> qshift) & ((1u << kNQ) - 1u);
+        const float4 p0 = p0n, p1 = p1n;
+        const int tn = min(t + 1, cnt - 1);
+        m_next = s.mask[tn];
+        p0n = s.xyab[tn];
+        p1n = s.crgb[tn];
+        if (!m) continue;   // warp-uniform
+        QuadGauss<kNQ> q;
+        quad_setup<kNQ>(p0, p1, ln, q);
+#else
 #pragma unroll 1
     for (int t = 0; t < cnt; ++t) {
         const unsigned m = ((unsigned)s.mask[t] >> qshift) & ((1u << kNQ) - 1u);
         if (!m) continue;   // warp-uniform
         QuadGauss<kNQ> q;
         quad_load<kNQ>(s, t, ln, q);
+#endif
 #pragma unroll
         for (int qi = 0; qi < kNQ; ++qi) {
             if (kNQ > 1 && !((m >> qi) & 1u)) continue;   // warp-uniform
