@@ -1281,19 +1281,17 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
                 if (px0 + 8 * (qi % kCols) >= p.img_width || py0 + 8 * (qi / kCols) + 4 * e >= p.img_height)
                     outside |= 1u << (2 * qi + e);
     }
-    // the target pixels are written by no kernel of the step: pull their lines towards L2 while the list is
-    // staged (they are loaded after the forward sweep, so they cost no registers here)
-    if (kHasLoss) {
-        const int bpp = gt ? 12 : 3;
-        const char *base = gt ? (const char *)gt : (const char *)gt_u8;
-#pragma unroll
-        for (int qi = 0; qi < kNQ; ++qi)
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-                if (!((outside >> (2 * qi + e)) & 1u) && (lane & 7) == 0) {
-                    const size_t pix = (size_t)(py0 + 8 * (qi / kCols) + 4 * e) * p.img_width + px0 + 8 * (qi % kCols);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + pix * bpp));
-                }
+    // the target pixels are written by no kernel of the step: pull the tile's 16 rows towards L2 while the list is
+    // staged (they are loaded after the forward sweep, so they cost no registers here).  One lane per row.
+    if (kHasLoss && tid < kTile) {
+        const int row = tile_y * kTile + tid;
+        if (row < p.img_height) {
+            const int bpp = gt ? 12 : 3;
+            const char *base = gt ? (const char *)gt : (const char *)gt_u8;
+            const char *a = base + ((size_t)row * p.img_width + tile_x * kTile) * bpp;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            if (gt) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));   // (a float row is 192 bytes)
+        }
     }
     const double n_isect = __ldcg(stats + GI2D_STAT_ISECTS);
     const int total_cnt = max(0, min(range.y, p.isect_capacity) - range.x);
@@ -1405,20 +1403,21 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
                         tg = u8_to_unit(__ldg(gt_u8 + 3 * pix + 1));
                         tb = u8_to_unit(__ldg(gt_u8 + 3 * pix + 2));
                     }
-                    const float dr = fminf(fmaxf(r, 0.f), 1.f) - tr;
-                    const float dg = fminf(fmaxf(g, 0.f), 1.f) - tg;
-                    const float db = fminf(fmaxf(b, 0.f), 1.f) - tb;
+                    const float kr = fminf(fmaxf(r, 0.f), 1.f), kg = fminf(fmaxf(g, 0.f), 1.f), kb = fminf(fmaxf(b, 0.f), 1.f);
+                    const float dr = kr - tr, dg = kg - tg, db = kb - tb;
+                    // torch.clamp's backward mask 0 <= out <= 1 is "the clamp changed nothing" (false for NaN too)
+                    const bool mr = kr == r, mg = kg == g, mb = kb == b;
                     se += dr * dr + dg * dg + db * db;
                     const float l1 = p.loss_l1_scale;
                     if (l1 != 0.f) {
                         ae += fabsf(dr) + fabsf(dg) + fabsf(db);
-                        wr = (r >= 0.f && r <= 1.f) ? fmaf(l1, (float)((dr > 0.f) - (dr < 0.f)), p.loss_scale * dr) : 0.f;
-                        wgc = (g >= 0.f && g <= 1.f) ? fmaf(l1, (float)((dg > 0.f) - (dg < 0.f)), p.loss_scale * dg) : 0.f;
-                        wb = (b >= 0.f && b <= 1.f) ? fmaf(l1, (float)((db > 0.f) - (db < 0.f)), p.loss_scale * db) : 0.f;
+                        wr = mr ? fmaf(l1, (float)((dr > 0.f) - (dr < 0.f)), p.loss_scale * dr) : 0.f;
+                        wgc = mg ? fmaf(l1, (float)((dg > 0.f) - (dg < 0.f)), p.loss_scale * dg) : 0.f;
+                        wb = mb ? fmaf(l1, (float)((db > 0.f) - (db < 0.f)), p.loss_scale * db) : 0.f;
                     } else {
-                        wr = (r >= 0.f && r <= 1.f) ? p.loss_scale * dr : 0.f;
-                        wgc = (g >= 0.f && g <= 1.f) ? p.loss_scale * dg : 0.f;
-                        wb = (b >= 0.f && b <= 1.f) ? p.loss_scale * db : 0.f;
+                        wr = mr ? p.loss_scale * dr : 0.f;
+                        wgc = mg ? p.loss_scale * dg : 0.f;
+                        wb = mb ? p.loss_scale * db : 0.f;
                     }
                     if (out_img) {
                         out_img[3 * pix] = r;
