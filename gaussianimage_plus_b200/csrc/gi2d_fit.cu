@@ -1281,9 +1281,10 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
                 if (px0 + 8 * (qi % kCols) >= p.img_width || py0 + 8 * (qi / kCols) + 4 * e >= p.img_height)
                     outside |= 1u << (2 * qi + e);
     }
-    // the target pixels are written by no kernel of the step: pull the tile's 16 rows towards L2 while the list is
-    // staged (they are loaded after the forward sweep, so they cost no registers here).  One lane per row.
-    if (kHasLoss && tid < kTile) {
+    // the target pixels are written by no kernel of the step: pull their lines towards L2 while the list is
+    // staged (they are loaded after the forward sweep, so they cost no registers here)
+#ifdef GI2D_PREFETCH_ROWS
+    if (kHasLoss && tid < kTile) {   // one lane per tile row
         const int row = tile_y * kTile + tid;
         if (row < p.img_height) {
             const int bpp = gt ? 12 : 3;
@@ -1293,6 +1294,20 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
             if (gt) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));   // (a float row is 192 bytes)
         }
     }
+#else
+    if (kHasLoss) {
+        const int bpp = gt ? 12 : 3;
+        const char *base = gt ? (const char *)gt : (const char *)gt_u8;
+#pragma unroll
+        for (int qi = 0; qi < kNQ; ++qi)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (!((outside >> (2 * qi + e)) & 1u) && (lane & 7) == 0) {
+                    const size_t pix = (size_t)(py0 + 8 * (qi / kCols) + 4 * e) * p.img_width + px0 + 8 * (qi % kCols);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + pix * bpp));
+                }
+    }
+#endif
     const double n_isect = __ldcg(stats + GI2D_STAT_ISECTS);
     const int total_cnt = max(0, min(range.y, p.isect_capacity) - range.x);
     const int cnt = min(kMaxPerTile, total_cnt);

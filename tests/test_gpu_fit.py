@@ -554,3 +554,55 @@ def test_fit_with_color_norm_matches_oracle(oracle):
         assert np.quantile(d, 0.99) < 2e-3, np.quantile(d, 0.99)
     r = N_(fit.forward()["render"])
     assert r.min() >= 0 and r.max() <= 1
+
+
+def test_bucket_overflow_of_one_tile_is_vetoed_and_regrown(oracle):
+    """Bucketed binning: tile t owns capacity / #tiles rows.  A scene whose Gaussians all sit
+    in ONE tile overflows that bucket long before the total count reaches the capacity: the step must be an
+    optimiser no-op (parameters, step counter untouched), GI2D_STAT_MAX_TILE must tell the host how far to regrow,
+    and after ONE regrow the binning must equal the oracle's bit for bit (incl. the >256-entries-per-tile path)."""
+    from gaussianimage_plus_b200.fit import GaussianImageFitter
+
+    N, H, W = 700, 128, 192                                  # 96 tiles
+    rng = np.random.default_rng(9)
+    xyz = (np.array([40.0, 40.0], np.float32) + rng.uniform(-3, 3, (N, 2))).astype(np.float32)   # all inside tile (2,2)
+    cov = np.tile(np.array([1.0, 0.0, 1.0], np.float32), (N, 1)) + rng.uniform(0, 0.2, (N, 3)).astype(np.float32)
+    cov[:, 1] = 0.0
+    bound = np.zeros((N, 3), np.float32)
+    rgb = rng.uniform(0, 0.01, (N, 3)).astype(np.float32)
+    gt = synth.target_image(H, W, seed=9)
+    fit = GaussianImageFitter(N, H, W, device=DEV, use_graph=False, isect_capacity=96 * 64)   # 64 rows per tile
+    assert fit.bucket_cap == 64
+    for dst, src in ((fit._xyz, xyz), (fit._cov2d, cov), (fit.cholesky_bound, bound), (fit._features_dc, rgb)):
+        dst.copy_(torch.from_numpy(src))
+    fit.set_target(torch.from_numpy(gt))
+    fit._bind()
+    x0 = fit._xyz.clone()
+    fit.train_iter()
+    fit.train_iter()
+    st = fit.stats()
+    tb = oracle.tile_bounds(H, W)
+    xys, depths, radii, conics, nth = oracle.project_cov_fwd(xyz, cov + bound, H, W, tb)
+    total, cum, ids, gids, ids_s, gids_s, bins = oracle.bin_and_sort(xys, depths, radii, nth, tb)
+    per_tile = np.bincount((ids_s >> 32).astype(np.int64), minlength=tb[0] * tb[1])
+    assert per_tile.max() > 256 and total < fit.isect_capacity          # one bucket overflows, the total would fit
+    assert st["overflow"] and st["step"] == 0 and st["num_intersects"] == total
+    assert st["max_tile"] == per_tile.max()
+    fit.sync_params()
+    assert torch.equal(x0, fit._xyz)                                     # the vetoed steps did not touch anything
+    st = fit.catch_up(st)                                                # regrow (from max_tile) + re-run the two lost iterations
+    assert st["step"] == 2 and not st["overflow"]
+    assert fit.bucket_cap >= per_tile.max()
+    # the binning of a fresh forward of the START parameters == the oracle's, bit for bit
+    fit2 = GaussianImageFitter(N, H, W, device=DEV, use_graph=False, isect_capacity=fit.isect_capacity)
+    for dst, src in ((fit2._xyz, xyz), (fit2._cov2d, cov), (fit2.cholesky_bound, bound), (fit2._features_dc, rgb)):
+        dst.copy_(torch.from_numpy(src))
+    fit2.set_target(torch.from_numpy(gt))
+    fit2._bind()
+    fit2.forward()
+    st2 = fit2.stats()
+    assert not st2["overflow"] and st2["num_intersects"] == total
+    keys = N_(fit2.sorted_keys[:total])
+    np.testing.assert_array_equal(keys >> 32, ids_s >> 32)
+    np.testing.assert_array_equal((keys & 0xFFFFFFFF).astype(np.int32), gids_s)
+    np.testing.assert_array_equal(N_(fit2.tile_bins), bins)
