@@ -327,7 +327,9 @@ def bin_sort(num_points, xys, depths, radii, tile_bounds, radius_clip=1.0) -> Bi
         _lib.check(lib.gi2d_bin_sort(n, _p(xys), _p(depths), _p(radii), tx, ty, float(radius_clip), cap,
                                      _p(res.isect_ids_sorted), _p(res.gaussian_ids_sorted), _p(res.tile_bins),
                                      _p(res.info), _p(ws), ws.numel(), _stream(dev)), "bin_sort")
-        ring = _BIN_RING.setdefault(idx, [[torch.zeros(3, dtype=i32).pin_memory() for _ in range(8)], 0])
+        ring = _BIN_RING.get(idx)
+        if ring is None:   # (NOT setdefault(idx, [...]): its argument would be built -- 8 pinned allocations -- on every call)
+            ring = _BIN_RING[idx] = [[torch.zeros(3, dtype=i32).pin_memory() for _ in range(8)], 0]
         res._host = ring[0][ring[1] & 7]     # (pinned allocations cost ~50 us each: a small ring, reused)
         ring[1] += 1
         res._host.copy_(res.info, non_blocking=True)
