@@ -426,6 +426,23 @@ __device__ __forceinline__ void quad_backward4(const QuadRecords &s, const int *
         const float frpt = (float)rpt;
         int off = (row * kTile + col) * 4;
         const int zoff = (kRows * kTile + col) * 4, doff = rpt * kTile * 4;
+#ifdef GI2D_BWD_SINGLE_ACC
+        // (variant: ONE accumulator set -- 16 registers less, one dependency chain per warp)
+        GroupAcc A{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+        const GroupAcc B{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+#pragma unroll 1
+        for (int i = 0; i < T; ++i) {
+            bool y0 = in0, y1 = in1;
+            if (kGuard) {
+                const bool ra = row < rows_inside;
+                y0 = in0 && ra; y1 = in1 && ra;
+                row += rpt;
+            }
+            group_trip<kRows, kGuard>(A, wg_base, off, zoff, fy, y0, y1, p0.y, p1.x, dx, adx, bdx, cr, cg, cb);
+            off += doff;
+            fy += frpt;
+        }
+#else
         // two trips per loop iteration with separate accumulators: two independent dependency chains per warp
         GroupAcc A{0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull}, B = A;
         int i = 0;
@@ -451,6 +468,7 @@ __device__ __forceinline__ void quad_backward4(const QuadRecords &s, const int *
             }
             group_trip<kRows, kGuard>(A, wg_base, off, zoff, fy, y0, y1, p0.y, p1.x, dx, adx, bdx, cr, cg, cb);
         }
+#endif
         float l0, l1, m0, m1, acc[8];
         unpk2(A.ax, l0, l1); unpk2(B.ax, m0, m1); const float sx = -((l0 + l1) + (m0 + m1));
         unpk2(A.ay, l0, l1); unpk2(B.ay, m0, m1); const float sy = -((l0 + l1) + (m0 + m1));
