@@ -158,8 +158,10 @@ Plan make_plan(const gi2d_fit_params &p) {
     pl.smem_scan = pl.num_tiles <= kMaxSmemTiles;
     // heaviest-first tile order: only where the grid is a wave or two (beyond, the tail is a few per cent and a
     // band of a tile-row split keeps its launch order)
-    // bucketed binning: everywhere except the tile-row exchange (whose owners scatter records across GPUs) and
-    // the round-1 rasterizer; needs at least 8 rows per tile (tiny capacities -- overflow tests -- keep the scan)
+    // bucketed binning: everywhere except the round-1 rasterizer and the tile-row split (measured at 8192^2 / 1M
+    // over 8 GPUs: a bucketed band step that walks all 1M boxes through the warp-cooperative placement takes
+    // 274-293 us, count + scan + placement 249-261 us: seven of eight warps find nothing to place); needs at
+    // least 8 rows per tile (tiny capacities -- overflow tests -- keep the scan)
     pl.bucket_cap = 0;
     if (p.external_optimizer != 2 && bucket_enabled() && pl.num_tiles > 0 && p.isect_capacity / pl.num_tiles >= 8)
         pl.bucket_cap = p.isect_capacity / pl.num_tiles;
@@ -507,6 +509,91 @@ __device__ __forceinline__ void k1_order_cta(const gi2d_fit_params &p, int with_
     }
 }
 
+// Placement of a warp's intersections into the buckets + the ticket (shared by the bucketed K1 and the tile-row
+// placement kernel).  Every thread of the CTA calls it, warp-converged; (x0,y0,x1,y1) is the thread's tile box
+// (empty: x1 == x0), (rec0, rec1) its Gaussian's record, g its Gaussian id (lane-consecutive within the warp).
+// s_isect: kProjThreads / 32 ints of shared memory; *s_ovf must have been zeroed before the CTA's last barrier.
+__device__ __forceinline__ void bucket_place_and_ticket(const gi2d_fit_params &p, int with_backward,
+                                                        double *__restrict__ stats, int bank, const BookInputs &bk,
+                                                        int g, int x0, int y0, int x1, int y1, float4 rec0,
+                                                        float4 rec1, int32_t *__restrict__ tile_count,
+                                                        int32_t *__restrict__ tile_fill,
+                                                        uint64_t *__restrict__ keys_out,
+                                                        float4 *__restrict__ records, int bucket_cap, int *s_isect,
+                                                        int *s_ovf) {
+    const int lane = threadIdx.x & 31;
+    int32_t *cursor = bank ? tile_fill : tile_count;
+    const int bw = x1 - x0;
+    const int n = bw * (y1 - y0);
+    const int incl = warp_scan_inclusive(n);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int max_fill = 0;
+    for (int batch = 0; batch < total; batch += 256) {
+        int slot[8], tile[8], owner[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            slot[k] = 0; tile[k] = 0; owner[k] = 0;
+            if (batch + 32 * k < total) {   // warp-uniform
+                const int it = batch + 32 * k + lane;
+                int lo = 0;   // owner = smallest j with incl_j > it
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+                    if (probe <= it) lo += step;
+                }
+                const int ow = min(lo, 31);
+                const int o_incl = __shfl_sync(0xffffffffu, incl, ow);
+                const int o_n = __shfl_sync(0xffffffffu, n, ow);
+                const int o_w = __shfl_sync(0xffffffffu, bw, ow);
+                const int o_x0 = __shfl_sync(0xffffffffu, x0, ow);
+                const int o_y0 = __shfl_sync(0xffffffffu, y0, ow);
+                owner[k] = ow;
+                if (it < total) {
+                    const int kk = it - (o_incl - o_n);
+                    const int ry = kk / o_w;
+                    tile[k] = (o_y0 + ry) * p.tiles_x + o_x0 + (kk - ry * o_w);
+                    GI2D_CHECK(stats, tile[k] >= 0 && tile[k] < p.tiles_x * p.tiles_y);
+                    slot[k] = atomicAdd(cursor + tile[k], 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (batch + 32 * k < total) {   // warp-uniform
+                const int ow = owner[k];
+                float4 q0, q1;
+                q0.x = __shfl_sync(0xffffffffu, rec0.x, ow); q0.y = __shfl_sync(0xffffffffu, rec0.y, ow);
+                q0.z = __shfl_sync(0xffffffffu, rec0.z, ow); q0.w = __shfl_sync(0xffffffffu, rec0.w, ow);
+                q1.x = __shfl_sync(0xffffffffu, rec1.x, ow); q1.y = __shfl_sync(0xffffffffu, rec1.y, ow);
+                q1.z = __shfl_sync(0xffffffffu, rec1.z, ow); q1.w = __shfl_sync(0xffffffffu, rec1.w, ow);
+                if (batch + 32 * k + lane < total) {
+                    if (slot[k] < bucket_cap) {
+                        const size_t pos = (size_t)tile[k] * bucket_cap + slot[k];
+                        keys_out[pos] = ((uint64_t)(uint32_t)tile[k] << 32) | (uint32_t)(g - lane + ow);
+                        records[2 * pos] = q0;
+                        records[2 * pos + 1] = q1;
+                    }
+                    max_fill = max(max_fill, slot[k] + 1);
+                }
+            }
+        }
+    }
+    // ---- ticket: the last CTA to get here does the bookkeeping of the step in flight (k1_ticket)
+    max_fill = __reduce_max_sync(0xffffffffu, max_fill);
+    if (lane == 0) s_isect[threadIdx.x >> 5] = total;
+    if (lane == 0 && max_fill > bucket_cap) {   // (rare) largest count seen, for the host's regrow
+        const unsigned long long old =
+            atomicMax(reinterpret_cast<unsigned long long *>(stats + kStatMaxFillAcc), (unsigned long long)max_fill);
+        if (old == 0ull) *s_ovf = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long mine_isects = 0ull;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mine_isects += (unsigned long long)s_isect[w];
+        k1_ticket(p, with_backward, stats, bank, mine_isects, *s_ovf != 0, bk);
+    }
+}
+
 // ------------------------------------------------------------------------------------ K1
 // Optimiser of the PREVIOUS step + projection of THIS step, per Gaussian, in one launch: the thread
 // that owns Gaussian g first applies projection-backward + Adam to it when a gradient is pending
@@ -540,7 +627,6 @@ fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_
     __shared__ int s_isect[kProjThreads / 32];
     pdl_launch_dependents();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
     if (kBucket && threadIdx.x == 0) s_ovf = 0;
     const bool in_cap = g < p.num_points;   // a row of the arrays (the live count comes back with the flags below)
     pdl_wait();  // the previous step's rasterizer wrote grads (and read proj, and zeroed the tile counters)
@@ -630,77 +716,9 @@ fit_project_kernel(gi2d_fit_params p, AdamPtrs a, const float *__restrict__ cov_
             }
         return;
     }
-    // ---- placement (warp-converged from here on)
-    int32_t *cursor = bank ? tile_fill : tile_count;
-    const int bw = x1 - x0;
-    const int n = bw * (y1 - y0);
-    const int incl = warp_scan_inclusive(n);
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int max_fill = 0;
-    for (int batch = 0; batch < total; batch += 256) {
-        int slot[8], tile[8], owner[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            slot[k] = 0; tile[k] = 0; owner[k] = 0;
-            if (batch + 32 * k < total) {   // warp-uniform
-                const int it = batch + 32 * k + lane;
-                int lo = 0;   // owner = smallest j with incl_j > it
-#pragma unroll
-                for (int step = 16; step >= 1; step >>= 1) {
-                    const int probe = __shfl_sync(0xffffffffu, incl, lo + step - 1);
-                    if (probe <= it) lo += step;
-                }
-                const int ow = min(lo, 31);
-                const int o_incl = __shfl_sync(0xffffffffu, incl, ow);
-                const int o_n = __shfl_sync(0xffffffffu, n, ow);
-                const int o_w = __shfl_sync(0xffffffffu, bw, ow);
-                const int o_x0 = __shfl_sync(0xffffffffu, x0, ow);
-                const int o_y0 = __shfl_sync(0xffffffffu, y0, ow);
-                owner[k] = ow;
-                if (it < total) {
-                    const int kk = it - (o_incl - o_n);
-                    const int ry = kk / o_w;
-                    tile[k] = (o_y0 + ry) * p.tiles_x + o_x0 + (kk - ry * o_w);
-                    GI2D_CHECK(stats, tile[k] >= 0 && tile[k] < p.tiles_x * p.tiles_y);
-                    slot[k] = atomicAdd(cursor + tile[k], 1);
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (batch + 32 * k < total) {   // warp-uniform
-                const int ow = owner[k];
-                float4 q0, q1;
-                q0.x = __shfl_sync(0xffffffffu, rec0.x, ow); q0.y = __shfl_sync(0xffffffffu, rec0.y, ow);
-                q0.z = __shfl_sync(0xffffffffu, rec0.z, ow); q0.w = __shfl_sync(0xffffffffu, rec0.w, ow);
-                q1.x = __shfl_sync(0xffffffffu, rec1.x, ow); q1.y = __shfl_sync(0xffffffffu, rec1.y, ow);
-                q1.z = __shfl_sync(0xffffffffu, rec1.z, ow); q1.w = __shfl_sync(0xffffffffu, rec1.w, ow);
-                if (batch + 32 * k + lane < total) {
-                    if (slot[k] < bucket_cap) {
-                        const size_t pos = (size_t)tile[k] * bucket_cap + slot[k];
-                        keys_out[pos] = ((uint64_t)(uint32_t)tile[k] << 32) | (uint32_t)(g - lane + ow);
-                        records[2 * pos] = q0;
-                        records[2 * pos + 1] = q1;
-                    }
-                    max_fill = max(max_fill, slot[k] + 1);
-                }
-            }
-        }
-    }
-    // ---- ticket: the last CTA to get here does the bookkeeping of the step in flight (k1_ticket)
-    max_fill = __reduce_max_sync(0xffffffffu, max_fill);
-    if (lane == 0) s_isect[threadIdx.x >> 5] = total;
-    if (lane == 0 && max_fill > bucket_cap) {   // (rare) largest count seen, for the host's regrow
-        const unsigned long long old =
-            atomicMax(reinterpret_cast<unsigned long long *>(stats + kStatMaxFillAcc), (unsigned long long)max_fill);
-        if (old == 0ull) s_ovf = 1;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long mine_isects = 0ull;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mine_isects += (unsigned long long)s_isect[w];
-        k1_ticket(p, with_backward, stats, bank, mine_isects, s_ovf != 0, bk);
-    }
+    // ---- placement + ticket (warp-converged from here on)
+    bucket_place_and_ticket(p, with_backward, stats, bank, bk, g, x0, y0, x1, y1, rec0, rec1, tile_count, tile_fill,
+                            keys_out, records, bucket_cap, s_isect, &s_ovf);
 }
 
 // Exclusive scan of count[0..T) into shared memory, T <= kMaxSmemTiles = kThreads * kPer.

@@ -371,9 +371,13 @@ class TileRowFit:
         st = self.fit.stats()
         while st["step"] < self.fit._expected_step:
             lost = self.fit._expected_step - st["step"]
-            if st["num_intersects"] > self.fit.isect_capacity:
+            # this rank's band overflowed: the whole buffer (scan + placement) or one tile's bucket (max_tile is set
+            # by the band step only when a bucket of THIS rank was too small)
+            if st["num_intersects"] > self.fit.isect_capacity or st.get("max_tile", 0) > 0:
                 expected = self.fit._expected_step
-                self.fit._capacity_hint = int(st["num_intersects"] * 2)
+                tiles = self.fit.tile_bounds[0] * self.fit.tile_bounds[1]
+                self.fit._capacity_hint = max(int(st["num_intersects"] * (2 if st.get("max_tile", 0) else 4)),
+                                              int(st.get("max_tile", 0) * 1.25 + 8) * tiles)
                 self.fit._step0 = st["step"]
                 self.fit._alloc_state(zero_moments=False)
                 self.fit._bind()
