@@ -713,7 +713,7 @@ def tilerow_leg(torch, dist, synth, _lib, dev, rank, world, name, K, Wm, exchang
     tr.train_iters(Wm)
     ms = timed(tr.train_iters)
     tr.check()
-    st = tr.catch_up() if False else tr.stats()
+    st = tr.stats()
     assert st["step"] == S, (st["step"], S)
     # in-run parity: the PSNR of the single-GPU fit at equal steps; every rank holds the owners' records bit for bit
     assert abs(st["psnr"] - st1["psnr"]) < 0.01, (st["psnr"], st1["psnr"])
