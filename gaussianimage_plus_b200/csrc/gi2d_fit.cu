@@ -1227,9 +1227,21 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     constexpr int kRegionRows = kTile / kRegions;
     __shared__ QuadRecords sg;
     __shared__ int s_ids[kMaxPerTile];
-    __shared__ __align__(16) int s_sort[kMaxPerTile + 4];
-    __shared__ __align__(16) WarpGrad<kRegionRows> s_wg[kRegions];
-    __shared__ unsigned char s_list[kWarps][kMaxPerTile];
+    // the ids being ranked share their shared memory with dL/d(out) and the backward's lists: the rank sort is over
+    // (block barrier) before either exists.  Up to kSortMax entries of a tile are ranked in shared memory.
+    constexpr int kSortMax = 960;
+    struct BwdShared {
+        WarpGrad<kRegionRows> wg[kRegions];
+        unsigned char list[kWarps][kMaxPerTile];
+    };
+    union SortOrBwd {
+        int sort[kSortMax + 4];
+        BwdShared bwd;
+    };
+    __shared__ __align__(16) SortOrBwd s_u;
+    int *s_sort = s_u.sort;
+    auto &s_wg = s_u.bwd.wg;
+    auto &s_list = s_u.bwd.list;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_dependents();
     // the warp's first quadrant (column, row) and its bit in the reach masks
@@ -1369,8 +1381,34 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
             // (keys are rebuilt from the tile id: nobody re-reads sorted_keys of this tile after the barrier)
             if (kWriteBack && rank != e) sorted_keys[range.x + rank] = ((uint64_t)(uint32_t)tile_id << 32) | (uint32_t)id;
         }
+    } else if (total_cnt <= kSortMax) {
+        // more than the 256 entries that get staged (densification clusters new Gaussians: 150-400 per tile were
+        // seen at 768x512): rank ALL ids in shared memory, stage the 256 smallest (forward.cu:673 truncates the
+        // sorted list), write the fully sorted keys back through the scratch array
+        for (int e = tid; e < total_cnt; e += kThreads) s_sort[e] = (int)(uint32_t)__ldcg(sorted_keys + range.x + e);
+        if (tid < 4) s_sort[total_cnt + tid] = 0x7fffffff;
+        __syncthreads();
+        for (int e = tid; e < total_cnt; e += kThreads) {
+            const int id = s_sort[e];
+            int rank = 0;
+            for (int jj = 0; jj < total_cnt; jj += 4) {
+                const int4 o = *reinterpret_cast<const int4 *>(s_sort + jj);
+                rank += (o.x < id) + (o.y < id) + (o.z < id) + (o.w < id);
+            }
+            GI2D_CHECK(stats, rank >= 0 && rank < total_cnt && id >= 0 && id < p.num_points);
+            keys_tmp[range.x + rank] = ((uint64_t)(uint32_t)tile_id << 32) | (uint32_t)id;
+            if (rank < kMaxPerTile) {
+                stage_quad(sg, rank, __ldcg(records + 2 * (size_t)(range.x + e)),
+                           __ldcg(records + 2 * (size_t)(range.x + e) + 1), tx0, ty0);
+                if (kHasBwd) s_ids[rank] = id;
+            }
+        }
+        if (kWriteBack) {
+            __syncthreads();
+            for (int e = tid; e < total_cnt; e += kThreads) sorted_keys[range.x + e] = __ldcg(keys_tmp + range.x + e);
+        }
     } else {
-        // more than 256 entries (a degenerate scene): full rank sort straight from global memory
+        // beyond that (a degenerate scene): full rank sort straight from global memory
         for (int e = tid; e < total_cnt; e += kThreads) {
             const uint64_t key = __ldcg(sorted_keys + range.x + e);
             const int id = (int)(uint32_t)key;

@@ -177,8 +177,9 @@ class GaussianImageFitter:
             self._t_v = {k: torch.zeros_like(t) for k, t in self._raw_params().items()}
         tiles = self.tile_bounds[0] * self.tile_bounds[1]
         # default: 32 intersections per Gaussian, and -- for the bucketed binning, whose tiles each own capacity / #tiles
-        # rows -- at least the 256 entries per tile the rasterizer stages (densification clusters new Gaussians)
-        cap = self._capacity_hint or max(1 << 16, 32 * n, 256 * tiles)
+        # rows -- at least 512 per tile, twice what the rasterizer stages (densification clusters new Gaussians: tiles
+        # with 150-300 entries were seen at 768x512; a full bucket costs a regrow and the re-run of the lost iterations)
+        cap = self._capacity_hint or max(1 << 16, 32 * n, 512 * tiles)
         self.isect_capacity = int(min(cap, max(n, 1) * tiles, 2 ** 31 - 1024))
         if not getattr(self, "_keep_exchange_buffers", False):   # (parallel.TileRowFit homes them in peer memory)
             self.grads = torch.zeros(n, 8, **f)
@@ -800,7 +801,7 @@ class GaussianImageFitter:
     # ------------------------------------------------------------------ the training loop
     def fit(self, iterations: int, max_num_points: Optional[int] = None, prune_iter: int = 100,
             grow_iter: int = 5000, adaptive_add: bool = True, prune: bool = True, callback=None,
-            check_iter: int = 1000) -> dict:
+            check_iter: int = 250) -> dict:
         """`SimpleTrainer2d.train` (train.py:120-176) without its per-iteration host work: every iteration is one
         graph replay; the best state is snapshotted by the kernels; pruning (every `prune_iter`) compacts the model
         on the device with no read-back; densification (every `grow_iter`) selects and appends on the device after
