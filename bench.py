@@ -53,6 +53,17 @@ def workload_string(name, H, W, N, preroll):
     return f"{name}: {W}x{H}, {N} Gaussians, covariance model, L2, {LR_NOTE}, state = iteration {preroll} of the fit"
 
 
+def bench_config(args, H, W, N, world):
+    """`config` of the JSON line -- the SAME dict in both arms (the reference arm runs "on your arm's config"): the
+    workload and the GPU arm's measurement protocol (L2 handling, where the target lives, how N > 1 is used)."""
+    return {"workload": workload_string(args.workload, H, W, N, args.preroll),
+            "target": "u8 HWC resident in HBM (value); pinned host u8 copied every step (e2e)",
+            "mode": args.mode, "cov_scale": args.cov_scale, "preroll_iterations": args.preroll,
+            "l2": "flushed between timed steps (256 MiB fill); value_l2_warm = back-to-back replay",
+            "parallelism": "one image per GPU, no collective" + (
+                "; + one 8192^2 / 1M image split by tile rows over the ranks (tilerow)" if world > 1 else "")}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,7 +175,7 @@ def run_reference(args):
         "impl": "reference", "metric": "fit_iters_per_s", "value": rate, "unit": "it/s", "n_gpus": args.gpus,
         "steps": n, "warmup": W_, "ms_per_step": 1000.0 / rate, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_string(args.workload, H, W, N, args.preroll), "cov_scale": args.cov_scale},
+        "config": bench_config(args, H, W, N, args.gpus),
         "cpu_baseline": {"value": rate, "unit": "it/s", "cores": cores, "kind": "port",
                          "sample": f"{n} full train_iter steps of the same workload ({el:.2f} s) after {args.preroll} "
                                    f"untimed pre-roll + {W_} warm-up iterations of the same port ({t_pre:.1f} s)"},
@@ -578,13 +589,7 @@ def main():
             "metric": "fit_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_string(args.workload, H, W, N, args.preroll),
-                       "target": "u8 HWC resident in HBM (value); pinned host u8 copied every step (e2e)",
-                       "mode": args.mode, "cov_scale": args.cov_scale, "preroll_iterations": args.preroll,
-                       "l2": "flushed between timed steps (256 MiB fill); value_l2_warm = back-to-back replay",
-                       "parallelism": "one image per GPU, no collective" + (
-                           "; + one 8192^2 / 1M image split by tile rows over the ranks (tilerow)" if world > 1 else ""),
-                       "host_cores_per_rank": pinned_cores},
+            "config": bench_config(args, H, W, N, world), "host_cores_per_rank": pinned_cores,
             "value_l2_warm": K * images / (warm_ms * K * 1e-3),
             "ms_per_step_l2_warm": warm_ms, "ms_per_step_l2_warm_single_step_graphs": warm1_ms,
             "value_l2_warm_init_state": images * 1e3 / init_warm_ms,
