@@ -218,6 +218,41 @@ __device__ __forceinline__ void quad_forward(const QuadRecords &s, int cnt, cons
     constexpr int kCols = QuadGeom<kNQ>::kCols;
     // (not unrolled: the kernel is instruction-cache bound when several CTAs of an SM sit in different phases --
     // ncu: 0.8 'no instruction' stalls per issue with the compiler's 4x unrolling; 2040x1356 -9 %, 8192^2 -13 %)
+#ifndef GI2D_FWD_ILP
+#define GI2D_FWD_ILP 64   // list length from which the 4-warp kernel's forward sweep takes two entries per trip (0: never)
+#endif
+#if GI2D_FWD_ILP > 0
+    // long lists (densification clusters new Gaussians: one tile can hold 10x the average, and its CTA ends up
+    // alone on its SM, one warp per scheduler, paying every Gaussian's ~150-cycle dependency chain in full): two
+    // entries per trip, both evaluated whenever either reaches the quadrant (outside its reach box a Gaussian's
+    // weight is 0 by the alpha test, and acc + 0 * colour == acc exactly), accumulated in list order
+    // (measured with one 170-entry tile among 1536: rasterizer 35.4 -> 31.1 us; no change in the steady state)
+    if (kNQ == 1 && cnt > GI2D_FWD_ILP) {
+        int t = 0;
+#pragma unroll 1
+        for (; t + 1 < cnt; t += 2) {
+            const unsigned m0 = ((unsigned)s.mask[t] >> qshift) & 1u, m1 = ((unsigned)s.mask[t + 1] >> qshift) & 1u;
+            if (!(m0 | m1)) continue;   // warp-uniform
+            QuadGauss<kNQ> q0, q1;
+            quad_setup<kNQ>(s.xyab[t], s.crgb[t], ln, q0);
+            quad_setup<kNQ>(s.xyab[t + 1], s.crgb[t + 1], ln, q1);
+            const f32x2 w0 = pair_weight(q0.dx[0], q0.adx[0], q0.bdx[0], q0.dy[0], q0.dycdy[0]);
+            const f32x2 w1 = pair_weight(q1.dx[0], q1.adx[0], q1.bdx[0], q1.dy[0], q1.dycdy[0]);
+            accR[0] = fma2(w1, q1.r, fma2(w0, q0.r, accR[0]));
+            accG[0] = fma2(w1, q1.g, fma2(w0, q0.g, accG[0]));
+            accB[0] = fma2(w1, q1.b, fma2(w0, q0.b, accB[0]));
+        }
+        if (t < cnt && (((unsigned)s.mask[t] >> qshift) & 1u)) {
+            QuadGauss<kNQ> q;
+            quad_load<kNQ>(s, t, ln, q);
+            const f32x2 w = pair_weight(q.dx[0], q.adx[0], q.bdx[0], q.dy[0], q.dycdy[0]);
+            accR[0] = fma2(w, q.r, accR[0]);
+            accG[0] = fma2(w, q.g, accG[0]);
+            accB[0] = fma2(w, q.b, accB[0]);
+        }
+        return;
+    }
+#endif
 #ifdef GI2D_FWD_PREFETCH
     // software pipeline: the next entry's mask and record are in flight while this one is evaluated (a warp
     // that is alone on its scheduler -- the long tile at the end of the grid -- otherwise pays the shared-memory
