@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 from gaussianimage_plus_b200 import synth
-from gaussianimage_plus_b200.codec import FusedQuantizedTrainer, QuantizedGaussianImage
+from gaussianimage_plus_b200.codec import FusedQuantizedTrainer, KernelQuantizedTrainer, QuantizedGaussianImage
 from gaussianimage_plus_b200.fit import GaussianImageFitter
 from gaussianimage_plus_b200.parallel import gather_metrics, shard_images
 
@@ -34,7 +34,9 @@ ap.add_argument("--grow-iter", type=int, default=1000)
 ap.add_argument("--qat", type=int, default=200)
 ap.add_argument("--color-norm", action="store_true")
 ap.add_argument("--qat-operator-path", action="store_true", help="quantisation-aware steps on the autograd operator "
-                "path instead of the fused, graph-captured FusedQuantizedTrainer")
+                "path instead of the kernel trainer")
+ap.add_argument("--qat-torch-graph", action="store_true", help="round 1's FusedQuantizedTrainer (torch quantiser modules "
+                "+ torch.optim.Adam replayed from a graph) instead of KernelQuantizedTrainer")
 args = ap.parse_args()
 
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -69,7 +71,7 @@ for i in shard_images(args.images, world, rank):
                 _, _, _, _, qpsnr = q.train_iter_quantize(gt_u8)
                 q_first = qpsnr if q_first is None else q_first
         else:
-            q = FusedQuantizedTrainer.from_fitter(fit, best=False)
+            q = (FusedQuantizedTrainer if args.qat_torch_graph else KernelQuantizedTrainer).from_fitter(fit, best=False)
             q.set_target(gt_u8)
             t0 = time.perf_counter()
             q.train_iter_quantize()
