@@ -1225,6 +1225,15 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     constexpr bool kTileWide = kWarps == 4;         // backward region: the whole tile, groups dealt to the warps
     constexpr int kRegions = kTileWide ? 1 : kWarps;
     constexpr int kRegionRows = kTile / kRegions;
+    // 4 warps per tile: ONE list for the CTA, built cooperatively while the entries are staged (each entry's sweep
+    // shape is computed once and packed; a shared-memory counter per trip-count bucket hands out list slots) instead
+    // of every warp building its own copy with ballots: +1 % at 768x512, -9 % kernel time when one tile holds 170
+    // entries.  (-DGI2D_NO_WIDE_LIST: the per-warp ballot lists, as the 1- and 2-warp variants use.)
+#ifndef GI2D_NO_WIDE_LIST
+    constexpr bool kWideList = kTileWide && (kMode == RasterMode::Fit || kMode == RasterMode::FitBackward);
+#else
+    constexpr bool kWideList = false;
+#endif
     __shared__ QuadRecords sg;
     __shared__ int s_ids[kMaxPerTile];
     // the ids being ranked share their shared memory with dL/d(out) and the backward's lists: the rank sort is over
@@ -1244,6 +1253,7 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     auto &s_list = s_u.bwd.list;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_launch_dependents();
+    if (kWideList && tid < 4) sg.bucket_count[tid] = 0;   // (visible after the first block barrier of the staging)
     // the warp's first quadrant (column, row) and its bit in the reach masks
     const int qcol0 = kWarps == 4 ? (warp & 1) : 0;
     const int qrow0 = kWarps == 4 ? (warp >> 1) : (kWarps == 2 ? warp : 0);
@@ -1376,7 +1386,7 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
                 rank += (o.x < id) + (o.y < id) + (o.z < id) + (o.w < id);
             }
             GI2D_CHECK(stats, rank >= 0 && rank < cnt && id >= 0 && id < p.num_points);
-            stage_quad(sg, rank, r0, r1, tx0, ty0);
+            if (kWideList) stage_quad_wide(sg, rank, r0, r1, tx0, ty0); else stage_quad(sg, rank, r0, r1, tx0, ty0);
             if (kHasBwd) s_ids[rank] = id;
             // (keys are rebuilt from the tile id: nobody re-reads sorted_keys of this tile after the barrier)
             if (kWriteBack && rank != e) sorted_keys[range.x + rank] = ((uint64_t)(uint32_t)tile_id << 32) | (uint32_t)id;
@@ -1398,8 +1408,8 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
             GI2D_CHECK(stats, rank >= 0 && rank < total_cnt && id >= 0 && id < p.num_points);
             keys_tmp[range.x + rank] = ((uint64_t)(uint32_t)tile_id << 32) | (uint32_t)id;
             if (rank < kMaxPerTile) {
-                stage_quad(sg, rank, __ldcg(records + 2 * (size_t)(range.x + e)),
-                           __ldcg(records + 2 * (size_t)(range.x + e) + 1), tx0, ty0);
+                const float4 q0 = __ldcg(records + 2 * (size_t)(range.x + e)), q1 = __ldcg(records + 2 * (size_t)(range.x + e) + 1);
+                if (kWideList) stage_quad_wide(sg, rank, q0, q1, tx0, ty0); else stage_quad(sg, rank, q0, q1, tx0, ty0);
                 if (kHasBwd) s_ids[rank] = id;
             }
         }
@@ -1409,6 +1419,7 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
         }
     } else {
         // beyond that (a degenerate scene): full rank sort straight from global memory
+        if (kWideList) __syncthreads();   // (the bucket counters were zeroed by four threads)
         for (int e = tid; e < total_cnt; e += kThreads) {
             const uint64_t key = __ldcg(sorted_keys + range.x + e);
             const int id = (int)(uint32_t)key;
@@ -1417,8 +1428,8 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
             GI2D_CHECK(stats, rank >= 0 && rank < total_cnt && (int)(key >> 32) == tile_id);
             keys_tmp[range.x + rank] = key;
             if (rank < kMaxPerTile) {
-                stage_quad(sg, rank, __ldcg(records + 2 * (size_t)(range.x + e)),
-                           __ldcg(records + 2 * (size_t)(range.x + e) + 1), tx0, ty0);
+                const float4 q0 = __ldcg(records + 2 * (size_t)(range.x + e)), q1 = __ldcg(records + 2 * (size_t)(range.x + e) + 1);
+                if (kWideList) stage_quad_wide(sg, rank, q0, q1, tx0, ty0); else stage_quad(sg, rank, q0, q1, tx0, ty0);
                 if (kHasBwd) s_ids[rank] = id;
             }
         }
@@ -1428,6 +1439,8 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
         }
     }
     __syncthreads();
+    int n_wide = 0;
+    if (kWideList) n_wide = finish_wide_list(sg, cnt, s_list[0]);   // (read after the barrier that precedes the backward)
     // ---- forward: lane = pixel pairs of the warp's quadrants
     f32x2 accR[kNQ], accG[kNQ], accB[kNQ];
 #pragma unroll
@@ -1524,9 +1537,9 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     if (!kHasBwd || cnt == 0) return;   // (CTA-uniform)
     // ---- backward: four Gaussians per warp at a time (gi2d_raster_quad.cuh, quad_backward4)
     // the staged Gaussians that can reach the region, ascending (every warp builds the list it walks)
-    unsigned char *list = s_list[warp];
+    unsigned char *list = s_list[kWideList ? 0 : warp];
     const unsigned region_bits = kTileWide ? 0xFu : (((1u << kNQ) - 1u) << qshift);
-    const int n = build_group_list<kRegionRows>(sg, cnt, region_bits, region_row0, list);
+    const int n = kWideList ? n_wide : build_group_list<kRegionRows>(sg, cnt, region_bits, region_row0, list);
     if (lane < kTile && (!kTileWide || warp == 0)) {   // the all-zero row a group reads past its own rows
         wg.v[0][kRegionRows][lane] = 0.f;
         wg.v[1][kRegionRows][lane] = 0.f;
@@ -1537,10 +1550,10 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
     const int region_py0 = tile_y * kTile + region_row0;
     const int first_group = kTileWide ? warp : 0, group_stride = kTileWide ? kWarps : 1;
     if (full_tile)
-        quad_backward4<kRegionRows, false>(sg, s_ids, list, n, first_group, group_stride, tile_x * kTile,
+        quad_backward4<kRegionRows, false, kWideList>(sg, s_ids, list, n, first_group, group_stride, tile_x * kTile,
                                            region_py0, region_row0, p.img_width, kRegionRows, wg, grads);
     else
-        quad_backward4<kRegionRows, true>(sg, s_ids, list, n, first_group, group_stride, tile_x * kTile,
+        quad_backward4<kRegionRows, true, kWideList>(sg, s_ids, list, n, first_group, group_stride, tile_x * kTile,
                                           region_py0, region_row0, p.img_width,
                                           min(kRegionRows, p.img_height - region_py0), wg, grads);
 }

@@ -100,6 +100,11 @@ struct QuadRecords {
     unsigned char mask[kMaxPerTile];
     unsigned char rows[kMaxPerTile];   // row_lo | row_hi << 4
     unsigned char cols[kMaxPerTile];   // col_lo | col_hi << 4
+    // tile-wide backward (4 warps per tile): the sweep shape of the entry over the whole tile, packed
+    // lo | c0 << 4 | lg << 8 | trips << 10, and its place in the backward's list, bucket | position << 2 (0xffff: none)
+    unsigned short shape[kMaxPerTile];
+    unsigned short place[kMaxPerTile];
+    int bucket_count[4];
 };
 
 __device__ __forceinline__ void stage_quad(QuadRecords &s, int slot, float4 p0, float4 p1, float tile_x0,
@@ -427,10 +432,53 @@ __device__ __forceinline__ void group_trip(GroupAcc &A, const char *wg_base, int
     A.ay = add2(A.ay, t2y);
 }
 
+// Tile-wide variant of the staging (4 warps per tile): the entry's sweep shape over the whole tile is computed ONCE
+// here (the backward reads it back instead of decoding rows / cols per group) and the entry takes its place in one
+// of the four trip-count buckets of the CTA's ONE list (a shared-memory counter per bucket; order inside a bucket is
+// irrelevant).  finish_wide_list() turns (bucket, position) into list slots once every entry has been staged.
+__device__ __forceinline__ unsigned pack_shape(const GroupShape &g) {
+    return (unsigned)g.lo | ((unsigned)g.c0 << 4) | ((unsigned)g.lg << 8) | ((unsigned)g.trips << 10);
+}
+__device__ __forceinline__ GroupShape unpack_shape(unsigned v) {
+    GroupShape g;
+    g.lo = (int)(v & 15u);
+    g.c0 = (int)((v >> 4) & 15u);
+    g.lg = (int)((v >> 8) & 3u);
+    g.trips = (int)(v >> 10);
+    return g;
+}
+
+__device__ __forceinline__ void stage_quad_wide(QuadRecords &s, int slot, float4 p0, float4 p1, float tile_x0,
+                                                float tile_y0) {
+    stage_quad(s, slot, p0, p1, tile_x0, tile_y0);
+    const GroupShape g = group_shape<kTile>(s.rows[slot], s.cols[slot], 0);
+    s.shape[slot] = (unsigned short)pack_shape(g);
+    unsigned place = 0xffffu;
+    if (s.mask[slot] != 0 && g.trips > 0) {
+        const int b = g.trips > 8 ? 0 : (g.trips > 4 ? 1 : (g.trips > 2 ? 2 : 3));
+        place = (unsigned)b | ((unsigned)atomicAdd(&s.bucket_count[b], 1) << 2);
+    }
+    s.place[slot] = (unsigned short)place;
+}
+
+// after the block barrier that ends the staging: every thread writes the list slots of ranks tid, tid + threads, ...
+// Returns the list length (the same in every thread).
+__device__ __forceinline__ int finish_wide_list(const QuadRecords &s, int cnt, unsigned char *list) {
+    const int n0 = s.bucket_count[0], n1 = s.bucket_count[1], n2 = s.bucket_count[2], n3 = s.bucket_count[3];
+    for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+        const unsigned pl = s.place[r];
+        if (pl == 0xffffu) continue;
+        const int b = (int)(pl & 3u), pos = (int)(pl >> 2);
+        const int off = b == 0 ? 0 : (b == 1 ? n0 : (b == 2 ? n0 + n1 : n0 + n1 + n2));
+        list[off + pos] = (unsigned char)r;
+    }
+    return n0 + n1 + n2 + n3;
+}
+
 // `list`: ranks of the staged Gaussians that reach the region (n of them, build_group_list order).  The warp
 // takes the groups first_group, first_group + group_stride, ...  (region = the warp's own rows: 0, 1; region =
 // the whole tile shared by the CTA's warps: warp, #warps).
-template <int kRows, bool kGuard>
+template <int kRows, bool kGuard, bool kPacked = false>
 __device__ __forceinline__ void quad_backward4(const QuadRecords &s, const int *s_ids, const unsigned char *list,
                                                int n, int first_group, int group_stride, int tile_px0,
                                                int region_py0, int region_row0, int img_w, int rows_inside,
@@ -441,7 +489,7 @@ __device__ __forceinline__ void quad_backward4(const QuadRecords &s, const int *
         const bool valid = base + grp < n;
         const int t = list[valid ? base + grp : n - 1];
         const float4 p0 = s.xyab[t], p1 = s.crgb[t];
-        GroupShape sh = group_shape<kRows>(s.rows[t], s.cols[t], region_row0);
+        GroupShape sh = kPacked ? unpack_shape(s.shape[t]) : group_shape<kRows>(s.rows[t], s.cols[t], region_row0);
         if (!valid) sh.trips = 0;
         const int T = __reduce_max_sync(0xffffffffu, sh.trips);   // warp-uniform
         const int rpt = 8 >> sh.lg;                                // rows per trip
