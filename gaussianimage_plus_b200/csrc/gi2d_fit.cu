@@ -1417,8 +1417,70 @@ fit_rasterq_kernel(gi2d_fit_params p, uint64_t *__restrict__ sorted_keys, uint64
             __syncthreads();
             for (int e = tid; e < total_cnt; e += kThreads) sorted_keys[range.x + e] = __ldcg(keys_tmp + range.x + e);
         }
+    } else if (bucket_cap > 0) {
+        // beyond that (right after a densification ~1000 new Gaussians can sit in ONE tile): only the 256 smallest
+        // ids get staged (forward.cu:673 truncates the sorted list), so SELECT them instead of sorting everything --
+        // an MSB-first radix select over the ids (8-bit digits, a 256-bin shared-memory histogram per digit: two
+        // passes over the tile's keys for up to 65536 Gaussians), then the usual rank sort of the 256 survivors.
+        // O(n) instead of the O(n^2) global-memory ranking below, which made such a step take a millisecond.  The
+        // tile's keys stay unsorted in their bucket; gi2d_fit_export_binning sorts such tiles when somebody asks.
+        int *sel_id = s_sort, *sel_e = s_sort + kMaxPerTile, *hist = s_sort + 2 * kMaxPerTile, *s_sel = s_sort + 3 * kMaxPerTile;
+        const int nbits = 32 - __clz(max(p.num_points - 1, 1));
+        unsigned prefix = 0, prefix_mask = 0;
+        int k = kMaxPerTile;
+        for (int shift = ((nbits - 1) / 8) * 8; shift >= 0; shift -= 8) {
+            for (int i = tid; i < 256; i += kThreads) hist[i] = 0;
+            __syncthreads();
+            for (int e = tid; e < total_cnt; e += kThreads) {
+                const unsigned id = (unsigned)__ldcg(sorted_keys + range.x + e);
+                if ((id & prefix_mask) == prefix) atomicAdd(&hist[(id >> shift) & 255u], 1);
+            }
+            __syncthreads();
+            if (warp == 0) {   // the digit at which the running count reaches k
+                int v[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v[j] = hist[8 * lane + j]; sum += v[j]; }
+                const int incl = warp_scan_inclusive(sum);
+                int run = incl - sum;
+                if (run < k && k <= incl) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (run < k && k <= run + v[j]) { s_sel[0] = 8 * lane + j; s_sel[1] = k - run; }
+                        run += v[j];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix |= (unsigned)s_sel[0] << shift;
+            prefix_mask |= 255u << shift;
+            k = s_sel[1];
+        }
+        if (tid == 0) s_sel[2] = 0;
+        __syncthreads();
+        for (int e = tid; e < total_cnt; e += kThreads) {   // ids are unique inside a tile: exactly 256 are <= prefix
+            const unsigned id = (unsigned)__ldcg(sorted_keys + range.x + e);
+            if (id <= prefix) {
+                const int slot = atomicAdd(&s_sel[2], 1);
+                if (slot < kMaxPerTile) { sel_id[slot] = (int)id; sel_e[slot] = e; }
+            }
+        }
+        __syncthreads();
+        GI2D_CHECK(stats, s_sel[2] == kMaxPerTile);
+        for (int e2 = tid; e2 < kMaxPerTile; e2 += kThreads) {
+            const int id = sel_id[e2];
+            int rank = 0;
+            for (int jj = 0; jj < kMaxPerTile; jj += 4) {
+                const int4 o = *reinterpret_cast<const int4 *>(sel_id + jj);
+                rank += (o.x < id) + (o.y < id) + (o.z < id) + (o.w < id);
+            }
+            const size_t src = (size_t)(range.x + sel_e[e2]);
+            const float4 q0 = __ldcg(records + 2 * src), q1 = __ldcg(records + 2 * src + 1);
+            if (kWideList) stage_quad_wide(sg, rank, q0, q1, tx0, ty0); else stage_quad(sg, rank, q0, q1, tx0, ty0);
+            if (kHasBwd) s_ids[rank] = id;
+        }
     } else {
-        // beyond that (a degenerate scene): full rank sort straight from global memory
+        // beyond that on the scan + placement path (whose compact key array is the step's public output): full
+        // rank sort straight from global memory
         if (kWideList) __syncthreads();   // (the bucket counters were zeroed by four threads)
         for (int e = tid; e < total_cnt; e += kThreads) {
             const uint64_t key = __ldcg(sorted_keys + range.x + e);
@@ -2099,8 +2161,19 @@ export_keys_kernel(int bucket_cap, const int32_t *__restrict__ tile_bins, const 
                    uint64_t *__restrict__ keys_out) {
     const int tile = blockIdx.x;
     const int2 range = __ldcg(reinterpret_cast<const int2 *>(tile_bins) + tile);
-    for (int e = threadIdx.x; e < range.y - range.x; e += 64)
-        keys_out[range.x + e] = __ldcg(bucket_keys + (size_t)tile * bucket_cap + e);
+    const int n = range.y - range.x;
+    const uint64_t *src = bucket_keys + (size_t)tile * bucket_cap;
+    if (n <= 960) {   // (sorted by the rasterizer)
+        for (int e = threadIdx.x; e < n; e += 64) keys_out[range.x + e] = __ldcg(src + e);
+        return;
+    }
+    // a tile the rasterizer only SELECTED its 256 smallest ids from: rank here (a diagnostic path)
+    for (int e = threadIdx.x; e < n; e += 64) {
+        const uint64_t key = __ldcg(src + e);
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (__ldcg(src + j) < key) ? 1 : 0;
+        keys_out[range.x + rank] = key;
+    }
 }
 
 int validate(const gi2d_fit_params *p, const gi2d_fit_buffers *b) {

@@ -556,14 +556,15 @@ def test_fit_with_color_norm_matches_oracle(oracle):
     assert r.min() >= 0 and r.max() <= 1
 
 
-def test_bucket_overflow_of_one_tile_is_vetoed_and_regrown(oracle):
+@pytest.mark.parametrize("N", [700, 1500])   # the fullest tile: ranked in shared memory (<= 960) / radix-selected (beyond)
+def test_bucket_overflow_of_one_tile_is_vetoed_and_regrown(oracle, N):
     """Bucketed binning: tile t owns capacity / #tiles rows.  A scene whose Gaussians all sit
     in ONE tile overflows that bucket long before the total count reaches the capacity: the step must be an
     optimiser no-op (parameters, step counter untouched), GI2D_STAT_MAX_TILE must tell the host how far to regrow,
     and after ONE regrow the binning must equal the oracle's bit for bit (incl. the >256-entries-per-tile path)."""
     from gaussianimage_plus_b200.fit import GaussianImageFitter
 
-    N, H, W = 700, 128, 192                                  # 96 tiles
+    H, W = 128, 192                                          # 96 tiles
     rng = np.random.default_rng(9)
     xyz = (np.array([40.0, 40.0], np.float32) + rng.uniform(-3, 3, (N, 2))).astype(np.float32)   # all inside tile (2,2)
     cov = np.tile(np.array([1.0, 0.0, 1.0], np.float32), (N, 1)) + rng.uniform(0, 0.2, (N, 3)).astype(np.float32)
@@ -598,11 +599,16 @@ def test_bucket_overflow_of_one_tile_is_vetoed_and_regrown(oracle):
     for dst, src in ((fit2._xyz, xyz), (fit2._cov2d, cov), (fit2.cholesky_bound, bound), (fit2._features_dc, rgb)):
         dst.copy_(torch.from_numpy(src))
     fit2.set_target(torch.from_numpy(gt))
+    fit2.keep_render = True
     fit2._bind()
-    fit2.forward()
+    out = fit2.forward()["render"]
     st2 = fit2.stats()
     assert not st2["overflow"] and st2["num_intersects"] == total
     keys = N_(fit2.sorted_keys[:total])
     np.testing.assert_array_equal(keys >> 32, ids_s >> 32)
     np.testing.assert_array_equal((keys & 0xFFFFFFFF).astype(np.int32), gids_s)
     np.testing.assert_array_equal(N_(fit2.tile_bins), bins)
+    # ... and the render of the over-full tile is the reference's: the 256 smallest ids of the sorted list
+    img_ref = oracle.rasterize_sum_fwd(H, W, gids_s, bins, xys, conics, rgb)[0]
+    got = N_(out[0].permute(1, 2, 0))
+    assert np.allclose(got, np.clip(img_ref, 0, 1), rtol=1e-4, atol=1e-6), np.abs(got - np.clip(img_ref, 0, 1)).max()
