@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -179,7 +180,7 @@ class GaussianImageFitter:
         # default: 32 intersections per Gaussian, and -- for the bucketed binning, whose tiles each own capacity / #tiles
         # rows -- at least 512 per tile, twice what the rasterizer stages (densification clusters new Gaussians: tiles
         # with 150-300 entries were seen at 768x512; a full bucket costs a regrow and the re-run of the lost iterations)
-        cap = self._capacity_hint or max(1 << 16, 32 * n, 512 * tiles)
+        cap = self._capacity_hint or max(1 << 16, 32 * n, int(os.environ.get("GI2D_ROWS_PER_TILE", "512")) * tiles)
         self.isect_capacity = int(min(cap, max(n, 1) * tiles, 2 ** 31 - 1024))
         if not getattr(self, "_keep_exchange_buffers", False):   # (parallel.TileRowFit homes them in peer memory)
             self.grads = torch.zeros(n, 8, **f)
