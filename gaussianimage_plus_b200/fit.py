@@ -3,7 +3,7 @@
 `GaussianImageFitter` keeps the reference model's vocabulary (models/gaussianimage_covariance.py):
 `_xyz`, `_cov2d`, `_features_dc`, `cholesky_bound`, `forward()`, `train_iter()`,
 `densification_postfix()`, `non_semi_definite_prune()` -- but one `train_iter` is a single CUDA
-graph replay of 3 kernels (gi2d_fit.cu) instead of ~70 launches and two host syncs
+graph replay of 2 kernels (gi2d_fit.cu) instead of ~70 launches and two host syncs
 (SURVEY 3.1).  Nothing here computes on the CPU; without libgi2d.so it raises.
 
 Two things differ from a literal transcription, both invisible in the results:
@@ -332,7 +332,7 @@ class GaussianImageFitter:
     def step_from_host(self, host_img: torch.Tensor, host_stats: torch.Tensor) -> int:
         """One train_iter whose target comes from PINNED host memory and whose stats block goes back to pinned
         host memory, through ONE C call (gi2d_fit_step_host): upload on the library's copy stream into the
-        other of two device buffers (under the step in flight), the 3 kernels, the 640-byte read-back.
+        other of two device buffers (under the step in flight), the step's kernels, the stats block's read-back.
         Asynchronous; returns the slot to hand to `wait_host_result`.  host_img: u8 or f32 [H,W,3];
         host_stats: f64[STAT_COUNT].  The fitter's device must be the current CUDA device."""
         pb = self._pipe_bound

@@ -191,10 +191,11 @@ int gi2d_rasterize_sum_bwd(int num_points, int tiles_x, int tiles_y, int img_wid
 /* ------------------------------------------------------------------------------------------
  * Fused fit step: the whole `train_iter` of
  * models/gaussianimage_covariance.py:249-259 for the covariance model, with no host synchronisation, in
- * 3 launches: [project backward + Adam of the previous step] + project + per-tile overlap counts ->
- * prefix sum of the counts + placement of the 64-bit (tile|gaussian) keys and 32-B records -> in-tile
- * key sort + rasterize forward + loss gradient (mse / l1 inline; SSIM through two more kernels) +
- * rasterize backward.
+ * 2 launches (bucketed binning, see gi2d_fit_bucket_capacity below): [project backward + Adam of the previous
+ * step] + project + placement of the 64-bit (tile|gaussian) keys and 32-B records into per-tile buckets ->
+ * in-tile key sort + rasterize forward + loss gradient (mse / l1 inline; SSIM / MS-SSIM through more kernels) +
+ * rasterize backward.  (Scan + placement path -- tile-row split, tiny capacities: per-tile overlap counts ->
+ * prefix sum + placement -> the same rasterizer: 3 launches up to 2048 tiles, 6 beyond.)
  * ------------------------------------------------------------------------------------------ */
 
 typedef struct gi2d_fit_params {
