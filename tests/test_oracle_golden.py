@@ -129,3 +129,41 @@ def test_ms_ssim_oracle_anchors():
     v = float(S.ms_ssim(x, y))
     assert 0.5 < v < 1.0 and abs(v - float(S.ms_ssim(y, x))) < 1e-12
     assert abs(sum(S.MS_WEIGHTS) - 1.0) < 1e-3
+
+
+def test_ms_ssim_oracle_anchors():
+    """oracle/ssim_oracle.ms_ssim (restated pytorch_msssim.ms_ssim; the package is absent: parity unpinned) against
+    closed forms: ms_ssim(x, x) == 1 for both window sizes the reference uses (11; 5 in `Fusion_hinerv`), symmetry,
+    the window sums to 1, and the two MS-SSIM losses of models/utils.py:76-79 vanish on identical images."""
+    import torch
+
+    from oracle import ssim_oracle as S
+
+    torch.manual_seed(0)
+    x = torch.rand(1, 3, 176, 200, dtype=torch.float64)
+    y = (x + 0.1 * torch.rand_like(x)).clamp(0, 1)
+    for win in (11, 5):
+        assert abs(float(S.fspecial_gauss_1d(win).sum()) - 1.0) < 1e-6
+        assert abs(float(S.ms_ssim(x, x, win_size=win)) - 1.0) < 1e-12
+        a, b = float(S.ms_ssim(x, y, win_size=win)), float(S.ms_ssim(y, x, win_size=win))
+        assert abs(a - b) < 1e-12 and 0.0 < a < 1.0
+    assert float(S.ms_ssim(x, y, win_size=5)) != float(S.ms_ssim(x, y, win_size=11))
+    for lt in ("Fusion4", "Fusion_hinerv"):
+        assert abs(float(S.loss_fn(x, x, lt))) < 1e-12
+        assert float(S.loss_fn(x, y, lt)) > 0
+
+
+def test_bench_arms_print_the_same_config():
+    """bench.py: `--impl reference` runs "on your arm's config" -- both arms build it with one function."""
+    import argparse
+    import sys
+
+    sys.path.insert(0, ROOT) if "ROOT" in globals() else None
+    import bench
+
+    args = argparse.Namespace(workload="kodak_5000", preroll=2000, mode="images", cov_scale=1.0)
+    c1, c8 = bench.bench_config(args, 512, 768, 5000, 1), bench.bench_config(args, 512, 768, 5000, 8)
+    assert c1["workload"].startswith("kodak_5000: 768x512, 5000 Gaussians") and "l2" in c1 and "flushed" in c1["l2"]
+    assert c1 == bench.bench_config(args, 512, 768, 5000, 1) and "tile rows" in c8["parallelism"]
+    src = open(bench.__file__).read()
+    assert src.count("\"config\": bench_config(args, H, W, N,") == 2      # the GPU arm and the reference arm
